@@ -1,0 +1,244 @@
+/*
+ * so101_b200.h — C ABI of the B200-native batched SO-ARM101 stepper.
+ *
+ * This is the drop-in boundary for ONE hot path of Hucheyu1/Lerobot-mujoco-sim2real:
+ * SOARM101Env.reset/step (frame_skip x mujoco.mj_step on the SO101 hinge chain) and the
+ * trajectory loop of SOARM101DataGenerator.generate_physics_based_data.
+ *
+ * The reference has no FFI of its own: it calls the third-party `mujoco` pybind module.
+ * Each entry point below names the reference call site(s) it replaces:
+ *
+ *   so101_model_create      <- mujoco.MjModel.from_xml_path         [REF SOARM101/SOARM101_Env.py:34]
+ *   so101_batch_create      <- mujoco.MjData(model)                 [REF SOARM101/SOARM101_Env.py:43]
+ *   so101_batch_reset*      <- mj_resetData + qpos/qvel write + mj_forward
+ *                                                                   [REF SOARM101/SOARM101_Env.py:87-102]
+ *   so101_batch_forward     <- mujoco.mj_forward                    [REF SOARM101/SOARM101_Env.py:102,
+ *                                                                    Koopman_MPC.py:90,126]
+ *   so101_batch_step*       <- data.ctrl[:5]=u ; frame_skip x mj_step ; _get_state
+ *                                                                   [REF SOARM101/SOARM101_Env.py:128-135, 69-75]
+ *   so101_batch_rollout     <- the (reset, T x step, row write) double loop
+ *                                                                   [REF SOARM101/SOARM101_DataCollection.py:108-134]
+ *   so101_batch_shoot       <- batched evaluation of control sequences from one shared state
+ *                              (Koopman_MPC.py:197-222 closed loop, BASELINE.json config 5)
+ *
+ * Conventions
+ *   - plain C, no exceptions; every call returns 0 on success, <0 on error (so101_last_error()
+ *     gives the text, thread-local).
+ *   - device buffers are structure-of-arrays `[field][N]` (N = n_envs), element type = the batch
+ *     dtype (SO101_F64 -> double, SO101_F32 -> float) unless stated; observations are always
+ *     float32 `[8][N]` = [ee_x, ee_y, ee_z, q0..q4] (reference order, SOARM101_Env.py:69-75).
+ *   - all device work is enqueued on the caller's stream (`stream` = cudaStream_t as void*,
+ *     pass torch.cuda.current_stream().cuda_stream); no hidden synchronisation except in the
+ *     *_host variants, which synchronise the stream before returning.
+ *   - a batch is bound to one device; handles are not thread-safe.
+ *   - there is no CPU fallback: every compute entry point fails if no CUDA device is present.
+ */
+#ifndef SO101_B200_H_
+#define SO101_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SO101_ABI_VERSION 3
+#define SO101_NV       6   /* hinge dofs: 5 arm joints + gripper */
+#define SO101_MAXBODY  8   /* world, fixed base, 6 links */
+#define SO101_MAXTRIP  8   /* contact-tripwire boxes */
+#define SO101_NOBS     8   /* observation: ee_pos(3) + qpos[0:5] */
+#define SO101_NU_ENV   5   /* controls exposed by SOARM101Env (gripper channel held at 0) */
+#define SO101_ROW     13   /* dataset row: u(5) | ee_pos(3) | qpos(5) */
+
+enum { SO101_F64 = 0, SO101_F32 = 1 };
+
+/* error codes */
+enum {
+  SO101_OK = 0,
+  SO101_EINVAL = -1,      /* bad argument */
+  SO101_EMODEL = -2,      /* model outside the supported subset (not a hinge chain, ...) */
+  SO101_ECUDA = -3,       /* CUDA runtime error */
+  SO101_ENODEVICE = -4    /* no CUDA device: there is no CPU fallback */
+};
+
+/* per-env status bits (so101_batch_get_flags) */
+enum {
+  SO101_FLAG_BADSTATE   = 1u << 0,  /* qpos/qvel/qacc NaN or |x|>1e10 (mj_checkPos/Vel/Acc) */
+  SO101_FLAG_TRIP_TABLE = 1u << 1,  /* a collision bounding box crossed the table plane    */
+  SO101_FLAG_TRIP_SELF  = 1u << 2,  /* joint vector left the self-collision-free box       */
+  SO101_FLAG_LIMIT      = 1u << 3,  /* a joint-limit row was active at least once (info)   */
+  SO101_FLAG_MAXITER    = 1u << 4   /* Newton hit opt.iterations (info)                    */
+};
+
+/* rollout / shoot option bits */
+enum {
+  SO101_ROLL_GRAVCOMP_HOLD = 1u << 0, /* qfrc_applied <- qfrc_bias at the start of every control
+                                         step, held over the sub-steps [REF Koopman_MPC.py:119] */
+  SO101_ROLL_NO_RESET      = 1u << 1, /* continue from the batch's current state               */
+  SO101_ROLL_ROWS_F32      = 1u << 2  /* rows written as float32 instead of float64            */
+};
+
+/* control generators of SOARM101DataGenerator [REF SOARM101_DataCollection.py:97-103,115,132] */
+enum {
+  SO101_CTRL_RANDOM = 0,  /* u ~ U(-amp, amp) i.i.d. per control step (Philox4x32-10)        */
+  SO101_CTRL_SIN    = 1,  /* u = a*sin(2*pi*f*t + phase), t = integer control step            */
+  SO101_CTRL_CHIRP  = 2,  /* f = f_traj + (f_hi - f_lo) * t / T_total                         */
+  SO101_CTRL_TENSOR = 3   /* u read from a device tensor [T+1][5][N] (batch dtype)            */
+};
+
+typedef struct So101CtrlSpec {
+  int32_t  kind;          /* SO101_CTRL_*                                                     */
+  int32_t  t_total;       /* chirp normaliser (reference: 200)                                */
+  uint64_t seed;          /* Philox key                                                       */
+  int64_t  env_offset;    /* global index of this shard's env 0 (results independent of the
+                             number of GPUs)                                                  */
+  double   amp;           /* random: half-range (0.5); sin/chirp: amplitude range +-amp       */
+  double   freq_lo;       /* 0.0025                                                           */
+  double   freq_hi;       /* 0.05                                                             */
+  double   reset_lo;      /* reset box for qpos[0:5]: U(reset_lo, reset_hi) = (-0.3, 0.3)     */
+  double   reset_hi;
+  const void* u;          /* SO101_CTRL_TENSOR: device pointer [T+1][5][N]                    */
+} So101CtrlSpec;
+
+/*
+ * Packed constant tables of one compiled MJCF scene (host -> library, once).  Built by the
+ * Python MJCF compiler (mjcf.py); mirrors the subset of mjModel that mj_step reads for this
+ * scene.  Index 0 of the body arrays is the world.  Joint j <-> dof j (hinges only).
+ */
+typedef struct So101Tables {
+  int32_t abi_version;
+  int32_t nbody;                 /* incl. world                                            */
+  int32_t nv;                    /* == SO101_NV                                            */
+  int32_t nu;                    /* == SO101_NV                                            */
+  /* mjOption */
+  int32_t iterations;            /* 100                                                    */
+  int32_t ls_iterations;         /* 50                                                     */
+  int32_t site_body;             /* body of the `gripperframe` site                        */
+  int32_t ntrip;                 /* number of tripwire boxes                               */
+  double  timestep;              /* 0.002                                                  */
+  double  gravity[3];
+  double  tolerance;             /* 1e-8                                                   */
+  double  ls_tolerance;          /* 0.01                                                   */
+  double  meaninertia;           /* mjModel.stat.meaninertia                               */
+  /* bodies */
+  int32_t body_parent[SO101_MAXBODY];
+  int32_t body_jnt[SO101_MAXBODY];            /* joint index or -1                         */
+  double  body_pos[SO101_MAXBODY][3];
+  double  body_quat[SO101_MAXBODY][4];
+  double  body_ipos[SO101_MAXBODY][3];
+  double  body_iquat[SO101_MAXBODY][4];
+  double  body_inertia[SO101_MAXBODY][3];     /* principal moments                         */
+  double  body_mass[SO101_MAXBODY];
+  /* joints / dofs */
+  int32_t jnt_body[SO101_NV];
+  int32_t jnt_limited[SO101_NV];
+  double  jnt_pos[SO101_NV][3];
+  double  jnt_axis[SO101_NV][3];
+  double  jnt_range[SO101_NV][2];
+  double  jnt_margin[SO101_NV];
+  double  jnt_solref[SO101_NV][2];            /* limit rows                                */
+  double  jnt_solimp[SO101_NV][5];
+  double  jnt_stiffness[SO101_NV];
+  double  qpos0[SO101_NV];
+  double  qpos_spring[SO101_NV];
+  double  dof_armature[SO101_NV];
+  double  dof_damping[SO101_NV];
+  double  dof_frictionloss[SO101_NV];
+  double  dof_solref[SO101_NV][2];            /* friction rows                             */
+  double  dof_solimp[SO101_NV][5];
+  double  dof_invweight0[SO101_NV];
+  double  dof_M0[SO101_NV];
+  /* actuators (joint transmission, affine bias) */
+  int32_t act_dof[SO101_NV];
+  int32_t act_ctrllimited[SO101_NV];
+  int32_t act_forcelimited[SO101_NV];
+  int32_t pad0_[2];
+  double  act_gear[SO101_NV];
+  double  act_gain[SO101_NV];                 /* gainprm[0]                                */
+  double  act_bias[SO101_NV][3];              /* biasprm[0..2]                             */
+  double  act_ctrlrange[SO101_NV][2];
+  double  act_forcerange[SO101_NV][2];
+  /* observation site */
+  double  site_pos[3];
+  /* keyframe 0 (`home`) — read by Koopman_MPC.py:65-71 through env.model */
+  double  key_qpos[SO101_NV];
+  double  key_ctrl[SO101_NV];
+  /* contact tripwire: oriented boxes fixed to bodies vs the plane z = trip_plane_z, and a
+     joint-space box outside which self-collision is possible */
+  int32_t trip_body[SO101_MAXTRIP];
+  double  trip_center[SO101_MAXTRIP][3];      /* body frame                                */
+  double  trip_axes[SO101_MAXTRIP][9];        /* rows = box axes in the body frame         */
+  double  trip_half[SO101_MAXTRIP][3];
+  double  trip_plane_z;                       /* table top (world z)                       */
+  double  trip_qbox[SO101_NV][2];             /* lo, hi                                    */
+} So101Tables;
+
+typedef struct So101Model So101Model;
+typedef struct So101Batch So101Batch;
+
+const char* so101_last_error(void);
+int         so101_abi_version(void);
+size_t      so101_tables_sizeof(void);
+int         so101_device_count(void);
+
+/* ---- model ---------------------------------------------------------------------------- */
+int  so101_model_create(const So101Tables* tables, So101Model** out);
+void so101_model_destroy(So101Model* model);
+
+/* ---- batch ---------------------------------------------------------------------------- */
+/* bytes of per-env state for n_envs (SoA rows: qpos[6] qvel[6] qacc_warmstart[6]
+   qfrc_applied[6] time[1], element = batch dtype; followed by uint32 flags[N]). */
+size_t so101_batch_state_bytes(int64_t n_envs, int dtype);
+/* state_buf: caller-owned device memory of so101_batch_state_bytes() (e.g. a torch tensor),
+   or NULL to let the library allocate. */
+int  so101_batch_create(const So101Model* model, int64_t n_envs, int dtype, int device,
+                        void* state_buf, So101Batch** out);
+void so101_batch_destroy(So101Batch* batch);
+
+/* mj_resetData, then qpos[0:nq] <- qpos0[j][N] (NULL: model qpos0), qvel likewise (NULL: 0),
+   then mj_forward; obs (nullable) receives float32 [8][N]. */
+int so101_batch_reset(So101Batch* b, const void* qpos0, const void* qvel0, void* obs, void* stream);
+/* same with qpos[0:5] ~ U(lo,hi) from Philox(seed, env_offset+env), qpos[5]=0, qvel=0. */
+int so101_batch_reset_random(So101Batch* b, uint64_t seed, int64_t env_offset, double lo, double hi,
+                             void* obs, void* stream);
+/* mj_forward at the current state: obs float32 [8][N] (nullable), qfrc_bias [6][N] (nullable). */
+int so101_batch_forward(So101Batch* b, void* obs, void* qfrc_bias, void* stream);
+/* ctrl [6][N] (row 5 = gripper; NULL row pointer semantics: pass n_ctrl=5 to hold it at 0);
+   n_substeps x mj_step; obs float32 [8][N] with the reference's one-sub-step ee lag. */
+int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps, void* obs, void* stream);
+/* host-buffer variants: pinned or pageable host pointers, H2D + kernel + D2H on `stream`,
+   stream synchronised before return.  These are what SOARM101Env.step()/reset() call. */
+int so101_batch_step_host(So101Batch* b, const void* ctrl_host, int n_ctrl, int n_substeps,
+                          void* obs_host, void* stream);
+int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qvel0_host,
+                           void* obs_host, void* stream);
+
+/* fused trajectory generation: rows [N][T+1][13] (float64, or float32 with ROWS_F32) =
+   [u_i(5) | ee_pos(3) | qpos(5)], row 0 from reset, row i after step(u_{i-1}); observation
+   values are rounded to float32 first, as the reference does. */
+int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip,
+                        void* rows, uint32_t flags, void* stream);
+/* B = n_envs control sequences from one shared state: state0 host pointer to 18 doubles
+   (qpos, qvel, qacc_warmstart), U device [H][5][B] (batch dtype), X device float32 [B][H+1][8]. */
+int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H, int frame_skip,
+                      void* X, uint32_t flags, void* stream);
+
+/* state access, device pointers [6][N] in the batch dtype (any may be NULL) */
+int so101_batch_get_state(So101Batch* b, void* qpos, void* qvel, void* qacc_warmstart, void* stream);
+int so101_batch_set_state(So101Batch* b, const void* qpos, const void* qvel, const void* qacc_warmstart,
+                          void* stream);
+int so101_batch_set_qfrc_applied(So101Batch* b, const void* qfrc_applied, void* stream);
+int so101_batch_get_flags(So101Batch* b, uint32_t* flags_dev, void* stream);
+int so101_batch_clear_flags(So101Batch* b, void* stream);
+/* solver statistics accumulated since the last call: [0]=physics steps, [1]=Newton iterations,
+   [2]=line-search evaluations, [3]=steps with an active limit row (host pointer, 4 x uint64). */
+int so101_batch_stats(So101Batch* b, uint64_t* stats_host, void* stream);
+
+/* measurement helper: register-resident FMA loop; returns achieved TFLOP/s (2 flop per FMA). */
+int so101_fma_peak(int dtype, int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SO101_B200_H_ */

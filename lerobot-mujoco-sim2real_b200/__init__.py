@@ -1,0 +1,10 @@
+"""B200-native batched SO-ARM101 stepper (drop-in for SOARM101Env / SOARM101DataGenerator).
+
+Only what the hot path needs lives here: the host MJCF compiler (mjcf.py), the packed tables
+(tables.py), the ctypes binding of the CUDA C-ABI library (_lib.py, csrc/), and the host-side
+mirrors of the reference interface (SOARM101_Env.py, SOARM101_DataCollection.py, vec_env.py).
+"""
+from . import tables  # noqa: F401
+from .tables import builtin_tables, load_tables, save_tables  # noqa: F401
+
+__all__ = ["tables", "builtin_tables", "load_tables", "save_tables"]
