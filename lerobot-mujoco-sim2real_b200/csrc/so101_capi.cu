@@ -1,0 +1,706 @@
+// so101_capi.cu — kernels and the C ABI of include/so101_b200.h (sm_100a).
+//
+// One thread owns one environment for a whole launch: its state (qpos, qvel, qacc_warmstart,
+// qfrc_applied: 25 scalars) is loaded once from the structure-of-arrays buffer, stepped
+// n_substeps (step) or T*frame_skip (rollout, shoot) times entirely in registers, and stored
+// once.  Loads/stores are coalesced (lane i <-> env i, consecutive addresses per SoA row).
+// The path is FP64/FP32-pipe bound (about 160 FLOP per byte of state traffic); tensor cores
+// and TMA are deliberately unused (no dense contraction, 100 bytes of state per thread).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "so101_physics.cuh"
+
+using namespace so101;
+
+// ==========================================================================================
+// device helpers
+// ==========================================================================================
+constexpr int ROW_Q = 0, ROW_QD = 6, ROW_WARM = 12, ROW_FA = 18, ROW_TIME = 24, NROWS = 25;
+
+template <typename T>
+struct StateView {
+  T* base;
+  uint32_t* flags;
+  int64_t n;
+};
+
+template <typename T> SO101_DEV void load_env(const StateView<T>& s, int64_t i, Env<T>& e) {
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    e.q[k] = s.base[(ROW_Q + k) * s.n + i];
+    e.qd[k] = s.base[(ROW_QD + k) * s.n + i];
+    e.warm[k] = s.base[(ROW_WARM + k) * s.n + i];
+    e.fa[k] = s.base[(ROW_FA + k) * s.n + i];
+  }
+  e.time = s.base[ROW_TIME * s.n + i];
+  e.flags = s.flags[i];
+}
+template <typename T> SO101_DEV void store_env(const StateView<T>& s, int64_t i, const Env<T>& e) {
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    s.base[(ROW_Q + k) * s.n + i] = e.q[k];
+    s.base[(ROW_QD + k) * s.n + i] = e.qd[k];
+    s.base[(ROW_WARM + k) * s.n + i] = e.warm[k];
+    s.base[(ROW_FA + k) * s.n + i] = e.fa[k];
+  }
+  s.base[ROW_TIME * s.n + i] = e.time;
+  s.flags[i] = e.flags;
+}
+template <typename T> SO101_DEV void reset_env(const DevModel<T>& m, Env<T>& e) {  // mj_resetData
+#pragma unroll
+  for (int k = 0; k < NV; k++) { e.q[k] = m.qpos0[k]; e.qd[k] = T(0); e.warm[k] = T(0); e.fa[k] = T(0); }
+  e.time = T(0);
+  e.flags = 0;
+}
+
+SO101_DEV void add_stats(unsigned long long* stats, const Counters& c) {
+  // warp-reduce, one atomic per warp and counter
+  uint32_t v[4] = {c.steps, c.newton, c.lsevals, c.limsteps};
+  const unsigned mask = __activemask();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    unsigned long long x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(mask, x, o);
+    // with a partial warp shfl_down reads inactive lanes as undefined; fall back to per-lane atomics
+    if (mask == 0xffffffffu) {
+      if ((threadIdx.x & 31) == 0) atomicAdd(&stats[k], x);
+    } else {
+      atomicAdd(&stats[k], (unsigned long long)v[k]);
+    }
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011).  Stream layout specified in DESIGN.md ("control RNG"):
+// key = seed, counter = (env_lo, env_hi, step, 2*stream + block); 32-bit lanes -> [0,1).
+SO101_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+enum { STREAM_RESET = 0, STREAM_CTRL = 1, STREAM_FREQ = 2, STREAM_AMP = 3, STREAM_PHASE = 4 };
+// first 5 of the 8 uniforms of (seed, env, step, stream)
+SO101_DEV void uniform5(uint64_t seed, int64_t env, uint32_t step, uint32_t stream, double (&out)[5]) {
+  uint32_t c[4] = {(uint32_t)env, (uint32_t)((uint64_t)env >> 32), step, stream * 2u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (double)c[k] * (1.0 / 4294967296.0);
+  uint32_t d[4] = {(uint32_t)env, (uint32_t)((uint64_t)env >> 32), step, stream * 2u + 1u};
+  philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+  out[4] = (double)d[0] * (1.0 / 4294967296.0);
+}
+// a + b*c without contraction: the control stream must be bit-identical to the CPU restatement
+SO101_DEV double muladd_rn(double a, double b, double c) { return __dadd_rn(a, __dmul_rn(b, c)); }
+
+struct CtrlGen {  // per-env generator state for SO101_CTRL_SIN / CHIRP
+  double freq[5], amp[5], phase[5];
+};
+struct DevSpec {
+  int32_t kind, t_total;
+  uint64_t seed;
+  int64_t env_offset;
+  double amp, freq_lo, freq_hi, reset_lo, reset_hi;
+  const void* u;
+};
+
+SO101_DEV void ctrl_init(const DevSpec& s, int64_t env, CtrlGen& g) {
+  if (s.kind == SO101_CTRL_SIN || s.kind == SO101_CTRL_CHIRP) {
+    double r[5];
+    uniform5(s.seed, env, 0, STREAM_FREQ, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.freq[k] = muladd_rn(s.freq_lo, s.freq_hi - s.freq_lo, r[k]);
+    uniform5(s.seed, env, 0, STREAM_AMP, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.amp[k] = muladd_rn(-s.amp, 2 * s.amp, r[k]);
+    uniform5(s.seed, env, 0, STREAM_PHASE, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.phase[k] = __dmul_rn(2 * 3.14159265358979323846, r[k]);
+  }
+}
+// u_t  [REF SOARM101_DataCollection.py:57-74 (sin/chirp), :115,132 (random)]
+template <typename T>
+SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t local, int64_t n, int t,
+                        double (&u)[5]) {
+  if (s.kind == SO101_CTRL_RANDOM) {
+    double r[5];
+    uniform5(s.seed, env, (uint32_t)t, STREAM_CTRL, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) u[k] = __dmul_rn(__dmul_rn(__dadd_rn(r[k], -0.5), 2.0), s.amp);
+  } else if (s.kind == SO101_CTRL_TENSOR) {
+    const T* ut = static_cast<const T*>(s.u);
+#pragma unroll
+    for (int k = 0; k < 5; k++) u[k] = (double)ut[((int64_t)t * 5 + k) * n + local];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      double f = g.freq[k];
+      if (s.kind == SO101_CTRL_CHIRP) f = muladd_rn(g.freq[k], s.freq_hi - s.freq_lo, (double)t / (double)s.t_total);
+      double arg = __dadd_rn(__dmul_rn(__dmul_rn(2 * 3.14159265358979323846, f), (double)t), g.phase[k]);
+      u[k] = __dmul_rn(g.amp[k], sin(arg));
+    }
+  }
+}
+
+// ==========================================================================================
+// kernels
+// ==========================================================================================
+#define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(128)
+
+// reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
+//   mode 0: qpos0/qvel0 [6][N] (nullable)   mode 1: qpos[0:5] ~ U(lo,hi) from Philox
+SO101_KERNEL(T)
+k_reset(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* qpos0, const T* qvel0, int mode,
+        uint64_t seed, int64_t env_offset, double lo, double hi, float* obs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  Env<T> e;
+  reset_env(m, e);
+  if (mode == 1) {
+    double r[5];
+    uniform5(seed, env_offset + i, 0, STREAM_RESET, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(lo, hi - lo, r[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      if (qpos0) e.q[k] = qpos0[k * s.n + i];
+      if (qvel0) e.qd[k] = qvel0[k * s.n + i];
+    }
+  }
+  store_env(s, i, e);
+  if (obs) {
+    T site[3];
+    site_fk(m, e.q, site);
+#pragma unroll
+    for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+  }
+}
+
+// mj_forward outputs the Env shims read: observation and qfrc_bias
+SO101_KERNEL(T)
+k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* qfrc_bias) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  Env<T> e;
+  load_env(s, i, e);
+  T M[21], bias[NV], site[3];
+  uint32_t fl = 0;
+  smooth_dynamics<T, false>(m, e.q, e.qd, M, bias, true, site, false, fl);
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+  }
+  if (qfrc_bias) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) qfrc_bias[k * s.n + i] = bias[k];
+  }
+}
+
+// SOARM101Env.step: ctrl rows [n_ctrl][N] (missing rows = 0), nsub x mj_step, observation
+SO101_KERNEL(T)
+k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
+       unsigned long long* stats) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  Env<T> e;
+  load_env(s, i, e);
+  T u[NV], site[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = 0; k < NV; k++) u[k] = (ctrl && k < n_ctrl) ? ctrl[k * s.n + i] : T(0);
+  Counters cnt = {0, 0, 0, 0};
+  const bool trip = m.ntrip > 0;
+  for (int ss = 0; ss < nsub; ss++) physics_step(m, e, u, false, ss == nsub - 1, site, trip, cnt);
+  if (nsub == 0) site_fk(m, e.q, site);
+  store_env(s, i, e);
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+  }
+  add_stats(stats, cnt);
+}
+
+// SOARM101DataGenerator.generate_physics_based_data, one env per thread:
+// rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
+template <typename T, typename ROW>
+__global__ void __launch_bounds__(128)
+k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int Tn, int frame_skip, ROW* rows,
+          uint32_t rflags, unsigned long long* stats) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  const int64_t env = spec.env_offset + i;
+  Env<T> e;
+  if (rflags & SO101_ROLL_NO_RESET) {
+    load_env(s, i, e);
+  } else {
+    reset_env(m, e);
+    double r[5];
+    uniform5(spec.seed, env, 0, STREAM_RESET, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(spec.reset_lo, spec.reset_hi - spec.reset_lo, r[k]);
+  }
+  CtrlGen g;
+  ctrl_init(spec, env, g);
+  Counters cnt = {0, 0, 0, 0};
+  const bool trip = m.ntrip > 0;
+  const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
+  T site[3];
+  site_fk(m, e.q, site);
+  double u[5];
+  T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  for (int t = 0; t <= Tn; t++) {
+    if (t > 0) {
+      for (int ss = 0; ss < frame_skip; ss++)
+        physics_step(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+    }
+    ctrl_gen<T>(spec, g, env, i, s.n, t, u);
+#pragma unroll
+    for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
+    if (rows) {
+      ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
+#pragma unroll
+      for (int k = 0; k < 5; k++) row[k] = (ROW)u[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) row[5 + k] = (ROW)(float)site[k];
+#pragma unroll
+      for (int k = 0; k < 5; k++) row[8 + k] = (ROW)(float)e.q[k];
+    }
+  }
+  store_env(s, i, e);
+  add_stats(stats, cnt);
+}
+
+struct State0 { double v[18]; };
+
+// B control sequences U[H][5][B] from one shared state; X[B][H+1][8] float32 observations
+SO101_KERNEL(T)
+k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
+        int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  Env<T> e;
+  reset_env(m, e);
+#pragma unroll
+  for (int k = 0; k < NV; k++) { e.q[k] = (T)s0.v[k]; e.qd[k] = (T)s0.v[6 + k]; e.warm[k] = (T)s0.v[12 + k]; }
+  Counters cnt = {0, 0, 0, 0};
+  const bool trip = m.ntrip > 0;
+  const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
+  T site[3];
+  site_fk(m, e.q, site);
+  T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  for (int t = 0; t <= H; t++) {
+    if (t > 0) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) uc[k] = U[((int64_t)(t - 1) * 5 + k) * s.n + i];
+      for (int ss = 0; ss < frame_skip; ss++)
+        physics_step(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+    }
+    float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = (float)site[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) x[3 + k] = (float)e.q[k];
+  }
+  store_env(s, i, e);
+  add_stats(stats, cnt);
+}
+
+// register-resident FMA loop for the roofline denominator ("of measured")
+template <typename T> __global__ void k_fma_peak(T* out, int iters, T a, T b) {
+  T x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = T(threadIdx.x + k) * T(1e-3);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = x[k] * a + b;
+  }
+  T s = T(0);
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += x[k];
+  if (s == T(-12345.678)) out[0] = s;  // never true; keeps the loop alive
+}
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t err__ = (expr);                                                                     \
+    if (err__ != cudaSuccess)                                                                       \
+      return fail(SO101_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));              \
+  } while (0)
+
+struct So101Model {
+  So101Tables tables;
+  DevModel<double> d;
+  DevModel<float> f;
+};
+
+struct So101Batch {
+  const So101Model* model;
+  int64_t n;
+  int dtype, device;
+  void* state;        // NROWS*n elements + n uint32 flags
+  bool owns_state;
+  unsigned long long* stats;  // device, 4 counters
+  void* ctrl_stage;   // [6][n] batch dtype (host variants)
+  float* obs_stage;   // [8][n]
+  void* init_stage;   // [12][n] (reset_host)
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+static size_t elem_size(int dtype) { return dtype == SO101_F64 ? sizeof(double) : sizeof(float); }
+
+template <typename T> static StateView<T> view(const So101Batch* b) {
+  StateView<T> v;
+  v.base = static_cast<T*>(b->state);
+  v.flags = reinterpret_cast<uint32_t*>(static_cast<char*>(b->state) + (size_t)NROWS * b->n * sizeof(T));
+  v.n = b->n;
+  return v;
+}
+// block size: small batches use one-warp blocks so that every SM gets work
+static int pick_block(int64_t n) {
+  if (n >= (int64_t)148 * 128 * 2) return 128;
+  if (n >= (int64_t)148 * 64 * 2) return 64;
+  return 32;
+}
+static unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" {
+
+const char* so101_last_error(void) { return g_err.c_str(); }
+int so101_abi_version(void) { return SO101_ABI_VERSION; }
+size_t so101_tables_sizeof(void) { return sizeof(So101Tables); }
+int so101_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int so101_model_create(const So101Tables* tables, So101Model** out) {
+  if (!tables || !out) return fail(SO101_EINVAL, "null argument");
+  So101Model* m = new So101Model();
+  m->tables = *tables;
+  std::string why = hostbuild::build(*tables, m->d);
+  if (!why.empty()) { delete m; return fail(SO101_EMODEL, "unsupported model: " + why); }
+  hostbuild::convert<float>(m->d, m->f);
+  *out = m;
+  return SO101_OK;
+}
+void so101_model_destroy(So101Model* m) { delete m; }
+
+size_t so101_batch_state_bytes(int64_t n, int dtype) {
+  if (n <= 0) return 0;
+  return (size_t)NROWS * n * elem_size(dtype) + (size_t)n * sizeof(uint32_t);
+}
+
+int so101_batch_create(const So101Model* model, int64_t n, int dtype, int device, void* state_buf, So101Batch** out) {
+  if (!model || !out || n <= 0) return fail(SO101_EINVAL, "bad argument");
+  if (dtype != SO101_F64 && dtype != SO101_F32) return fail(SO101_EINVAL, "dtype must be SO101_F64 or SO101_F32");
+  int ndev = so101_device_count();
+  if (ndev <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SO101_EINVAL, "device index out of range");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SO101_ECUDA, "cudaSetDevice failed");
+  So101Batch* b = new So101Batch();
+  std::memset(b, 0, sizeof *b);
+  b->model = model; b->n = n; b->dtype = dtype; b->device = device;
+  size_t bytes = so101_batch_state_bytes(n, dtype);
+  if (state_buf) { b->state = state_buf; b->owns_state = false; }
+  else {
+    cudaError_t e = cudaMalloc(&b->state, bytes);
+    if (e != cudaSuccess) { delete b; return fail(SO101_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    b->owns_state = true;
+  }
+  cudaError_t e = cudaMalloc(&b->stats, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(b->stats, 0, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(b->state, 0, bytes);
+  if (e != cudaSuccess) {
+    if (b->owns_state) cudaFree(b->state);
+    cudaFree(b->stats);
+    delete b;
+    return fail(SO101_ECUDA, std::string("batch init: ") + cudaGetErrorString(e));
+  }
+  *out = b;
+  return SO101_OK;
+}
+void so101_batch_destroy(So101Batch* b) {
+  if (!b) return;
+  DeviceGuard g(b->device);
+  if (b->owns_state) cudaFree(b->state);
+  cudaFree(b->stats);
+  cudaFree(b->ctrl_stage);
+  cudaFree(b->obs_stage);
+  cudaFree(b->init_stage);
+  delete b;
+}
+
+#define DISPATCH(b, CALL_D, CALL_F)              \
+  do {                                           \
+    if ((b)->dtype == SO101_F64) { CALL_D; }     \
+    else { CALL_F; }                             \
+  } while (0)
+
+int so101_batch_reset(So101Batch* b, const void* qpos0, const void* qvel0, void* obs, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blk = pick_block(b->n);
+  DISPATCH(b,
+    (k_reset<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), (const double*)qpos0,
+        (const double*)qvel0, 0, 0, 0, 0.0, 0.0, (float*)obs)),
+    (k_reset<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), (const float*)qpos0,
+        (const float*)qvel0, 0, 0, 0, 0.0, 0.0, (float*)obs)));
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+int so101_batch_reset_random(So101Batch* b, uint64_t seed, int64_t env_offset, double lo, double hi, void* obs,
+                             void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blk = pick_block(b->n);
+  DISPATCH(b,
+    (k_reset<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), nullptr, nullptr, 1, seed,
+        env_offset, lo, hi, (float*)obs)),
+    (k_reset<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), nullptr, nullptr, 1, seed,
+        env_offset, lo, hi, (float*)obs)));
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+int so101_batch_forward(So101Batch* b, void* obs, void* qfrc_bias, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blk = pick_block(b->n);
+  DISPATCH(b,
+    (k_forward<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), (float*)obs, (double*)qfrc_bias)),
+    (k_forward<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), (float*)obs, (float*)qfrc_bias)));
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps, void* obs, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  if (n_ctrl < 0 || n_ctrl > NV || n_substeps < 0) return fail(SO101_EINVAL, "n_ctrl must be 0..6, n_substeps >= 0");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blk = pick_block(b->n);
+  DISPATCH(b,
+    (k_step<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), (const double*)ctrl, n_ctrl,
+        n_substeps, (float*)obs, b->stats)),
+    (k_step<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), (const float*)ctrl, n_ctrl,
+        n_substeps, (float*)obs, b->stats)));
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+static int ensure_stage(So101Batch* b) {
+  if (!b->ctrl_stage) CUDA_TRY(cudaMalloc(&b->ctrl_stage, (size_t)NV * b->n * elem_size(b->dtype)));
+  if (!b->obs_stage) CUDA_TRY(cudaMalloc(&b->obs_stage, (size_t)SO101_NOBS * b->n * sizeof(float)));
+  return SO101_OK;
+}
+
+int so101_batch_step_host(So101Batch* b, const void* ctrl_host, int n_ctrl, int n_substeps, void* obs_host,
+                          void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  if (n_ctrl < 0 || n_ctrl > NV) return fail(SO101_EINVAL, "n_ctrl must be 0..6");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_stage(b);
+  if (rc) return rc;
+  if (ctrl_host && n_ctrl > 0)
+    CUDA_TRY(cudaMemcpyAsync(b->ctrl_stage, ctrl_host, (size_t)n_ctrl * b->n * elem_size(b->dtype),
+                             cudaMemcpyHostToDevice, st));
+  rc = so101_batch_step(b, ctrl_host ? b->ctrl_stage : nullptr, n_ctrl, n_substeps, b->obs_stage, stream);
+  if (rc) return rc;
+  if (obs_host)
+    CUDA_TRY(cudaMemcpyAsync(obs_host, b->obs_stage, (size_t)SO101_NOBS * b->n * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return SO101_OK;
+}
+
+int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qvel0_host, void* obs_host,
+                           void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ensure_stage(b);
+  if (rc) return rc;
+  size_t blockb = (size_t)NV * b->n * elem_size(b->dtype);
+  if (!b->init_stage) CUDA_TRY(cudaMalloc(&b->init_stage, 2 * blockb));
+  char* qd = static_cast<char*>(b->init_stage);
+  if (qpos0_host) CUDA_TRY(cudaMemcpyAsync(qd, qpos0_host, blockb, cudaMemcpyHostToDevice, st));
+  if (qvel0_host) CUDA_TRY(cudaMemcpyAsync(qd + blockb, qvel0_host, blockb, cudaMemcpyHostToDevice, st));
+  rc = so101_batch_reset(b, qpos0_host ? qd : nullptr, qvel0_host ? qd + blockb : nullptr, b->obs_stage, stream);
+  if (rc) return rc;
+  if (obs_host)
+    CUDA_TRY(cudaMemcpyAsync(obs_host, b->obs_stage, (size_t)SO101_NOBS * b->n * sizeof(float),
+                             cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return SO101_OK;
+}
+
+int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip, void* rows, uint32_t flags,
+                        void* stream) {
+  if (!b || !spec) return fail(SO101_EINVAL, "null argument");
+  if (T < 0 || frame_skip < 1) return fail(SO101_EINVAL, "T must be >= 0 and frame_skip >= 1");
+  if (spec->kind < SO101_CTRL_RANDOM || spec->kind > SO101_CTRL_TENSOR) return fail(SO101_EINVAL, "bad control kind");
+  if (spec->kind == SO101_CTRL_TENSOR && !spec->u) return fail(SO101_EINVAL, "SO101_CTRL_TENSOR needs spec->u");
+  if (spec->kind == SO101_CTRL_CHIRP && spec->t_total <= 0) return fail(SO101_EINVAL, "chirp needs t_total > 0");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DevSpec ds;
+  ds.kind = spec->kind; ds.t_total = spec->t_total; ds.seed = spec->seed; ds.env_offset = spec->env_offset;
+  ds.amp = spec->amp; ds.freq_lo = spec->freq_lo; ds.freq_hi = spec->freq_hi;
+  ds.reset_lo = spec->reset_lo; ds.reset_hi = spec->reset_hi; ds.u = spec->u;
+  int blk = pick_block(b->n);
+  unsigned grid = grid_for(b->n, blk);
+  const bool r32 = flags & SO101_ROLL_ROWS_F32;
+  if (b->dtype == SO101_F64) {
+    if (r32) k_rollout<double, float><<<grid, blk, 0, st>>>(b->model->d, view<double>(b), ds, T, frame_skip, (float*)rows, flags, b->stats);
+    else k_rollout<double, double><<<grid, blk, 0, st>>>(b->model->d, view<double>(b), ds, T, frame_skip, (double*)rows, flags, b->stats);
+  } else {
+    if (r32) k_rollout<float, float><<<grid, blk, 0, st>>>(b->model->f, view<float>(b), ds, T, frame_skip, (float*)rows, flags, b->stats);
+    else k_rollout<float, double><<<grid, blk, 0, st>>>(b->model->f, view<float>(b), ds, T, frame_skip, (double*)rows, flags, b->stats);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H, int frame_skip, void* X,
+                      uint32_t flags, void* stream) {
+  if (!b || !state0 || !U || !X) return fail(SO101_EINVAL, "null argument");
+  if (H < 0 || frame_skip < 1) return fail(SO101_EINVAL, "H must be >= 0 and frame_skip >= 1");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  State0 s0;
+  std::memcpy(s0.v, state0, sizeof s0.v);
+  int blk = pick_block(b->n);
+  DISPATCH(b,
+    (k_shoot<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), s0, (const double*)U, H,
+        frame_skip, (float*)X, flags, b->stats)),
+    (k_shoot<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), s0, (const float*)U, H,
+        frame_skip, (float*)X, flags, b->stats)));
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+static int copy_rows(So101Batch* b, int row, void* dst, const void* src, void* stream) {
+  size_t es = elem_size(b->dtype), bytes = (size_t)NV * b->n * es;
+  char* base = static_cast<char*>(b->state) + (size_t)row * b->n * es;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dst) CUDA_TRY(cudaMemcpyAsync(dst, base, bytes, cudaMemcpyDeviceToDevice, st));
+  if (src) CUDA_TRY(cudaMemcpyAsync(base, src, bytes, cudaMemcpyDeviceToDevice, st));
+  return SO101_OK;
+}
+int so101_batch_get_state(So101Batch* b, void* qpos, void* qvel, void* warm, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  int rc;
+  if ((rc = copy_rows(b, ROW_Q, qpos, nullptr, stream))) return rc;
+  if ((rc = copy_rows(b, ROW_QD, qvel, nullptr, stream))) return rc;
+  return copy_rows(b, ROW_WARM, warm, nullptr, stream);
+}
+int so101_batch_set_state(So101Batch* b, const void* qpos, const void* qvel, const void* warm, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  int rc;
+  if ((rc = copy_rows(b, ROW_Q, nullptr, qpos, stream))) return rc;
+  if ((rc = copy_rows(b, ROW_QD, nullptr, qvel, stream))) return rc;
+  return copy_rows(b, ROW_WARM, nullptr, warm, stream);
+}
+int so101_batch_set_qfrc_applied(So101Batch* b, const void* fa, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  return copy_rows(b, ROW_FA, nullptr, fa, stream);
+}
+int so101_batch_get_flags(So101Batch* b, uint32_t* flags_dev, void* stream) {
+  if (!b || !flags_dev) return fail(SO101_EINVAL, "null argument");
+  DeviceGuard g(b->device);
+  const char* src = static_cast<char*>(b->state) + (size_t)NROWS * b->n * elem_size(b->dtype);
+  CUDA_TRY(cudaMemcpyAsync(flags_dev, src, (size_t)b->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                           static_cast<cudaStream_t>(stream)));
+  return SO101_OK;
+}
+int so101_batch_clear_flags(So101Batch* b, void* stream) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  DeviceGuard g(b->device);
+  char* dst = static_cast<char*>(b->state) + (size_t)NROWS * b->n * elem_size(b->dtype);
+  CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)b->n * sizeof(uint32_t), static_cast<cudaStream_t>(stream)));
+  return SO101_OK;
+}
+int so101_batch_stats(So101Batch* b, uint64_t* stats_host, void* stream) {
+  if (!b || !stats_host) return fail(SO101_EINVAL, "null argument");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(stats_host, b->stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemsetAsync(b->stats, 0, 4 * sizeof(uint64_t), st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return SO101_OK;
+}
+
+int so101_fma_peak(int dtype, int device, double* tflops_out) {
+  if (!tflops_out) return fail(SO101_EINVAL, "null argument");
+  if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SO101_ECUDA, "cudaSetDevice failed");
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  void* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, 64));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    if (dtype == SO101_F64) k_fma_peak<double><<<blocks, threads>>>((double*)out, iters, 0.999999, 1e-7);
+    else k_fma_peak<float><<<blocks, threads>>>((float*)out, iters, 0.999999f, 1e-7f);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  double flops = 2.0 * 8 * (double)iters * threads * blocks;
+  *tflops_out = flops / (best * 1e-3) / 1e12;
+  return SO101_OK;
+}
+
+}  // extern "C"

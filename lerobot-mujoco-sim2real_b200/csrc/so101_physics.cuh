@@ -1,0 +1,700 @@
+// so101_physics.cuh — one mj_step-equivalent physics step for one env, held by one thread.
+//
+// Pipeline (reference: mujoco.mj_step as called at SOARM101/SOARM101_Env.py:132; algorithm
+// restated in oracle/so101_oracle.c):
+//   checkPos/Vel -> smooth dynamics (RNEA bias + CRBA mass matrix, link-local frames)
+//   -> passive + affine actuators -> qacc_smooth = M^-1 qfrc_smooth
+//   -> friction-loss + joint-limit rows -> warm start pick -> Newton with exact line search
+//   -> checkAcc -> Euler with implicit joint damping.
+// Everything is fully unrolled over the 6 links so that table reads are constant-bank
+// operands and all per-env quantities are registers (or L1-resident spills).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "so101_model.h"
+
+namespace so101 {
+
+#define SO101_DEV __device__ __forceinline__
+#define MJ_MINVAL 1e-15
+#define MJ_MAXVAL 1e10
+
+// ------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------
+SO101_DEV double rcp_(double x) {
+  // MUFU.RCP64H seed (~20 bits) + two Newton steps: <= 1 ulp, ~7 instructions instead of the
+  // ~20 of an IEEE division.  Arguments here are diagonal pivots / curvatures, never subnormal.
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+SO101_DEV float rcp_(float x) { return __frcp_rn(x); }
+SO101_DEV void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+SO101_DEV void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+SO101_DEV double sqrt_(double x) { return sqrt(x); }
+SO101_DEV float sqrt_(float x) { return sqrtf(x); }
+SO101_DEV double abs_(double x) { return fabs(x); }
+SO101_DEV float abs_(float x) { return fabsf(x); }
+SO101_DEV double pow_(double x, double y) { return pow(x, y); }
+SO101_DEV float pow_(float x, float y) { return powf(x, y); }
+template <typename T> SO101_DEV T min_(T a, T b) { return a < b ? a : b; }
+template <typename T> SO101_DEV T max_(T a, T b) { return a > b ? a : b; }
+template <typename T> SO101_DEV bool bad_(T x) { return !(x <= T(MJ_MAXVAL) && x >= T(-MJ_MAXVAL)); }
+
+// index into a packed lower triangle, i >= j
+__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// ------------------------------------------------------------------------------------------
+// 3-vector / rotation helpers.  R (row-major 3x3) maps child coordinates to parent coordinates.
+// ------------------------------------------------------------------------------------------
+template <typename T> SO101_DEV void make_R(const T (&E)[9], T c, T s, T (&R)[9]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    R[3 * i + 0] = c * E[3 * i] + s * E[3 * i + 1];
+    R[3 * i + 1] = c * E[3 * i + 1] - s * E[3 * i];
+    R[3 * i + 2] = E[3 * i + 2];
+  }
+}
+template <typename T> SO101_DEV void rot(const T (&R)[9], const T* v, T* o) {  // o = R v
+  T a = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  T b = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  T c = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+template <typename T> SO101_DEV void rotT(const T (&R)[9], const T* v, T* o) {  // o = R^T v
+  T a = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  T b = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  T c = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = a; o[1] = b; o[2] = c;
+}
+// spatial motion vector parent -> child: ang' = R^T ang, lin' = R^T (lin + ang x r)
+template <typename T> SO101_DEV void xmotion(const T (&R)[9], const T (&r)[3], const T (&p)[6], T (&c)[6]) {
+  T u[3] = {p[3] + (p[1] * r[2] - p[2] * r[1]), p[4] + (p[2] * r[0] - p[0] * r[2]),
+            p[5] + (p[0] * r[1] - p[1] * r[0])};
+  rotT(R, &p[0], &c[0]);
+  rotT(R, u, &c[3]);
+}
+// spatial force vector child -> parent: lin' = R lin, ang' = R ang + r x lin'
+template <typename T> SO101_DEV void xforce(const T (&R)[9], const T (&r)[3], const T (&c)[6], T (&p)[6]) {
+  T a[3], l[3];
+  rot(R, &c[0], a);
+  rot(R, &c[3], l);
+  p[0] = a[0] + (r[1] * l[2] - r[2] * l[1]);
+  p[1] = a[1] + (r[2] * l[0] - r[0] * l[2]);
+  p[2] = a[2] + (r[0] * l[1] - r[1] * l[0]);
+  p[3] = l[0]; p[4] = l[1]; p[5] = l[2];
+}
+// 10-parameter spatial inertia times motion vector (same layout as mju_mulInertVec)
+template <typename T> SO101_DEV void inert_mul(const T (&i)[10], const T (&v)[6], T (&o)[6]) {
+  o[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  o[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  o[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  o[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  o[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  o[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+// composite inertia child -> parent, accumulated into the parent's
+template <typename T> SO101_DEV void xinertia_add(const T (&R)[9], const T (&r)[3], const T (&c)[10], T (&p)[10]) {
+  // rotate the symmetric 3x3 block: S = R * I * R^T
+  T A[9];  // A = R * I
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    A[3 * i + 0] = R[3 * i] * c[0] + R[3 * i + 1] * c[3] + R[3 * i + 2] * c[4];
+    A[3 * i + 1] = R[3 * i] * c[3] + R[3 * i + 1] * c[1] + R[3 * i + 2] * c[5];
+    A[3 * i + 2] = R[3 * i] * c[4] + R[3 * i + 1] * c[5] + R[3 * i + 2] * c[2];
+  }
+  T Sxx = A[0] * R[0] + A[1] * R[1] + A[2] * R[2];
+  T Syy = A[3] * R[3] + A[4] * R[4] + A[5] * R[5];
+  T Szz = A[6] * R[6] + A[7] * R[7] + A[8] * R[8];
+  T Sxy = A[0] * R[3] + A[1] * R[4] + A[2] * R[5];
+  T Sxz = A[0] * R[6] + A[1] * R[7] + A[2] * R[8];
+  T Syz = A[3] * R[6] + A[4] * R[7] + A[5] * R[8];
+  T h[3];
+  rot(R, &c[6], h);
+  // shift the reference point by r: I += 2(u.r)1 - (r u' + u r'), u = h + m r / 2
+  T hm = T(0.5) * c[9];
+  T u0 = h[0] + hm * r[0], u1 = h[1] + hm * r[1], u2 = h[2] + hm * r[2];
+  T d0 = u0 * r[0], d1 = u1 * r[1], d2 = u2 * r[2];
+  p[0] += Sxx + T(2) * (d1 + d2);
+  p[1] += Syy + T(2) * (d0 + d2);
+  p[2] += Szz + T(2) * (d0 + d1);
+  p[3] += Sxy - (r[0] * u1 + u0 * r[1]);
+  p[4] += Sxz - (r[0] * u2 + u0 * r[2]);
+  p[5] += Syz - (r[1] * u2 + u1 * r[2]);
+  p[6] += h[0] + c[9] * r[0];
+  p[7] += h[1] + c[9] * r[1];
+  p[8] += h[2] + c[9] * r[2];
+  p[9] += c[9];
+}
+
+// ------------------------------------------------------------------------------------------
+// dense 6x6 LDL^T on a packed lower triangle (A = L D L^T, unit L), and solve
+// ------------------------------------------------------------------------------------------
+template <typename T> SO101_DEV void ldl6(const T (&A)[21], T (&L)[21], T (&Dinv)[NV]) {
+  T D[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    T d = A[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)] * D[k];
+    d = max_(d, T(MJ_MINVAL));
+    D[j] = d;
+    Dinv[j] = rcp_(d);
+#pragma unroll
+    for (int i = j + 1; i < NV; i++) {
+      T s = A[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[tri(i, k)] * L[tri(j, k)] * D[k];
+      L[tri(i, j)] = s * Dinv[j];
+    }
+  }
+}
+template <typename T> SO101_DEV void ldl6_solve(const T (&L)[21], const T (&Dinv)[NV], T (&x)[NV]) {
+#pragma unroll
+  for (int i = 1; i < NV; i++) {
+#pragma unroll
+    for (int k = 0; k < i; k++) x[i] -= L[tri(i, k)] * x[k];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; i++) x[i] *= Dinv[i];
+#pragma unroll
+  for (int i = NV - 2; i >= 0; i--) {
+#pragma unroll
+    for (int k = i + 1; k < NV; k++) x[i] -= L[tri(k, i)] * x[k];
+  }
+}
+template <typename T> SO101_DEV void symv6(const T (&M)[21], const T (&x)[NV], T (&y)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T s = T(0);
+#pragma unroll
+    for (int j = 0; j < NV; j++) s += M[i >= j ? tri(i, j) : tri(j, i)] * x[j];
+    y[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread environment and solver counters
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Env {
+  T q[NV], qd[NV], warm[NV], fa[NV];  // qpos, qvel, qacc_warmstart, qfrc_applied
+  T time;
+  uint32_t flags;
+};
+struct Counters {
+  uint32_t steps, newton, lsevals, limsteps;
+};
+
+// ------------------------------------------------------------------------------------------
+// smooth dynamics: qfrc_bias (RNEA, flg_acc = 0) and M (CRBA) in link-local frames.
+// Optionally the world position of the observation site and the contact tripwire.
+// ------------------------------------------------------------------------------------------
+template <typename T, bool WANT_M>
+SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (&qd)[NV], T (&M)[21],
+                               T (&bias)[NV], bool want_site, T (&site)[3], bool trip, uint32_t& flags) {
+  T sn[NV], cs[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) sincos_(q[k] - m.qpos0[k], &sn[k], &cs[k]);
+
+  // ---- forward pass: velocities, accelerations, link forces --------------------------------
+  T f[NV][6];
+  {
+    T v[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    T a[6] = {T(0), T(0), T(0), m.accg[0], m.accg[1], m.accg[2]};
+    T zw[3] = {T(0), T(0), T(1)};  // world z axis in the current frame (tripwire)
+    T zo = T(0);                   // world height of the current frame origin
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      T R[9], vc[6], ac[6];
+      make_R(m.E[k], cs[k], sn[k], R);
+      xmotion(R, m.r[k], v, vc);
+      xmotion(R, m.r[k], a, ac);
+      vc[2] += qd[k];
+      // a += v x (S qd), S = [0 0 1 | 0 0 0]
+      ac[0] += qd[k] * vc[1];
+      ac[1] -= qd[k] * vc[0];
+      ac[3] += qd[k] * vc[4];
+      ac[4] -= qd[k] * vc[3];
+      T Ia[6], Iv[6];
+      inert_mul(m.I[k], ac, Ia);
+      inert_mul(m.I[k], vc, Iv);
+      // f = I a + v x* (I v)
+      f[k][0] = Ia[0] + (vc[1] * Iv[2] - vc[2] * Iv[1]) + (vc[4] * Iv[5] - vc[5] * Iv[4]);
+      f[k][1] = Ia[1] + (vc[2] * Iv[0] - vc[0] * Iv[2]) + (vc[5] * Iv[3] - vc[3] * Iv[5]);
+      f[k][2] = Ia[2] + (vc[0] * Iv[1] - vc[1] * Iv[0]) + (vc[3] * Iv[4] - vc[4] * Iv[3]);
+      f[k][3] = Ia[3] + (vc[1] * Iv[5] - vc[2] * Iv[4]);
+      f[k][4] = Ia[4] + (vc[2] * Iv[3] - vc[0] * Iv[5]);
+      f[k][5] = Ia[5] + (vc[0] * Iv[4] - vc[1] * Iv[3]);
+#pragma unroll
+      for (int c = 0; c < 6; c++) { v[c] = vc[c]; a[c] = ac[c]; }
+      if (trip) {
+        zo += zw[0] * m.r[k][0] + zw[1] * m.r[k][1] + zw[2] * m.r[k][2];
+        T zc[3];
+        rotT(R, zw, zc);
+        zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          if (m.trip_n[k] > b) {
+            T zc0 = zo + zw[0] * m.trip_c[k][b][0] + zw[1] * m.trip_c[k][b][1] + zw[2] * m.trip_c[k][b][2];
+            T ext = T(0);
+#pragma unroll
+            for (int ax = 0; ax < 3; ax++)
+              ext += abs_(zw[0] * m.trip_ax[k][b][3 * ax] + zw[1] * m.trip_ax[k][b][3 * ax + 1] +
+                          zw[2] * m.trip_ax[k][b][3 * ax + 2]) * m.trip_half[k][b][ax];
+            if (zc0 - ext < m.trip_z) flags |= SO101_FLAG_TRIP_TABLE;
+          }
+        }
+        if (q[k] < m.trip_qlo[k] || q[k] > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
+      }
+    }
+  }
+
+  // ---- backward pass: bias forces, composite inertias, mass matrix ---------------------------
+  T fs[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // accumulated force in the current frame
+  T Ic[10] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+  T F[NV][6];                                        // F[j] = Ic_j * S propagated to the current frame
+  T p[3] = {T(0), T(0), T(0)};                       // site position in the current frame
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) fs[c] += f[k][c];
+    bias[k] = fs[2];
+    if (WANT_M) {
+#pragma unroll
+      for (int c = 0; c < 10; c++) Ic[c] += m.I[k][c];
+      F[k][0] = Ic[4]; F[k][1] = Ic[5]; F[k][2] = Ic[2];
+      F[k][3] = -Ic[7]; F[k][4] = Ic[6]; F[k][5] = T(0);
+      M[tri(k, k)] = Ic[2] + m.armature[k];
+    }
+    if (want_site && k == m.site_link) { p[0] = m.site[0]; p[1] = m.site[1]; p[2] = m.site[2]; }
+    if (k > 0 || want_site) {
+      T R[9];
+      make_R(m.E[k], cs[k], sn[k], R);
+      if (want_site && k <= m.site_link) {
+        T o[3];
+        rot(R, p, o);
+        p[0] = o[0] + m.r[k][0]; p[1] = o[1] + m.r[k][1]; p[2] = o[2] + m.r[k][2];
+      }
+      if (k > 0) {
+        T t6[6];
+        xforce(R, m.r[k], fs, t6);
+#pragma unroll
+        for (int c = 0; c < 6; c++) fs[c] = t6[c];
+        if (WANT_M) {
+#pragma unroll
+          for (int j = NV - 1; j >= k; j--) {
+            xforce(R, m.r[k], F[j], t6);
+#pragma unroll
+            for (int c = 0; c < 6; c++) F[j][c] = t6[c];
+            M[tri(j, k - 1)] = t6[2];
+          }
+          T Ip[10] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+          xinertia_add(R, m.r[k], Ic, Ip);
+#pragma unroll
+          for (int c = 0; c < 10; c++) Ic[c] = Ip[c];
+        }
+      }
+    }
+  }
+  if (want_site) { site[0] = p[0]; site[1] = p[1]; site[2] = p[2]; }
+}
+
+// forward kinematics of the observation site only (reset / mj_forward observations)
+template <typename T> SO101_DEV void site_fk(const DevModel<T>& m, const T (&q)[NV], T (&site)[3]) {
+  T p[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    if (k == m.site_link) { p[0] = m.site[0]; p[1] = m.site[1]; p[2] = m.site[2]; }
+    if (k <= m.site_link) {
+      T s, c, R[9], o[3];
+      sincos_(q[k] - m.qpos0[k], &s, &c);
+      make_R(m.E[k], c, s, R);
+      rot(R, p, o);
+      p[0] = o[0] + m.r[k][0]; p[1] = o[1] + m.r[k][1]; p[2] = o[2] + m.r[k][2];
+    }
+  }
+  site[0] = p[0]; site[1] = p[1]; site[2] = p[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// constraint rows.  Row order follows mj_makeConstraint: friction rows (dof order), then the
+// active joint-limit row of each joint.  All Jacobian rows are +-e_i, so J is never formed.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Rows {
+  T aref_f[NV];                      // friction rows: jar = a_i - aref_f
+  T side[NV], aref_l[NV], D_l[NV];   // limit rows: jar = side*a_i - aref_l ; side = 0: inactive
+  bool anylim;
+};
+
+// getimpedance (engine_core_constraint.c) for a limit row
+template <typename T> SO101_DEV T limit_impedance(const T (&si)[5], T pos, T margin) {
+  if (si[0] == si[1] || si[2] <= T(MJ_MINVAL)) return T(0.5) * (si[0] + si[1]);
+  T x = abs_((pos - margin) * rcp_(si[2]));
+  if (x >= T(1)) return si[1];
+  if (x <= T(0)) return si[0];
+  T y;
+  if (si[4] == T(1)) y = x;
+  else if (si[4] == T(2)) {
+    if (x <= si[3]) y = x * x * rcp_(si[3]);
+    else y = T(1) - (T(1) - x) * (T(1) - x) * rcp_(T(1) - si[3]);
+  } else {
+    if (x <= si[3]) y = pow_(x, si[4]) / pow_(si[3], si[4] - T(1));
+    else y = T(1) - pow_(T(1) - x, si[4]) / pow_(T(1) - si[3], si[4] - T(1));
+  }
+  return si[0] + y * (si[1] - si[0]);
+}
+
+// mj_constraintUpdate + the Gauss term: total cost at acceleration a; also qfrc_constraint and
+// the diagonal that the quadratic rows add to the Hessian.
+template <typename T, bool WANT_FORCE>
+SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV], const T (&Ma)[NV],
+                        const T (&fsm)[NV], const T (&asm_)[NV], bool with_gauss, T (&qc)[NV], T (&hd)[NV]) {
+  T s = T(0);
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T jar = a[i] - rw.aref_f[i];
+    T f = m.fr_f[i];
+    bool neg = jar <= -m.fr_Rf[i], pos = jar >= m.fr_Rf[i];
+    T cq = T(0.5) * m.fr_D[i] * jar * jar;
+    T cl = (neg ? -f : f) * jar - m.fr_hRff[i];
+    s += (neg || pos) ? cl : cq;
+    if (WANT_FORCE) {
+      qc[i] = neg ? f : (pos ? -f : -m.fr_D[i] * jar);
+      hd[i] = (neg || pos) ? T(0) : m.fr_D[i];
+    }
+  }
+  if (rw.anylim) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      if (rw.side[i] != T(0)) {
+        T jar = rw.side[i] * a[i] - rw.aref_l[i];
+        if (jar < T(0)) {
+          s += T(0.5) * rw.D_l[i] * jar * jar;
+          if (WANT_FORCE) { qc[i] += rw.side[i] * (-rw.D_l[i] * jar); hd[i] += rw.D_l[i]; }
+        }
+      }
+    }
+  }
+  if (with_gauss) {
+    T g = T(0);
+#pragma unroll
+    for (int i = 0; i < NV; i++) g += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
+    s += g;
+  }
+  return s;
+}
+
+template <typename T> struct LsPnt { T alpha, cost, d0, d1; };
+
+// PrimalEval: cost and derivatives of the exact piecewise-quadratic along the search direction
+template <typename T>
+SO101_DEV void ls_eval(const DevModel<T>& m, const Rows<T>& rw, const T (&jar0)[NV], const T (&sr)[NV],
+                       const T (&qf)[NV][3], const T (&jarl)[NV], const T (&ql)[NV][3], const T (&G)[3],
+                       T alpha, LsPnt<T>& p, uint32_t& nev) {
+  T q0 = G[0], q1 = G[1], q2 = G[2];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T x = jar0[i] + alpha * sr[i];
+    T f = m.fr_f[i], Rf = m.fr_Rf[i];
+    bool quad = (-Rf < x) && (x < Rf);
+    bool neg = x <= -Rf;
+    T l0 = f * (T(-0.5) * Rf + (neg ? -jar0[i] : jar0[i]));
+    T l1 = (neg ? -f : f) * sr[i];
+    q0 += quad ? qf[i][0] : l0;
+    q1 += quad ? qf[i][1] : l1;
+    q2 += quad ? qf[i][2] : T(0);
+  }
+  if (rw.anylim) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      if (rw.side[i] != T(0)) {
+        T x = jarl[i] + alpha * (rw.side[i] * sr[i]);
+        if (x < T(0)) { q0 += ql[i][0]; q1 += ql[i][1]; q2 += ql[i][2]; }
+      }
+    }
+  }
+  p.alpha = alpha;
+  p.cost = alpha * alpha * q2 + alpha * q1 + q0;
+  p.d0 = T(2) * alpha * q2 + q1;
+  p.d1 = T(2) * q2;
+  if (p.d1 <= T(0)) p.d1 = T(MJ_MINVAL);
+  nev++;
+}
+
+// updateBracket of engine_solver.c
+template <typename T>
+SO101_DEV int ls_bracket(const DevModel<T>& m, const Rows<T>& rw, const T (&jar0)[NV], const T (&sr)[NV],
+                         const T (&qf)[NV][3], const T (&jarl)[NV], const T (&ql)[NV][3], const T (&G)[3],
+                         LsPnt<T>& p, const LsPnt<T> (&cand)[3], LsPnt<T>& pnext, uint32_t& nev) {
+  int flag = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (p.d0 < T(0) && cand[i].d0 < T(0) && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
+    else if (p.d0 > T(0) && cand[i].d0 > T(0) && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
+  }
+  if (flag) ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p.alpha - p.d0 * rcp_(p.d1), pnext, nev);
+  return flag;
+}
+
+// PrimalSearch: exact line search along sr from acceleration a.  Returns alpha; Mv = M*sr out.
+template <typename T>
+SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[21], const T (&a)[NV],
+                        const T (&Ma)[NV], const T (&fsm)[NV], const T (&sr)[NV], T gauss0, T (&Mv)[NV],
+                        uint32_t& nev_total) {
+  T ss = T(0);
+#pragma unroll
+  for (int i = 0; i < NV; i++) ss += sr[i] * sr[i];
+  T snorm = sqrt_(ss);
+  if (snorm < T(MJ_MINVAL)) return T(0);
+  const T gtol = m.gtol_fac * snorm;
+  symv6(Mm, sr, Mv);
+  // PrimalPrepare
+  T G[3] = {gauss0, T(0), T(0)};
+  {
+    T g1a = T(0), g1b = T(0), g2 = T(0);
+#pragma unroll
+    for (int i = 0; i < NV; i++) { g1a += sr[i] * Ma[i]; g1b += fsm[i] * sr[i]; g2 += sr[i] * Mv[i]; }
+    G[1] = g1a - g1b;
+    G[2] = T(0.5) * g2;
+  }
+  T jar0[NV], qf[NV][3], jarl[NV], ql[NV][3];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    jar0[i] = a[i] - rw.aref_f[i];
+    T DJ0 = m.fr_D[i] * jar0[i];
+    qf[i][0] = T(0.5) * jar0[i] * DJ0;
+    qf[i][1] = sr[i] * DJ0;
+    qf[i][2] = T(0.5) * sr[i] * m.fr_D[i] * sr[i];
+    jarl[i] = T(0); ql[i][0] = ql[i][1] = ql[i][2] = T(0);
+  }
+  if (rw.anylim) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      if (rw.side[i] != T(0)) {
+        T jv = rw.side[i] * sr[i];
+        jarl[i] = rw.side[i] * a[i] - rw.aref_l[i];
+        T DJ0 = rw.D_l[i] * jarl[i];
+        ql[i][0] = T(0.5) * jarl[i] * DJ0;
+        ql[i][1] = jv * DJ0;
+        ql[i][2] = T(0.5) * jv * rw.D_l[i] * jv;
+      }
+    }
+  }
+  uint32_t nev = 0;
+  const uint32_t maxev = (uint32_t)m.ls_iterations;
+  LsPnt<T> p0, p1, p2, pmid, p1next, p2next;
+  T result;
+  ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, T(0), p0, nev);
+  ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p0.alpha - p0.d0 * rcp_(p0.d1), p1, nev);
+  if (p0.cost < p1.cost) p1 = p0;
+  if (abs_(p1.d0) < gtol) {
+    result = p1.alpha;
+  } else {
+    const T dir = p1.d0 < T(0) ? T(1) : T(-1);
+    bool done = false;
+    p2 = p1;
+    // phase 1: Newton steps until the slope changes sign
+    while (p1.d0 * dir <= -gtol && nev < maxev) {
+      p2 = p1;
+      ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p1.alpha - p1.d0 * rcp_(p1.d1), p1, nev);
+      if (abs_(p1.d0) < gtol) { done = true; break; }
+    }
+    if (done || nev >= maxev) {
+      result = p1.alpha;
+    } else {
+      // phase 2: bracketed
+      p2next = p1;
+      ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p1.alpha - p1.d0 * rcp_(p1.d1), p1next, nev);
+      bool ret = false;
+      result = T(0);
+      while (nev < maxev) {
+        ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, T(0.5) * (p1.alpha + p2.alpha), pmid, nev);
+        LsPnt<T> cand[3] = {p1next, p2next, pmid};
+        T bestcost = T(0);
+        int best = -1;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+          if (abs_(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
+        if (best >= 0) { result = best == 0 ? cand[0].alpha : (best == 1 ? cand[1].alpha : cand[2].alpha); ret = true; break; }
+        int b1 = ls_bracket(m, rw, jar0, sr, qf, jarl, ql, G, p1, cand, p1next, nev);
+        int b2 = ls_bracket(m, rw, jar0, sr, qf, jarl, ql, G, p2, cand, p2next, nev);
+        if (!b1 && !b2) { result = pmid.alpha; ret = true; break; }
+      }
+      if (!ret) {
+        if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
+        else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
+        else result = T(0);
+      }
+    }
+  }
+  nev_total += nev;
+  return result;
+}
+
+// ------------------------------------------------------------------------------------------
+// one physics step
+// ------------------------------------------------------------------------------------------
+template <typename T>
+SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
+                            bool want_site, T (&site)[3], bool trip, Counters& cnt) {
+  // mj_checkPos / mj_checkVel
+  {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < NV; i++) bad |= bad_(e.q[i]) | bad_(e.qd[i]);
+    if (bad) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
+      e.time = T(0);
+      e.flags |= SO101_FLAG_BADSTATE;
+    }
+  }
+  T M[21], bias[NV];
+  smooth_dynamics<T, true>(m, e.q, e.qd, M, bias, want_site, site, trip, e.flags);
+  if (gravcomp_capture) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
+  }
+  // mj_passive, mj_fwdActuation, mj_fwdAcceleration
+  T fsm[NV], asm_[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T passive = -m.damping[i] * e.qd[i];
+    if (m.any_stiffness) passive = -m.stiffness[i] * (e.q[i] - m.qspring[i]) - m.damping[i] * e.qd[i];
+    T c = ctrl[i];
+    if (m.ctrllim_mask >> i & 1) c = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], c));
+    T force = m.act_gain[i] * c + m.act_b0[i] + m.act_b1[i] * (m.act_gear[i] * e.q[i]) +
+              m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
+    if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
+    fsm[i] = passive - bias[i] + e.fa[i] + m.act_gear[i] * force;
+    asm_[i] = fsm[i];
+  }
+  T L[21], Dinv[NV];
+  ldl6(M, L, Dinv);
+  ldl6_solve(L, Dinv, asm_);
+
+  T a[NV], qc[NV];
+  Rows<T> rw;
+  rw.anylim = false;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    rw.aref_f[i] = -m.fr_B[i] * e.qd[i];
+    rw.side[i] = T(0); rw.aref_l[i] = T(0); rw.D_l[i] = T(0);
+    if (m.limited_mask >> i & 1) {
+      T dlo = e.q[i] - m.lim_lo[i], dhi = m.lim_hi[i] - e.q[i];
+      bool lo = dlo < m.lim_margin[i], hi = dhi < m.lim_margin[i];
+      if (lo || hi) {
+        T side = lo ? T(1) : T(-1), pos = lo ? dlo : dhi;
+        T imp = limit_impedance(m.lim_imp[i], pos, m.lim_margin[i]);
+        T R = max_(T(MJ_MINVAL), (T(1) - imp) * m.lim_invw[i] / imp);
+        rw.side[i] = side;
+        rw.D_l[i] = T(1) / R;
+        rw.aref_l[i] = -m.lim_B[i] * (side * e.qd[i]) - m.lim_K[i] * imp * (pos - m.lim_margin[i]);
+        rw.anylim = true;
+      }
+    }
+  }
+  if (rw.anylim) { e.flags |= SO101_FLAG_LIMIT; cnt.limsteps++; }
+
+  if (m.nfriction == 0 && !rw.anylim) {
+    // nefc == 0: mj_fwdConstraint copies qacc_smooth
+#pragma unroll
+    for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); }
+  } else {
+    // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth ---------------------------
+    T Ma[NV], hd[NV];
+    {
+      T Mw[NV];
+      symv6(M, e.warm, Mw);
+      T cw = cost_update<T, false>(m, rw, e.warm, Mw, fsm, asm_, true, qc, hd);
+      T csm = cost_update<T, false>(m, rw, asm_, Mw, fsm, asm_, false, qc, hd);
+      bool use_smooth = cw > csm;
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        a[i] = use_smooth ? asm_[i] : e.warm[i];
+        Ma[i] = Mw[i];
+      }
+      if (use_smooth) symv6(M, a, Ma);
+    }
+    // ---- Newton (mj_solPrimal) ---------------------------------------------------------------
+    T cost = cost_update<T, true>(m, rw, a, Ma, fsm, asm_, true, qc, hd);
+    T grad[NV], sr[NV], H[21], LH[21], DHinv[NV];
+    auto gradient_and_direction = [&]() {
+#pragma unroll
+      for (int i = 0; i < 21; i++) H[i] = M[i];
+#pragma unroll
+      for (int i = 0; i < NV; i++) { H[tri(i, i)] += hd[i]; grad[i] = Ma[i] - fsm[i] - qc[i]; sr[i] = grad[i]; }
+      ldl6(H, LH, DHinv);
+      ldl6_solve(LH, DHinv, sr);
+#pragma unroll
+      for (int i = 0; i < NV; i++) sr[i] = -sr[i];
+    };
+    gradient_and_direction();
+    int iter = 0;
+    while (iter < m.iterations) {
+      T gauss0 = T(0);
+#pragma unroll
+      for (int i = 0; i < NV; i++) gauss0 += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
+      T Mv[NV];
+      T alpha = line_search(m, rw, M, a, Ma, fsm, sr, gauss0, Mv, cnt.lsevals);
+      if (alpha == T(0)) break;
+#pragma unroll
+      for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
+      T oldcost = cost;
+      cost = cost_update<T, true>(m, rw, a, Ma, fsm, asm_, true, qc, hd);
+      gradient_and_direction();
+      T gg = T(0);
+#pragma unroll
+      for (int i = 0; i < NV; i++) gg += grad[i] * grad[i];
+      T improvement = m.scale * (oldcost - cost);
+      T gradnorm = m.scale * sqrt_(gg);
+      iter++;
+      if (improvement < m.tolerance || gradnorm < m.tolerance) break;
+    }
+    cnt.newton += iter;
+    if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
+  }
+
+  // mj_checkAcc
+  {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < NV; i++) bad |= bad_(a[i]);
+    if (bad) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
+      e.time = T(0);
+      e.flags |= SO101_FLAG_BADSTATE;
+      cnt.steps++;
+      return;
+    }
+  }
+  // mj_Euler: implicit in joint damping, semi-implicit in position
+  T acc[NV];
+  if (m.any_damping) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) { M[tri(i, i)] += m.h * m.damping[i]; acc[i] = fsm[i] + qc[i]; }
+    ldl6(M, L, Dinv);
+    ldl6_solve(L, Dinv, acc);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = a[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    e.qd[i] += m.h * acc[i];
+    e.q[i] += m.h * e.qd[i];
+    e.warm[i] = a[i];
+  }
+  e.time += m.h;
+  cnt.steps++;
+}
+
+}  // namespace so101

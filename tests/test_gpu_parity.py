@@ -1,0 +1,152 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Protocol (because scene A is chaotic under kv=50, F3):
+  P1  teacher-forced: every one of 1000 physics steps of an oracle trajectory is replayed on
+      the GPU from the oracle's own (qpos, qvel, qacc_warmstart, ctrl); next state must agree
+      to 1e-12 relative (fp64).
+  P2  free-running on scene A: error-vs-step against the oracle's own 1-ulp self-divergence.
+  P3  free-running on scene B (position servos, contractive): 1e-9 relative after 1000 steps.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.abs(a - b) / (1e-3 + np.maximum(np.abs(a), np.abs(b)))
+
+
+def _oracle_traj(O, tables, n, steps, seed, ctrl_hold=10, qscale=0.3, uscale=0.5):
+    rng = np.random.default_rng(seed)
+    state = np.zeros((n, 18))
+    state[:, :5] = rng.uniform(-qscale, qscale, (n, 5))
+    states, ctrls = [], []
+    ctrl = np.zeros((n, 6))
+    for t in range(steps):
+        if t % ctrl_hold == 0:
+            ctrl = np.zeros((n, 6))
+            ctrl[:, :5] = rng.uniform(-uscale, uscale, (n, 5))
+        states.append(state)
+        ctrls.append(ctrl)
+        state, _, _ = O.step_batch(tables, state, ctrl, 1)
+    states.append(state)
+    return np.stack(states), np.stack(ctrls)   # [steps+1, n, 18], [steps, n, 6]
+
+
+def _gpu_step(tables, state, ctrl, nsub=1, dtype="float64"):
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    n = state.shape[0]
+    env = SOARM101VecEnv(tables=tables, num_envs=n, dtype=dtype)
+    env.set_state(state[:, :6], state[:, 6:12], state[:, 12:18])
+    u = torch.as_tensor(ctrl.T.copy(), dtype=env.torch_dtype, device=env.device).contiguous()
+    obs = env.step_soa(u, nsub).t().cpu().numpy()
+    q, v, w = env.get_state()
+    out = np.concatenate([q.cpu().numpy(), v.cpu().numpy(), w.cpu().numpy()], axis=1).astype(np.float64)
+    return out, obs, env
+
+
+@pytest.mark.parametrize("scene", ["v", "p"])
+def test_p1_teacher_forced_fp64(oracle_mod, tables_v, tables_p, scene):
+    O = oracle_mod
+    tables = tables_v if scene == "v" else tables_p
+    n, steps = 128, 1000
+    uscale = 0.5 if scene == "v" else 1.5
+    states, ctrls = _oracle_traj(O, tables, n, steps, seed=7, uscale=uscale)
+    s_in = states[:-1].reshape(-1, 18)
+    s_ref = states[1:].reshape(-1, 18)
+    out, _, env = _gpu_step(tables, s_in, ctrls.reshape(-1, 6), 1)
+    err = _rel(out, s_ref)
+    st = env.stats()
+    print(f"scene {scene}: max rel err qpos {err[:, :6].max():.3e} qvel {err[:, 6:12].max():.3e} "
+          f"qacc {err[:, 12:].max():.3e}; newton/step {st['newton_iters'] / st['physics_steps']:.3f}")
+    assert err[:, :6].max() < 1e-12
+    assert err[:, 6:12].max() < 1e-12
+    # qacc_warmstart is the solver's output: converged to the solver tolerance, not to rounding
+    assert np.quantile(err[:, 12:], 0.999) < 1e-9
+
+
+def test_p1_teacher_forced_fp32(oracle_mod, tables_v):
+    O = oracle_mod
+    n, steps = 64, 500
+    states, ctrls = _oracle_traj(O, tables_v, n, steps, seed=11)
+    out, _, _ = _gpu_step(tables_v, states[:-1].reshape(-1, 18), ctrls.reshape(-1, 6), 1, dtype="float32")
+    ref = states[1:].reshape(-1, 18)
+    dq = np.abs(out[:, :6] - ref[:, :6]).max()
+    dv = np.abs(out[:, 6:12] - ref[:, 6:12])
+    print(f"fp32 one-step: |dq| max {dq:.3e}, |dqvel| max {dv.max():.3e} median {np.median(dv):.3e}")
+    # stated fp32 tolerance for ONE teacher-forced physics step
+    assert dq < 2e-6
+    assert np.quantile(dv, 0.99) < 2e-3
+
+
+def test_obs_ee_lag_and_rounding(oracle_mod, tables_v):
+    """step() observation = site of the last sub-step's forward (lags qpos by one sub-step), float32."""
+    O = oracle_mod
+    n = 256
+    states, ctrls = _oracle_traj(O, tables_v, n, 50, seed=3)
+    s_in, c_in = states[-1], ctrls[-1]
+    ref_state, ref_obs, _ = O.step_batch(tables_v, s_in, c_in, 10)
+    out, obs, _ = _gpu_step(tables_v, s_in, c_in, 10)
+    assert obs.dtype == np.float32
+    assert np.abs(obs - ref_obs.astype(np.float32)).max() <= 2e-7
+    # the lag: the ee position is NOT the site at the returned qpos
+    from lerobot_mujoco_sim2real_b200 import mjcf
+    lagfree = np.stack([mjcf.site_numpy(tables_v, ref_state[i, :6]) for i in range(8)])
+    assert np.abs(lagfree - ref_obs[:8, :3]).max() > 1e-7
+
+
+def test_p3_free_running_scene_b(oracle_mod, tables_p):
+    """BASELINE.json bar taken literally on the contractive position-servo scene."""
+    O = oracle_mod
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    n, T_ctrl = 512, 100
+    rng = np.random.default_rng(5)
+    q0 = np.zeros((n, 6)); q0[:, :5] = rng.uniform(-0.3, 0.3, (n, 5))
+    # random-walk position targets around the initial pose
+    U = np.cumsum(rng.uniform(-0.05, 0.05, (T_ctrl + 1, 5, n)), axis=0) + q0[:, :5].T[None]
+    spec = O.make_spec(kind=3, u=np.ascontiguousarray(U))
+    _, fin, _ = O.rollout(tables_p, spec, n, T_ctrl, 10, qpos0=q0, want_rows=False)
+    env = SOARM101VecEnv(tables=tables_p, num_envs=n, dtype="float64")
+    env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
+    Ud = torch.as_tensor(U, dtype=torch.float64, device=env.device).contiguous()
+    from lerobot_mujoco_sim2real_b200 import tables as T
+    env.rollout(T_ctrl, "tensor", u=Ud, flags=T.ROLL_NO_RESET)
+    q, v, _ = env.get_state()
+    eq = _rel(q.cpu().numpy(), fin[:, :6]).max()
+    ev = np.abs(v.cpu().numpy() - fin[:, 6:12]).max() / max(1e-3, np.abs(fin[:, 6:12]).max())
+    print(f"scene B free-running 1000 physics steps: rel err qpos {eq:.3e} qvel {ev:.3e}")
+    assert eq < 1e-9 and ev < 1e-9
+
+
+def test_p2_free_running_scene_a_curve(oracle_mod, tables_v):
+    """Chaotic scene: GPU-vs-oracle divergence must track the oracle's own 1-ulp self-divergence."""
+    O = oracle_mod
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    from lerobot_mujoco_sim2real_b200 import tables as T
+    n, T_ctrl = 256, 100
+    rng = np.random.default_rng(9)
+    q0 = np.zeros((n, 6)); q0[:, :5] = rng.uniform(-0.3, 0.3, (n, 5))
+    q0p = q0.copy(); q0p[:, :5] = np.nextafter(q0[:, :5], 1.0)   # 1-ulp perturbation
+    U = rng.uniform(-0.5, 0.5, (T_ctrl + 1, 5, n))
+    spec = O.make_spec(kind=3, u=np.ascontiguousarray(U))
+    env = SOARM101VecEnv(tables=tables_v, num_envs=n, dtype="float64")
+    Ud = torch.as_tensor(U, dtype=torch.float64, device=env.device).contiguous()
+    curve = []
+    for Tc in (1, 3, 10, 30, 100):
+        _, fin, _ = O.rollout(tables_v, spec, n, Tc, 10, qpos0=q0, want_rows=False)
+        _, finp, _ = O.rollout(tables_v, spec, n, Tc, 10, qpos0=q0p, want_rows=False)
+        env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
+        env.rollout(Tc, "tensor", u=Ud[: Tc + 1].contiguous(), flags=T.ROLL_NO_RESET)
+        q, _, _ = env.get_state()
+        self_div = np.median(np.abs(fin[:, :6] - finp[:, :6]).max(axis=1))
+        gpu_div = np.median(np.abs(q.cpu().numpy() - fin[:, :6]).max(axis=1))
+        curve.append((Tc * 10, self_div, gpu_div))
+    for s, a, b in curve:
+        print(f"physics step {s:5d}: oracle 1-ulp self-divergence {a:.3e}   gpu-vs-oracle {b:.3e}")
+    # before chaos amplifies rounding: tight agreement
+    assert curve[0][2] < 1e-12
+    # afterwards the GPU error must stay within 100x of what a 1-ulp perturbation does to the oracle itself
+    for s, a, b in curve:
+        assert b <= max(1e-12, 100 * a), (s, a, b)
