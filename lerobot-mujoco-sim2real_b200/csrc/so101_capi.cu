@@ -78,7 +78,7 @@ SO101_DEV void add_stats(unsigned long long* stats, const Counters& c) {
 // Philox4x32-10 (Salmon et al. 2011).  Stream layout specified in DESIGN.md ("control RNG"):
 // key = seed, counter = (env_lo, env_hi, step, 2*stream + block); 32-bit lanes -> [0,1).
 SO101_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < 10; r++) {
     uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
     uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
@@ -89,7 +89,7 @@ SO101_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 }
 enum { STREAM_RESET = 0, STREAM_CTRL = 1, STREAM_FREQ = 2, STREAM_AMP = 3, STREAM_PHASE = 4 };
 // first 5 of the 8 uniforms of (seed, env, step, stream)
-SO101_DEV void uniform5(uint64_t seed, int64_t env, uint32_t step, uint32_t stream, double (&out)[5]) {
+__device__ __noinline__ void uniform5(uint64_t seed, int64_t env, uint32_t step, uint32_t stream, double* out) {
   uint32_t c[4] = {(uint32_t)env, (uint32_t)((uint64_t)env >> 32), step, stream * 2u};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
@@ -140,7 +140,7 @@ SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t
 #pragma unroll
     for (int k = 0; k < 5; k++) u[k] = (double)ut[((int64_t)t * 5 + k) * n + local];
   } else {
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 5; k++) {
       double f = g.freq[k];
       if (s.kind == SO101_CTRL_CHIRP) f = muladd_rn(g.freq[k], s.freq_hi - s.freq_lo, (double)t / (double)s.t_total);
@@ -153,7 +153,7 @@ SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t
 // ==========================================================================================
 // kernels
 // ==========================================================================================
-#define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(128)
+#define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(256)
 
 // reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
 //   mode 0: qpos0/qvel0 [6][N] (nullable)   mode 1: qpos[0:5] ~ U(lo,hi) from Philox
@@ -214,7 +214,8 @@ SO101_KERNEL(T)
 k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
        unsigned long long* stats) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s.n) return;
+  const bool active = i < s.n;   // idle lanes shadow the last env: every thread reaches the barriers
+  if (!active) i = s.n - 1;
   Env<T> e;
   load_env(s, i, e);
   T u[NV], site[3] = {T(0), T(0), T(0)};
@@ -222,14 +223,19 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   for (int k = 0; k < NV; k++) u[k] = (ctrl && k < n_ctrl) ? ctrl[k * s.n + i] : T(0);
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
-  for (int ss = 0; ss < nsub; ss++) physics_step(m, e, u, false, ss == nsub - 1, site, trip, cnt);
+#pragma unroll 1
+  for (int ss = 0; ss < nsub; ss++) physics_step<T, true>(m, e, u, false, ss == nsub - 1, site, trip, cnt);
   if (nsub == 0) site_fk(m, e.q, site);
-  store_env(s, i, e);
-  if (obs) {
+  if (active) {
+    store_env(s, i, e);
+    if (obs) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+      for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
 #pragma unroll
-    for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+      for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+    }
+  } else {
+    cnt = {0, 0, 0, 0};
   }
   add_stats(stats, cnt);
 }
@@ -237,11 +243,12 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
 template <typename T, typename ROW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int Tn, int frame_skip, ROW* rows,
           uint32_t rflags, unsigned long long* stats) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s.n) return;
+  const bool active = i < s.n;
+  if (!active) i = s.n - 1;
   const int64_t env = spec.env_offset + i;
   Env<T> e;
   if (rflags & SO101_ROLL_NO_RESET) {
@@ -262,15 +269,17 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   site_fk(m, e.q, site);
   double u[5];
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+#pragma unroll 1
   for (int t = 0; t <= Tn; t++) {
     if (t > 0) {
+#pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++)
-        physics_step(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+        physics_step<T, true>(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
     }
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
 #pragma unroll
     for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
-    if (rows) {
+    if (rows && active) {
       ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
 #pragma unroll
       for (int k = 0; k < 5; k++) row[k] = (ROW)u[k];
@@ -280,7 +289,8 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
       for (int k = 0; k < 5; k++) row[8 + k] = (ROW)(float)e.q[k];
     }
   }
-  store_env(s, i, e);
+  if (active) store_env(s, i, e);
+  if (!active) cnt = {0, 0, 0, 0};
   add_stats(stats, cnt);
 }
 
@@ -291,7 +301,8 @@ SO101_KERNEL(T)
 k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
         int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s.n) return;
+  const bool active = i < s.n;
+  if (!active) i = s.n - 1;
   Env<T> e;
   reset_env(m, e);
 #pragma unroll
@@ -302,20 +313,25 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   T site[3];
   site_fk(m, e.q, site);
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+#pragma unroll 1
   for (int t = 0; t <= H; t++) {
     if (t > 0) {
 #pragma unroll
       for (int k = 0; k < 5; k++) uc[k] = U[((int64_t)(t - 1) * 5 + k) * s.n + i];
+#pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++)
-        physics_step(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+        physics_step<T, true>(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
     }
-    float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;
+    if (active) {
+      float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;
 #pragma unroll
-    for (int k = 0; k < 3; k++) x[k] = (float)site[k];
+      for (int k = 0; k < 3; k++) x[k] = (float)site[k];
 #pragma unroll
-    for (int k = 0; k < 5; k++) x[3 + k] = (float)e.q[k];
+      for (int k = 0; k < 5; k++) x[3 + k] = (float)e.q[k];
+    }
   }
-  store_env(s, i, e);
+  if (active) store_env(s, i, e);
+  else cnt = {0, 0, 0, 0};
   add_stats(stats, cnt);
 }
 
@@ -386,10 +402,13 @@ template <typename T> static StateView<T> view(const So101Batch* b) {
   v.n = b->n;
   return v;
 }
-// block size: small batches use one-warp blocks so that every SM gets work
+// block size: big batches use 256-thread blocks (8 warps share the instruction stream of a step,
+// see physics_step SYNC); small batches use smaller blocks so that every SM gets work
 static int pick_block(int64_t n) {
-  if (n >= (int64_t)148 * 128 * 2) return 128;
-  if (n >= (int64_t)148 * 64 * 2) return 64;
+  if (const char* ev = getenv("SO101_BLK")) { int v = atoi(ev); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }
+  if (n >= (int64_t)148 * 256) return 256;
+  if (n >= (int64_t)148 * 128) return 128;
+  if (n >= (int64_t)148 * 64) return 64;
   return 32;
 }
 static unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }

@@ -258,6 +258,8 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
     // limit row k
     if (t.jnt_limited[k]) {
       m.limited_mask |= 1 << k;
+      if (t.jnt_solimp[k][4] != 1.0 && t.jnt_solimp[k][4] != 2.0)
+        return "joint-limit solimp power must be 1 or 2 on the CUDA path";
       if (!(t.jnt_range[k][1] - t.jnt_range[k][0] > 2 * t.jnt_margin[k]))
         return "joint range narrower than 2*margin (both limit rows could be active)";
     }

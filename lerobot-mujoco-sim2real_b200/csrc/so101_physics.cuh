@@ -34,14 +34,60 @@ SO101_DEV double rcp_(double x) {
   return y;
 }
 SO101_DEV float rcp_(float x) { return __frcp_rn(x); }
-SO101_DEV void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
-SO101_DEV void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+// sin/cos by Cody-Waite reduction to [-pi/4, pi/4] + fdlibm / Cephes kernels (<= 1 ulp for the
+// joint angles of a limited hinge chain; arguments beyond 2^18 fall back to the library, which
+// keeps its large-argument reduction out of the hot instruction stream).
+__device__ __noinline__ void sincos_slow_(double x, double* sp, double* cp) { sincos(x, sp, cp); }
+__device__ __noinline__ void sincos_slow_(float x, float* sp, float* cp) { sincosf(x, sp, cp); }
+SO101_DEV void sincos_(double x, double* sp, double* cp) {
+  if (!(fabs(x) < 262144.0)) { sincos_slow_(x, sp, cp); return; }
+  double k = rint(x * 0.63661977236758134308);
+  double r = fma(-k, 1.57079632679489655800e+00, x);
+  r = fma(-k, 6.12323399573676603587e-17, r);
+  double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(z, ps, 2.75573137070700676789e-06);
+  ps = fma(z, ps, -1.98412698298579493134e-04);
+  ps = fma(z, ps, 8.33333333332248946124e-03);
+  ps = fma(z, ps, -1.66666666666666324348e-01);
+  double s = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(z, pc, -2.75573143513906633035e-07);
+  pc = fma(z, pc, 2.48015872894767294178e-05);
+  pc = fma(z, pc, -1.38888888888741095749e-03);
+  pc = fma(z, pc, 4.16666666666666019037e-02);
+  double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+  int q = (int)k;
+  double ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
+  *sp = (q & 2) ? -ss : ss;
+  *cp = ((q + 1) & 2) ? -cc : cc;
+}
+SO101_DEV void sincos_(float x, float* sp, float* cp) {
+  if (!(fabsf(x) < 8192.0f)) { sincos_slow_(x, sp, cp); return; }
+  float k = rintf(x * 0.636619772f);
+  float r = fmaf(-k, 1.5703125f, x);
+  r = fmaf(-k, 4.837512969970703125e-4f, r);
+  r = fmaf(-k, 7.54978995489188e-8f, r);
+  float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(z, ps, -1.6666654611e-1f);
+  float s = fmaf(r * z, ps, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(z, pc, 4.166664568298827e-2f);
+  float c = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+  int q = (int)k;
+  float ss = (q & 1) ? c : s, cc = (q & 1) ? s : c;
+  *sp = (q & 2) ? -ss : ss;
+  *cp = ((q + 1) & 2) ? -cc : cc;
+}
 SO101_DEV double sqrt_(double x) { return sqrt(x); }
 SO101_DEV float sqrt_(float x) { return sqrtf(x); }
 SO101_DEV double abs_(double x) { return fabs(x); }
 SO101_DEV float abs_(float x) { return fabsf(x); }
-SO101_DEV double pow_(double x, double y) { return pow(x, y); }
-SO101_DEV float pow_(float x, float y) { return powf(x, y); }
+// relative noise floor added to the solver's stopping tests: 0 in fp64 (MuJoCo's tests verbatim);
+// in fp32 the absolute tolerances 1e-8 sit below rounding noise and would never fire.
+template <typename T> struct Noise { static constexpr bool on = false; static constexpr double eps = 0.0; };
+template <> struct Noise<float> { static constexpr bool on = true; static constexpr double eps = 1e-5; };
 template <typename T> SO101_DEV T min_(T a, T b) { return a < b ? a : b; }
 template <typename T> SO101_DEV T max_(T a, T b) { return a > b ? a : b; }
 template <typename T> SO101_DEV bool bad_(T x) { return !(x <= T(MJ_MAXVAL) && x >= T(-MJ_MAXVAL)); }
@@ -135,13 +181,17 @@ template <typename T> SO101_DEV void xinertia_add(const T (&R)[9], const T (&r)[
 // ------------------------------------------------------------------------------------------
 // dense 6x6 LDL^T on a packed lower triangle (A = L D L^T, unit L), and solve
 // ------------------------------------------------------------------------------------------
-template <typename T> SO101_DEV void ldl6(const T (&A)[21], T (&L)[21], T (&Dinv)[NV]) {
-  T D[NV];
+// solve (A) x = b in place for a packed lower triangle A (A = L D L^T, unit L)
+template <typename T> SO101_DEV void ldl6_factor_solve(const T (&A)[21], T (&x)[NV]) {
+  T L[21], Dinv[NV], D[NV];
 #pragma unroll
   for (int j = 0; j < NV; j++) {
+    T W[NV];
+#pragma unroll
+    for (int k = 0; k < j; k++) W[k] = L[tri(j, k)] * D[k];
     T d = A[tri(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)] * D[k];
+    for (int k = 0; k < j; k++) d -= L[tri(j, k)] * W[k];
     d = max_(d, T(MJ_MINVAL));
     D[j] = d;
     Dinv[j] = rcp_(d);
@@ -149,12 +199,10 @@ template <typename T> SO101_DEV void ldl6(const T (&A)[21], T (&L)[21], T (&Dinv
     for (int i = j + 1; i < NV; i++) {
       T s = A[tri(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; k++) s -= L[tri(i, k)] * L[tri(j, k)] * D[k];
+      for (int k = 0; k < j; k++) s -= L[tri(i, k)] * W[k];
       L[tri(i, j)] = s * Dinv[j];
     }
   }
-}
-template <typename T> SO101_DEV void ldl6_solve(const T (&L)[21], const T (&Dinv)[NV], T (&x)[NV]) {
 #pragma unroll
   for (int i = 1; i < NV; i++) {
 #pragma unroll
@@ -325,6 +373,7 @@ template <typename T> SO101_DEV void site_fk(const DevModel<T>& m, const T (&q)[
 // ------------------------------------------------------------------------------------------
 // constraint rows.  Row order follows mj_makeConstraint: friction rows (dof order), then the
 // active joint-limit row of each joint.  All Jacobian rows are +-e_i, so J is never formed.
+// Limit rows are rare: their arrays are indexed in rolled loops (local memory, tiny code).
 // ------------------------------------------------------------------------------------------
 template <typename T>
 struct Rows {
@@ -333,29 +382,25 @@ struct Rows {
   bool anylim;
 };
 
-// getimpedance (engine_core_constraint.c) for a limit row
-template <typename T> SO101_DEV T limit_impedance(const T (&si)[5], T pos, T margin) {
+// getimpedance (engine_core_constraint.c) for a limit row; solimp power 1 or 2 (checked at
+// model creation: MuJoCo's default is 2)
+template <typename T> SO101_DEV T limit_impedance(const T* si, T pos, T margin) {
   if (si[0] == si[1] || si[2] <= T(MJ_MINVAL)) return T(0.5) * (si[0] + si[1]);
-  T x = abs_((pos - margin) * rcp_(si[2]));
+  T x = abs_((pos - margin) / si[2]);
   if (x >= T(1)) return si[1];
   if (x <= T(0)) return si[0];
   T y;
   if (si[4] == T(1)) y = x;
-  else if (si[4] == T(2)) {
-    if (x <= si[3]) y = x * x * rcp_(si[3]);
-    else y = T(1) - (T(1) - x) * (T(1) - x) * rcp_(T(1) - si[3]);
-  } else {
-    if (x <= si[3]) y = pow_(x, si[4]) / pow_(si[3], si[4] - T(1));
-    else y = T(1) - pow_(T(1) - x, si[4]) / pow_(T(1) - si[3], si[4] - T(1));
-  }
+  else if (x <= si[3]) y = x * x / si[3];
+  else y = T(1) - (T(1) - x) * (T(1) - x) / (T(1) - si[3]);
   return si[0] + y * (si[1] - si[0]);
 }
 
-// mj_constraintUpdate + the Gauss term: total cost at acceleration a; also qfrc_constraint and
-// the diagonal that the quadratic rows add to the Hessian.
-template <typename T, bool WANT_FORCE>
+// mj_constraintUpdate + Gauss term: total cost at acceleration a, qfrc_constraint and the diagonal
+// that the quadratic rows add to the Hessian.
+template <typename T>
 SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV], const T (&Ma)[NV],
-                        const T (&fsm)[NV], const T (&asm_)[NV], bool with_gauss, T (&qc)[NV], T (&hd)[NV]) {
+                        const T (&fsm)[NV], const T (&asm_)[NV], T (&qc)[NV], T (&hd)[NV]) {
   T s = T(0);
 #pragma unroll
   for (int i = 0; i < NV; i++) {
@@ -365,106 +410,71 @@ SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV
     T cq = T(0.5) * m.fr_D[i] * jar * jar;
     T cl = (neg ? -f : f) * jar - m.fr_hRff[i];
     s += (neg || pos) ? cl : cq;
-    if (WANT_FORCE) {
-      qc[i] = neg ? f : (pos ? -f : -m.fr_D[i] * jar);
-      hd[i] = (neg || pos) ? T(0) : m.fr_D[i];
-    }
+    qc[i] = neg ? f : (pos ? -f : -m.fr_D[i] * jar);
+    hd[i] = (neg || pos) ? T(0) : m.fr_D[i];
   }
   if (rw.anylim) {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < NV; i++) {
       if (rw.side[i] != T(0)) {
         T jar = rw.side[i] * a[i] - rw.aref_l[i];
         if (jar < T(0)) {
           s += T(0.5) * rw.D_l[i] * jar * jar;
-          if (WANT_FORCE) { qc[i] += rw.side[i] * (-rw.D_l[i] * jar); hd[i] += rw.D_l[i]; }
+          qc[i] += rw.side[i] * (-rw.D_l[i] * jar);
+          hd[i] += rw.D_l[i];
         }
       }
     }
   }
-  if (with_gauss) {
-    T g = T(0);
+  T g = T(0);
 #pragma unroll
-    for (int i = 0; i < NV; i++) g += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
-    s += g;
-  }
-  return s;
+  for (int i = 0; i < NV; i++) g += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
+  return s + g;
 }
 
-template <typename T> struct LsPnt { T alpha, cost, d0, d1; };
+template <typename T> struct LsPnt { T alpha, cost, d0, d1, gt; };
 
-// PrimalEval: cost and derivatives of the exact piecewise-quadratic along the search direction
+// updateBracket of engine_solver.c without its trailing evaluation
 template <typename T>
-SO101_DEV void ls_eval(const DevModel<T>& m, const Rows<T>& rw, const T (&jar0)[NV], const T (&sr)[NV],
-                       const T (&qf)[NV][3], const T (&jarl)[NV], const T (&ql)[NV][3], const T (&G)[3],
-                       T alpha, LsPnt<T>& p, uint32_t& nev) {
-  T q0 = G[0], q1 = G[1], q2 = G[2];
-#pragma unroll
-  for (int i = 0; i < NV; i++) {
-    T x = jar0[i] + alpha * sr[i];
-    T f = m.fr_f[i], Rf = m.fr_Rf[i];
-    bool quad = (-Rf < x) && (x < Rf);
-    bool neg = x <= -Rf;
-    T l0 = f * (T(-0.5) * Rf + (neg ? -jar0[i] : jar0[i]));
-    T l1 = (neg ? -f : f) * sr[i];
-    q0 += quad ? qf[i][0] : l0;
-    q1 += quad ? qf[i][1] : l1;
-    q2 += quad ? qf[i][2] : T(0);
-  }
-  if (rw.anylim) {
-#pragma unroll
-    for (int i = 0; i < NV; i++) {
-      if (rw.side[i] != T(0)) {
-        T x = jarl[i] + alpha * (rw.side[i] * sr[i]);
-        if (x < T(0)) { q0 += ql[i][0]; q1 += ql[i][1]; q2 += ql[i][2]; }
-      }
-    }
-  }
-  p.alpha = alpha;
-  p.cost = alpha * alpha * q2 + alpha * q1 + q0;
-  p.d0 = T(2) * alpha * q2 + q1;
-  p.d1 = T(2) * q2;
-  if (p.d1 <= T(0)) p.d1 = T(MJ_MINVAL);
-  nev++;
-}
-
-// updateBracket of engine_solver.c
-template <typename T>
-SO101_DEV int ls_bracket(const DevModel<T>& m, const Rows<T>& rw, const T (&jar0)[NV], const T (&sr)[NV],
-                         const T (&qf)[NV][3], const T (&jarl)[NV], const T (&ql)[NV][3], const T (&G)[3],
-                         LsPnt<T>& p, const LsPnt<T> (&cand)[3], LsPnt<T>& pnext, uint32_t& nev) {
+SO101_DEV int ls_bracket(LsPnt<T>& p, const LsPnt<T>& c0, const LsPnt<T>& c1, const LsPnt<T>& c2) {
   int flag = 0;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    if (p.d0 < T(0) && cand[i].d0 < T(0) && p.d0 < cand[i].d0) { p = cand[i]; flag = 1; }
-    else if (p.d0 > T(0) && cand[i].d0 > T(0) && p.d0 > cand[i].d0) { p = cand[i]; flag = 2; }
-  }
-  if (flag) ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p.alpha - p.d0 * rcp_(p.d1), pnext, nev);
+  if (p.d0 < T(0) && c0.d0 < T(0) && p.d0 < c0.d0) { p = c0; flag = 1; }
+  else if (p.d0 > T(0) && c0.d0 > T(0) && p.d0 > c0.d0) { p = c0; flag = 2; }
+  if (p.d0 < T(0) && c1.d0 < T(0) && p.d0 < c1.d0) { p = c1; flag = 1; }
+  else if (p.d0 > T(0) && c1.d0 > T(0) && p.d0 > c1.d0) { p = c1; flag = 2; }
+  if (p.d0 < T(0) && c2.d0 < T(0) && p.d0 < c2.d0) { p = c2; flag = 1; }
+  else if (p.d0 > T(0) && c2.d0 > T(0) && p.d0 > c2.d0) { p = c2; flag = 2; }
   return flag;
 }
 
 // PrimalSearch: exact line search along sr from acceleration a.  Returns alpha; Mv = M*sr out.
+// MuJoCo's control flow is kept decision for decision, but folded into a state machine around a
+// single PrimalEval site: one copy of the evaluation code, and lanes that need different numbers
+// of evaluations still execute them together.
 template <typename T>
 SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[21], const T (&a)[NV],
-                        const T (&Ma)[NV], const T (&fsm)[NV], const T (&sr)[NV], T gauss0, T (&Mv)[NV],
-                        uint32_t& nev_total) {
+                        const T (&Ma)[NV], const T (&fsm)[NV], const T (&asm_)[NV], const T (&sr)[NV],
+                        T (&Mv)[NV], uint32_t& nev_total) {
   T ss = T(0);
 #pragma unroll
   for (int i = 0; i < NV; i++) ss += sr[i] * sr[i];
-  T snorm = sqrt_(ss);
+  const T snorm = sqrt_(ss);
   if (snorm < T(MJ_MINVAL)) return T(0);
   const T gtol = m.gtol_fac * snorm;
   symv6(Mm, sr, Mv);
   // PrimalPrepare
-  T G[3] = {gauss0, T(0), T(0)};
+  T G0 = T(0), G1, G2;
   {
     T g1a = T(0), g1b = T(0), g2 = T(0);
 #pragma unroll
-    for (int i = 0; i < NV; i++) { g1a += sr[i] * Ma[i]; g1b += fsm[i] * sr[i]; g2 += sr[i] * Mv[i]; }
-    G[1] = g1a - g1b;
-    G[2] = T(0.5) * g2;
+    for (int i = 0; i < NV; i++) {
+      G0 += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
+      g1a += sr[i] * Ma[i]; g1b += fsm[i] * sr[i]; g2 += sr[i] * Mv[i];
+    }
+    G1 = g1a - g1b;
+    G2 = T(0.5) * g2;
   }
-  T jar0[NV], qf[NV][3], jarl[NV], ql[NV][3];
+  T jar0[NV], qf[NV][3];
 #pragma unroll
   for (int i = 0; i < NV; i++) {
     jar0[i] = a[i] - rw.aref_f[i];
@@ -472,65 +482,112 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
     qf[i][0] = T(0.5) * jar0[i] * DJ0;
     qf[i][1] = sr[i] * DJ0;
     qf[i][2] = T(0.5) * sr[i] * m.fr_D[i] * sr[i];
-    jarl[i] = T(0); ql[i][0] = ql[i][1] = ql[i][2] = T(0);
   }
-  if (rw.anylim) {
-#pragma unroll
-    for (int i = 0; i < NV; i++) {
-      if (rw.side[i] != T(0)) {
-        T jv = rw.side[i] * sr[i];
-        jarl[i] = rw.side[i] * a[i] - rw.aref_l[i];
-        T DJ0 = rw.D_l[i] * jarl[i];
-        ql[i][0] = T(0.5) * jarl[i] * DJ0;
-        ql[i][1] = jv * DJ0;
-        ql[i][2] = T(0.5) * jv * rw.D_l[i] * jv;
-      }
-    }
-  }
+  enum { S_P0, S_P1, S_PH1, S_P1N, S_MID, S_B1, S_B2 };
+  int st = S_P0, b1 = 0, b2 = 0;
   uint32_t nev = 0;
   const uint32_t maxev = (uint32_t)m.ls_iterations;
-  LsPnt<T> p0, p1, p2, pmid, p1next, p2next;
-  T result;
-  ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, T(0), p0, nev);
-  ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p0.alpha - p0.d0 * rcp_(p0.d1), p1, nev);
-  if (p0.cost < p1.cost) p1 = p0;
-  if (abs_(p1.d0) < gtol) {
-    result = p1.alpha;
-  } else {
-    const T dir = p1.d0 < T(0) ? T(1) : T(-1);
-    bool done = false;
-    p2 = p1;
-    // phase 1: Newton steps until the slope changes sign
-    while (p1.d0 * dir <= -gtol && nev < maxev) {
-      p2 = p1;
-      ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p1.alpha - p1.d0 * rcp_(p1.d1), p1, nev);
-      if (abs_(p1.d0) < gtol) { done = true; break; }
-    }
-    if (done || nev >= maxev) {
-      result = p1.alpha;
-    } else {
-      // phase 2: bracketed
-      p2next = p1;
-      ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, p1.alpha - p1.d0 * rcp_(p1.d1), p1next, nev);
-      bool ret = false;
-      result = T(0);
-      while (nev < maxev) {
-        ls_eval(m, rw, jar0, sr, qf, jarl, ql, G, T(0.5) * (p1.alpha + p2.alpha), pmid, nev);
-        LsPnt<T> cand[3] = {p1next, p2next, pmid};
-        T bestcost = T(0);
-        int best = -1;
+  LsPnt<T> p0, p1, p2, pmid, p1n, p2n, c0, c1, c2, pt;
+  p0 = p1 = p2 = pmid = p1n = p2n = c0 = c1 = c2 = LsPnt<T>{T(0), T(0), T(0), T(1), T(0)};
+  T alpha = T(0), result = T(0), dir = T(1);
+  bool done = false;
+  while (!done) {
+    // ---- PrimalEval(alpha) -> pt ---------------------------------------------------------------
+    {
+      T q0 = G0, q1 = G1, q2 = G2;
 #pragma unroll
-        for (int i = 0; i < 3; i++)
-          if (abs_(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
-        if (best >= 0) { result = best == 0 ? cand[0].alpha : (best == 1 ? cand[1].alpha : cand[2].alpha); ret = true; break; }
-        int b1 = ls_bracket(m, rw, jar0, sr, qf, jarl, ql, G, p1, cand, p1next, nev);
-        int b2 = ls_bracket(m, rw, jar0, sr, qf, jarl, ql, G, p2, cand, p2next, nev);
-        if (!b1 && !b2) { result = pmid.alpha; ret = true; break; }
+      for (int i = 0; i < NV; i++) {
+        T x = jar0[i] + alpha * sr[i];
+        T f = m.fr_f[i], Rf = m.fr_Rf[i];
+        bool quad = (-Rf < x) && (x < Rf);
+        bool neg = x <= -Rf;
+        T l0 = f * (T(-0.5) * Rf + (neg ? -jar0[i] : jar0[i]));
+        T l1 = (neg ? -f : f) * sr[i];
+        q0 += quad ? qf[i][0] : l0;
+        q1 += quad ? qf[i][1] : l1;
+        q2 += quad ? qf[i][2] : T(0);
       }
-      if (!ret) {
+      if (rw.anylim) {
+#pragma unroll 1
+        for (int i = 0; i < NV; i++) {
+          if (rw.side[i] != T(0)) {
+            T jv = rw.side[i] * sr[i], jl = rw.side[i] * a[i] - rw.aref_l[i];
+            if (jl + alpha * jv < T(0)) {
+              T DJ0 = rw.D_l[i] * jl;
+              q0 += T(0.5) * jl * DJ0; q1 += jv * DJ0; q2 += T(0.5) * jv * rw.D_l[i] * jv;
+            }
+          }
+        }
+      }
+      pt.alpha = alpha;
+      pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
+      pt.d0 = T(2) * alpha * q2 + q1;
+      pt.d1 = T(2) * q2;
+      if (pt.d1 <= T(0)) pt.d1 = T(MJ_MINVAL);
+      pt.gt = gtol;
+      if (Noise<T>::on) pt.gt = gtol + T(Noise<T>::eps) * (abs_(q1) + abs_(T(2) * alpha * q2));
+      nev++;
+    }
+    // ---- transitions ---------------------------------------------------------------------------
+    bool ph1check = false, ph2check = false, tryb2 = false, afterb = false;
+    if (st == S_P0) {
+      p0 = pt;
+      alpha = p0.alpha - p0.d0 * rcp_(p0.d1);
+      st = S_P1;
+    } else if (st == S_P1) {
+      p1 = pt;
+      if (p0.cost < p1.cost) p1 = p0;
+      if (abs_(p1.d0) < p1.gt) { result = p1.alpha; done = true; }
+      else { dir = p1.d0 < T(0) ? T(1) : T(-1); p2 = p1; ph1check = true; }
+    } else if (st == S_PH1) {
+      p1 = pt;
+      if (abs_(p1.d0) < p1.gt) { result = p1.alpha; done = true; }
+      else ph1check = true;
+    } else if (st == S_P1N) {
+      p1n = pt;
+      ph2check = true;
+    } else if (st == S_MID) {
+      pmid = pt;
+      c0 = p1n; c1 = p2n; c2 = pmid;
+      T bestcost = T(0), bestalpha = T(0);
+      bool found = false;
+      if (abs_(c0.d0) < c0.gt) { bestcost = c0.cost; bestalpha = c0.alpha; found = true; }
+      if (abs_(c1.d0) < c1.gt && (!found || c1.cost < bestcost)) { bestcost = c1.cost; bestalpha = c1.alpha; found = true; }
+      if (abs_(c2.d0) < c2.gt && (!found || c2.cost < bestcost)) { bestcost = c2.cost; bestalpha = c2.alpha; found = true; }
+      if (found) { result = bestalpha; done = true; }
+      else {
+        b1 = ls_bracket(p1, c0, c1, c2);
+        if (b1) { alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_B1; }
+        else tryb2 = true;
+      }
+    } else if (st == S_B1) {
+      p1n = pt;
+      tryb2 = true;
+    } else {  // S_B2
+      p2n = pt;
+      afterb = true;
+    }
+    if (tryb2) {
+      b2 = ls_bracket(p2, c0, c1, c2);
+      if (b2) { alpha = p2.alpha - p2.d0 * rcp_(p2.d1); st = S_B2; }
+      else afterb = true;
+    }
+    if (afterb) {
+      if (!b1 && !b2) { result = pmid.alpha; done = true; }
+      else ph2check = true;
+    }
+    if (ph1check) {
+      if (p1.d0 * dir <= -p1.gt && nev < maxev) { p2 = p1; alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_PH1; }
+      else if (nev >= maxev) { result = p1.alpha; done = true; }
+      else { p2n = p1; alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_P1N; }
+    }
+    if (ph2check) {
+      if (nev < maxev) { alpha = T(0.5) * (p1.alpha + p2.alpha); st = S_MID; }
+      else {
         if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
         else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
         else result = T(0);
+        done = true;
       }
     }
   }
@@ -539,11 +596,17 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
 }
 
 // ------------------------------------------------------------------------------------------
-// one physics step
+// one physics step.  After the smooth dynamics every lane runs the same small phase machine
+//   SMOOTH (qacc_smooth = M^-1 qfrc_smooth) -> NEWTON x n -> EULER ((M + hB)^-1 ...)
+// whose three phases share ONE factor-and-solve of M + diag(dd): the code of the 6x6 LDL^T
+// exists once, and lanes in different phases execute it together.  SYNC: the block re-converges
+// on a barrier at the phase boundaries so that its warps stream the same instructions through
+// the instruction cache together (the step is ~50 KB of SASS; ncu: stall_no_instruction).
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool SYNC>
 SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
                             bool want_site, T (&site)[3], bool trip, Counters& cnt) {
+  if (SYNC) __syncthreads();
   // mj_checkPos / mj_checkVel
   {
     bool bad = false;
@@ -558,12 +621,15 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   }
   T M[21], bias[NV];
   smooth_dynamics<T, true>(m, e.q, e.qd, M, bias, want_site, site, trip, e.flags);
+  if (SYNC) __syncthreads();
   if (gravcomp_capture) {
 #pragma unroll
     for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
   }
-  // mj_passive, mj_fwdActuation, mj_fwdAcceleration
-  T fsm[NV], asm_[NV];
+  // mj_passive, mj_fwdActuation, mj_fwdAcceleration (right-hand side)
+  T fsm[NV], x[NV], dd[NV];
+  Rows<T> rw;
+  rw.anylim = false;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
     T passive = -m.damping[i] * e.qd[i];
@@ -574,20 +640,16 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
               m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
     if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
     fsm[i] = passive - bias[i] + e.fa[i] + m.act_gear[i] * force;
-    asm_[i] = fsm[i];
-  }
-  T L[21], Dinv[NV];
-  ldl6(M, L, Dinv);
-  ldl6_solve(L, Dinv, asm_);
-
-  T a[NV], qc[NV];
-  Rows<T> rw;
-  rw.anylim = false;
-#pragma unroll
-  for (int i = 0; i < NV; i++) {
+    x[i] = fsm[i];
+    dd[i] = T(0);
     rw.aref_f[i] = -m.fr_B[i] * e.qd[i];
     rw.side[i] = T(0); rw.aref_l[i] = T(0); rw.D_l[i] = T(0);
-    if (m.limited_mask >> i & 1) {
+  }
+  // mj_instantiateLimit + mj_makeImpedance + mj_referenceConstraint for the limit rows
+  if (m.limited_mask) {
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      if (!(m.limited_mask >> i & 1)) continue;
       T dlo = e.q[i] - m.lim_lo[i], dhi = m.lim_hi[i] - e.q[i];
       bool lo = dlo < m.lim_margin[i], hi = dhi < m.lim_margin[i];
       if (lo || hi) {
@@ -602,98 +664,124 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   if (rw.anylim) { e.flags |= SO101_FLAG_LIMIT; cnt.limsteps++; }
+  const bool constrained = m.nfriction != 0 || rw.anylim;
 
-  if (m.nfriction == 0 && !rw.anylim) {
-    // nefc == 0: mj_fwdConstraint copies qacc_smooth
-#pragma unroll
-    for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); }
-  } else {
-    // ---- warm start: the cheaper of qacc_warmstart and qacc_smooth ---------------------------
-    T Ma[NV], hd[NV];
+  enum { PH_SMOOTH, PH_NEWTON, PH_EULER, PH_DONE };
+  int phase = PH_SMOOTH, iter = 0;
+  T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV];
+  T cost = T(0);
+  while (phase != PH_DONE) {
     {
-      T Mw[NV];
-      symv6(M, e.warm, Mw);
-      T cw = cost_update<T, false>(m, rw, e.warm, Mw, fsm, asm_, true, qc, hd);
-      T csm = cost_update<T, false>(m, rw, asm_, Mw, fsm, asm_, false, qc, hd);
-      bool use_smooth = cw > csm;
+      T A[21];
+#pragma unroll
+      for (int i = 0; i < 21; i++) A[i] = M[i];
+#pragma unroll
+      for (int i = 0; i < NV; i++) A[tri(i, i)] += dd[i];
+      ldl6_factor_solve(A, x);
+    }
+    bool to_euler = false;
+    if (phase == PH_SMOOTH) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) { asm_[i] = x[i]; a[i] = x[i]; qc[i] = T(0); hd[i] = T(0); }
+      if (!constrained) {
+        to_euler = true;  // nefc == 0: qacc = qacc_smooth
+      } else {
+        // warmstart(): the cheaper of qacc_warmstart and qacc_smooth, evaluated by one code site
+        T cost0 = T(0);
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+          T ca[NV], cMa[NV], cqc[NV], chd[NV];
+#pragma unroll
+          for (int i = 0; i < NV; i++) ca[i] = c ? asm_[i] : e.warm[i];
+          symv6(M, ca, cMa);
+          T cc = cost_update(m, rw, ca, cMa, fsm, asm_, cqc, chd);
+          if (c == 0 || cost0 > cc) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) { a[i] = ca[i]; Ma[i] = cMa[i]; qc[i] = cqc[i]; hd[i] = chd[i]; }
+            cost = cc;
+          }
+          if (c == 0) cost0 = cc;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; i++) { x[i] = Ma[i] - fsm[i] - qc[i]; dd[i] = hd[i]; }
+        phase = PH_NEWTON;
+      }
+    } else if (phase == PH_NEWTON) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) sr[i] = -x[i];
+      bool stop = iter >= m.iterations;
+      if (!stop) {
+        T Mv[NV];
+        T alpha = line_search(m, rw, M, a, Ma, fsm, asm_, sr, Mv, cnt.lsevals);
+        if (alpha == T(0)) {
+          stop = true;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
+          T oldcost = cost;
+          cost = cost_update(m, rw, a, Ma, fsm, asm_, qc, hd);
+          T gg = T(0), nn = T(0);
+#pragma unroll
+          for (int i = 0; i < NV; i++) {
+            x[i] = Ma[i] - fsm[i] - qc[i];
+            dd[i] = hd[i];
+            gg += x[i] * x[i];
+            if (Noise<T>::on) nn += fsm[i] * fsm[i] + qc[i] * qc[i];
+          }
+          T improvement = m.scale * (oldcost - cost);
+          T gradnorm = m.scale * sqrt_(gg);
+          T tol_i = m.tolerance, tol_g = m.tolerance;
+          if (Noise<T>::on) {
+            tol_i += T(Noise<T>::eps) * m.scale * abs_(cost);
+            tol_g += T(Noise<T>::eps) * m.scale * sqrt_(nn);
+          }
+          iter++;
+          if (improvement < tol_i || gradnorm < tol_g) stop = true;
+        }
+      }
+      if (stop) {
+        cnt.newton += iter;
+        if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
+        to_euler = true;
+      }
+    } else {  // PH_EULER: x = (M + h B)^-1 (qfrc_smooth + qfrc_constraint)
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        a[i] = use_smooth ? asm_[i] : e.warm[i];
-        Ma[i] = Mw[i];
+        e.qd[i] += m.h * x[i];
+        e.q[i] += m.h * e.qd[i];
+        e.warm[i] = a[i];
       }
-      if (use_smooth) symv6(M, a, Ma);
+      e.time += m.h;
+      phase = PH_DONE;
     }
-    // ---- Newton (mj_solPrimal) ---------------------------------------------------------------
-    T cost = cost_update<T, true>(m, rw, a, Ma, fsm, asm_, true, qc, hd);
-    T grad[NV], sr[NV], H[21], LH[21], DHinv[NV];
-    auto gradient_and_direction = [&]() {
+    if (to_euler) {
+      // mj_checkAcc
+      bool bad = false;
 #pragma unroll
-      for (int i = 0; i < 21; i++) H[i] = M[i];
+      for (int i = 0; i < NV; i++) bad |= bad_(a[i]);
+      if (bad) {
 #pragma unroll
-      for (int i = 0; i < NV; i++) { H[tri(i, i)] += hd[i]; grad[i] = Ma[i] - fsm[i] - qc[i]; sr[i] = grad[i]; }
-      ldl6(H, LH, DHinv);
-      ldl6_solve(LH, DHinv, sr);
+        for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
+        e.time = T(0);
+        e.flags |= SO101_FLAG_BADSTATE;
+        phase = PH_DONE;
+      } else if (m.any_damping) {
+        // mj_Euler, implicit in joint damping
 #pragma unroll
-      for (int i = 0; i < NV; i++) sr[i] = -sr[i];
-    };
-    gradient_and_direction();
-    int iter = 0;
-    while (iter < m.iterations) {
-      T gauss0 = T(0);
+        for (int i = 0; i < NV; i++) { dd[i] = m.h * m.damping[i]; x[i] = fsm[i] + qc[i]; }
+        phase = PH_EULER;
+      } else {
 #pragma unroll
-      for (int i = 0; i < NV; i++) gauss0 += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
-      T Mv[NV];
-      T alpha = line_search(m, rw, M, a, Ma, fsm, sr, gauss0, Mv, cnt.lsevals);
-      if (alpha == T(0)) break;
-#pragma unroll
-      for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
-      T oldcost = cost;
-      cost = cost_update<T, true>(m, rw, a, Ma, fsm, asm_, true, qc, hd);
-      gradient_and_direction();
-      T gg = T(0);
-#pragma unroll
-      for (int i = 0; i < NV; i++) gg += grad[i] * grad[i];
-      T improvement = m.scale * (oldcost - cost);
-      T gradnorm = m.scale * sqrt_(gg);
-      iter++;
-      if (improvement < m.tolerance || gradnorm < m.tolerance) break;
-    }
-    cnt.newton += iter;
-    if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
-  }
-
-  // mj_checkAcc
-  {
-    bool bad = false;
-#pragma unroll
-    for (int i = 0; i < NV; i++) bad |= bad_(a[i]);
-    if (bad) {
-#pragma unroll
-      for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
-      e.time = T(0);
-      e.flags |= SO101_FLAG_BADSTATE;
-      cnt.steps++;
-      return;
+        for (int i = 0; i < NV; i++) {
+          e.qd[i] += m.h * a[i];
+          e.q[i] += m.h * e.qd[i];
+          e.warm[i] = a[i];
+        }
+        e.time += m.h;
+        phase = PH_DONE;
+      }
     }
   }
-  // mj_Euler: implicit in joint damping, semi-implicit in position
-  T acc[NV];
-  if (m.any_damping) {
-#pragma unroll
-    for (int i = 0; i < NV; i++) { M[tri(i, i)] += m.h * m.damping[i]; acc[i] = fsm[i] + qc[i]; }
-    ldl6(M, L, Dinv);
-    ldl6_solve(L, Dinv, acc);
-  } else {
-#pragma unroll
-    for (int i = 0; i < NV; i++) acc[i] = a[i];
-  }
-#pragma unroll
-  for (int i = 0; i < NV; i++) {
-    e.qd[i] += m.h * acc[i];
-    e.q[i] += m.h * e.qd[i];
-    e.warm[i] = a[i];
-  }
-  e.time += m.h;
   cnt.steps++;
 }
 
