@@ -1,0 +1,144 @@
+"""Drop-in `SOARM101DataGenerator` backed by the fused B200 rollout kernel.
+
+Mirrors [REF SOARM101/SOARM101_DataCollection.py:77-205]: same constructor (`args` with
+`xml_path, x_dim, u_dim, device, train_samples, train_steps, test_samples, test_steps,
+data_dir_save, data_dir_load_train, data_dir_load_val, env, batch_size, eval_batch_size`), same
+`generate_physics_based_data(traj_num, steps, input_type) -> float64 [traj_num, steps+1, 13]`
+with columns `[u(5) | ee_pos(3) | qpos(5)]`, same `.npy` cache files and loaders.
+
+Differences, all deliberate:
+  * the serial double loop over (trajectory, step) [REF :108-134] is ONE kernel launch per chunk
+    of trajectories (`so101_batch_rollout`): reset, control generation, frame_skip x mj_step and
+    the row writer are fused; rows stay on the device until the final copy.
+  * random numbers come from a counter-based Philox stream keyed (seed, trajectory, step) instead
+    of the unseeded global numpy RNG [REF :115,132, train.py:270] — datasets are reproducible and
+    independent of batch chunking and of the number of GPUs.
+  * under `torch.distributed` the trajectories are sharded across ranks and gathered on rank 0.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+
+from . import sharding
+from . import tables as T
+from .vec_env import SOARM101VecEnv
+
+
+class Collater:
+    """[REF SOARM101_DataCollection.py:13-29]"""
+
+    def __init__(self, x_dim: int, u_dim: int, device: str = "cuda"):
+        self.x_dim, self.u_dim, self.device = x_dim, u_dim, device
+
+    def __call__(self, batch_list: list):
+        batch_data = torch.stack(list(zip(*batch_list))[0], dim=0)
+        return dict(x=batch_data[:, :, self.u_dim:self.u_dim + self.x_dim].to(self.device),
+                    u=batch_data[:, :, :self.u_dim].to(self.device))
+
+
+class SOARM101DataGenerator:
+    #: trajectories per launch (bounds device memory: rows are 104 B x (steps+1) per trajectory)
+    max_batch = 1 << 20
+
+    def __init__(self, args, dtype: str = "float64", device: Optional[int] = None, tables=None) -> None:
+        self.args = args
+        self.udim = self.args.u_dim
+        self.xdim = self.args.x_dim
+        if self.udim != T.NU_ENV or self.xdim != T.NOBS:
+            raise ValueError("SOARM101 data layout is u_dim=5, x_dim=8")
+        print("正在初始化物理仿真环境...")
+        self.dtype = dtype
+        self.device = torch.cuda.current_device() if device is None else device
+        if tables is None:
+            from .mjcf import compile_mjcf
+            tables = compile_mjcf(self.args.xml_path).tables
+        self.tables = tables
+        self.frame_skip = max(1, int(np.round(0.02 / tables.timestep)))
+        self.seed = int(getattr(args, "seed", 42))
+        self._calls = 0
+        self._envs: Dict[int, SOARM101VecEnv] = {}
+        print("物理环境初始化完成。")
+        self.collate_fn = Collater(self.args.x_dim, self.args.u_dim, getattr(self.args, "device", "cuda"))
+        self.last_flags: Optional[np.ndarray] = None
+
+    def _env(self, n: int) -> SOARM101VecEnv:
+        if n not in self._envs:
+            self._envs.clear()
+            self._envs[n] = SOARM101VecEnv(tables=self.tables, num_envs=n, dtype=self.dtype, device=self.device)
+        return self._envs[n]
+
+    def generate_device(self, traj_num: int, steps: int, input_type: str, seed: Optional[int] = None,
+                        env_offset: int = 0) -> torch.Tensor:
+        """Rows `[traj_num, steps+1, 13]` float64 as a device tensor (no host copy)."""
+        if input_type not in ("random", "sin", "chirp"):
+            raise ValueError(f"unknown input_type {input_type!r}")
+        seed = self.seed if seed is None else seed
+        out = torch.empty((traj_num, steps + 1, T.ROW), dtype=torch.float64, device=torch.device("cuda", self.device))
+        flags = []
+        for lo in range(0, traj_num, self.max_batch):
+            n = min(self.max_batch, traj_num - lo)
+            env = self._env(n)
+            env.rollout(steps, input_type, seed=seed, env_offset=env_offset + lo, out=out[lo:lo + n])
+            flags.append(env.flags())
+        self.last_flags = torch.cat(flags).cpu().numpy() if flags else np.zeros(0, dtype=np.int32)
+        return out
+
+    def generate_physics_based_data(self, traj_num, steps, input_type, seed: Optional[int] = None):
+        """[REF SOARM101_DataCollection.py:90-136] -> numpy float64 [traj_num, steps+1, 13].
+
+        With torch.distributed initialised, every rank simulates its shard of the trajectories and
+        rank 0 returns the full array (other ranks return None)."""
+        if seed is None:   # a fresh stream per call, like consecutive draws from the reference's RNG
+            seed = self.seed + 7919 * self._calls
+        self._calls += 1
+        rank, world = sharding.dist_info()
+        lo, hi = sharding.shard_range(traj_num, rank, world)
+        local = self.generate_device(hi - lo, steps, input_type, seed=seed, env_offset=lo)
+        full = sharding.gather_rows(local, traj_num, dst=0)
+        return None if full is None else full.cpu().numpy()
+
+    def generate_and_save_data(self):
+        """[REF SOARM101_DataCollection.py:138-181]: same cache files, same order."""
+        a = self.args
+        os.makedirs(a.data_dir_save, exist_ok=True)
+        rank, _ = sharding.dist_info()
+
+        def get(path: str, n: int, steps: int, kind: str, what: str):
+            if os.path.exists(path):
+                return np.load(path)
+            print(f"生成{what}: {n}条轨迹，每条{steps}步")
+            data = self.generate_physics_based_data(n, steps, kind)
+            if rank == 0:
+                np.save(path, data)
+                print(f"{what}保存到: {path}, 形状: {data.shape}")
+            return data
+
+        self.train_data = get(a.data_dir_load_train, a.train_samples, a.train_steps, "random", "训练数据")
+        self.val_data = get(a.data_dir_load_val, a.test_samples, a.test_steps, "random", "验证数据")
+        self.test_data_dict = {}
+        for test_type in ["random", "sin", "chirp"]:
+            path = os.path.join(os.path.dirname(a.data_dir_load_train),
+                                f"test_data_{test_type}_{a.test_samples}_{a.test_steps}.npy")
+            self.test_data_dict[test_type] = get(path, a.test_samples, a.test_steps, test_type, f"'{test_type}'测试数据")
+        self.close()
+
+    def _loader(self, data: np.ndarray, batch_size: int, shuffle: bool) -> DataLoader:
+        ds = TensorDataset(torch.tensor(data, dtype=torch.float32))
+        return DataLoader(ds, batch_size=batch_size, collate_fn=self.collate_fn, shuffle=shuffle)
+
+    def get_train_loader(self):
+        """[REF SOARM101_DataCollection.py:184-196]"""
+        return (self._loader(self.train_data, self.args.batch_size, True),
+                self._loader(self.val_data, self.args.eval_batch_size, False))
+
+    def get_test_loader(self, test_type):
+        """[REF SOARM101_DataCollection.py:198-205]"""
+        return self._loader(self.test_data_dict[test_type], self.args.eval_batch_size, False)
+
+    def close(self):
+        self._envs.clear()

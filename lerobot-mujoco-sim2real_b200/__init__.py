@@ -8,3 +8,16 @@ from . import tables  # noqa: F401
 from .tables import builtin_tables, load_tables, save_tables  # noqa: F401
 
 __all__ = ["tables", "builtin_tables", "load_tables", "save_tables"]
+
+
+def __getattr__(name):  # heavy modules (torch, ctypes library) load on first use
+    if name in ("SOARM101VecEnv", "fma_peak_tflops"):
+        from . import vec_env
+        return getattr(vec_env, name)
+    if name == "SOARM101Env":
+        from .SOARM101_Env import SOARM101Env
+        return SOARM101Env
+    if name in ("SOARM101DataGenerator", "Collater"):
+        from . import SOARM101_DataCollection as dc
+        return getattr(dc, name)
+    raise AttributeError(name)

@@ -82,6 +82,8 @@ SO101_DEV void sincos_(float x, float* sp, float* cp) {
 }
 SO101_DEV double sqrt_(double x) { return sqrt(x); }
 SO101_DEV float sqrt_(float x) { return sqrtf(x); }
+SO101_DEV double copysign_(double a, double b) { return copysign(a, b); }
+SO101_DEV float copysign_(float a, float b) { return copysignf(a, b); }
 SO101_DEV double abs_(double x) { return fabs(x); }
 SO101_DEV float abs_(float x) { return fabsf(x); }
 // relative noise floor added to the solver's stopping tests: 0 in fp64 (MuJoCo's tests verbatim);
@@ -397,7 +399,8 @@ template <typename T> SO101_DEV T limit_impedance(const T* si, T pos, T margin) 
 }
 
 // mj_constraintUpdate + Gauss term: total cost at acceleration a, qfrc_constraint and the diagonal
-// that the quadratic rows add to the Hessian.
+// that the quadratic rows add to the Hessian.  Friction row i (Huber): quadratic for |jar| < R f,
+// linear outside; sign handling by copysign keeps the row at ~10 instructions.
 template <typename T>
 SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV], const T (&Ma)[NV],
                         const T (&fsm)[NV], const T (&asm_)[NV], T (&qc)[NV], T (&hd)[NV]) {
@@ -405,13 +408,11 @@ SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV
 #pragma unroll
   for (int i = 0; i < NV; i++) {
     T jar = a[i] - rw.aref_f[i];
-    T f = m.fr_f[i];
-    bool neg = jar <= -m.fr_Rf[i], pos = jar >= m.fr_Rf[i];
-    T cq = T(0.5) * m.fr_D[i] * jar * jar;
-    T cl = (neg ? -f : f) * jar - m.fr_hRff[i];
-    s += (neg || pos) ? cl : cq;
-    qc[i] = neg ? f : (pos ? -f : -m.fr_D[i] * jar);
-    hd[i] = (neg || pos) ? T(0) : m.fr_D[i];
+    bool lin = abs_(jar) >= m.fr_Rf[i];
+    T fs = copysign_(m.fr_f[i], jar);
+    T Dj = m.fr_D[i] * jar;
+    if (lin) { s += fs * jar - m.fr_hRff[i]; qc[i] = -fs; hd[i] = T(0); }
+    else { s += T(0.5) * Dj * jar; qc[i] = -Dj; hd[i] = m.fr_D[i]; }
   }
   if (rw.anylim) {
 #pragma unroll 1
@@ -448,9 +449,9 @@ SO101_DEV int ls_bracket(LsPnt<T>& p, const LsPnt<T>& c0, const LsPnt<T>& c1, co
 }
 
 // PrimalSearch: exact line search along sr from acceleration a.  Returns alpha; Mv = M*sr out.
-// MuJoCo's control flow is kept decision for decision, but folded into a state machine around a
-// single PrimalEval site: one copy of the evaluation code, and lanes that need different numbers
-// of evaluations still execute them together.
+// MuJoCo's control flow decision for decision: two evaluations (alpha = 0 and the Newton point),
+// phase 1 (Newton steps until the slope changes sign), phase 2 (bracketing).  Phase 2 is rare
+// and is folded into a small state machine around one PrimalEval site.
 template <typename T>
 SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[21], const T (&a)[NV],
                         const T (&Ma)[NV], const T (&fsm)[NV], const T (&asm_)[NV], const T (&sr)[NV],
@@ -483,111 +484,109 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
     qf[i][1] = sr[i] * DJ0;
     qf[i][2] = T(0.5) * sr[i] * m.fr_D[i] * sr[i];
   }
-  enum { S_P0, S_P1, S_PH1, S_P1N, S_MID, S_B1, S_B2 };
-  int st = S_P0, b1 = 0, b2 = 0;
   uint32_t nev = 0;
   const uint32_t maxev = (uint32_t)m.ls_iterations;
-  LsPnt<T> p0, p1, p2, pmid, p1n, p2n, c0, c1, c2, pt;
-  p0 = p1 = p2 = pmid = p1n = p2n = c0 = c1 = c2 = LsPnt<T>{T(0), T(0), T(0), T(1), T(0)};
-  T alpha = T(0), result = T(0), dir = T(1);
-  bool done = false;
-  while (!done) {
-    // ---- PrimalEval(alpha) -> pt ---------------------------------------------------------------
-    {
-      T q0 = G0, q1 = G1, q2 = G2;
+  // PrimalEval
+  auto eval = [&](T alpha, LsPnt<T>& p) {
+    T q0 = G0, q1 = G1, q2 = G2;
 #pragma unroll
-      for (int i = 0; i < NV; i++) {
-        T x = jar0[i] + alpha * sr[i];
-        T f = m.fr_f[i], Rf = m.fr_Rf[i];
-        bool quad = (-Rf < x) && (x < Rf);
-        bool neg = x <= -Rf;
-        T l0 = f * (T(-0.5) * Rf + (neg ? -jar0[i] : jar0[i]));
-        T l1 = (neg ? -f : f) * sr[i];
-        q0 += quad ? qf[i][0] : l0;
-        q1 += quad ? qf[i][1] : l1;
-        q2 += quad ? qf[i][2] : T(0);
-      }
-      if (rw.anylim) {
+    for (int i = 0; i < NV; i++) {
+      T x = jar0[i] + alpha * sr[i];
+      T fs = copysign_(m.fr_f[i], x);
+      if (abs_(x) < m.fr_Rf[i]) { q0 += qf[i][0]; q1 += qf[i][1]; q2 += qf[i][2]; }
+      else { q0 += fs * jar0[i] - m.fr_hRff[i]; q1 += fs * sr[i]; }
+    }
+    if (rw.anylim) {
 #pragma unroll 1
-        for (int i = 0; i < NV; i++) {
-          if (rw.side[i] != T(0)) {
-            T jv = rw.side[i] * sr[i], jl = rw.side[i] * a[i] - rw.aref_l[i];
-            if (jl + alpha * jv < T(0)) {
-              T DJ0 = rw.D_l[i] * jl;
-              q0 += T(0.5) * jl * DJ0; q1 += jv * DJ0; q2 += T(0.5) * jv * rw.D_l[i] * jv;
-            }
+      for (int i = 0; i < NV; i++) {
+        if (rw.side[i] != T(0)) {
+          T jv = rw.side[i] * sr[i], jl = rw.side[i] * a[i] - rw.aref_l[i];
+          if (jl + alpha * jv < T(0)) {
+            T DJ0 = rw.D_l[i] * jl;
+            q0 += T(0.5) * jl * DJ0; q1 += jv * DJ0; q2 += T(0.5) * jv * rw.D_l[i] * jv;
           }
         }
       }
-      pt.alpha = alpha;
-      pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
-      pt.d0 = T(2) * alpha * q2 + q1;
-      pt.d1 = T(2) * q2;
-      if (pt.d1 <= T(0)) pt.d1 = T(MJ_MINVAL);
-      pt.gt = gtol;
-      if (Noise<T>::on) pt.gt = gtol + T(Noise<T>::eps) * (abs_(q1) + abs_(T(2) * alpha * q2));
-      nev++;
     }
-    // ---- transitions ---------------------------------------------------------------------------
-    bool ph1check = false, ph2check = false, tryb2 = false, afterb = false;
-    if (st == S_P0) {
-      p0 = pt;
-      alpha = p0.alpha - p0.d0 * rcp_(p0.d1);
-      st = S_P1;
-    } else if (st == S_P1) {
-      p1 = pt;
-      if (p0.cost < p1.cost) p1 = p0;
-      if (abs_(p1.d0) < p1.gt) { result = p1.alpha; done = true; }
-      else { dir = p1.d0 < T(0) ? T(1) : T(-1); p2 = p1; ph1check = true; }
-    } else if (st == S_PH1) {
-      p1 = pt;
-      if (abs_(p1.d0) < p1.gt) { result = p1.alpha; done = true; }
-      else ph1check = true;
-    } else if (st == S_P1N) {
-      p1n = pt;
-      ph2check = true;
-    } else if (st == S_MID) {
-      pmid = pt;
-      c0 = p1n; c1 = p2n; c2 = pmid;
-      T bestcost = T(0), bestalpha = T(0);
-      bool found = false;
-      if (abs_(c0.d0) < c0.gt) { bestcost = c0.cost; bestalpha = c0.alpha; found = true; }
-      if (abs_(c1.d0) < c1.gt && (!found || c1.cost < bestcost)) { bestcost = c1.cost; bestalpha = c1.alpha; found = true; }
-      if (abs_(c2.d0) < c2.gt && (!found || c2.cost < bestcost)) { bestcost = c2.cost; bestalpha = c2.alpha; found = true; }
-      if (found) { result = bestalpha; done = true; }
-      else {
-        b1 = ls_bracket(p1, c0, c1, c2);
-        if (b1) { alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_B1; }
-        else tryb2 = true;
+    p.alpha = alpha;
+    p.cost = alpha * alpha * q2 + alpha * q1 + q0;
+    p.d0 = T(2) * alpha * q2 + q1;
+    p.d1 = T(2) * q2;
+    if (p.d1 <= T(0)) p.d1 = T(MJ_MINVAL);
+    p.gt = gtol;
+    if (Noise<T>::on) p.gt = gtol + T(Noise<T>::eps) * (abs_(q1) + abs_(T(2) * alpha * q2));
+    nev++;
+  };
+  LsPnt<T> p0, p1, p2;
+  eval(T(0), p0);
+  eval(-p0.d0 * rcp_(p0.d1), p1);
+  if (p0.cost < p1.cost) p1 = p0;
+  T result = p1.alpha;
+  bool done = abs_(p1.d0) < p1.gt, ph2 = false;
+  const T dir = p1.d0 < T(0) ? T(1) : T(-1);
+  p2 = p1;
+  // phase 1: Newton steps until the slope changes sign (bracket) or converges
+  while (!done) {
+    if (!(p1.d0 * dir <= -p1.gt && nev < maxev)) {
+      if (nev >= maxev) { result = p1.alpha; done = true; }
+      else ph2 = true;
+      break;
+    }
+    p2 = p1;
+    eval(p1.alpha - p1.d0 * rcp_(p1.d1), p1);
+    if (abs_(p1.d0) < p1.gt) { result = p1.alpha; done = true; }
+  }
+  if (ph2) {
+    // phase 2: bracket [p1, p2]; candidates = Newton-from-p1, Newton-from-p2, midpoint
+    enum { S_N, S_MID, S_B1, S_B2 };
+    int st = S_N, b1 = 0, b2 = 0;
+    LsPnt<T> p1n = p1, p2n = p1, pmid = p1, c0 = p1, pt;
+    T alpha = p1.alpha - p1.d0 * rcp_(p1.d1);
+    while (!done) {
+      eval(alpha, pt);
+      bool check = false, tryb2 = false, afterb = false;
+      if (st == S_N) {
+        p1n = pt;
+        check = true;
+      } else if (st == S_MID) {
+        pmid = pt;
+        c0 = p1n;   // snapshot: p1n may be re-evaluated before p2 is updated against it
+        T bestcost = T(0), bestalpha = T(0);
+        bool found = false;
+        if (abs_(p1n.d0) < p1n.gt) { bestcost = p1n.cost; bestalpha = p1n.alpha; found = true; }
+        if (abs_(p2n.d0) < p2n.gt && (!found || p2n.cost < bestcost)) { bestcost = p2n.cost; bestalpha = p2n.alpha; found = true; }
+        if (abs_(pmid.d0) < pmid.gt && (!found || pmid.cost < bestcost)) { bestcost = pmid.cost; bestalpha = pmid.alpha; found = true; }
+        if (found) { result = bestalpha; done = true; }
+        else {
+          b1 = ls_bracket(p1, c0, p2n, pmid);
+          if (b1) { alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_B1; }
+          else tryb2 = true;
+        }
+      } else if (st == S_B1) {
+        p1n = pt;
+        tryb2 = true;
+      } else {  // S_B2
+        p2n = pt;
+        afterb = true;
       }
-    } else if (st == S_B1) {
-      p1n = pt;
-      tryb2 = true;
-    } else {  // S_B2
-      p2n = pt;
-      afterb = true;
-    }
-    if (tryb2) {
-      b2 = ls_bracket(p2, c0, c1, c2);
-      if (b2) { alpha = p2.alpha - p2.d0 * rcp_(p2.d1); st = S_B2; }
-      else afterb = true;
-    }
-    if (afterb) {
-      if (!b1 && !b2) { result = pmid.alpha; done = true; }
-      else ph2check = true;
-    }
-    if (ph1check) {
-      if (p1.d0 * dir <= -p1.gt && nev < maxev) { p2 = p1; alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_PH1; }
-      else if (nev >= maxev) { result = p1.alpha; done = true; }
-      else { p2n = p1; alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_P1N; }
-    }
-    if (ph2check) {
-      if (nev < maxev) { alpha = T(0.5) * (p1.alpha + p2.alpha); st = S_MID; }
-      else {
-        if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
-        else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
-        else result = T(0);
-        done = true;
+      if (tryb2) {
+        // p2n is still the candidate evaluated before this round (S_B2 has not run yet)
+        b2 = ls_bracket(p2, c0, p2n, pmid);
+        if (b2) { alpha = p2.alpha - p2.d0 * rcp_(p2.d1); st = S_B2; }
+        else afterb = true;
+      }
+      if (afterb) {
+        if (!b1 && !b2) { result = pmid.alpha; done = true; }
+        else check = true;
+      }
+      if (check && !done) {
+        if (nev < maxev) { alpha = T(0.5) * (p1.alpha + p2.alpha); st = S_MID; }
+        else {
+          if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
+          else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
+          else result = T(0);
+          done = true;
+        }
       }
     }
   }
