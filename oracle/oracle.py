@@ -144,6 +144,14 @@ def uniform8(seed: int, env: int, step: int, stream: int) -> np.ndarray:
     return out
 
 
+def philox4x32_10(ctr, key) -> np.ndarray:
+    c = np.asarray(ctr, dtype=np.uint32).copy()
+    k = np.asarray(key, dtype=np.uint32).copy()
+    out = np.zeros(4, dtype=np.uint32)
+    lib().so101o_philox4x32_10(c.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def make_spec(kind: int = 0, seed: int = 42, env_offset: int = 0, amp: float = 0.5, t_total: int = 200,
               freq_lo: float = 0.0025, freq_hi: float = 0.05, reset_lo: float = -0.3, reset_hi: float = 0.3,
               u: Optional[np.ndarray] = None) -> So101CtrlSpec:

@@ -865,6 +865,10 @@ static void philox4x32_10(uint32_t ctr[4], uint32_t k0, uint32_t k1) {
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
 }
+void so101o_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key[2], uint32_t out[4]) {
+  memcpy(out, ctr_in, 4 * sizeof(uint32_t));
+  philox4x32_10(out, key[0], key[1]);
+}
 /* 8 uniforms in [0,1) with 32 bits each for (seed, env, step, stream): dims 0..3 from block 0,
    4..7 from block 1 */
 void so101o_uniform8(uint64_t seed, int64_t env, uint32_t step, uint32_t stream, double out[8]) {
