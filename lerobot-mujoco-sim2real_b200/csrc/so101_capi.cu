@@ -153,7 +153,13 @@ SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t
 // ==========================================================================================
 // kernels
 // ==========================================================================================
-#define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(256)
+#ifndef SO101_LB_THREADS
+#define SO101_LB_THREADS 256
+#endif
+#ifndef SO101_LB_BLOCKS
+#define SO101_LB_BLOCKS 1
+#endif
+#define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 
 // reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
 //   mode 0: qpos0/qvel0 [6][N] (nullable)   mode 1: qpos[0:5] ~ U(lo,hi) from Philox
@@ -243,7 +249,7 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
 template <typename T, typename ROW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int Tn, int frame_skip, ROW* rows,
           uint32_t rflags, unsigned long long* stats) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,7 +412,7 @@ template <typename T> static StateView<T> view(const So101Batch* b) {
 // see physics_step SYNC); small batches use smaller blocks so that every SM gets work
 static int pick_block(int64_t n) {
   if (const char* ev = getenv("SO101_BLK")) { int v = atoi(ev); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }
-  if (n >= (int64_t)148 * 256) return 256;
+  if (n >= (int64_t)148 * 256 && SO101_LB_THREADS >= 256) return 256;
   if (n >= (int64_t)148 * 128) return 128;
   if (n >= (int64_t)148 * 64) return 64;
   return 32;
