@@ -43,10 +43,10 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 3
+#define SO101_ABI_VERSION 4
 #define SO101_NV       6   /* hinge dofs: 5 arm joints + gripper */
 #define SO101_MAXBODY  8   /* world, fixed base, 6 links */
-#define SO101_MAXTRIP  8   /* contact-tripwire boxes */
+#define SO101_MAXTRIP 16   /* contact-tripwire boxes (<= 3 per link) */
 #define SO101_NOBS     8   /* observation: ee_pos(3) + qpos[0:5] */
 #define SO101_NU_ENV   5   /* controls exposed by SOARM101Env (gripper channel held at 0) */
 #define SO101_ROW     13   /* dataset row: u(5) | ee_pos(3) | qpos(5) */

@@ -24,6 +24,7 @@
 namespace so101 {
 
 constexpr int NV = SO101_NV;
+constexpr int TRIP_PER_LINK = 3;
 
 template <typename T>
 struct DevModel {
@@ -48,7 +49,7 @@ struct DevModel {
   // option / solver
   T h, tolerance, gtol_fac, scale;
   // contact tripwire: up to TRIP_PER_LINK oriented boxes per link, in the link frame
-  T trip_c[NV][2][3], trip_ax[NV][2][9], trip_half[NV][2][3];
+  T trip_c[NV][TRIP_PER_LINK][3], trip_ax[NV][TRIP_PER_LINK][9], trip_half[NV][TRIP_PER_LINK][3];
   T trip_z, trip_qlo[NV], trip_qhi[NV];
   int32_t trip_n[NV];   // <- first non-T field (see hostbuild::convert)
   int32_t ntrip;
@@ -203,7 +204,7 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
     for (int i = 0; i < t.ntrip && i < SO101_MAXTRIP; i++) {
       if (t.trip_body[i] != b) continue;
       int slot = m.trip_n[k];
-      if (slot >= 2) return "more than 2 tripwire boxes on one link";
+      if (slot >= TRIP_PER_LINK) return "more than 3 tripwire boxes on one link";
       double c3[3];
       for (int c = 0; c < 3; c++) c3[c] = t.trip_center[i][c] - t.jnt_pos[k][c];
       mv(At, c3, m.trip_c[k][slot]);

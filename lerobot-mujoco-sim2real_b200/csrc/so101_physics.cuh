@@ -289,7 +289,7 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
         rotT(R, zw, zc);
         zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < TRIP_PER_LINK; b++) {
           if (m.trip_n[k] > b) {
             T zc0 = zo + zw[0] * m.trip_c[k][b][0] + zw[1] * m.trip_c[k][b][1] + zw[2] * m.trip_c[k][b][2];
             T ext = T(0);

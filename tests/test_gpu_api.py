@@ -263,3 +263,27 @@ def test_fma_peak_is_plausible():
     from lerobot_mujoco_sim2real_b200.vec_env import fma_peak_tflops
     p64, p32 = fma_peak_tflops("float64"), fma_peak_tflops("float32")
     assert 20 < p64 < 45 and 40 < p32 < 90
+
+
+def test_contact_tripwire_flags(tables_v):
+    """TRIP_TABLE <=> some collision box below the table plane (numpy restatement); TRIP_SELF <=> q
+    outside the certified joint box.  Evaluated at the pose the step starts from."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_, tripwire
+    t = tables_v
+    n = 4096
+    rng = np.random.default_rng(8)
+    q = rng.uniform(-1.0, 1.0, (n, 6)); q[:, 5] = np.clip(q[:, 5], -0.17, None)
+    q[: n // 4, :5] = rng.uniform(-0.3, 0.3, (n // 4, 5)); q[: n // 4, 5] = 0     # the reset box
+    env = _vec(t, n)
+    env.set_state(q, np.zeros((n, 6)), np.zeros((n, 6)))
+    env.clear_flags()
+    env.step_soa(torch.zeros((5, n), dtype=torch.float64, device="cuda"), 1)
+    f = env.flags().cpu().numpy()
+    clear = np.array([tripwire.table_clearance_numpy(t, q[i]) for i in range(n)])
+    sure = np.abs(clear) > 1e-9
+    assert np.array_equal(((f & T_.FLAG_TRIP_TABLE) != 0)[sure], (clear < 0)[sure])
+    lo = np.array([t.trip_qbox[k][0] for k in range(6)]); hi = np.array([t.trip_qbox[k][1] for k in range(6)])
+    outside = ((q < lo) | (q > hi)).any(axis=1)
+    assert np.array_equal((f & T_.FLAG_TRIP_SELF) != 0, outside)
+    assert (f[: n // 4] & T_.FLAG_TRIP).sum() == 0            # nothing trips inside the reset box
+    assert 0.1 < (clear < 0).mean() < 0.4                     # ~19 % of |q| <= 1 poses touch the table (SURVEY F5)

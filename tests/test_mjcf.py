@@ -163,3 +163,19 @@ def test_fullinertia_principal_axes():
                                [8.3759e-05, 8.10403e-05, 2.39783e-05, 7.55525e-08, -1.16342e-06, 1.54663e-07],
                                atol=1e-18)
     assert abs(np.linalg.det(R) - 1) < 1e-12
+
+
+def test_tripwire_tables(tables_v):
+    """Committed tripwire boxes: clear at rest, tripped at the survey's first-contact pose (F5)."""
+    from lerobot_mujoco_sim2real_b200 import tripwire
+    t = tables_v
+    assert t.ntrip == 10 and abs(t.trip_plane_z + 0.0009) < 1e-12       # table top
+    assert tripwire.table_clearance_numpy(t, np.zeros(6)) > 0.05
+    rng = np.random.default_rng(0)
+    for _ in range(200):                                                 # the reset box never trips
+        q = np.zeros(6); q[:5] = rng.uniform(-0.3, 0.3, 5)
+        assert tripwire.table_clearance_numpy(t, q) > 0
+    q = np.zeros(6); q[1] = q[2] = q[3] = 0.33                           # SURVEY F5: first contact at 0.315
+    assert tripwire.table_clearance_numpy(t, q) < 0
+    for k in range(6):
+        assert t.trip_qbox[k][0] < -0.15 and t.trip_qbox[k][1] > 0.5
