@@ -67,7 +67,8 @@ def oracle_rate(n_envs: int, reps: int, warm: int, threads: int = 0):
     from oracle import oracle as O
     O.build()
     tables = builtin_tables("scene_with_table_v.xml")
-    nthr = threads or O.num_threads()
+    # torchrun exports OMP_NUM_THREADS=1: ask the OS for the cores this process may use instead
+    nthr = threads or len(os.sched_getaffinity(0))
     times = []
     for r in range(warm + reps):
         spec = O.make_spec(kind=0, seed=SEED + r)
@@ -328,6 +329,32 @@ def run_b200(args) -> None:
         extra["fp64_131072_per_gpu(config4 shard at 8 GPUs)"] = quick(131072, "float64", 20)
         extra["fp32_4096"] = quick(4096, "float32", 100)
         extra["fma_peak_tflops"] = {"fp64": peak64, "fp32": peak32}
+        # config 4 shape on one GPU: train-shaped rollouts WITH the dataset rows written (T = 20)
+        e4 = SOARM101VecEnv(tables=tables, num_envs=131072, dtype="float64", device=dev.index, seed=SEED)
+        rows4 = torch.empty((131072, 21, T.ROW), dtype=torch.float64, device=dev)
+        e4.rollout(20, "random", out=rows4)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); e4.rollout(20, "random", seed=SEED + 1, out=rows4); b.record(); torch.cuda.synchronize()
+        f4 = e4.flags()
+        extra["config4_shard_131072_T20_with_rows"] = {
+            "ms": a.elapsed_time(b), "env_steps_per_s": 131072 * 20 / (a.elapsed_time(b) * 1e-3),
+            "rows_bytes": rows4.numel() * 8, "envs_tripwire": int((f4 & T.FLAG_TRIP).ne(0).sum().item())}
+        del e4, rows4
+        # config 5: 8192 control sequences x 50 env-steps from one shared state
+        e5 = SOARM101VecEnv(tables=tables, num_envs=8192, dtype="float64", device=dev.index, seed=SEED)
+        U5 = (torch.rand((50, T.NU_ENV, 8192), dtype=torch.float64, device=dev) - 0.5).contiguous()
+        s0 = [0.1, -0.2, 0.15, 0.05, -0.1, 0.0] + [0.0] * 12
+        e5.shoot(s0, U5)
+        torch.cuda.synchronize()
+        best5 = 1e30
+        for gflag in (0, T.ROLL_GRAVCOMP_HOLD):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); e5.shoot(s0, U5, flags=gflag); b.record(); torch.cuda.synchronize()
+            best5 = min(best5, a.elapsed_time(b))
+        extra["config5_shoot_8192x50"] = {"ms": best5, "env_steps_per_s": 8192 * 50 / (best5 * 1e-3),
+                                          "rollouts_per_s": 8192 / (best5 * 1e-3)}
+        del e5
 
     # CPU baseline: bounded sample sized for ~10-20 s of CPU work
     cal_rate, _, nthr = oracle_rate(64, 1, 1)
