@@ -27,7 +27,19 @@ struct StateView {
   T* base;
   uint32_t* flags;
   int64_t n;
+  int lanes;   // env lanes used per warp (32, or fewer for small batches: see pick_lanes)
 };
+
+// thread -> env for the stepping kernels.  A warp carries `lanes` envs; its other lanes shadow
+// them (same instruction stream, same data, no extra divergence) and never store.  Idle lanes and
+// tail threads are clamped to a valid env so that every thread reaches the block barriers.
+template <typename T> SO101_DEV int64_t env_of_thread(const StateView<T>& s, bool& active) {
+  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int64_t i = (gthread >> 5) * s.lanes + (lane & (s.lanes - 1));
+  active = lane < s.lanes && i < s.n;
+  return i < s.n ? i : s.n - 1;
+}
 
 template <typename T> SO101_DEV void load_env(const StateView<T>& s, int64_t i, Env<T>& e) {
 #pragma unroll
@@ -219,9 +231,8 @@ k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* 
 SO101_KERNEL(T)
 k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
        unsigned long long* stats) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < s.n;   // idle lanes shadow the last env: every thread reaches the barriers
-  if (!active) i = s.n - 1;
+  bool active;
+  const int64_t i = env_of_thread(s, active);
   Env<T> e;
   load_env(s, i, e);
   T u[NV], site[3] = {T(0), T(0), T(0)};
@@ -252,9 +263,8 @@ template <typename T, typename ROW>
 __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int Tn, int frame_skip, ROW* rows,
           uint32_t rflags, unsigned long long* stats) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < s.n;
-  if (!active) i = s.n - 1;
+  bool active;
+  const int64_t i = env_of_thread(s, active);
   const int64_t env = spec.env_offset + i;
   Env<T> e;
   if (rflags & SO101_ROLL_NO_RESET) {
@@ -306,9 +316,8 @@ struct State0 { double v[18]; };
 SO101_KERNEL(T)
 k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
         int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < s.n;
-  if (!active) i = s.n - 1;
+  bool active;
+  const int64_t i = env_of_thread(s, active);
   Env<T> e;
   reset_env(m, e);
 #pragma unroll
@@ -401,13 +410,6 @@ struct DeviceGuard {
 
 static size_t elem_size(int dtype) { return dtype == SO101_F64 ? sizeof(double) : sizeof(float); }
 
-template <typename T> static StateView<T> view(const So101Batch* b) {
-  StateView<T> v;
-  v.base = static_cast<T*>(b->state);
-  v.flags = reinterpret_cast<uint32_t*>(static_cast<char*>(b->state) + (size_t)NROWS * b->n * sizeof(T));
-  v.n = b->n;
-  return v;
-}
 // block size: big batches use 256-thread blocks (8 warps share the instruction stream of a step,
 // see physics_step SYNC); small batches use smaller blocks so that every SM gets work
 static int pick_block(int64_t n) {
@@ -418,6 +420,31 @@ static int pick_block(int64_t n) {
   return 32;
 }
 static unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+template <typename T> static StateView<T> view(const So101Batch* b) {
+  StateView<T> v;
+  v.base = static_cast<T*>(b->state);
+  v.flags = reinterpret_cast<uint32_t*>(static_cast<char*>(b->state) + (size_t)NROWS * b->n * sizeof(T));
+  v.n = b->n;
+  v.lanes = 32;
+  return v;
+}
+// Small batches cannot fill the GPU (592 warp schedulers): spreading the envs over more, partially
+// filled warps costs nothing and shortens every warp's critical path, because a warp executes the
+// union of its lanes' solver iterations (max over 8 envs instead of max over 32).
+static int pick_lanes(int64_t n) {
+  if (const char* ev = getenv("SO101_LANES")) { int v = atoi(ev); if (v == 32 || v == 16 || v == 8 || v == 4 || v == 2 || v == 1) return v; }
+  return 32;
+}
+template <typename T> static StateView<T> step_view(const So101Batch* b, int& blk, unsigned& grid) {
+  StateView<T> v = view<T>(b);
+  v.lanes = pick_lanes(b->n);
+  blk = v.lanes == 32 ? pick_block(b->n) : 128;
+  if (const char* ev = getenv("SO101_BLK")) { int x = atoi(ev); if (x >= 32 && x <= 256 && x % 32 == 0) blk = x; }
+  const int64_t warps = (b->n + v.lanes - 1) / v.lanes;
+  grid = (unsigned)((warps * 32 + blk - 1) / blk);
+  return v;
+}
 
 extern "C" {
 
@@ -540,12 +567,14 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
   if (n_ctrl < 0 || n_ctrl > NV || n_substeps < 0) return fail(SO101_EINVAL, "n_ctrl must be 0..6, n_substeps >= 0");
   DeviceGuard g(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int blk = pick_block(b->n);
-  DISPATCH(b,
-    (k_step<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), (const double*)ctrl, n_ctrl,
-        n_substeps, (float*)obs, b->stats)),
-    (k_step<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), (const float*)ctrl, n_ctrl,
-        n_substeps, (float*)obs, b->stats)));
+  int blk; unsigned grid;
+  if (b->dtype == SO101_F64) {
+    StateView<double> v = step_view<double>(b, blk, grid);
+    k_step<double><<<grid, blk, 0, st>>>(b->model->d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+  } else {
+    StateView<float> v = step_view<float>(b, blk, grid);
+    k_step<float><<<grid, blk, 0, st>>>(b->model->f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+  }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
 }
@@ -610,15 +639,16 @@ int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int fra
   ds.kind = spec->kind; ds.t_total = spec->t_total; ds.seed = spec->seed; ds.env_offset = spec->env_offset;
   ds.amp = spec->amp; ds.freq_lo = spec->freq_lo; ds.freq_hi = spec->freq_hi;
   ds.reset_lo = spec->reset_lo; ds.reset_hi = spec->reset_hi; ds.u = spec->u;
-  int blk = pick_block(b->n);
-  unsigned grid = grid_for(b->n, blk);
+  int blk; unsigned grid;
   const bool r32 = flags & SO101_ROLL_ROWS_F32;
   if (b->dtype == SO101_F64) {
-    if (r32) k_rollout<double, float><<<grid, blk, 0, st>>>(b->model->d, view<double>(b), ds, T, frame_skip, (float*)rows, flags, b->stats);
-    else k_rollout<double, double><<<grid, blk, 0, st>>>(b->model->d, view<double>(b), ds, T, frame_skip, (double*)rows, flags, b->stats);
+    StateView<double> v = step_view<double>(b, blk, grid);
+    if (r32) k_rollout<double, float><<<grid, blk, 0, st>>>(b->model->d, v, ds, T, frame_skip, (float*)rows, flags, b->stats);
+    else k_rollout<double, double><<<grid, blk, 0, st>>>(b->model->d, v, ds, T, frame_skip, (double*)rows, flags, b->stats);
   } else {
-    if (r32) k_rollout<float, float><<<grid, blk, 0, st>>>(b->model->f, view<float>(b), ds, T, frame_skip, (float*)rows, flags, b->stats);
-    else k_rollout<float, double><<<grid, blk, 0, st>>>(b->model->f, view<float>(b), ds, T, frame_skip, (double*)rows, flags, b->stats);
+    StateView<float> v = step_view<float>(b, blk, grid);
+    if (r32) k_rollout<float, float><<<grid, blk, 0, st>>>(b->model->f, v, ds, T, frame_skip, (float*)rows, flags, b->stats);
+    else k_rollout<float, double><<<grid, blk, 0, st>>>(b->model->f, v, ds, T, frame_skip, (double*)rows, flags, b->stats);
   }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -632,12 +662,14 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   State0 s0;
   std::memcpy(s0.v, state0, sizeof s0.v);
-  int blk = pick_block(b->n);
-  DISPATCH(b,
-    (k_shoot<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), s0, (const double*)U, H,
-        frame_skip, (float*)X, flags, b->stats)),
-    (k_shoot<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), s0, (const float*)U, H,
-        frame_skip, (float*)X, flags, b->stats)));
+  int blk; unsigned grid;
+  if (b->dtype == SO101_F64) {
+    StateView<double> v = step_view<double>(b, blk, grid);
+    k_shoot<double><<<grid, blk, 0, st>>>(b->model->d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
+  } else {
+    StateView<float> v = step_view<float>(b, blk, grid);
+    k_shoot<float><<<grid, blk, 0, st>>>(b->model->f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
+  }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
 }
