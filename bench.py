@@ -238,25 +238,19 @@ def run_b200(args) -> None:
     # ---- e2e: host buffers through the C ABI ------------------------------------------------------
     g = torch.Generator().manual_seed(SEED + rank)
     U_host = ((torch.rand((T_CTRL + 1, T.NU_ENV, N_ENVS), generator=g, dtype=torch.float64) - 0.5)).pin_memory()
-    init_host = torch.zeros((N_ENVS, 10), dtype=torch.float64)
-    init_host[:, :5] = (torch.rand((N_ENVS, 5), generator=g, dtype=torch.float64) - 0.5) * 0.6
-    init_host = init_host.pin_memory()
+    q0_host = torch.zeros((T.NV, N_ENVS), dtype=torch.float64)
+    q0_host[:5] = (torch.rand((5, N_ENVS), generator=g, dtype=torch.float64) - 0.5) * 0.6
+    q0_host = q0_host.pin_memory()
     rows_host = torch.empty((N_ENVS, T_CTRL + 1, T.ROW), dtype=torch.float64).pin_memory()
-    U_dev = torch.empty_like(U_host, device=dev)
-    init_dev = torch.empty_like(init_host, device=dev)
 
     def step_e2e(i):
-        U_dev.copy_(U_host, non_blocking=True)
-        init_dev.copy_(init_host, non_blocking=True)
-        env.reset(options={"initial_state": init_dev})
-        env.rollout(T_CTRL, "tensor", u=U_dev, flags=T.ROLL_NO_RESET, out=rows)
-        rows_host.copy_(rows, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller holds the dataset on the host
+        # ONE C-ABI call with host buffers: H2D controls + initial angles, k_reset, k_rollout, D2H rows, sync
+        env.rollout_host(T_CTRL, "tensor", u_host=U_host, qpos0_host=q0_host, out_host=rows_host)
 
     e2e_ms, _ = timed(step_e2e, K, W)
     e2e_ms = max_over_ranks(e2e_ms) / K
     e2e_value = n_gpus * env_steps_per_launch / (e2e_ms * 1e-3)
-    h2d = U_host.numel() * 8 + init_host.numel() * 8
+    h2d = U_host.numel() * 8 + q0_host.numel() * 8
     d2h = rows_host.numel() * 8
 
     # ---- dataset gather over NCCL (config 4's only collective), timed separately ------------------
@@ -373,8 +367,8 @@ def run_b200(args) -> None:
         "physics_steps_per_s": value * FRAME_SKIP,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms,
-                "path": "pinned host control tensor + initial states -> so101_batch_reset / so101_batch_rollout "
-                        "(SO101_CTRL_TENSOR) -> dataset rows to pinned host"},
+                "path": "so101_batch_rollout_host: pinned host control tensor [T+1,5,N] + initial angles [6,N] -> "
+                        "k_reset + k_rollout (SO101_CTRL_TENSOR) -> dataset rows [N,T+1,13] to pinned host, stream sync"},
         "gpu_launches": K,
         "gpu_launches_note": "one k_rollout<double,double> launch per step in the device-resident region; "
                              "the e2e region adds one k_reset launch per step",

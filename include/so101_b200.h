@@ -16,7 +16,7 @@
  *                                                                    Koopman_MPC.py:90,126]
  *   so101_batch_step*       <- data.ctrl[:5]=u ; frame_skip x mj_step ; _get_state
  *                                                                   [REF SOARM101/SOARM101_Env.py:128-135, 69-75]
- *   so101_batch_rollout     <- the (reset, T x step, row write) double loop
+ *   so101_batch_rollout*    <- the (reset, T x step, row write) double loop
  *                                                                   [REF SOARM101/SOARM101_DataCollection.py:108-134]
  *   so101_batch_shoot       <- batched evaluation of control sequences from one shared state
  *                              (Koopman_MPC.py:197-222 closed loop, BASELINE.json config 5)
@@ -219,6 +219,11 @@ int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qv
    values are rounded to float32 first, as the reference does. */
 int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip,
                         void* rows, uint32_t flags, void* stream);
+/* host-buffer variant (what SOARM101DataGenerator calls): spec->u (SO101_CTRL_TENSOR) and qpos0_host
+   [6][N] (nullable: random reset) are HOST pointers, rows_host receives the dataset; H2D + kernel +
+   D2H on `stream`, stream synchronised before return.  Pinned host memory makes the copies async. */
+int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const void* qpos0_host, int T,
+                             int frame_skip, void* rows_host, uint32_t flags, void* stream);
 /* B = n_envs control sequences from one shared state: state0 host pointer to 18 doubles
    (qpos, qvel, qacc_warmstart), U device [H][5][B] (batch dtype), X device float32 [B][H+1][8]. */
 int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H, int frame_skip,

@@ -393,6 +393,10 @@ struct So101Batch {
   void* ctrl_stage;   // [6][n] batch dtype (host variants)
   float* obs_stage;   // [8][n]
   void* init_stage;   // [12][n] (reset_host)
+  void* u_stage;      // [T+1][5][n] control tensor (rollout_host)
+  size_t u_stage_bytes;
+  void* rows_stage;   // [n][T+1][13] dataset rows (rollout_host)
+  size_t rows_stage_bytes;
 };
 
 struct DeviceGuard {
@@ -512,6 +516,8 @@ void so101_batch_destroy(So101Batch* b) {
   cudaFree(b->ctrl_stage);
   cudaFree(b->obs_stage);
   cudaFree(b->init_stage);
+  cudaFree(b->u_stage);
+  cudaFree(b->rows_stage);
   delete b;
 }
 
@@ -651,6 +657,46 @@ int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int fra
     else k_rollout<float, double><<<grid, blk, 0, st>>>(b->model->f, v, ds, T, frame_skip, (double*)rows, flags, b->stats);
   }
   CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+
+static int grow(void** buf, size_t* have, size_t need) {
+  if (*have >= need) return SO101_OK;
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *have = 0;
+  CUDA_TRY(cudaMalloc(buf, need));
+  *have = need;
+  return SO101_OK;
+}
+
+int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const void* qpos0_host, int T, int frame_skip,
+                             void* rows_host, uint32_t flags, void* stream) {
+  if (!b || !spec || !rows_host) return fail(SO101_EINVAL, "null argument");
+  if (T < 0) return fail(SO101_EINVAL, "T must be >= 0");
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t es = elem_size(b->dtype);
+  So101CtrlSpec dspec = *spec;
+  int rc;
+  if (spec->kind == SO101_CTRL_TENSOR) {
+    if (!spec->u) return fail(SO101_EINVAL, "SO101_CTRL_TENSOR needs spec->u");
+    const size_t ub = (size_t)(T + 1) * SO101_NU_ENV * b->n * es;
+    if ((rc = grow(&b->u_stage, &b->u_stage_bytes, ub))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b->u_stage, spec->u, ub, cudaMemcpyHostToDevice, st));
+    dspec.u = b->u_stage;
+  }
+  if (qpos0_host) {   // explicit initial joint angles: reset on the device, then continue from that state
+    const size_t qb = (size_t)NV * b->n * es;
+    if (!b->init_stage) CUDA_TRY(cudaMalloc(&b->init_stage, 2 * qb));
+    CUDA_TRY(cudaMemcpyAsync(b->init_stage, qpos0_host, qb, cudaMemcpyHostToDevice, st));
+    if ((rc = so101_batch_reset(b, b->init_stage, nullptr, nullptr, stream))) return rc;
+    flags |= SO101_ROLL_NO_RESET;
+  }
+  const size_t rb = (size_t)b->n * (T + 1) * SO101_ROW * ((flags & SO101_ROLL_ROWS_F32) ? sizeof(float) : sizeof(double));
+  if ((rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
+  if ((rc = so101_batch_rollout(b, &dspec, T, frame_skip, b->rows_stage, flags, stream))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(rows_host, b->rows_stage, rb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return SO101_OK;
 }
 

@@ -170,6 +170,30 @@ class SOARM101VecEnv:
                                                   out.data_ptr(), flags, self._stream()))
         return out
 
+    def rollout_host(self, steps: int, input_type: str = "random", seed: Optional[int] = None, env_offset: int = 0,
+                     u_host: Optional[torch.Tensor] = None, qpos0_host: Optional[torch.Tensor] = None,
+                     out_host: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+        """`generate_physics_based_data` with HOST buffers through one C-ABI call
+        (`so101_batch_rollout_host`): controls [steps+1, 5, N] / initial angles [6, N] in, rows out."""
+        row_dtype = torch.float32 if flags & T.ROLL_ROWS_F32 else torch.float64
+        if out_host is None:
+            out_host = torch.empty((self.num_envs, steps + 1, T.ROW), dtype=row_dtype).pin_memory()
+        assert out_host.device.type == "cpu" and out_host.is_contiguous() and out_host.dtype == row_dtype
+        assert out_host.shape == (self.num_envs, steps + 1, T.ROW)
+        spec = self.make_spec(input_type, seed, env_offset)
+        if input_type == "tensor":
+            assert u_host is not None and u_host.device.type == "cpu" and u_host.is_contiguous()
+            assert u_host.dtype == self.torch_dtype and u_host.shape == (steps + 1, T.NU_ENV, self.num_envs)
+            spec.u = u_host.data_ptr()
+        q0 = None
+        if qpos0_host is not None:
+            assert qpos0_host.device.type == "cpu" and qpos0_host.is_contiguous()
+            assert qpos0_host.dtype == self.torch_dtype and qpos0_host.shape == (T.NV, self.num_envs)
+            q0 = qpos0_host.data_ptr()
+        _lib.check(_lib.lib().so101_batch_rollout_host(self._h, C.byref(spec), q0, steps, self.frame_skip,
+                                                       out_host.data_ptr(), flags, self._stream()))
+        return out_host
+
     def rollout_discard(self, steps: int, input_type: str = "random", seed: Optional[int] = None,
                         flags: int = 0, frame_skip: Optional[int] = None) -> None:
         """Rollout without writing rows (throughput measurements, warm-up)."""

@@ -287,3 +287,71 @@ def test_contact_tripwire_flags(tables_v):
     assert np.array_equal((f & T_.FLAG_TRIP_SELF) != 0, outside)
     assert (f[: n // 4] & T_.FLAG_TRIP).sum() == 0            # nothing trips inside the reset box
     assert 0.1 < (clear < 0).mean() < 0.4                     # ~19 % of |q| <= 1 poses touch the table
+
+
+def test_rollout_host_single_abi_call(tables_v):
+    """so101_batch_rollout_host (host controls + initial angles in, rows out) == the device-tensor path."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    n, T = 777, 4                              # not a multiple of the warp / block size
+    g = torch.Generator().manual_seed(3)
+    U = (torch.rand((T + 1, 5, n), generator=g, dtype=torch.float64) - 0.5).contiguous()
+    q0 = torch.zeros((6, n), dtype=torch.float64); q0[:5] = (torch.rand((5, n), generator=g, dtype=torch.float64) - 0.5) * 0.6
+    env = _vec(tables_v, n)
+    rows_h = env.rollout_host(T, "tensor", u_host=U.pin_memory(), qpos0_host=q0.pin_memory())
+    assert rows_h.device.type == "cpu" and rows_h.shape == (n, T + 1, 13)
+    env2 = _vec(tables_v, n)
+    env2.set_state(q0.t(), torch.zeros((n, 6)), torch.zeros((n, 6)))
+    rows_d = env2.rollout(T, "tensor", u=U.cuda(), flags=T_.ROLL_NO_RESET)
+    assert torch.equal(rows_h, rows_d.cpu())
+    # generator-driven variant: random reset + Philox controls, pageable host memory
+    out = torch.empty((n, T + 1, 13), dtype=torch.float64)
+    env.rollout_host(T, "random", seed=5, out_host=out)
+    assert torch.equal(out, env2.rollout(T, "random", seed=5).cpu())
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000])
+def test_odd_batch_sizes_and_f32_rows(oracle_mod, tables_v, n):
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    O = oracle_mod
+    env = _vec(tables_v, n)
+    rows = env.rollout(3, "random", seed=77).cpu().numpy()
+    ref, _, _ = O.rollout(tables_v, O.make_spec(kind=0, seed=77), n, 3, 10)
+    np.testing.assert_array_equal(rows[:, :, :5], ref[:, :, :5])
+    assert np.abs(rows - ref).max() <= 6e-8
+    r32 = env.rollout(3, "random", seed=77, flags=T_.ROLL_ROWS_F32)
+    assert r32.dtype == torch.float32
+    np.testing.assert_array_equal(r32.cpu().numpy(), rows.astype(np.float32))
+
+
+def test_gravcomp_hold_rollout_matches_oracle(oracle_mod, tables_v):
+    """qfrc_applied <- qfrc_bias at the start of each control step, held over the sub-steps
+    [REF Koopman_MPC.py:119]."""
+    O = oracle_mod
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    n, T = 256, 4
+    env = _vec(tables_v, n)
+    rows = env.rollout(T, "random", seed=21, flags=T_.ROLL_GRAVCOMP_HOLD).cpu().numpy()
+    ref, final, _ = O.rollout(tables_v, O.make_spec(kind=0, seed=21), n, T, 10, flags=T_.ROLL_GRAVCOMP_HOLD)
+    assert np.abs(rows - ref).max() <= 6e-8
+    np.testing.assert_allclose(env.get_state()[0].cpu().numpy(), final[:, :6], atol=1e-11)
+    plain, _, _ = O.rollout(tables_v, O.make_spec(kind=0, seed=21), n, T, 10)
+    assert np.abs(ref - plain).max() > 1e-4
+
+
+def test_two_models_coexist_and_bad_arguments(tables_v, tables_p):
+    import ctypes as C
+    from lerobot_mujoco_sim2real_b200 import _lib
+    a, b = _vec(tables_v, 64), _vec(tables_p, 64)
+    ra1 = a.rollout(3, "random", seed=1); rb1 = b.rollout(3, "random", seed=1)
+    ra2 = a.rollout(3, "random", seed=1); rb2 = b.rollout(3, "random", seed=1)
+    assert torch.equal(ra1, ra2) and torch.equal(rb1, rb2) and not torch.equal(ra1, rb1)
+    L = _lib.lib()
+    spec = a.make_spec("tensor")            # tensor controls without a pointer
+    assert L.so101_batch_rollout(a._h, C.byref(spec), 3, 10, None, 0, None) == -1
+    assert b"spec->u" in L.so101_last_error()
+    assert L.so101_batch_step(a._h, None, 7, 10, None, None) == -1
+    with pytest.raises(_lib.So101Error):
+        _lib.check(L.so101_batch_rollout(a._h, C.byref(a.make_spec("random")), -1, 10, None, 0, None))
+    h = C.c_void_p()
+    assert L.so101_batch_create(a.model._h, 0, 0, 0, None, C.byref(h)) == -1
+    assert L.so101_batch_create(a.model._h, 8, 5, 0, None, C.byref(h)) == -1
