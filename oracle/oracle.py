@@ -50,6 +50,7 @@ class OracleData(C.Structure):
         ("dof_parent", _i * NV), ("dof_Madr", _i * NV), ("dof_body", _i * NV), ("body_root", _i * NB),
         ("nM", _i),
         ("body_subtreemass", _d * NB),
+        ("ls_evals_iter", _i * 8),
     ]
 
 

@@ -72,6 +72,7 @@ typedef struct OracleData {
   /* tree bookkeeping (filled by so101o_init) */
   int32_t dof_parent[NV], dof_Madr[NV], dof_body[NV], body_root[NB], nM;
   double body_subtreemass[NB];
+  int32_t ls_evals_iter[8];   /* diagnostics: PrimalEval count of the first 8 line searches of the last solve */
 } OracleData;
 
 /* ---------------------------------------------------------------------------------------- */
@@ -671,9 +672,11 @@ static void solNewton(const So101Tables* m, OracleData* d) {
   for (int i = 0; i < NV; i++) c.search[i] = -c.Mgrad[i];
   double scale = 1 / (m->meaninertia * (NV > 1 ? NV : 1));
   int iter = 0, nls = 0;
+  memset(d->ls_evals_iter, 0, sizeof d->ls_evals_iter);
   while (iter < m->iterations) {
     double alpha = primalSearch(m, d, &c);
     nls += c.LSiter;
+    if (iter < 8) d->ls_evals_iter[iter] = c.LSiter;
     if (alpha == 0) break;
     for (int i = 0; i < NV; i++) { d->qacc[i] += alpha * c.search[i]; c.Ma[i] += alpha * c.Mv[i]; }
     for (int i = 0; i < d->nefc; i++) c.Jaref[i] += alpha * c.Jv[i];
