@@ -542,56 +542,28 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
   }
   if (ph2) {
     // phase 2: bracket [p1, p2]; candidates = Newton-from-p1, Newton-from-p2, midpoint
-    enum { S_N, S_MID, S_B1, S_B2 };
-    int st = S_N, b1 = 0, b2 = 0;
-    LsPnt<T> p1n = p1, p2n = p1, pmid = p1, c0 = p1, pt;
-    T alpha = p1.alpha - p1.d0 * rcp_(p1.d1);
-    while (!done) {
-      eval(alpha, pt);
-      bool check = false, tryb2 = false, afterb = false;
-      if (st == S_N) {
-        p1n = pt;
-        check = true;
-      } else if (st == S_MID) {
-        pmid = pt;
-        c0 = p1n;   // snapshot: p1n may be re-evaluated before p2 is updated against it
-        T bestcost = T(0), bestalpha = T(0);
-        bool found = false;
-        if (abs_(p1n.d0) < p1n.gt) { bestcost = p1n.cost; bestalpha = p1n.alpha; found = true; }
-        if (abs_(p2n.d0) < p2n.gt && (!found || p2n.cost < bestcost)) { bestcost = p2n.cost; bestalpha = p2n.alpha; found = true; }
-        if (abs_(pmid.d0) < pmid.gt && (!found || pmid.cost < bestcost)) { bestcost = pmid.cost; bestalpha = pmid.alpha; found = true; }
-        if (found) { result = bestalpha; done = true; }
-        else {
-          b1 = ls_bracket(p1, c0, p2n, pmid);
-          if (b1) { alpha = p1.alpha - p1.d0 * rcp_(p1.d1); st = S_B1; }
-          else tryb2 = true;
-        }
-      } else if (st == S_B1) {
-        p1n = pt;
-        tryb2 = true;
-      } else {  // S_B2
-        p2n = pt;
-        afterb = true;
-      }
-      if (tryb2) {
-        // p2n is still the candidate evaluated before this round (S_B2 has not run yet)
-        b2 = ls_bracket(p2, c0, p2n, pmid);
-        if (b2) { alpha = p2.alpha - p2.d0 * rcp_(p2.d1); st = S_B2; }
-        else afterb = true;
-      }
-      if (afterb) {
-        if (!b1 && !b2) { result = pmid.alpha; done = true; }
-        else check = true;
-      }
-      if (check && !done) {
-        if (nev < maxev) { alpha = T(0.5) * (p1.alpha + p2.alpha); st = S_MID; }
-        else {
-          if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
-          else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
-          else result = T(0);
-          done = true;
-        }
-      }
+    LsPnt<T> p1n, p2n = p1, pmid;
+    eval(p1.alpha - p1.d0 * rcp_(p1.d1), p1n);
+    while (nev < maxev) {
+      eval(T(0.5) * (p1.alpha + p2.alpha), pmid);
+      const LsPnt<T> c0 = p1n;   // candidates of this round (p1n / p2n are re-evaluated below)
+      T bestcost = T(0), bestalpha = T(0);
+      bool found = false;
+      if (abs_(c0.d0) < c0.gt) { bestcost = c0.cost; bestalpha = c0.alpha; found = true; }
+      if (abs_(p2n.d0) < p2n.gt && (!found || p2n.cost < bestcost)) { bestcost = p2n.cost; bestalpha = p2n.alpha; found = true; }
+      if (abs_(pmid.d0) < pmid.gt && (!found || pmid.cost < bestcost)) { bestcost = pmid.cost; bestalpha = pmid.alpha; found = true; }
+      if (found) { result = bestalpha; done = true; break; }
+      const int b1 = ls_bracket(p1, c0, p2n, pmid);
+      if (b1) eval(p1.alpha - p1.d0 * rcp_(p1.d1), p1n);
+      const LsPnt<T> c1 = p2n;
+      const int b2 = ls_bracket(p2, c0, c1, pmid);
+      if (b2) eval(p2.alpha - p2.d0 * rcp_(p2.d1), p2n);
+      if (!b1 && !b2) { result = pmid.alpha; done = true; break; }
+    }
+    if (!done) {
+      if (p1.cost <= p2.cost && p1.cost < p0.cost) result = p1.alpha;
+      else if (p2.cost <= p1.cost && p2.cost < p0.cost) result = p2.alpha;
+      else result = T(0);
     }
   }
   nev_total += nev;
