@@ -257,6 +257,7 @@ def run_b200(args) -> None:
     gather_ms = None
     if world > 1:
         from lerobot_mujoco_sim2real_b200 import sharding
+        sharding.gather_rows(rows, N_ENVS * world, dst=0)     # untimed: first use sets up the NCCL channels
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
