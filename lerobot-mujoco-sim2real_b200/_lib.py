@@ -41,9 +41,19 @@ def lib() -> C.CDLL:
     if _LIB is not None:
         return _LIB
     if not os.path.exists(LIB_PATH):
-        raise So101Error(
-            f"{LIB_PATH} is missing: build it with `python {os.path.dirname(LIB_PATH)}/build.py` "
-            "(nvcc, sm_100a).  There is no CPU fallback for this path.")
+        # not built yet (fresh checkout): compile it now if nvcc is here; never fall back to a CPU path
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location(
+                "_so101_build", os.path.join(os.path.dirname(LIB_PATH), "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as exc:
+            raise So101Error(
+                f"{LIB_PATH} is missing and could not be built ({exc}): run "
+                f"`python {os.path.dirname(LIB_PATH)}/build.py` (nvcc, sm_100a).  "
+                "There is no CPU fallback for this path.") from exc
     L = C.CDLL(LIB_PATH)
     vp, i32, i64, u32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_uint64
     L.so101_last_error.restype = C.c_char_p
