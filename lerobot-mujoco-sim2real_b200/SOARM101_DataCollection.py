@@ -55,8 +55,10 @@ class SOARM101DataGenerator:
         self.dtype = dtype
         self.device = torch.cuda.current_device() if device is None else device
         if tables is None:
-            from .mjcf import compile_mjcf
-            tables = compile_mjcf(self.args.xml_path).tables
+            from .mjcf import attach_tripwire, compile_mjcf
+            cm = compile_mjcf(self.args.xml_path)
+            attach_tripwire(cm, self.args.xml_path)
+            tables = cm.tables
         self.tables = tables
         self.frame_skip = max(1, int(np.round(0.02 / tables.timestep)))
         self.seed = int(getattr(args, "seed", 42))

@@ -186,8 +186,9 @@ class SOARM101Env(_EnvBase):
         if render_mode:
             raise NotImplementedError("the interactive MuJoCo viewer is out of scope of the B200 path "
                                       "(use the reference env for rendering)")
-        from .mjcf import compile_mjcf
-        self._compiled = compile_mjcf(xml_path)   # raises FileNotFoundError like the reference
+        from . import mjcf
+        self._compiled = mjcf.compile_mjcf(xml_path)   # raises FileNotFoundError like the reference
+        mjcf.attach_tripwire(self._compiled, xml_path)
         t = self._compiled.tables
         self._vec = SOARM101VecEnv(tables=t, num_envs=1, dt=dt, dtype=dtype, device=device)
         self.frame_skip = self._vec.frame_skip

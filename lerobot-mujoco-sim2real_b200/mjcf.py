@@ -340,6 +340,39 @@ def _principal(full6: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return w, mat_q(V)
 
 
+_TRIP_FIELDS = ("ntrip", "trip_body", "trip_center", "trip_axes", "trip_half", "trip_plane_z", "trip_qbox")
+
+
+def attach_tripwire(cm: "CompiledModel", xml_path: str) -> str:
+    """Fill the contact-tripwire tables of a freshly compiled model.
+
+    Fast path: the scene is one of the built-in ones and compiles to the committed tables bit for bit
+    -> reuse their precomputed tripwire.  Otherwise build it from the collision meshes (tripwire.py,
+    needs scipy and the STL files, ~15 s).  Returns how it was obtained; "none" leaves the tripwire
+    disabled (no env is ever flagged) and says why on stderr."""
+    import ctypes
+    import sys
+    key = os.path.basename(xml_path)
+    if key in T.BUILTIN_SCENES:
+        try:
+            ref = T.builtin_tables(key)
+            probe = T.So101Tables.from_buffer_copy(bytes(cm.tables))
+            for f in _TRIP_FIELDS:
+                setattr(probe, f, getattr(ref, f))
+            if bytes(probe) == bytes(ref):
+                ctypes.memmove(ctypes.byref(cm.tables), ctypes.byref(ref), ctypes.sizeof(ref))
+                return "builtin"
+        except Exception:
+            pass
+    try:
+        from . import tripwire
+        tripwire.fill_tripwire(cm)
+        return "meshes"
+    except Exception as exc:   # scipy or meshes missing: stepping still works, contact is just not flagged
+        print(f"[so101] contact tripwire disabled for {xml_path}: {exc}", file=sys.stderr)
+        return "none"
+
+
 def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledModel:
     root = load_xml(xml_path)
     xml_dir = os.path.dirname(os.path.abspath(xml_path))

@@ -53,8 +53,9 @@ class SOARM101VecEnv:
         if tables is None:
             if xml_path is None:
                 raise ValueError("give xml_path or tables")
-            from .mjcf import compile_mjcf
+            from .mjcf import attach_tripwire, compile_mjcf
             self.compiled = compile_mjcf(xml_path)
+            attach_tripwire(self.compiled, xml_path)
             tables = self.compiled.tables
         else:
             self.compiled = None
