@@ -158,3 +158,34 @@ def test_p2_free_running_scene_a_curve(oracle_mod, tables_v):
     # afterwards the GPU error must stay within 100x of what a 1-ulp perturbation does to the oracle itself
     for s, a, b in curve:
         assert b <= max(1e-12, 100 * a), (s, a, b)
+
+
+def test_free_running_against_joint_limits_scene_b(oracle_mod, tables_p):
+    """Position targets far beyond the joint ranges (ctrl clamp, force clamp, limit rows active for
+    hundreds of steps): free-running agreement with the oracle on the contractive scene."""
+    O = oracle_mod
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    from lerobot_mujoco_sim2real_b200 import tables as T
+    n, T_ctrl = 256, 60
+    rng = np.random.default_rng(12)
+    q0 = np.zeros((n, 6)); q0[:, :5] = rng.uniform(-0.3, 0.3, (n, 5))
+    U = np.repeat(rng.choice([-3.0, 3.0], (1, 5, n)), T_ctrl + 1, axis=0)     # clamped to the ctrlrange = joint range
+    U += rng.uniform(-0.01, 0.01, U.shape)
+    spec = O.make_spec(kind=3, u=np.ascontiguousarray(U))
+    _, fin, _ = O.rollout(tables_p, spec, n, T_ctrl, 10, qpos0=q0, want_rows=False)
+    env = SOARM101VecEnv(tables=tables_p, num_envs=n, dtype="float64")
+    env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
+    env.rollout(T_ctrl, "tensor", u=torch.as_tensor(U).cuda().contiguous(), flags=T.ROLL_NO_RESET)
+    q, v, _ = env.get_state()
+    q, v = q.cpu().numpy(), v.cpu().numpy()
+    lim = np.array([[tables_p.jnt_range[k][0], tables_p.jnt_range[k][1]] for k in range(6)])
+    at_limit = (np.abs(q[:, :5] - lim[:5, 0]) < 0.02) | (np.abs(q[:, :5] - lim[:5, 1]) < 0.02)
+    frac_lim = at_limit.mean()
+    st = env.stats()
+    eq = _rel(q, fin[:, :6]).max()
+    ev = np.abs(v - fin[:, 6:12]).max()
+    print(f"joints resting at a limit: {frac_lim:.2f}; steps with limit rows {st['limit_steps'] / st['physics_steps']:.2f}; "
+          f"rel err qpos {eq:.2e}, abs err qvel {ev:.2e}")
+    assert frac_lim > 0.5 and st["limit_steps"] > 0.3 * st["physics_steps"]
+    assert int((env.flags() & T.FLAG_LIMIT).ne(0).sum()) > 0.9 * n
+    assert eq < 1e-9 and ev < 1e-8
