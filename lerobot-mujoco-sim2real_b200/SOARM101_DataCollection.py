@@ -45,8 +45,12 @@ class SOARM101DataGenerator:
     #: trajectories per launch (bounds device memory: rows are 104 B x (steps+1) per trajectory)
     max_batch = 1 << 20
 
-    def __init__(self, args, dtype: str = "float64", device: Optional[int] = None, tables=None) -> None:
+    def __init__(self, args, dtype: str = "float64", device: Optional[int] = None, tables=None,
+                 gravity_compensation: bool = False) -> None:
+        """gravity_compensation: generate the data as with the (commented-out) gravity-compensation line of
+        SOARM101Env.step active [REF SOARM101_Env.py:120] — what the shipped Koopman model was trained on."""
         self.args = args
+        self.gravity_compensation = bool(gravity_compensation)
         self.udim = self.args.u_dim
         self.xdim = self.args.x_dim
         if self.udim != T.NU_ENV or self.xdim != T.NOBS:
@@ -85,7 +89,8 @@ class SOARM101DataGenerator:
         for lo in range(0, traj_num, self.max_batch):
             n = min(self.max_batch, traj_num - lo)
             env = self._env(n)
-            env.rollout(steps, input_type, seed=seed, env_offset=env_offset + lo, out=out[lo:lo + n])
+            env.rollout(steps, input_type, seed=seed, env_offset=env_offset + lo, out=out[lo:lo + n],
+                        flags=T.ROLL_GRAVCOMP_HOLD if self.gravity_compensation else 0)
             flags.append(env.flags())
         self.last_flags = torch.cat(flags).cpu().numpy() if flags else np.zeros(0, dtype=np.int32)
         return out

@@ -181,8 +181,12 @@ class SOARM101Env(_EnvBase):
     metadata = {"render_modes": ["human"]}
 
     def __init__(self, xml_path: str, dt: float = 0.02, render_mode=False, dtype: str = "float64",
-                 device: int = 0):
+                 device: int = 0, gravity_compensation: bool = False):
+        """gravity_compensation=True re-enables the line the reference keeps commented out in step()
+        (`self.data.qfrc_applied[:] = self.data.qfrc_bias[:]`, [REF SOARM101_Env.py:120]); the reference's
+        shipped Koopman model was trained on data generated that way."""
         super().__init__()
+        self.gravity_compensation = bool(gravity_compensation)
         if render_mode:
             raise NotImplementedError("the interactive MuJoCo viewer is out of scope of the B200 path "
                                       "(use the reference env for rendering)")
@@ -254,6 +258,8 @@ class SOARM101Env(_EnvBase):
         return self._obs(), {}
 
     def step(self, action: np.ndarray) -> Tuple[np.ndarray, float, bool, bool, Dict]:
+        if self.gravity_compensation:
+            self.data.qfrc_applied[:] = self.data.qfrc_bias[:]
         target_velocity = np.asarray(action, dtype=np.float64).reshape(-1)[: self.udim]
         self._ctrl[: self.udim] = target_velocity          # ctrl[5] keeps its value (0 after reset)
         u = np.ascontiguousarray(self._ctrl.reshape(T.NV, 1), dtype=self._np_dtype)

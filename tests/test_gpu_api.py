@@ -355,3 +355,34 @@ def test_two_models_coexist_and_bad_arguments(tables_v, tables_p):
     h = C.c_void_p()
     assert L.so101_batch_create(a.model._h, 0, 0, 0, None, C.byref(h)) == -1
     assert L.so101_batch_create(a.model._h, 8, 5, 0, None, C.byref(h)) == -1
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_reference_published_eval_metric_reproduced_on_gpu(tables_v, dtype):
+    """The reference's only published number for data from this path: open-loop 200-step MAE of its
+    trained Koopman model = 6.84e-3 [REF results/SOARM101/11_27/DKUC/best_scores.json:7].  The CUDA
+    rollout (2000 x 200 'random' validation trajectories, gravity-compensation line active, see
+    tests/test_oracle.py::test_koopman_long_horizon_fingerprint) reproduces it."""
+    import os
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    W = {k: torch.as_tensor(v, dtype=torch.float64, device="cuda")
+         for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "koopman_dkuc.npz")).items()}
+
+    def predict(x, u):
+        h = x
+        for i in range(5):
+            h = h @ W[f"x_encode_net.linear_{i}.weight"].T + W[f"x_encode_net.linear_{i}.bias"]
+            if i != 4:
+                h = torch.relu(h)
+        return (torch.cat([x, h], -1) @ W["lA.weight"].T + u @ W["lB.weight"].T) @ W["lC.weight"].T
+
+    env = _vec(tables_v, 2000, dtype=dtype)
+    rows = env.rollout(200, "random", seed=2024, flags=T_.ROLL_GRAVCOMP_HOLD)
+    x, u = rows[:, :, 5:], rows[:, :, :5]
+    x0, mae = x[:, 0], 0.0
+    for i in range(200):
+        x0 = predict(x0, u[:, i])
+        mae += float((x0 - x[:, i + 1]).abs().mean())
+    mae /= 200
+    print(f"{dtype}: open-loop 200-step MAE of the reference's trained model on GPU data = {mae:.3e} (published 6.84e-3)")
+    assert 5.5e-3 < mae < 8.5e-3

@@ -170,6 +170,44 @@ def test_koopman_fingerprint(oracle_mod, tables_v):
         assert abs(slope - W["lB.weight"][3 + j, j]) < 0.0015     # ~0.0175 rad per unit control
 
 
+def test_koopman_long_horizon_fingerprint(oracle_mod, tables_v):
+    """Second, stronger pin against the reference's own artefacts: the shipped model's 200-step open-loop MAE on
+    its validation set is 6.84e-3 [REF results/SOARM101/11_27/DKUC/best_scores.json:7, train.py:35-87,
+    models/losses.py:132-173].  Re-running that evaluation on oracle data reproduces it (6.8e-3) if and only if
+    the data is generated with the gravity-compensation line of SOARM101Env.step active
+    (`qfrc_applied = qfrc_bias`, [REF SOARM101_Env.py:120], commented out in the current tree): without it the
+    arm sags 7e-4 rad per control step on the two gravity-loaded joints, which the model (trained on real MuJoCo
+    data) does not predict, and the MAE is 3.2e-2.  So the artefact was trained with that line on, and the
+    oracle's chatter-regime dynamics agree with real MuJoCo statistically over 2000 physics steps."""
+    from lerobot_mujoco_sim2real_b200 import tables as T
+    O = oracle_mod
+    W = {k: v.astype(np.float64) for k, v in np.load(os.path.join(GOLD, "koopman_dkuc.npz")).items()}
+
+    def predict(x, u):
+        h = x
+        for i in range(5):
+            h = h @ W[f"x_encode_net.linear_{i}.weight"].T + W[f"x_encode_net.linear_{i}.bias"]
+            if i != 4:
+                h = np.maximum(h, 0)
+        return (np.concatenate([x, h], -1) @ W["lA.weight"].T + u @ W["lB.weight"].T) @ W["lC.weight"].T
+
+    out = {}
+    for name, flags in (("plain", 0), ("gravcomp", T.ROLL_GRAVCOMP_HOLD)):
+        rows, _, _ = O.rollout(tables_v, O.make_spec(kind=0, seed=3), 600, 200, 10, flags=flags)
+        x, u = rows[:, :, 5:], rows[:, :, :5]
+        x0, mae = x[:, 0], 0.0
+        for i in range(200):
+            x0 = predict(x0, u[:, i])
+            mae += np.abs(x0 - x[:, i + 1]).mean()
+        drift = (x[:, 1:, 3:] - x[:, :-1, 3:]).mean(axis=(0, 1))
+        out[name] = (mae / 200, drift)
+    mae_g, drift_g = out["gravcomp"]
+    mae_p, drift_p = out["plain"]
+    assert 5.5e-3 < mae_g < 8.5e-3, mae_g                 # reference: 6.84e-3
+    assert np.abs(drift_g).max() < 1.5e-4                 # no sag, as the trained model implies
+    assert mae_p > 3 * mae_g and drift_p[1] > 4e-4 and drift_p[2] > 4e-4
+
+
 def test_step_batch_matches_single_env(oracle_mod, tables_v):
     O, t = oracle_mod, tables_v
     rng = np.random.default_rng(0)
