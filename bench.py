@@ -36,7 +36,6 @@ T_CTRL = 100           # control steps per rollout
 FRAME_SKIP = 10
 SEED = 42
 FLOP_PER_PHYSICS_STEP = 6.2e3   # SURVEY.md 8d / BASELINE.md (4.9 k + 0.63 k x 2 Newton iterations)
-ROW_BYTES = 13 * 8
 METRIC, UNIT = "env-steps/sec", "env-steps/s"
 
 

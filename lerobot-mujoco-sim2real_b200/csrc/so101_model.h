@@ -112,10 +112,6 @@ inline double impedance(const double* solimp, double pos, double margin) {
   return solimp[0] + y * (solimp[1] - solimp[0]);
 }
 
-struct DModel {  // double-precision master copy
-  DevModel<double> d;
-};
-
 // Returns "" on success, else the reason the model is outside the supported subset.
 inline std::string build(const So101Tables& t, DevModel<double>& m) {
   std::memset(&m, 0, sizeof m);
