@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         L.so101o_shoot.argtypes = [P(So101Tables), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_void_p, C.c_uint32, C.c_int]
         L.so101o_num_threads.restype = C.c_int
+        L.so101o_set_line_search.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -208,6 +209,11 @@ def shoot(tables: So101Tables, state0: np.ndarray, U: np.ndarray, frame_skip: in
     X = np.empty((B, H + 1, 8), dtype=np.float32)
     lib().so101o_shoot(C.byref(tables), _ptr(state0), _ptr(U), B, H, frame_skip, _ptr(X), flags, nthreads)
     return X
+
+
+def set_line_search(mode: int) -> None:
+    """0: MuJoCo's PrimalSearch (default).  1: the exact piece-walking search the CUDA kernels use."""
+    lib().so101o_set_line_search(int(mode))
 
 
 def num_threads() -> int:

@@ -663,6 +663,67 @@ static double primalSearch(const So101Tables* m, OracleData* d, Primal* c) {
   return 0;
 }
 
+/*
+ * ALTERNATIVE UNDER TEST, not MuJoCo: exact minimiser of the line-search objective.  Along the search
+ * direction f'(alpha) is continuous, piecewise linear and non-decreasing (Huber friction rows, one-sided
+ * limit rows); PrimalSearch above converges to its root within gtol.  walkSearch finds the root directly,
+ * one linear piece at a time (next zone breakpoint -> slope/curvature at the piece's midpoint -> stop when
+ * the piece's own root lies inside it).  The CUDA kernels use this form; so101o_set_line_search(1) switches
+ * the oracle to it so that the equivalence can be measured on the CPU (tests/test_oracle.py).
+ */
+static int g_line_search = 0;   /* 0: PrimalSearch (MuJoCo, default)   1: walkSearch */
+void so101o_set_line_search(int mode) { g_line_search = mode; }
+
+static void slopeAt(const OracleData* d, const Primal* c, double alpha, double* d0, double* d1) {
+  double s0 = c->quadGauss[1] + 2 * c->quadGauss[2] * alpha, s1 = 2 * c->quadGauss[2];
+  for (int i = 0; i < d->nefc; i++) {
+    double x = c->Jaref[i] + alpha * c->Jv[i];
+    if (i < d->nf) {
+      double f = d->efc_frictionloss[i], Rf = d->efc_R[i] * f;
+      if (-Rf < x && x < Rf) { s0 += d->efc_D[i] * x * c->Jv[i]; s1 += d->efc_D[i] * c->Jv[i] * c->Jv[i]; }
+      else s0 += (x <= -Rf ? -f : f) * c->Jv[i];
+    } else if (x < 0) {
+      s0 += d->efc_D[i] * x * c->Jv[i];
+      s1 += d->efc_D[i] * c->Jv[i] * c->Jv[i];
+    }
+  }
+  *d0 = s0;
+  *d1 = s1 > 0 ? s1 : mjMINVAL;
+}
+
+static double walkSearch(OracleData* d, Primal* c) {
+  c->LSiter = 0;
+  if (sqrt(dotn(c->search, c->search, NV)) < mjMINVAL) return 0;
+  mulM(d, c->Mv, c->search);
+  for (int i = 0; i < d->nefc; i++) c->Jv[i] = dotn(d->efc_J[i], c->search, NV);
+  primalPrepare(d, c);
+  double alpha = 0;
+  for (int it = 0; it < 2 * MAXEFC + 2; it++) {
+    double nb = INFINITY;   /* next zone breakpoint beyond alpha */
+    for (int i = 0; i < d->nefc; i++) {
+      double jv = c->Jv[i];
+      if (jv == 0) continue;
+      if (i < d->nf) {
+        double Rf = d->efc_R[i] * d->efc_frictionloss[i];
+        double b1 = (Rf - c->Jaref[i]) / jv, b2 = (-Rf - c->Jaref[i]) / jv;
+        if (b1 > alpha && b1 < nb) nb = b1;
+        if (b2 > alpha && b2 < nb) nb = b2;
+      } else {
+        double b1 = -c->Jaref[i] / jv;
+        if (b1 > alpha && b1 < nb) nb = b1;
+      }
+    }
+    int last = !(nb < INFINITY);
+    double mid = last ? alpha + 1 : 0.5 * (alpha + nb), d0, d1;
+    slopeAt(d, c, mid, &d0, &d1);
+    c->LSiter++;
+    double root = mid - d0 / d1;
+    if (root <= nb || last) return root > alpha ? root : alpha;
+    alpha = nb;
+  }
+  return alpha;
+}
+
 /* mj_solPrimal(flg_Newton=1) */
 static void solNewton(const So101Tables* m, OracleData* d) {
   Primal c;
@@ -677,7 +738,7 @@ static void solNewton(const So101Tables* m, OracleData* d) {
   int iter = 0, nls = 0;
   memset(d->ls_evals_iter, 0, sizeof d->ls_evals_iter);
   while (iter < m->iterations) {
-    double alpha = primalSearch(m, d, &c);
+    double alpha = g_line_search ? walkSearch(d, &c) : primalSearch(m, d, &c);
     nls += c.LSiter;
     if (iter < 8) d->ls_evals_iter[iter] = c.LSiter;
     if (alpha == 0) break;
