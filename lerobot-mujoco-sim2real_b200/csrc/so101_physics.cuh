@@ -446,7 +446,7 @@ SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV
 // decided on a boundary), stop if the piece's own root lies inside it.  One iteration per piece
 // crossed (mean 1.7, at most one per breakpoint).  Against the literal search the step result differs by
 // <= 3e-16 (qpos), <= 1.4e-13 (qvel), <= 3e-12 (qacc) relative with identical Newton iteration
-// counts (tests/test_oracle.py::test_exact_line_search_is_equivalent), below the CUDA-vs-oracle
+// counts (CPU test `test_exact_line_search_is_equivalent` under tests/), below the CUDA-vs-CPU
 // differences of the smooth dynamics.
 // ------------------------------------------------------------------------------------------
 template <typename T> SO101_DEV T inf_();
