@@ -621,21 +621,49 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
       if (!constrained) {
         to_euler = true;  // nefc == 0: qacc = qacc_smooth
       } else {
-        // warmstart(): the cheaper of qacc_warmstart and qacc_smooth, evaluated by one code site
-        T cost0 = T(0);
-#pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-          T ca[NV], cMa[NV], cqc[NV], chd[NV];
+        // Starting point.  MuJoCo starts Newton from the cheaper of qacc_warmstart and qacc_smooth and then
+        // needs 3 iterations in ~43 % of this scene's steps.  The cost is strictly convex (unique minimiser), so
+        // the start only decides how many iterations are needed: start from the closed-form minimiser of the
+        // per-dof problem 0.5 M_ii (a - qacc_smooth_i)^2 + huber_i(a - aref_i).  M is armature dominated, this
+        // identifies the active set of the coupled problem in > 99.5 % of the steps and the first Newton step
+        // is exact (CPU test `test_prox_start_is_equivalent`: same result to ~1e-13, 1.0 instead of 1.9-2.3
+        // iterations; warp-level maximum 1.06 instead of 3.1).  qacc_warmstart is still written every step
+        // (it is part of the state the API exposes) and read only when a joint-limit row is active.
+        if (!rw.anylim) {
 #pragma unroll
-          for (int i = 0; i < NV; i++) ca[i] = c ? asm_[i] : e.warm[i];
-          symv6(M, ca, cMa);
-          T cc = cost_update(m, rw, ca, cMa, fsm, asm_, cqc, chd);
-          if (c == 0 || cost0 > cc) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) { a[i] = ca[i]; Ma[i] = cMa[i]; qc[i] = cqc[i]; hd[i] = chd[i]; }
-            cost = cc;
+          for (int i = 0; i < NV; i++) {
+            const T Mii = M[tri(i, i)], as = asm_[i], ar = rw.aref_f[i];
+            const T aq = (Mii * as + m.fr_D[i] * ar) * rcp_(Mii + m.fr_D[i]);   // quadratic zone
+            const T df = m.fr_f[i] * rcp_(Mii);                                 // linear zones: as -+ f / M_ii
+            const T ap = as - df, an = as + df;
+            T ai;
+            if (abs_(aq - ar) < m.fr_Rf[i]) ai = aq;
+            else if (ap - ar >= m.fr_Rf[i]) ai = ap;
+            else if (an - ar <= -m.fr_Rf[i]) ai = an;
+            else ai = ar + copysign_(m.fr_Rf[i], as - ar);
+            a[i] = ai;
           }
-          if (c == 0) cost0 = cc;
+          symv6(M, a, Ma);
+          cost = cost_update(m, rw, a, Ma, fsm, asm_, qc, hd);
+        } else {
+          // A joint-limit row is active (rare): stiff rows make MuJoCo stop at its tolerance rather than at
+          // rounding, so follow its own warm start here - the cheaper of qacc_warmstart and qacc_smooth - to
+          // stay on its iterates.
+          T cost0 = T(0);
+#pragma unroll 1
+          for (int c = 0; c < 2; c++) {
+            T ca[NV], cMa[NV], cqc[NV], chd[NV];
+#pragma unroll
+            for (int i = 0; i < NV; i++) ca[i] = c ? asm_[i] : e.warm[i];
+            symv6(M, ca, cMa);
+            T cc = cost_update(m, rw, ca, cMa, fsm, asm_, cqc, chd);
+            if (c == 0 || cost0 > cc) {
+#pragma unroll
+              for (int i = 0; i < NV; i++) { a[i] = ca[i]; Ma[i] = cMa[i]; qc[i] = cqc[i]; hd[i] = chd[i]; }
+              cost = cc;
+            }
+            if (c == 0) cost0 = cc;
+          }
         }
 #pragma unroll
         for (int i = 0; i < NV; i++) { x[i] = Ma[i] - fsm[i] - qc[i]; dd[i] = hd[i]; }

@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
                                    C.c_void_p, C.c_uint32, C.c_int]
         L.so101o_num_threads.restype = C.c_int
         L.so101o_set_line_search.argtypes = [C.c_int]
+        L.so101o_set_solver_start.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -214,6 +215,11 @@ def shoot(tables: So101Tables, state0: np.ndarray, U: np.ndarray, frame_skip: in
 def set_line_search(mode: int) -> None:
     """0: MuJoCo's PrimalSearch (default).  1: the exact piece-walking search the CUDA kernels use."""
     lib().so101o_set_line_search(int(mode))
+
+
+def set_solver_start(mode: int) -> None:
+    """0: MuJoCo's warm start (default).  1: the per-dof prox start the CUDA kernels use."""
+    lib().so101o_set_solver_start(int(mode))
 
 
 def num_threads() -> int:

@@ -242,6 +242,41 @@ def test_exact_line_search_is_equivalent(oracle_mod, tables_v, tables_p, scene):
     assert np.quantile(rel[:, 6:12], 0.999) < 1e-12
 
 
+@pytest.mark.parametrize("scene", ["v", "p"])
+def test_prox_start_is_equivalent(oracle_mod, tables_v, tables_p, scene):
+    """The CUDA kernels start Newton at the per-dof prox point instead of MuJoCo's warm-start pick and use
+    the exact line search: same unique minimiser, one iteration instead of three."""
+    O = oracle_mod
+    t = tables_v if scene == "v" else tables_p
+    rng = np.random.default_rng(1)
+    n = 256
+    state = np.zeros((n, 18)); state[:, :5] = rng.uniform(-0.3, 0.3, (n, 5))
+    S, U = [], []
+    for s in range(300):
+        if s % 10 == 0:
+            ctrl = np.zeros((n, 6))
+            ctrl[:, :5] = rng.uniform(-0.5, 0.5, (n, 5)) if scene == "v" else state[:, :5] + rng.uniform(-0.3, 0.3, (n, 5))
+        if s % 50 == 0 and s:
+            state[: n // 8, 2] = t.jnt_range[2][1] + rng.uniform(-1e-3, 5e-3, n // 8)
+        S.append(state); U.append(ctrl)
+        state, _, _ = O.step_batch(t, state, ctrl, 1)
+    S, U = np.concatenate(S[20:]), np.concatenate(U[20:])
+    ref, _, aux = O.step_batch(t, S, U, 1)
+    try:
+        O.set_line_search(1); O.set_solver_start(1)
+        alt, _, aux2 = O.step_batch(t, S, U, 1)
+    finally:
+        O.set_line_search(0); O.set_solver_start(0)
+    free = aux[:, 2] == 6                                   # no limit row active
+    assert (~free).sum() > 100
+    assert aux[free, 0].mean() > 1.7 and aux2[free, 0].mean() < 1.02     # 1 iteration instead of ~1.9-2.3
+    assert aux2[:, 0].reshape(-1, 32).max(axis=1).mean() < 0.6 * aux[:, 0].reshape(-1, 32).max(axis=1).mean()
+    rel = np.abs(alt - ref) / (1e-3 + np.abs(ref))
+    assert rel[:, :6].max() < 1e-13
+    assert np.quantile(rel[:, 6:12], 0.999) < 2e-12 and rel[:, 6:12].max() < 1e-10
+    assert np.quantile(rel[:, 12:], 0.999) < 1e-10 and rel[:, 12:].max() < 1e-7
+
+
 def test_step_batch_matches_single_env(oracle_mod, tables_v):
     O, t = oracle_mod, tables_v
     rng = np.random.default_rng(0)
