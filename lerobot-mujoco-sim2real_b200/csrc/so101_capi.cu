@@ -165,12 +165,15 @@ SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t
 // ==========================================================================================
 // kernels
 // ==========================================================================================
+// Launch bounds, from the ncu / timing experiments in profiles/README.md: f64 needs all 255 registers
+// (one 256-thread block = 8 warps per SM; 168- or 128-register builds lose 20-30 % to spills); the f32
+// instantiation fits 128 registers with few spills and gains 5-16 % from 16 warps per SM.
 #ifndef SO101_LB_THREADS
 #define SO101_LB_THREADS 256
 #endif
-#ifndef SO101_LB_BLOCKS
-#define SO101_LB_BLOCKS 1
-#endif
+template <typename T> struct MinBlocks { static constexpr int value = 1; };
+template <> struct MinBlocks<float> { static constexpr int value = 2; };
+#define SO101_LB_BLOCKS MinBlocks<T>::value
 #define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 
 // reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
