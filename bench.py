@@ -295,7 +295,7 @@ def run_b200(args) -> None:
         "kernel_ms": kernel_ms,
         "bound_note": "neither hbm nor tensor: ~300 FLOP per byte of state/row traffic, no contraction; the limiter is "
                       "the FP64 FMA pipe.  At this config (4096 envs = 128 warps on 592 warp schedulers) the launch is "
-                      "latency-bound; the large-batch fraction is in extra (fp64 131072: ~0.27, ncu: FP64 pipe 41 % busy)",
+                      "latency-bound; the large-batch fraction is in extra (fp64 131072: ~0.40 - the accounting budgets 2 Newton iterations, the kernels need 1.0; ncu: FP64 pipe 45 % busy)",
         "hbm_sanity": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                        "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                        "algorithmic_bytes_per_env_step": 208},
