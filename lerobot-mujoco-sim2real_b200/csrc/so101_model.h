@@ -50,6 +50,7 @@ struct DevModel {
   T h, tolerance, gtol_fac, scale;
   // contact tripwire: up to TRIP_PER_LINK oriented boxes per link, in the link frame
   T trip_c[NV][TRIP_PER_LINK][3], trip_ax[NV][TRIP_PER_LINK][9], trip_half[NV][TRIP_PER_LINK][3];
+  T trip_rad[NV][TRIP_PER_LINK];   // |half|_2: bounding-sphere pre-check
   T trip_z, trip_qlo[NV], trip_qhi[NV];
   int32_t trip_n[NV];   // <- first non-T field (see hostbuild::convert)
   int32_t ntrip;
@@ -206,6 +207,8 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
       mv(At, c3, m.trip_c[k][slot]);
       for (int a = 0; a < 3; a++) mv(At, &t.trip_axes[i][3 * a], &m.trip_ax[k][slot][3 * a]);
       for (int c = 0; c < 3; c++) m.trip_half[k][slot][c] = t.trip_half[i][c];
+      m.trip_rad[k][slot] = std::sqrt(t.trip_half[i][0] * t.trip_half[i][0] + t.trip_half[i][1] * t.trip_half[i][1] +
+                                      t.trip_half[i][2] * t.trip_half[i][2]) * (1 + 1e-5);  // margin covers f32 rounding of |zw|
       m.trip_n[k] = slot + 1;
     }
     std::memcpy(Aprev, A, sizeof A);

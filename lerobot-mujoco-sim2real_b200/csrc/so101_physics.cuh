@@ -292,6 +292,7 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
         for (int b = 0; b < TRIP_PER_LINK; b++) {
           if (m.trip_n[k] > b) {
             T zc0 = zo + zw[0] * m.trip_c[k][b][0] + zw[1] * m.trip_c[k][b][1] + zw[2] * m.trip_c[k][b][2];
+            if (zc0 - m.trip_rad[k][b] >= m.trip_z) continue;   // bounding sphere clears the plane: box does too
             T ext = T(0);
 #pragma unroll
             for (int ax = 0; ax < 3; ax++)
