@@ -165,15 +165,15 @@ SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t
 // ==========================================================================================
 // kernels
 // ==========================================================================================
-// Launch bounds, from the ncu / timing experiments in profiles/README.md: f64 needs all 255 registers
-// (one 256-thread block = 8 warps per SM; 168- or 128-register builds lose 20-30 % to spills); the f32
-// instantiation fits 128 registers with few spills and gains 5-16 % from 16 warps per SM.
-#ifndef SO101_LB_THREADS
-#define SO101_LB_THREADS 256
-#endif
-template <typename T> struct MinBlocks { static constexpr int value = 1; };
-template <> struct MinBlocks<float> { static constexpr int value = 2; };
-#define SO101_LB_BLOCKS MinBlocks<T>::value
+// Launch bounds, from the ncu / timing experiments in profiles/README.md.  f64 needs all 255 registers
+// (one 256-thread block = 8 warps per SM; 168- or 128-register builds lose 20-30 % to spills).  The f32
+// instantiation fits 128 registers with few spills: 16 warps per SM as ONE 512-thread block, so that all
+// of them share the instruction stream between the block barriers (+5-16 % for 16 warps, +17 % more
+// for the single block; stall_no_instruction was the top f32 stall with two independent blocks).
+template <typename T> struct LBThreads { static constexpr int value = 256; };
+template <> struct LBThreads<float> { static constexpr int value = 512; };
+#define SO101_LB_THREADS LBThreads<T>::value
+#define SO101_LB_BLOCKS 1
 #define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 
 // reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
@@ -421,7 +421,7 @@ static size_t elem_size(int dtype) { return dtype == SO101_F64 ? sizeof(double) 
 // see physics_step SYNC); small batches use smaller blocks so that every SM gets work
 static int pick_block(int64_t n) {
   if (const char* ev = getenv("SO101_BLK")) { int v = atoi(ev); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }
-  if (n >= (int64_t)148 * 256 && SO101_LB_THREADS >= 256) return 256;
+  if (n >= (int64_t)148 * 256) return 256;
   if (n >= (int64_t)148 * 128) return 128;
   if (n >= (int64_t)148 * 64) return 64;
   return 32;
@@ -448,7 +448,8 @@ template <typename T> static StateView<T> step_view(const So101Batch* b, int& bl
   StateView<T> v = view<T>(b);
   v.lanes = pick_lanes(b->n);
   blk = v.lanes == 32 ? pick_block(b->n) : 128;
-  if (const char* ev = getenv("SO101_BLK")) { int x = atoi(ev); if (x >= 32 && x <= 256 && x % 32 == 0) blk = x; }
+  if (sizeof(T) == 4 && blk == 256 && b->n >= (int64_t)148 * 512) blk = 512;
+  if (const char* ev = getenv("SO101_BLK")) { int x = atoi(ev); if (x >= 32 && x <= 512 && x % 32 == 0) blk = x; }
   const int64_t warps = (b->n + v.lanes - 1) / v.lanes;
   grid = (unsigned)((warps * 32 + blk - 1) / blk);
   return v;
