@@ -33,6 +33,52 @@ struct StateView {
 // thread -> env for the stepping kernels.  A warp carries `lanes` envs; its other lanes shadow
 // them (same instruction stream, same data, no extra divergence) and never store.  Idle lanes and
 // tail threads are clamped to a valid env so that every thread reaches the block barriers.
+// SPLIT kernels (small batches): a 96-thread block is a TEAM of three warps on the same 32 envs, warp 0 = dynamics
+// role (owns the env, loads and stores), warps 1, 2 = geometry and lookout roles (see so101_physics.cuh, SplitXch).
+template <typename T> SO101_DEV int64_t env_of_pair(const StateView<T>& s, bool& active) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  active = threadIdx.x < 32 && i < s.n;
+  return i < s.n ? i : s.n - 1;
+}
+template <typename T, bool SPLIT> struct XchStorage { char unused; };
+template <typename T> struct XchStorage<T, true> { SplitXch<T> x; };
+template <typename T> SO101_DEV SplitXch<T>& xch_of(XchStorage<T, true>& st) { return st.x; }
+template <typename T> SO101_DEV SplitXch<T>& xch_of(XchStorage<T, false>& st) { return *reinterpret_cast<SplitXch<T>*>(&st); }
+
+// helper roles of a SPLIT kernel: pick up the initial state, then shadow `nsteps` physics steps
+template <typename T>
+SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps, int frame_skip) {
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const bool trip = m.ntrip > 0;
+  T q[NV], qd[NV];
+  __syncthreads();   // (0) initial state published
+#pragma unroll
+  for (int k = 0; k < NV; k++) { q[k] = x.q[k][lane]; qd[k] = x.qd[k][lane]; }
+  if (role == 1) {
+#pragma unroll 1
+    for (int64_t n = 0; n < nsteps; n++) split_geometry_step(m, x, lane, q, qd);
+  } else {
+    int ss = 0;
+#pragma unroll 1
+    for (int64_t n = 0; n < nsteps; n++) {
+      split_lookout_step(m, x, lane, q, qd, ss == frame_skip - 1, trip);
+      if (++ss == frame_skip) ss = 0;
+    }
+  }
+}
+template <typename T> SO101_DEV void publish_state(SplitXch<T>& x, const Env<T>& e) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; k++) { x.q[k][lane] = e.q[k]; x.qd[k][lane] = e.qd[k]; }
+  __syncthreads();   // (0)
+}
+template <typename T, bool SPLIT>
+SO101_DEV void step_env(const DevModel<T>& m, SplitXch<T>& x, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
+                        bool want_site, T (&site)[3], bool trip, Counters& cnt) {
+  if (SPLIT) split_dynamics_step(m, x, threadIdx.x & 31, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
+  else physics_step<T, true>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
+}
+
 template <typename T> SO101_DEV int64_t env_of_thread(const StateView<T>& s, bool& active) {
   const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -175,6 +221,8 @@ template <> struct LBThreads<float> { static constexpr int value = 512; };
 #define SO101_LB_THREADS LBThreads<T>::value
 #define SO101_LB_BLOCKS 1
 #define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
+#define SO101_STEP_KERNEL(T) \
+  template <typename T, bool SPLIT> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SO101_LB_BLOCKS)
 
 // reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
 //   mode 0: qpos0/qvel0 [6][N] (nullable)   mode 1: qpos[0:5] ~ U(lo,hi) from Philox
@@ -217,7 +265,9 @@ k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* 
   load_env(s, i, e);
   T M[21], bias[NV], site[3];
   uint32_t fl = 0;
-  smooth_dynamics<T, false>(m, e.q, e.qd, M, bias, true, site, false, fl);
+  T sn[NV], cs[NV];
+  joint_sincos(m, e.q, sn, cs);
+  smooth_dynamics<T, false>(m, e.q, e.qd, sn, cs, M, bias, true, site, false, fl);
   if (obs) {
 #pragma unroll
     for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
@@ -231,20 +281,24 @@ k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* 
 }
 
 // SOARM101Env.step: ctrl rows [n_ctrl][N] (missing rows = 0), nsub x mj_step, observation
-SO101_KERNEL(T)
+SO101_STEP_KERNEL(T)
 k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
        unsigned long long* stats) {
+  __shared__ XchStorage<T, SPLIT> xst;
+  SplitXch<T>& xch = xch_of(xst);
+  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, nsub, nsub); return; }
   bool active;
-  const int64_t i = env_of_thread(s, active);
+  const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   Env<T> e;
   load_env(s, i, e);
+  if (SPLIT) publish_state(xch, e);
   T u[NV], site[3] = {T(0), T(0), T(0)};
 #pragma unroll
   for (int k = 0; k < NV; k++) u[k] = (ctrl && k < n_ctrl) ? ctrl[k * s.n + i] : T(0);
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
 #pragma unroll 1
-  for (int ss = 0; ss < nsub; ss++) physics_step<T, true>(m, e, u, false, ss == nsub - 1, site, trip, cnt);
+  for (int ss = 0; ss < nsub; ss++) step_env<T, SPLIT>(m, xch, e, u, false, ss == nsub - 1, site, trip, cnt);
   if (nsub == 0) site_fk(m, e.q, site);
   if (active) {
     store_env(s, i, e);
@@ -262,12 +316,15 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
-template <typename T, typename ROW>
-__global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
+template <typename T, typename ROW, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SO101_LB_BLOCKS)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int Tn, int frame_skip, ROW* rows,
           uint32_t rflags, unsigned long long* stats) {
+  __shared__ XchStorage<T, SPLIT> xst;
+  SplitXch<T>& xch = xch_of(xst);
+  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)Tn * frame_skip, frame_skip); return; }
   bool active;
-  const int64_t i = env_of_thread(s, active);
+  const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   const int64_t env = spec.env_offset + i;
   Env<T> e;
   if (rflags & SO101_ROLL_NO_RESET) {
@@ -286,6 +343,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
   T site[3];
   site_fk(m, e.q, site);
+  if (SPLIT) publish_state(xch, e);
   double u[5];
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
 #pragma unroll 1
@@ -293,7 +351,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
     if (t > 0) {
 #pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++)
-        physics_step<T, true>(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
     }
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
 #pragma unroll
@@ -316,11 +374,14 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
 struct State0 { double v[18]; };
 
 // B control sequences U[H][5][B] from one shared state; X[B][H+1][8] float32 observations
-SO101_KERNEL(T)
+SO101_STEP_KERNEL(T)
 k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
         int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
+  __shared__ XchStorage<T, SPLIT> xst;
+  SplitXch<T>& xch = xch_of(xst);
+  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)H * frame_skip, frame_skip); return; }
   bool active;
-  const int64_t i = env_of_thread(s, active);
+  const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   Env<T> e;
   reset_env(m, e);
 #pragma unroll
@@ -330,6 +391,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
   T site[3];
   site_fk(m, e.q, site);
+  if (SPLIT) publish_state(xch, e);
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
 #pragma unroll 1
   for (int t = 0; t <= H; t++) {
@@ -338,7 +400,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
       for (int k = 0; k < 5; k++) uc[k] = U[((int64_t)(t - 1) * 5 + k) * s.n + i];
 #pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++)
-        physics_step<T, true>(m, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
     }
     if (active) {
       float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;
@@ -444,8 +506,21 @@ static int pick_lanes(int64_t n) {
   if (const char* ev = getenv("SO101_LANES")) { int v = atoi(ev); if (v == 32 || v == 16 || v == 8 || v == 4 || v == 2 || v == 1) return v; }
   return 32;
 }
-template <typename T> static StateView<T> step_view(const So101Batch* b, int& blk, unsigned& grid) {
+// Small batches (at most one team per SM: 148 x 32 envs) run the SPLIT kernels: three warps per 32 envs, 96-thread
+// blocks.  Measured on B200 (tools/split_probe.py, 100 control steps): 1024 envs 10.7 -> 6.6 ms, 4096 envs
+// 12.0 -> 9.9 ms, break-even near 7000 envs.  SO101_SPLIT=0|1 overrides (experiments, bitwise-equality test).
+static bool pick_split(int64_t n) {
+  if (const char* ev = getenv("SO101_SPLIT")) return atoi(ev) != 0;
+  return n <= (int64_t)148 * 32;
+}
+template <typename T> static StateView<T> step_view(const So101Batch* b, int& blk, unsigned& grid, bool& split) {
   StateView<T> v = view<T>(b);
+  split = pick_lanes(b->n) == 32 && pick_split(b->n);
+  if (split) {
+    blk = 32 * TEAM_WARPS;
+    grid = (unsigned)((b->n + 31) / 32);
+    return v;
+  }
   v.lanes = pick_lanes(b->n);
   blk = v.lanes == 32 ? pick_block(b->n) : 128;
   if (sizeof(T) == 4 && blk == 256 && b->n >= (int64_t)148 * 512) blk = 512;
@@ -578,13 +653,15 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
   if (n_ctrl < 0 || n_ctrl > NV || n_substeps < 0) return fail(SO101_EINVAL, "n_ctrl must be 0..6, n_substeps >= 0");
   DeviceGuard g(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int blk; unsigned grid;
+  int blk; unsigned grid; bool split;
   if (b->dtype == SO101_F64) {
-    StateView<double> v = step_view<double>(b, blk, grid);
-    k_step<double><<<grid, blk, 0, st>>>(b->model->d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    StateView<double> v = step_view<double>(b, blk, grid, split);
+    if (split) k_step<double, true><<<grid, blk, 0, st>>>(b->model->d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    else k_step<double, false><<<grid, blk, 0, st>>>(b->model->d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
   } else {
-    StateView<float> v = step_view<float>(b, blk, grid);
-    k_step<float><<<grid, blk, 0, st>>>(b->model->f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    StateView<float> v = step_view<float>(b, blk, grid, split);
+    if (split) k_step<float, true><<<grid, blk, 0, st>>>(b->model->f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    else k_step<float, false><<<grid, blk, 0, st>>>(b->model->f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
   }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -650,16 +727,19 @@ int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int fra
   ds.kind = spec->kind; ds.t_total = spec->t_total; ds.seed = spec->seed; ds.env_offset = spec->env_offset;
   ds.amp = spec->amp; ds.freq_lo = spec->freq_lo; ds.freq_hi = spec->freq_hi;
   ds.reset_lo = spec->reset_lo; ds.reset_hi = spec->reset_hi; ds.u = spec->u;
-  int blk; unsigned grid;
+  int blk; unsigned grid; bool split;
   const bool r32 = flags & SO101_ROLL_ROWS_F32;
   if (b->dtype == SO101_F64) {
-    StateView<double> v = step_view<double>(b, blk, grid);
-    if (r32) k_rollout<double, float><<<grid, blk, 0, st>>>(b->model->d, v, ds, T, frame_skip, (float*)rows, flags, b->stats);
-    else k_rollout<double, double><<<grid, blk, 0, st>>>(b->model->d, v, ds, T, frame_skip, (double*)rows, flags, b->stats);
+    StateView<double> v = step_view<double>(b, blk, grid, split);
+#define SO101_ROLL(TT, RR, SS, mdl) \
+  k_rollout<TT, RR, SS><<<grid, blk, 0, st>>>(b->model->mdl, v, ds, T, frame_skip, (RR*)rows, flags, b->stats)
+    if (split) { if (r32) SO101_ROLL(double, float, true, d); else SO101_ROLL(double, double, true, d); }
+    else { if (r32) SO101_ROLL(double, float, false, d); else SO101_ROLL(double, double, false, d); }
   } else {
-    StateView<float> v = step_view<float>(b, blk, grid);
-    if (r32) k_rollout<float, float><<<grid, blk, 0, st>>>(b->model->f, v, ds, T, frame_skip, (float*)rows, flags, b->stats);
-    else k_rollout<float, double><<<grid, blk, 0, st>>>(b->model->f, v, ds, T, frame_skip, (double*)rows, flags, b->stats);
+    StateView<float> v = step_view<float>(b, blk, grid, split);
+    if (split) { if (r32) SO101_ROLL(float, float, true, f); else SO101_ROLL(float, double, true, f); }
+    else { if (r32) SO101_ROLL(float, float, false, f); else SO101_ROLL(float, double, false, f); }
+#undef SO101_ROLL
   }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -713,13 +793,15 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   State0 s0;
   std::memcpy(s0.v, state0, sizeof s0.v);
-  int blk; unsigned grid;
+  int blk; unsigned grid; bool split;
   if (b->dtype == SO101_F64) {
-    StateView<double> v = step_view<double>(b, blk, grid);
-    k_shoot<double><<<grid, blk, 0, st>>>(b->model->d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
+    StateView<double> v = step_view<double>(b, blk, grid, split);
+    if (split) k_shoot<double, true><<<grid, blk, 0, st>>>(b->model->d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
+    else k_shoot<double, false><<<grid, blk, 0, st>>>(b->model->d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
   } else {
-    StateView<float> v = step_view<float>(b, blk, grid);
-    k_shoot<float><<<grid, blk, 0, st>>>(b->model->f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
+    StateView<float> v = step_view<float>(b, blk, grid, split);
+    if (split) k_shoot<float, true><<<grid, blk, 0, st>>>(b->model->f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
+    else k_shoot<float, false><<<grid, blk, 0, st>>>(b->model->f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
   }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;

@@ -218,6 +218,48 @@ template <typename T> SO101_DEV void ldl6_factor_solve(const T (&A)[21], T (&x)[
     for (int k = i + 1; k < NV; k++) x[i] -= L[tri(k, i)] * x[k];
   }
 }
+// factor only: A + diag(dd) = L D L^T (strictly-lower L packed in 15, 1/D in 6)
+template <typename T> SO101_DEV void ldl6_factor(const T (&A)[21], const T (&dd)[NV], T (&Ls)[15], T (&Dinv)[NV]) {
+  T L[21], D[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    T W[NV];
+#pragma unroll
+    for (int k = 0; k < j; k++) W[k] = L[tri(j, k)] * D[k];
+    T d = A[tri(j, j)] + dd[j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= L[tri(j, k)] * W[k];
+    d = max_(d, T(MJ_MINVAL));
+    D[j] = d;
+    Dinv[j] = rcp_(d);
+#pragma unroll
+    for (int i = j + 1; i < NV; i++) {
+      T s = A[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[tri(i, k)] * W[k];
+      L[tri(i, j)] = s * Dinv[j];
+    }
+  }
+#pragma unroll
+  for (int i = 1; i < NV; i++) {
+#pragma unroll
+    for (int k = 0; k < i; k++) Ls[i * (i - 1) / 2 + k] = L[tri(i, k)];
+  }
+}
+template <typename T> SO101_DEV void ldl6_solve(const T (&Ls)[15], const T (&Dinv)[NV], T (&x)[NV]) {
+#pragma unroll
+  for (int i = 1; i < NV; i++) {
+#pragma unroll
+    for (int k = 0; k < i; k++) x[i] -= Ls[i * (i - 1) / 2 + k] * x[k];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; i++) x[i] *= Dinv[i];
+#pragma unroll
+  for (int i = NV - 2; i >= 0; i--) {
+#pragma unroll
+    for (int k = i + 1; k < NV; k++) x[i] -= Ls[k * (k - 1) / 2 + i] * x[k];
+  }
+}
 template <typename T> SO101_DEV void symv6(const T (&M)[21], const T (&x)[NV], T (&y)[NV]) {
 #pragma unroll
   for (int i = 0; i < NV; i++) {
@@ -245,16 +287,42 @@ struct Counters {
 // smooth dynamics: qfrc_bias (RNEA, flg_acc = 0) and M (CRBA) in link-local frames.
 // Optionally the world position of the observation site and the contact tripwire.
 // ------------------------------------------------------------------------------------------
-template <typename T, bool WANT_M>
-SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (&qd)[NV], T (&M)[21],
-                               T (&bias)[NV], bool want_site, T (&site)[3], bool trip, uint32_t& flags) {
-  T sn[NV], cs[NV];
+// sin/cos of the joint angles (relative to the reference pose the frames were folded at)
+template <typename T> SO101_DEV void joint_sincos(const DevModel<T>& m, const T (&q)[NV], T (&sn)[NV], T (&cs)[NV]) {
 #pragma unroll
   for (int k = 0; k < NV; k++) sincos_(q[k] - m.qpos0[k], &sn[k], &cs[k]);
+}
 
+// contact tripwire of link k: zw = world z axis in the frame of link k, zo = world height of its origin
+template <typename T>
+SO101_DEV void tripwire_link(const DevModel<T>& m, int k, const T (&R)[9], T qk, T (&zw)[3], T& zo, uint32_t& flags) {
+  zo += zw[0] * m.r[k][0] + zw[1] * m.r[k][1] + zw[2] * m.r[k][2];
+  T zc[3];
+  rotT(R, zw, zc);
+  zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
+#pragma unroll
+  for (int b = 0; b < TRIP_PER_LINK; b++) {
+    if (m.trip_n[k] > b) {
+      T zc0 = zo + zw[0] * m.trip_c[k][b][0] + zw[1] * m.trip_c[k][b][1] + zw[2] * m.trip_c[k][b][2];
+      if (zc0 - m.trip_rad[k][b] >= m.trip_z) continue;   // bounding sphere clears the plane: box does too
+      T ext = T(0);
+#pragma unroll
+      for (int ax = 0; ax < 3; ax++)
+        ext += abs_(zw[0] * m.trip_ax[k][b][3 * ax] + zw[1] * m.trip_ax[k][b][3 * ax + 1] +
+                    zw[2] * m.trip_ax[k][b][3 * ax + 2]) * m.trip_half[k][b][ax];
+      if (zc0 - ext < m.trip_z) flags |= SO101_FLAG_TRIP_TABLE;
+    }
+  }
+  if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
+}
+
+template <typename T, bool WANT_M, bool WANT_BIAS = true>
+SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (&qd)[NV], const T (&sn)[NV],
+                               const T (&cs)[NV], T (&M)[21], T (&bias)[NV], bool want_site, T (&site)[3], bool trip,
+                               uint32_t& flags) {
   // ---- forward pass: velocities, accelerations, link forces --------------------------------
   T f[NV][6];
-  {
+  if (WANT_BIAS) {
     T v[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
     T a[6] = {T(0), T(0), T(0), m.accg[0], m.accg[1], m.accg[2]};
     T zw[3] = {T(0), T(0), T(1)};  // world z axis in the current frame (tripwire)
@@ -283,26 +351,7 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
       f[k][5] = Ia[5] + (vc[0] * Iv[4] - vc[1] * Iv[3]);
 #pragma unroll
       for (int c = 0; c < 6; c++) { v[c] = vc[c]; a[c] = ac[c]; }
-      if (trip) {
-        zo += zw[0] * m.r[k][0] + zw[1] * m.r[k][1] + zw[2] * m.r[k][2];
-        T zc[3];
-        rotT(R, zw, zc);
-        zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
-#pragma unroll
-        for (int b = 0; b < TRIP_PER_LINK; b++) {
-          if (m.trip_n[k] > b) {
-            T zc0 = zo + zw[0] * m.trip_c[k][b][0] + zw[1] * m.trip_c[k][b][1] + zw[2] * m.trip_c[k][b][2];
-            if (zc0 - m.trip_rad[k][b] >= m.trip_z) continue;   // bounding sphere clears the plane: box does too
-            T ext = T(0);
-#pragma unroll
-            for (int ax = 0; ax < 3; ax++)
-              ext += abs_(zw[0] * m.trip_ax[k][b][3 * ax] + zw[1] * m.trip_ax[k][b][3 * ax + 1] +
-                          zw[2] * m.trip_ax[k][b][3 * ax + 2]) * m.trip_half[k][b][ax];
-            if (zc0 - ext < m.trip_z) flags |= SO101_FLAG_TRIP_TABLE;
-          }
-        }
-        if (q[k] < m.trip_qlo[k] || q[k] > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
-      }
+      if (trip) tripwire_link(m, k, R, q[k], zw, zo, flags);
     }
   }
 
@@ -313,9 +362,11 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
   T p[3] = {T(0), T(0), T(0)};                       // site position in the current frame
 #pragma unroll
   for (int k = NV - 1; k >= 0; k--) {
+    if (WANT_BIAS) {
 #pragma unroll
-    for (int c = 0; c < 6; c++) fs[c] += f[k][c];
-    bias[k] = fs[2];
+      for (int c = 0; c < 6; c++) fs[c] += f[k][c];
+      bias[k] = fs[2];
+    }
     if (WANT_M) {
 #pragma unroll
       for (int c = 0; c < 10; c++) Ic[c] += m.I[k][c];
@@ -324,7 +375,7 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
       M[tri(k, k)] = Ic[2] + m.armature[k];
     }
     if (want_site && k == m.site_link) { p[0] = m.site[0]; p[1] = m.site[1]; p[2] = m.site[2]; }
-    if (k > 0 || want_site) {
+    if ((k > 0 && (WANT_M || WANT_BIAS)) || want_site) {
       T R[9];
       make_R(m.E[k], cs[k], sn[k], R);
       if (want_site && k <= m.site_link) {
@@ -334,9 +385,11 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
       }
       if (k > 0) {
         T t6[6];
-        xforce(R, m.r[k], fs, t6);
+        if (WANT_BIAS) {
+          xforce(R, m.r[k], fs, t6);
 #pragma unroll
-        for (int c = 0; c < 6; c++) fs[c] = t6[c];
+          for (int c = 0; c < 6; c++) fs[c] = t6[c];
+        }
         if (WANT_M) {
 #pragma unroll
           for (int j = NV - 1; j >= k; j--) {
@@ -556,7 +609,11 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   T M[21], bias[NV];
-  smooth_dynamics<T, true>(m, e.q, e.qd, M, bias, want_site, site, trip, e.flags);
+  {
+    T sn[NV], cs[NV];
+    joint_sincos(m, e.q, sn, cs);
+    smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags);
+  }
   if (SYNC) __syncthreads();
   if (gravcomp_capture) {
 #pragma unroll
@@ -747,6 +804,321 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   cnt.steps++;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Small batches: one physics step shared by a TEAM of three warps working on the same 32 envs.
+// A lone warp per SM is latency bound (ncu: 25 % of the issue slots of its scheduler, 4.4 cycles per
+// instruction) and a step is one serial chain of ~5.6 k instructions.  The chain has parallel parts that do
+// not need each other until the constraint solve:
+//   warp 0 "dynamics" : sincos(q0,q1) | RNEA bias forces, actuation, constraint rows | Newton solve, Euler step
+//   warp 1 "geometry" : sincos(q2,q3) | CRBA mass matrix, LDL^T of M (qacc_smooth) and of M + h B (implicit Euler)
+//   warp 2 "lookout"  : sincos(q4,q5) | contact tripwire, observation site
+// Exchange through shared memory at three block barriers per step: (S) sin/cos, (A) M + factors + flags + site,
+// (B) the new (qpos, qvel).  Every value is produced by the same expression as in physics_step, so the result is
+// bit-identical to the one-warp path (GPU test `test_split_team_is_bitwise_identical`): which kernel a batch size
+// selects never changes a trajectory.
+// ------------------------------------------------------------------------------------------
+constexpr int TEAM_WARPS = 3;
+template <typename T>
+struct SplitXch {      // shared memory of one team, structure-of-arrays over the 32 lanes
+  T sn[NV][32], cs[NV][32];
+  T M[21][32];
+  T L1[15][32], D1inv[NV][32];   // M       = L1 D1 L1^T
+  T L2[15][32], D2inv[NV][32];   // M + h B = L2 D2 L2^T
+  T site[3][32];
+  uint32_t trip[32];
+  T q[NV][32], qd[NV][32];       // state handed back by the dynamics warp
+};
+
+// every role takes the same mj_checkPos / mj_checkVel decision on its own copy of (qpos, qvel)
+template <typename T> SO101_DEV bool team_check_state(const DevModel<T>& m, T (&q)[NV], T (&qd)[NV]) {
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < NV; i++) bad |= bad_(q[i]) | bad_(qd[i]);
+  if (bad) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) { q[i] = m.qpos0[i]; qd[i] = T(0); }
+  }
+  return bad;
+}
+// sin/cos of the two joints of this role -> shared, barrier (S), all six back
+template <typename T>
+SO101_DEV void team_sincos(const DevModel<T>& m, SplitXch<T>& x, int lane, int role, const T (&q)[NV], T (&sn)[NV],
+                           T (&cs)[NV]) {
+#pragma unroll
+  for (int r = 0; r < TEAM_WARPS; r++) {
+    if (r == role) {
+#pragma unroll
+      for (int k = 2 * r; k < 2 * r + 2; k++) {
+        T s_, c_;
+        sincos_(q[k] - m.qpos0[k], &s_, &c_);
+        x.sn[k][lane] = s_; x.cs[k][lane] = c_;
+      }
+    }
+  }
+  __syncthreads();   // (S)
+#pragma unroll
+  for (int k = 0; k < NV; k++) { sn[k] = x.sn[k][lane]; cs[k] = x.cs[k][lane]; }
+}
+
+// geometry warp: M(q) and the two factorisations -> shared memory
+template <typename T>
+SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV]) {
+  team_check_state(m, q, qd);
+  T sn[NV], cs[NV];
+  team_sincos(m, x, lane, 1, q, sn, cs);
+  T M[21], bias[NV], site[3];
+  uint32_t fl = 0;
+  smooth_dynamics<T, true, false>(m, q, qd, sn, cs, M, bias, false, site, false, fl);
+  T zero[NV], hB[NV], Ls[15], Dinv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) { zero[i] = T(0); hB[i] = m.h * m.damping[i]; }
+#pragma unroll
+  for (int i = 0; i < 21; i++) x.M[i][lane] = M[i];
+  ldl6_factor(M, zero, Ls, Dinv);
+#pragma unroll
+  for (int i = 0; i < 15; i++) x.L1[i][lane] = Ls[i];
+#pragma unroll
+  for (int i = 0; i < NV; i++) x.D1inv[i][lane] = Dinv[i];
+  ldl6_factor(M, hB, Ls, Dinv);
+#pragma unroll
+  for (int i = 0; i < 15; i++) x.L2[i][lane] = Ls[i];
+#pragma unroll
+  for (int i = 0; i < NV; i++) x.D2inv[i][lane] = Dinv[i];
+  __syncthreads();   // (A) M and factors published
+  __syncthreads();   // (B) new state published by the dynamics warp
+#pragma unroll
+  for (int i = 0; i < NV; i++) { q[i] = x.q[i][lane]; qd[i] = x.qd[i][lane]; }
+}
+
+// lookout warp: contact tripwire and (on the last substep of a control step) the observation site
+template <typename T>
+SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
+                                  bool want_site, bool trip) {
+  team_check_state(m, q, qd);
+  T sn[NV], cs[NV];
+  team_sincos(m, x, lane, 2, q, sn, cs);
+  uint32_t fl = 0;
+  if (trip) {
+    T zw[3] = {T(0), T(0), T(1)};
+    T zo = T(0);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      T R[9];
+      make_R(m.E[k], cs[k], sn[k], R);
+      tripwire_link(m, k, R, q[k], zw, zo, fl);
+    }
+  }
+  x.trip[lane] = fl;
+  if (want_site) {
+    T p[3] = {T(0), T(0), T(0)};
+#pragma unroll
+    for (int k = NV - 1; k >= 0; k--) {
+      if (k == m.site_link) { p[0] = m.site[0]; p[1] = m.site[1]; p[2] = m.site[2]; }
+      if (k <= m.site_link) {
+        T R[9], o[3];
+        make_R(m.E[k], cs[k], sn[k], R);
+        rot(R, p, o);
+        p[0] = o[0] + m.r[k][0]; p[1] = o[1] + m.r[k][1]; p[2] = o[2] + m.r[k][2];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) x.site[c][lane] = p[c];
+  }
+  __syncthreads();   // (A)
+  __syncthreads();   // (B)
+#pragma unroll
+  for (int i = 0; i < NV; i++) { q[i] = x.q[i][lane]; qd[i] = x.qd[i][lane]; }
+}
+
+// dynamics warp: everything else of the step
+template <typename T>
+SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lane, Env<T>& e, const T (&ctrl)[NV],
+                                   bool gravcomp_capture, bool want_site, T (&site)[3], bool trip, Counters& cnt) {
+  if (team_check_state(m, e.q, e.qd)) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) { e.warm[i] = T(0); e.fa[i] = T(0); }
+    e.time = T(0);
+    e.flags |= SO101_FLAG_BADSTATE;
+  }
+  T M[21], bias[NV];
+  {
+    T sn[NV], cs[NV];
+    team_sincos(m, x, lane, 0, e.q, sn, cs);
+    uint32_t fl = 0;
+    smooth_dynamics<T, false, true>(m, e.q, e.qd, sn, cs, M, bias, false, site, false, fl);
+  }
+  if (gravcomp_capture) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
+  }
+  T fsm[NV], asm_[NV];
+  Rows<T> rw;
+  rw.anylim = false;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T passive = -m.damping[i] * e.qd[i];
+    if (m.any_stiffness) passive = -m.stiffness[i] * (e.q[i] - m.qspring[i]) - m.damping[i] * e.qd[i];
+    T c = ctrl[i];
+    if (m.ctrllim_mask >> i & 1) c = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], c));
+    T force = m.act_gain[i] * c + m.act_b0[i] + m.act_b1[i] * (m.act_gear[i] * e.q[i]) +
+              m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
+    if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
+    fsm[i] = passive - bias[i] + e.fa[i] + m.act_gear[i] * force;
+    asm_[i] = fsm[i];
+    rw.aref_f[i] = -m.fr_B[i] * e.qd[i];
+    rw.side[i] = T(0); rw.aref_l[i] = T(0); rw.D_l[i] = T(0);
+  }
+  if (m.limited_mask) {
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      if (!(m.limited_mask >> i & 1)) continue;
+      T dlo = e.q[i] - m.lim_lo[i], dhi = m.lim_hi[i] - e.q[i];
+      bool lo = dlo < m.lim_margin[i], hi = dhi < m.lim_margin[i];
+      if (lo || hi) {
+        T side = lo ? T(1) : T(-1), pos = lo ? dlo : dhi;
+        T imp = limit_impedance(m.lim_imp[i], pos, m.lim_margin[i]);
+        T R = max_(T(MJ_MINVAL), (T(1) - imp) * m.lim_invw[i] / imp);
+        rw.side[i] = side;
+        rw.D_l[i] = T(1) / R;
+        rw.aref_l[i] = -m.lim_B[i] * (side * e.qd[i]) - m.lim_K[i] * imp * (pos - m.lim_margin[i]);
+        rw.anylim = true;
+      }
+    }
+  }
+  if (rw.anylim) { e.flags |= SO101_FLAG_LIMIT; cnt.limsteps++; }
+  const bool constrained = m.nfriction != 0 || rw.anylim;
+
+  __syncthreads();   // (A) wait for the geometry and lookout warps
+  if (trip) e.flags |= x.trip[lane];
+  if (want_site) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) site[c] = x.site[c][lane];
+  }
+#pragma unroll
+  for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
+  T Ls[15], Dinv[NV];
+#pragma unroll
+  for (int i = 0; i < 15; i++) Ls[i] = x.L1[i][lane];
+#pragma unroll
+  for (int i = 0; i < NV; i++) Dinv[i] = x.D1inv[i][lane];
+  ldl6_solve(Ls, Dinv, asm_);
+
+  T a[NV], Ma[NV], qc[NV], hd[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); hd[i] = T(0); }
+  if (constrained) {
+    T cost;
+    if (!rw.anylim) {   // prox start (see physics_step)
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        const T Mii = M[tri(i, i)], as = asm_[i], ar = rw.aref_f[i];
+        const T aq = (Mii * as + m.fr_D[i] * ar) * rcp_(Mii + m.fr_D[i]);
+        const T df = m.fr_f[i] * rcp_(Mii);
+        const T ap = as - df, an = as + df;
+        T ai;
+        if (abs_(aq - ar) < m.fr_Rf[i]) ai = aq;
+        else if (ap - ar >= m.fr_Rf[i]) ai = ap;
+        else if (an - ar <= -m.fr_Rf[i]) ai = an;
+        else ai = ar + copysign_(m.fr_Rf[i], as - ar);
+        a[i] = ai;
+      }
+      symv6(M, a, Ma);
+      cost = cost_update(m, rw, a, Ma, fsm, asm_, qc, hd);
+    } else {            // MuJoCo's warm start when a limit row is active
+      T cost0 = T(0);
+      cost = T(0);
+#pragma unroll 1
+      for (int c = 0; c < 2; c++) {
+        T ca[NV], cMa[NV], cqc[NV], chd[NV];
+#pragma unroll
+        for (int i = 0; i < NV; i++) ca[i] = c ? asm_[i] : e.warm[i];
+        symv6(M, ca, cMa);
+        T cc = cost_update(m, rw, ca, cMa, fsm, asm_, cqc, chd);
+        if (c == 0 || cost0 > cc) {
+#pragma unroll
+          for (int i = 0; i < NV; i++) { a[i] = ca[i]; Ma[i] = cMa[i]; qc[i] = cqc[i]; hd[i] = chd[i]; }
+          cost = cc;
+        }
+        if (c == 0) cost0 = cc;
+      }
+    }
+    int iter = 0;
+    while (iter < m.iterations) {
+      T sr[NV], Mv[NV];
+#pragma unroll
+      for (int i = 0; i < NV; i++) sr[i] = Ma[i] - fsm[i] - qc[i];
+      {
+        T A[21];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] = M[i];
+#pragma unroll
+        for (int i = 0; i < NV; i++) A[tri(i, i)] += hd[i];
+        ldl6_factor_solve(A, sr);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; i++) sr[i] = -sr[i];
+      T alpha = line_search(m, rw, M, a, Ma, fsm, sr, Mv, cnt.lsevals);
+      if (alpha == T(0)) break;
+#pragma unroll
+      for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
+      T oldcost = cost;
+      cost = cost_update(m, rw, a, Ma, fsm, asm_, qc, hd);
+      T gg = T(0), nn = T(0);
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        T g = Ma[i] - fsm[i] - qc[i];
+        gg += g * g;
+        if (Noise<T>::on) nn += fsm[i] * fsm[i] + qc[i] * qc[i];
+      }
+      T improvement = m.scale * (oldcost - cost);
+      T gradnorm = m.scale * sqrt_(gg);
+      T tol_i = m.tolerance, tol_g = m.tolerance;
+      if (Noise<T>::on) {
+        tol_i += T(Noise<T>::eps) * m.scale * abs_(cost);
+        tol_g += T(Noise<T>::eps) * m.scale * sqrt_(nn);
+      }
+      iter++;
+      if (improvement < tol_i || gradnorm < tol_g) break;
+    }
+    cnt.newton += iter;
+    if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
+  }
+  // mj_checkAcc, mj_Euler
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < NV; i++) bad |= bad_(a[i]);
+  if (bad) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
+    e.time = T(0);
+    e.flags |= SO101_FLAG_BADSTATE;
+  } else {
+    T acc[NV];
+    if (m.any_damping) {
+#pragma unroll
+      for (int i = 0; i < 15; i++) Ls[i] = x.L2[i][lane];
+#pragma unroll
+      for (int i = 0; i < NV; i++) { Dinv[i] = x.D2inv[i][lane]; acc[i] = fsm[i] + qc[i]; }
+      ldl6_solve(Ls, Dinv, acc);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; i++) acc[i] = a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      e.qd[i] += m.h * acc[i];
+      e.q[i] += m.h * e.qd[i];
+      e.warm[i] = a[i];
+    }
+    e.time += m.h;
+  }
+  cnt.steps++;
+#pragma unroll
+  for (int i = 0; i < NV; i++) { x.q[i][lane] = e.q[i]; x.qd[i][lane] = e.qd[i]; }
+  __syncthreads();   // (B) new state published
 }
 
 }  // namespace so101

@@ -387,3 +387,25 @@ def test_reference_published_eval_metric_reproduced_on_gpu(tables_v, dtype):
     mae /= 200
     print(f"{dtype}: open-loop 200-step MAE of the reference's trained model on GPU data = {mae:.3e} (published 6.84e-3)")
     assert 5.5e-3 < mae < 8.5e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# small batches run the three-warp "team" kernels (so101_physics.cuh, SplitXch): same bits as the one-warp kernels,
+# so the batch size (and with it the shard a rank holds) never changes a trajectory
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("n", [1, 300, 4096])
+def test_split_team_is_bitwise_identical(tables_v, monkeypatch, dtype, n):
+    out = {}
+    for split in ("0", "1"):
+        monkeypatch.setenv("SO101_SPLIT", split)
+        env = _vec(tables_v, n, dtype)
+        rows = env.rollout(60, "random", seed=11, env_offset=5)          # 600 chaotic physics steps
+        q, v, w = env.get_state()
+        obs = env.step(torch.full((n, 5), 0.3, dtype=env.torch_dtype, device=env.device))   # k_step path
+        U = torch.rand((7, 5, n), dtype=env.torch_dtype, device=env.device, generator=torch.Generator(env.device).manual_seed(3)) - 0.5
+        X = env.shoot(np.concatenate([tables_v.key_qpos[:], np.zeros(12)]), U)               # k_shoot path
+        out[split] = [t.clone() for t in (rows, q, v, w, obs if torch.is_tensor(obs) else obs[0], X, env.flags())]
+        assert env.stats()["physics_steps"] == n * (60 + 1 + 7) * 10
+    for a, b in zip(out["0"], out["1"]):
+        assert torch.equal(a, b)
