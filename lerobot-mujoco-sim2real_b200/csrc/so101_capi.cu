@@ -266,8 +266,9 @@ k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* 
   T M[21], bias[NV], site[3];
   uint32_t fl = 0;
   T sn[NV], cs[NV];
-  joint_sincos(m, e.q, sn, cs);
-  smooth_dynamics<T, false>(m, e.q, e.qd, sn, cs, M, bias, true, site, false, fl);
+  joint_sincos_range(m, e.q, 1, sn, cs, 1, 0, NV);
+  rnea_bias(m, sn, cs, 1, e.qd, 1, bias);
+  site_from_trig(m, sn, cs, 1, site);
   if (obs) {
 #pragma unroll
     for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];

@@ -98,32 +98,51 @@ template <typename T> SO101_DEV bool bad_(T x) { return !(x <= T(MJ_MAXVAL) && x
 __host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // ------------------------------------------------------------------------------------------
+// Rounding-explicit arithmetic for the smooth dynamics.  The same link bodies are compiled in several
+// contexts (fully unrolled in the one-warp kernels, rolled over the link index in the team kernels);
+// every multiply-add below is written as an explicit fma / mul / add intrinsic, so that where the
+// compiler contracts is not a per-context choice and all kernels produce the same bits.
+// ------------------------------------------------------------------------------------------
+SO101_DEV double fma_(double a, double b, double c) { return __fma_rn(a, b, c); }
+SO101_DEV float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+SO101_DEV double mul_(double a, double b) { return __dmul_rn(a, b); }
+SO101_DEV float mul_(float a, float b) { return __fmul_rn(a, b); }
+SO101_DEV double add_(double a, double b) { return __dadd_rn(a, b); }
+SO101_DEV float add_(float a, float b) { return __fadd_rn(a, b); }
+SO101_DEV double sub_(double a, double b) { return __dsub_rn(a, b); }
+SO101_DEV float sub_(float a, float b) { return __fsub_rn(a, b); }
+template <typename T> SO101_DEV T dot3_(T a0, T b0, T a1, T b1, T a2, T b2) {   // (a0 b0 + a1 b1) + a2 b2
+  return fma_(a2, b2, fma_(a1, b1, mul_(a0, b0)));
+}
+template <typename T> SO101_DEV T det2_(T a, T b, T c, T d) { return fma_(-c, d, mul_(a, b)); }   // a b - c d
+
+// ------------------------------------------------------------------------------------------
 // 3-vector / rotation helpers.  R (row-major 3x3) maps child coordinates to parent coordinates.
 // ------------------------------------------------------------------------------------------
 template <typename T> SO101_DEV void make_R(const T (&E)[9], T c, T s, T (&R)[9]) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    R[3 * i + 0] = c * E[3 * i] + s * E[3 * i + 1];
-    R[3 * i + 1] = c * E[3 * i + 1] - s * E[3 * i];
+    R[3 * i + 0] = fma_(s, E[3 * i + 1], mul_(c, E[3 * i]));
+    R[3 * i + 1] = det2_(c, E[3 * i + 1], s, E[3 * i]);
     R[3 * i + 2] = E[3 * i + 2];
   }
 }
 template <typename T> SO101_DEV void rot(const T (&R)[9], const T* v, T* o) {  // o = R v
-  T a = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
-  T b = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
-  T c = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  T a = dot3_(R[0], v[0], R[1], v[1], R[2], v[2]);
+  T b = dot3_(R[3], v[0], R[4], v[1], R[5], v[2]);
+  T c = dot3_(R[6], v[0], R[7], v[1], R[8], v[2]);
   o[0] = a; o[1] = b; o[2] = c;
 }
 template <typename T> SO101_DEV void rotT(const T (&R)[9], const T* v, T* o) {  // o = R^T v
-  T a = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
-  T b = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
-  T c = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  T a = dot3_(R[0], v[0], R[3], v[1], R[6], v[2]);
+  T b = dot3_(R[1], v[0], R[4], v[1], R[7], v[2]);
+  T c = dot3_(R[2], v[0], R[5], v[1], R[8], v[2]);
   o[0] = a; o[1] = b; o[2] = c;
 }
 // spatial motion vector parent -> child: ang' = R^T ang, lin' = R^T (lin + ang x r)
 template <typename T> SO101_DEV void xmotion(const T (&R)[9], const T (&r)[3], const T (&p)[6], T (&c)[6]) {
-  T u[3] = {p[3] + (p[1] * r[2] - p[2] * r[1]), p[4] + (p[2] * r[0] - p[0] * r[2]),
-            p[5] + (p[0] * r[1] - p[1] * r[0])};
+  T u[3] = {add_(p[3], det2_(p[1], r[2], p[2], r[1])), add_(p[4], det2_(p[2], r[0], p[0], r[2])),
+            add_(p[5], det2_(p[0], r[1], p[1], r[0]))};
   rotT(R, &p[0], &c[0]);
   rotT(R, u, &c[3]);
 }
@@ -132,19 +151,19 @@ template <typename T> SO101_DEV void xforce(const T (&R)[9], const T (&r)[3], co
   T a[3], l[3];
   rot(R, &c[0], a);
   rot(R, &c[3], l);
-  p[0] = a[0] + (r[1] * l[2] - r[2] * l[1]);
-  p[1] = a[1] + (r[2] * l[0] - r[0] * l[2]);
-  p[2] = a[2] + (r[0] * l[1] - r[1] * l[0]);
+  p[0] = add_(a[0], det2_(r[1], l[2], r[2], l[1]));
+  p[1] = add_(a[1], det2_(r[2], l[0], r[0], l[2]));
+  p[2] = add_(a[2], det2_(r[0], l[1], r[1], l[0]));
   p[3] = l[0]; p[4] = l[1]; p[5] = l[2];
 }
 // 10-parameter spatial inertia times motion vector (same layout as mju_mulInertVec)
 template <typename T> SO101_DEV void inert_mul(const T (&i)[10], const T (&v)[6], T (&o)[6]) {
-  o[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
-  o[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
-  o[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
-  o[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
-  o[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
-  o[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+  o[0] = fma_(i[7], v[5], fma_(-i[8], v[4], dot3_(i[0], v[0], i[3], v[1], i[4], v[2])));
+  o[1] = fma_(-i[6], v[5], fma_(i[8], v[3], dot3_(i[3], v[0], i[1], v[1], i[5], v[2])));
+  o[2] = fma_(i[6], v[4], fma_(-i[7], v[3], dot3_(i[4], v[0], i[5], v[1], i[2], v[2])));
+  o[3] = fma_(i[9], v[3], det2_(i[8], v[1], i[7], v[2]));
+  o[4] = fma_(i[9], v[4], det2_(i[6], v[2], i[8], v[0]));
+  o[5] = fma_(i[9], v[5], det2_(i[7], v[0], i[6], v[1]));
 }
 // composite inertia child -> parent, accumulated into the parent's
 template <typename T> SO101_DEV void xinertia_add(const T (&R)[9], const T (&r)[3], const T (&c)[10], T (&p)[10]) {
@@ -152,32 +171,75 @@ template <typename T> SO101_DEV void xinertia_add(const T (&R)[9], const T (&r)[
   T A[9];  // A = R * I
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    A[3 * i + 0] = R[3 * i] * c[0] + R[3 * i + 1] * c[3] + R[3 * i + 2] * c[4];
-    A[3 * i + 1] = R[3 * i] * c[3] + R[3 * i + 1] * c[1] + R[3 * i + 2] * c[5];
-    A[3 * i + 2] = R[3 * i] * c[4] + R[3 * i + 1] * c[5] + R[3 * i + 2] * c[2];
+    A[3 * i + 0] = dot3_(R[3 * i], c[0], R[3 * i + 1], c[3], R[3 * i + 2], c[4]);
+    A[3 * i + 1] = dot3_(R[3 * i], c[3], R[3 * i + 1], c[1], R[3 * i + 2], c[5]);
+    A[3 * i + 2] = dot3_(R[3 * i], c[4], R[3 * i + 1], c[5], R[3 * i + 2], c[2]);
   }
-  T Sxx = A[0] * R[0] + A[1] * R[1] + A[2] * R[2];
-  T Syy = A[3] * R[3] + A[4] * R[4] + A[5] * R[5];
-  T Szz = A[6] * R[6] + A[7] * R[7] + A[8] * R[8];
-  T Sxy = A[0] * R[3] + A[1] * R[4] + A[2] * R[5];
-  T Sxz = A[0] * R[6] + A[1] * R[7] + A[2] * R[8];
-  T Syz = A[3] * R[6] + A[4] * R[7] + A[5] * R[8];
+  T Sxx = dot3_(A[0], R[0], A[1], R[1], A[2], R[2]);
+  T Syy = dot3_(A[3], R[3], A[4], R[4], A[5], R[5]);
+  T Szz = dot3_(A[6], R[6], A[7], R[7], A[8], R[8]);
+  T Sxy = dot3_(A[0], R[3], A[1], R[4], A[2], R[5]);
+  T Sxz = dot3_(A[0], R[6], A[1], R[7], A[2], R[8]);
+  T Syz = dot3_(A[3], R[6], A[4], R[7], A[5], R[8]);
   T h[3];
   rot(R, &c[6], h);
   // shift the reference point by r: I += 2(u.r)1 - (r u' + u r'), u = h + m r / 2
-  T hm = T(0.5) * c[9];
-  T u0 = h[0] + hm * r[0], u1 = h[1] + hm * r[1], u2 = h[2] + hm * r[2];
-  T d0 = u0 * r[0], d1 = u1 * r[1], d2 = u2 * r[2];
-  p[0] += Sxx + T(2) * (d1 + d2);
-  p[1] += Syy + T(2) * (d0 + d2);
-  p[2] += Szz + T(2) * (d0 + d1);
-  p[3] += Sxy - (r[0] * u1 + u0 * r[1]);
-  p[4] += Sxz - (r[0] * u2 + u0 * r[2]);
-  p[5] += Syz - (r[1] * u2 + u1 * r[2]);
-  p[6] += h[0] + c[9] * r[0];
-  p[7] += h[1] + c[9] * r[1];
-  p[8] += h[2] + c[9] * r[2];
-  p[9] += c[9];
+  T hm = mul_(T(0.5), c[9]);
+  T u0 = fma_(hm, r[0], h[0]), u1 = fma_(hm, r[1], h[1]), u2 = fma_(hm, r[2], h[2]);
+  T d0 = mul_(u0, r[0]), d1 = mul_(u1, r[1]), d2 = mul_(u2, r[2]);
+  p[0] = add_(p[0], fma_(T(2), add_(d1, d2), Sxx));
+  p[1] = add_(p[1], fma_(T(2), add_(d0, d2), Syy));
+  p[2] = add_(p[2], fma_(T(2), add_(d0, d1), Szz));
+  p[3] = add_(p[3], sub_(Sxy, fma_(u0, r[1], mul_(r[0], u1))));
+  p[4] = add_(p[4], sub_(Sxz, fma_(u0, r[2], mul_(r[0], u2))));
+  p[5] = add_(p[5], sub_(Syz, fma_(u1, r[2], mul_(r[1], u2))));
+  p[6] = add_(p[6], fma_(c[9], r[0], h[0]));
+  p[7] = add_(p[7], fma_(c[9], r[1], h[1]));
+  p[8] = add_(p[8], fma_(c[9], r[2], h[2]));
+  p[9] = add_(p[9], c[9]);
+}
+// RNEA forward step of one link: v, a (parent frame, in/out: this link's frame), joint rate w -> link force f
+template <typename T>
+SO101_DEV void rnea_link(const T (&R)[9], const T (&r)[3], const T (&I)[10], T w, T (&v)[6], T (&a)[6], T* f) {
+  T vc[6], ac[6];
+  xmotion(R, r, v, vc);
+  xmotion(R, r, a, ac);
+  vc[2] = add_(vc[2], w);
+  // a += v x (S qd), S = [0 0 1 | 0 0 0]
+  ac[0] = fma_(w, vc[1], ac[0]);
+  ac[1] = fma_(-w, vc[0], ac[1]);
+  ac[3] = fma_(w, vc[4], ac[3]);
+  ac[4] = fma_(-w, vc[3], ac[4]);
+  T Ia[6], Iv[6];
+  inert_mul(I, ac, Ia);
+  inert_mul(I, vc, Iv);
+  // f = I a + v x* (I v)
+  f[0] = add_(add_(Ia[0], det2_(vc[1], Iv[2], vc[2], Iv[1])), det2_(vc[4], Iv[5], vc[5], Iv[4]));
+  f[1] = add_(add_(Ia[1], det2_(vc[2], Iv[0], vc[0], Iv[2])), det2_(vc[5], Iv[3], vc[3], Iv[5]));
+  f[2] = add_(add_(Ia[2], det2_(vc[0], Iv[1], vc[1], Iv[0])), det2_(vc[3], Iv[4], vc[4], Iv[3]));
+  f[3] = add_(Ia[3], det2_(vc[1], Iv[5], vc[2], Iv[4]));
+  f[4] = add_(Ia[4], det2_(vc[2], Iv[3], vc[0], Iv[5]));
+  f[5] = add_(Ia[5], det2_(vc[0], Iv[4], vc[1], Iv[3]));
+#pragma unroll
+  for (int c = 0; c < 6; c++) { v[c] = vc[c]; a[c] = ac[c]; }
+}
+// contact tripwire of one link: zw = world z axis in the link frame, zo = world height of its origin
+template <typename T, typename BOX>
+SO101_DEV void tripwire_box(const BOX& m, int k, int b, const T (&zw)[3], T zo, uint32_t& flags) {
+  T zc0 = add_(zo, dot3_(zw[0], m.trip_c[k][b][0], zw[1], m.trip_c[k][b][1], zw[2], m.trip_c[k][b][2]));
+  if (sub_(zc0, m.trip_rad[k][b]) >= m.trip_z) return;   // bounding sphere clears the plane: box does too
+  T ext = T(0);
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++)
+    ext = fma_(abs_(dot3_(zw[0], m.trip_ax[k][b][3 * ax], zw[1], m.trip_ax[k][b][3 * ax + 1], zw[2],
+                          m.trip_ax[k][b][3 * ax + 2])), m.trip_half[k][b][ax], ext);
+  if (sub_(zc0, ext) < m.trip_z) flags |= SO101_FLAG_TRIP_TABLE;
+}
+template <typename T> SO101_DEV void tripwire_frame(const T (&R)[9], const T (&r)[3], T (&zw)[3], T& zo) {
+  zo = add_(zo, dot3_(zw[0], r[0], zw[1], r[1], zw[2], r[2]));
+  T zc[3];
+  rotT(R, zw, zc);
+  zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -293,25 +355,13 @@ template <typename T> SO101_DEV void joint_sincos(const DevModel<T>& m, const T 
   for (int k = 0; k < NV; k++) sincos_(q[k] - m.qpos0[k], &sn[k], &cs[k]);
 }
 
-// contact tripwire of link k: zw = world z axis in the frame of link k, zo = world height of its origin
+// contact tripwire of link k, unrolled form
 template <typename T>
 SO101_DEV void tripwire_link(const DevModel<T>& m, int k, const T (&R)[9], T qk, T (&zw)[3], T& zo, uint32_t& flags) {
-  zo += zw[0] * m.r[k][0] + zw[1] * m.r[k][1] + zw[2] * m.r[k][2];
-  T zc[3];
-  rotT(R, zw, zc);
-  zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
+  tripwire_frame(R, m.r[k], zw, zo);
 #pragma unroll
   for (int b = 0; b < TRIP_PER_LINK; b++) {
-    if (m.trip_n[k] > b) {
-      T zc0 = zo + zw[0] * m.trip_c[k][b][0] + zw[1] * m.trip_c[k][b][1] + zw[2] * m.trip_c[k][b][2];
-      if (zc0 - m.trip_rad[k][b] >= m.trip_z) continue;   // bounding sphere clears the plane: box does too
-      T ext = T(0);
-#pragma unroll
-      for (int ax = 0; ax < 3; ax++)
-        ext += abs_(zw[0] * m.trip_ax[k][b][3 * ax] + zw[1] * m.trip_ax[k][b][3 * ax + 1] +
-                    zw[2] * m.trip_ax[k][b][3 * ax + 2]) * m.trip_half[k][b][ax];
-      if (zc0 - ext < m.trip_z) flags |= SO101_FLAG_TRIP_TABLE;
-    }
+    if (m.trip_n[k] > b) tripwire_box(m, k, b, zw, zo, flags);
   }
   if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
 }
@@ -329,28 +379,9 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
     T zo = T(0);                   // world height of the current frame origin
 #pragma unroll
     for (int k = 0; k < NV; k++) {
-      T R[9], vc[6], ac[6];
+      T R[9];
       make_R(m.E[k], cs[k], sn[k], R);
-      xmotion(R, m.r[k], v, vc);
-      xmotion(R, m.r[k], a, ac);
-      vc[2] += qd[k];
-      // a += v x (S qd), S = [0 0 1 | 0 0 0]
-      ac[0] += qd[k] * vc[1];
-      ac[1] -= qd[k] * vc[0];
-      ac[3] += qd[k] * vc[4];
-      ac[4] -= qd[k] * vc[3];
-      T Ia[6], Iv[6];
-      inert_mul(m.I[k], ac, Ia);
-      inert_mul(m.I[k], vc, Iv);
-      // f = I a + v x* (I v)
-      f[k][0] = Ia[0] + (vc[1] * Iv[2] - vc[2] * Iv[1]) + (vc[4] * Iv[5] - vc[5] * Iv[4]);
-      f[k][1] = Ia[1] + (vc[2] * Iv[0] - vc[0] * Iv[2]) + (vc[5] * Iv[3] - vc[3] * Iv[5]);
-      f[k][2] = Ia[2] + (vc[0] * Iv[1] - vc[1] * Iv[0]) + (vc[3] * Iv[4] - vc[4] * Iv[3]);
-      f[k][3] = Ia[3] + (vc[1] * Iv[5] - vc[2] * Iv[4]);
-      f[k][4] = Ia[4] + (vc[2] * Iv[3] - vc[0] * Iv[5]);
-      f[k][5] = Ia[5] + (vc[0] * Iv[4] - vc[1] * Iv[3]);
-#pragma unroll
-      for (int c = 0; c < 6; c++) { v[c] = vc[c]; a[c] = ac[c]; }
+      rnea_link(R, m.r[k], m.I[k], qd[k], v, a, f[k]);
       if (trip) tripwire_link(m, k, R, q[k], zw, zo, flags);
     }
   }
@@ -364,15 +395,15 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
   for (int k = NV - 1; k >= 0; k--) {
     if (WANT_BIAS) {
 #pragma unroll
-      for (int c = 0; c < 6; c++) fs[c] += f[k][c];
+      for (int c = 0; c < 6; c++) fs[c] = add_(fs[c], f[k][c]);
       bias[k] = fs[2];
     }
     if (WANT_M) {
 #pragma unroll
-      for (int c = 0; c < 10; c++) Ic[c] += m.I[k][c];
+      for (int c = 0; c < 10; c++) Ic[c] = add_(Ic[c], m.I[k][c]);
       F[k][0] = Ic[4]; F[k][1] = Ic[5]; F[k][2] = Ic[2];
       F[k][3] = -Ic[7]; F[k][4] = Ic[6]; F[k][5] = T(0);
-      M[tri(k, k)] = Ic[2] + m.armature[k];
+      M[tri(k, k)] = add_(Ic[2], m.armature[k]);
     }
     if (want_site && k == m.site_link) { p[0] = m.site[0]; p[1] = m.site[1]; p[2] = m.site[2]; }
     if ((k > 0 && (WANT_M || WANT_BIAS)) || want_site) {
@@ -381,7 +412,7 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
       if (want_site && k <= m.site_link) {
         T o[3];
         rot(R, p, o);
-        p[0] = o[0] + m.r[k][0]; p[1] = o[1] + m.r[k][1]; p[2] = o[2] + m.r[k][2];
+        p[0] = add_(o[0], m.r[k][0]); p[1] = add_(o[1], m.r[k][1]); p[2] = add_(o[2], m.r[k][2]);
       }
       if (k > 0) {
         T t6[6];
@@ -409,6 +440,131 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
   if (want_site) { site[0] = p[0]; site[1] = p[1]; site[2] = p[2]; }
 }
 
+// ------------------------------------------------------------------------------------------
+// Compact ("rolled") smooth dynamics.  The unrolled smooth_dynamics above is ~4 k SASS instructions (64 KB);
+// a physics step then exceeds the 32 KB L1.5 instruction cache several times over and every block streams
+// its code from L2 once per step.  ncu: with 128 blocks doing that `stall_no_instruction` is 2.8 per issue
+// (0.6 with 16 blocks), i.e. L2 instruction fetch is the shared bottleneck of the small-batch configuration,
+// and it costs the large-batch one a barrier per phase to keep warps on one fetch stream.
+// These versions loop over the links with ONE copy of each link body: link constants come from the
+// constant bank through uniform loads (the link index is warp-uniform), per-thread link arrays (sin/cos,
+// link forces f_k) are indexed dynamically (local memory or shared memory, L1 resident).
+// `st` = element stride of the per-thread arrays (1: thread-local array, 32: shared memory [k][lane]).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+SO101_DEV void joint_sincos_range(const DevModel<T>& m, const T* q, int qst, T* sn, T* cs, int st, int k0, int k1) {
+#pragma unroll 1
+  for (int k = k0; k < k1; k++) {
+    T s_, c_;
+    sincos_(q[k * qst] - m.qpos0[k], &s_, &c_);
+    sn[k * st] = s_; cs[k * st] = c_;
+  }
+}
+
+// qfrc_bias by RNEA (flg_acc = 0): forward pass over the links (velocity, bias acceleration, link force),
+// backward pass accumulating the forces down the chain
+template <typename T>
+SO101_DEV void rnea_bias(const DevModel<T>& m, const T* sn, const T* cs, int st, const T* qd, int qst, T* bias) {
+  T f[NV][6];
+  {
+    T v[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+    T a[6] = {T(0), T(0), T(0), m.accg[0], m.accg[1], m.accg[2]};
+#pragma unroll 1
+    for (int k = 0; k < NV; k++) {
+      T R[9];
+      make_R(m.E[k], cs[k * st], sn[k * st], R);
+      rnea_link(R, m.r[k], m.I[k], qd[k * qst], v, a, f[k]);
+    }
+  }
+  T fs[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // accumulated force in the current frame
+#pragma unroll 1
+  for (int k = NV - 1; k >= 0; k--) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) fs[c] = add_(fs[c], f[k][c]);
+    bias[k] = fs[2];
+    if (k > 0) {
+      T R[9], t6[6];
+      make_R(m.E[k], cs[k * st], sn[k * st], R);
+      xforce(R, m.r[k], fs, t6);
+#pragma unroll
+      for (int c = 0; c < 6; c++) fs[c] = t6[c];
+    }
+  }
+}
+
+// mass matrix by CRBA + armature, packed lower triangle written to M[tri(i,j) * mst].  The link loop is
+// rolled; the column loop is unrolled under warp-uniform branches (F_j stay in registers, no work for j < k).
+template <typename T>
+SO101_DEV void crba_mass(const DevModel<T>& m, const T* sn, const T* cs, int st, T* M, int mst) {
+  T Ic[10] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+  T F[NV][6];                                        // F[j] = Ic_j * S propagated to the current frame
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) F[j][c] = T(0);
+  }
+#pragma unroll 1
+  for (int k = NV - 1; k >= 0; k--) {
+#pragma unroll
+    for (int c = 0; c < 10; c++) Ic[c] = add_(Ic[c], m.I[k][c]);
+    M[tri(k, k) * mst] = add_(Ic[2], m.armature[k]);
+    if (k > 0) {
+      T R[9];
+      make_R(m.E[k], cs[k * st], sn[k * st], R);
+#pragma unroll
+      for (int j = NV - 1; j >= 1; j--) {
+        if (j >= k) {                                // warp-uniform
+          if (j == k) {
+            F[j][0] = Ic[4]; F[j][1] = Ic[5]; F[j][2] = Ic[2];
+            F[j][3] = -Ic[7]; F[j][4] = Ic[6]; F[j][5] = T(0);
+          }
+          T t6[6];
+          xforce(R, m.r[k], F[j], t6);
+#pragma unroll
+          for (int c = 0; c < 6; c++) F[j][c] = t6[c];
+          M[(j * (j + 1) / 2 + k - 1) * mst] = t6[2];
+        }
+      }
+      T Ip[10] = {T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0), T(0)};
+      xinertia_add(R, m.r[k], Ic, Ip);
+#pragma unroll
+      for (int c = 0; c < 10; c++) Ic[c] = Ip[c];
+    }
+  }
+}
+
+// contact tripwire over all links (flags only)
+template <typename T>
+SO101_DEV void tripwire_all(const DevModel<T>& m, const T* sn, const T* cs, int st, const T* q, int qst,
+                            uint32_t& flags) {
+  T zw[3] = {T(0), T(0), T(1)};  // world z axis in the current frame
+  T zo = T(0);                   // world height of the current frame origin
+#pragma unroll 1
+  for (int k = 0; k < NV; k++) {
+    T R[9];
+    make_R(m.E[k], cs[k * st], sn[k * st], R);
+    tripwire_frame(R, m.r[k], zw, zo);
+#pragma unroll 1
+    for (int b = 0; b < m.trip_n[k]; b++) tripwire_box(m, k, b, zw, zo, flags);
+    const T qk = q[k * qst];
+    if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
+  }
+}
+
+// world position of the observation site from the joint sin/cos
+template <typename T>
+SO101_DEV void site_from_trig(const DevModel<T>& m, const T* sn, const T* cs, int st, T (&site)[3]) {
+  T p[3] = {m.site[0], m.site[1], m.site[2]};
+#pragma unroll 1
+  for (int k = m.site_link; k >= 0; k--) {
+    T R[9], o[3];
+    make_R(m.E[k], cs[k * st], sn[k * st], R);
+    rot(R, p, o);
+    p[0] = add_(o[0], m.r[k][0]); p[1] = add_(o[1], m.r[k][1]); p[2] = add_(o[2], m.r[k][2]);
+  }
+  site[0] = p[0]; site[1] = p[1]; site[2] = p[2];
+}
+
 // forward kinematics of the observation site only (reset / mj_forward observations)
 template <typename T> SO101_DEV void site_fk(const DevModel<T>& m, const T (&q)[NV], T (&site)[3]) {
   T p[3] = {T(0), T(0), T(0)};
@@ -420,7 +576,7 @@ template <typename T> SO101_DEV void site_fk(const DevModel<T>& m, const T (&q)[
       sincos_(q[k] - m.qpos0[k], &s, &c);
       make_R(m.E[k], c, s, R);
       rot(R, p, o);
-      p[0] = o[0] + m.r[k][0]; p[1] = o[1] + m.r[k][1]; p[2] = o[2] + m.r[k][2];
+      p[0] = add_(o[0], m.r[k][0]); p[1] = add_(o[1], m.r[k][1]); p[2] = add_(o[2], m.r[k][2]);
     }
   }
   site[0] = p[0]; site[1] = p[1]; site[2] = p[2];
@@ -843,10 +999,9 @@ template <typename T> SO101_DEV bool team_check_state(const DevModel<T>& m, T (&
   }
   return bad;
 }
-// sin/cos of the two joints of this role -> shared, barrier (S), all six back
+// sin/cos of the two joints of this role -> shared, barrier (S)
 template <typename T>
-SO101_DEV void team_sincos(const DevModel<T>& m, SplitXch<T>& x, int lane, int role, const T (&q)[NV], T (&sn)[NV],
-                           T (&cs)[NV]) {
+SO101_DEV void team_sincos(const DevModel<T>& m, SplitXch<T>& x, int lane, int role, const T (&q)[NV]) {
 #pragma unroll
   for (int r = 0; r < TEAM_WARPS; r++) {
     if (r == role) {
@@ -859,24 +1014,19 @@ SO101_DEV void team_sincos(const DevModel<T>& m, SplitXch<T>& x, int lane, int r
     }
   }
   __syncthreads();   // (S)
-#pragma unroll
-  for (int k = 0; k < NV; k++) { sn[k] = x.sn[k][lane]; cs[k] = x.cs[k][lane]; }
 }
 
 // geometry warp: M(q) and the two factorisations -> shared memory
 template <typename T>
 SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV]) {
   team_check_state(m, q, qd);
-  T sn[NV], cs[NV];
-  team_sincos(m, x, lane, 1, q, sn, cs);
-  T M[21], bias[NV], site[3];
-  uint32_t fl = 0;
-  smooth_dynamics<T, true, false>(m, q, qd, sn, cs, M, bias, false, site, false, fl);
-  T zero[NV], hB[NV], Ls[15], Dinv[NV];
+  team_sincos(m, x, lane, 1, q);
+  crba_mass(m, &x.sn[0][lane], &x.cs[0][lane], 32, &x.M[0][lane], 32);
+  T M[21], zero[NV], hB[NV], Ls[15], Dinv[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) { zero[i] = T(0); hB[i] = m.h * m.damping[i]; }
 #pragma unroll
-  for (int i = 0; i < 21; i++) x.M[i][lane] = M[i];
+  for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
   ldl6_factor(M, zero, Ls, Dinv);
 #pragma unroll
   for (int i = 0; i < 15; i++) x.L1[i][lane] = Ls[i];
@@ -898,32 +1048,18 @@ template <typename T>
 SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
                                   bool want_site, bool trip) {
   team_check_state(m, q, qd);
-  T sn[NV], cs[NV];
-  team_sincos(m, x, lane, 2, q, sn, cs);
+  team_sincos(m, x, lane, 2, q);
   uint32_t fl = 0;
   if (trip) {
-    T zw[3] = {T(0), T(0), T(1)};
-    T zo = T(0);
+    T lq[NV];
 #pragma unroll
-    for (int k = 0; k < NV; k++) {
-      T R[9];
-      make_R(m.E[k], cs[k], sn[k], R);
-      tripwire_link(m, k, R, q[k], zw, zo, fl);
-    }
+    for (int i = 0; i < NV; i++) lq[i] = q[i];
+    tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl);
   }
   x.trip[lane] = fl;
   if (want_site) {
-    T p[3] = {T(0), T(0), T(0)};
-#pragma unroll
-    for (int k = NV - 1; k >= 0; k--) {
-      if (k == m.site_link) { p[0] = m.site[0]; p[1] = m.site[1]; p[2] = m.site[2]; }
-      if (k <= m.site_link) {
-        T R[9], o[3];
-        make_R(m.E[k], cs[k], sn[k], R);
-        rot(R, p, o);
-        p[0] = o[0] + m.r[k][0]; p[1] = o[1] + m.r[k][1]; p[2] = o[2] + m.r[k][2];
-      }
-    }
+    T p[3];
+    site_from_trig(m, &x.sn[0][lane], &x.cs[0][lane], 32, p);
 #pragma unroll
     for (int c = 0; c < 3; c++) x.site[c][lane] = p[c];
   }
@@ -945,10 +1081,11 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
   T M[21], bias[NV];
   {
-    T sn[NV], cs[NV];
-    team_sincos(m, x, lane, 0, e.q, sn, cs);
-    uint32_t fl = 0;
-    smooth_dynamics<T, false, true>(m, e.q, e.qd, sn, cs, M, bias, false, site, false, fl);
+    team_sincos(m, x, lane, 0, e.q);
+    T lqd[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) lqd[i] = e.qd[i];
+    rnea_bias(m, &x.sn[0][lane], &x.cs[0][lane], 32, lqd, 1, bias);
   }
   if (gravcomp_capture) {
 #pragma unroll
