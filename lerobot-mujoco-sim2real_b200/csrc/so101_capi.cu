@@ -319,11 +319,13 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
 template <typename T, typename ROW, bool SPLIT>
 __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SO101_LB_BLOCKS)
-k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int Tn, int frame_skip, ROW* rows,
-          uint32_t rflags, unsigned long long* stats) {
+k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
+          ROW* rows, uint32_t rflags, unsigned long long* stats) {
+  // control steps (t0, t1] of a rollout of Tn steps; t0 > 0 continues a previous launch (row t0 is already written,
+  // u_t0 is regenerated: the control stream is a pure function of (seed, env, t))
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
-  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)Tn * frame_skip, frame_skip); return; }
+  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)(t1 - t0) * frame_skip, frame_skip); return; }
   bool active;
   const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   const int64_t env = spec.env_offset + i;
@@ -348,8 +350,8 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   double u[5];
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
 #pragma unroll 1
-  for (int t = 0; t <= Tn; t++) {
-    if (t > 0) {
+  for (int t = t0; t <= t1; t++) {
+    if (t > t0) {
 #pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++)
         step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
@@ -357,7 +359,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
 #pragma unroll
     for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
-    if (rows && active) {
+    if (rows && active && (t > t0 || t0 == 0)) {
       ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
 #pragma unroll
       for (int k = 0; k < 5; k++) row[k] = (ROW)u[k];
@@ -463,6 +465,11 @@ struct So101Batch {
   size_t u_stage_bytes;
   void* rows_stage;   // [n][T+1][13] dataset rows (rollout_host)
   size_t rows_stage_bytes;
+  // rollout_host pipeline: upload / download streams and per-chunk events
+  static constexpr int MAXCHUNK = 4;
+  bool pipe_ready;
+  cudaStream_t s_up, s_down;
+  cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
 };
 
 struct DeviceGuard {
@@ -599,6 +606,12 @@ void so101_batch_destroy(So101Batch* b) {
   cudaFree(b->init_stage);
   cudaFree(b->u_stage);
   cudaFree(b->rows_stage);
+  if (b->pipe_ready) {
+    cudaStreamDestroy(b->s_up);
+    cudaStreamDestroy(b->s_down);
+    for (int c = 0; c < So101Batch::MAXCHUNK; c++) { cudaEventDestroy(b->ev_up[c]); cudaEventDestroy(b->ev_k[c]); }
+    cudaEventDestroy(b->ev_start);
+  }
   delete b;
 }
 
@@ -715,8 +728,8 @@ int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qv
   return SO101_OK;
 }
 
-int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip, void* rows, uint32_t flags,
-                        void* stream) {
+static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t1, int T, int frame_skip, void* rows,
+                         uint32_t flags, void* stream) {
   if (!b || !spec) return fail(SO101_EINVAL, "null argument");
   if (T < 0 || frame_skip < 1) return fail(SO101_EINVAL, "T must be >= 0 and frame_skip >= 1");
   if (spec->kind < SO101_CTRL_RANDOM || spec->kind > SO101_CTRL_TENSOR) return fail(SO101_EINVAL, "bad control kind");
@@ -733,7 +746,7 @@ int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int fra
   if (b->dtype == SO101_F64) {
     StateView<double> v = step_view<double>(b, blk, grid, split);
 #define SO101_ROLL(TT, RR, SS, mdl) \
-  k_rollout<TT, RR, SS><<<grid, blk, 0, st>>>(b->model->mdl, v, ds, T, frame_skip, (RR*)rows, flags, b->stats)
+  k_rollout<TT, RR, SS><<<grid, blk, 0, st>>>(b->model->mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats)
     if (split) { if (r32) SO101_ROLL(double, float, true, d); else SO101_ROLL(double, double, true, d); }
     else { if (r32) SO101_ROLL(double, float, false, d); else SO101_ROLL(double, double, false, d); }
   } else {
@@ -746,12 +759,34 @@ int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int fra
   return SO101_OK;
 }
 
+int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip, void* rows, uint32_t flags,
+                        void* stream) {
+  return rollout_range(b, spec, 0, T, T, frame_skip, rows, flags, stream);
+}
+
 static int grow(void** buf, size_t* have, size_t need) {
   if (*have >= need) return SO101_OK;
   if (*buf) cudaFree(*buf);
   *buf = nullptr; *have = 0;
   CUDA_TRY(cudaMalloc(buf, need));
   *have = need;
+  return SO101_OK;
+}
+
+// Host-buffer rollout, pipelined over time: the rollout is cut into up to 4 chunks of control steps; the control
+// tensor of chunk c+1 is uploaded (stream up) and the rows of chunk c-1 are downloaded (stream down, strided copy into
+// the caller's [N][T+1][13] layout) while chunk c computes on the caller's stream.  Only the first upload and the last
+// download are exposed.
+static int ensure_pipe(So101Batch* b) {
+  if (b->pipe_ready) return SO101_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->s_up, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&b->s_down, cudaStreamNonBlocking));
+  for (int c = 0; c < So101Batch::MAXCHUNK; c++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_up[c], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&b->ev_k[c], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&b->ev_start, cudaEventDisableTiming));
+  b->pipe_ready = true;
   return SO101_OK;
 }
 
@@ -762,15 +797,28 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   DeviceGuard g(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t es = elem_size(b->dtype);
+  const size_t rs = (flags & SO101_ROLL_ROWS_F32) ? sizeof(float) : sizeof(double);
   So101CtrlSpec dspec = *spec;
   int rc;
-  if (spec->kind == SO101_CTRL_TENSOR) {
+  if ((rc = ensure_pipe(b))) return rc;
+  const bool tensor = spec->kind == SO101_CTRL_TENSOR;
+  const size_t ustep = (size_t)SO101_NU_ENV * b->n * es;         // one control step of the tensor
+  if (tensor) {
     if (!spec->u) return fail(SO101_EINVAL, "SO101_CTRL_TENSOR needs spec->u");
-    const size_t ub = (size_t)(T + 1) * SO101_NU_ENV * b->n * es;
-    if ((rc = grow(&b->u_stage, &b->u_stage_bytes, ub))) return rc;
-    CUDA_TRY(cudaMemcpyAsync(b->u_stage, spec->u, ub, cudaMemcpyHostToDevice, st));
+    if ((rc = grow(&b->u_stage, &b->u_stage_bytes, (size_t)(T + 1) * ustep))) return rc;
     dspec.u = b->u_stage;
   }
+  const size_t rb = (size_t)b->n * (T + 1) * SO101_ROW * rs;
+  if ((rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
+  // chunking: worth it only when there is something to overlap
+  int nchunk = 1;
+  if (T >= 8 && rb >= ((size_t)4 << 20)) nchunk = So101Batch::MAXCHUNK;
+  if (const char* ev = getenv("SO101_HOST_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= So101Batch::MAXCHUNK) nchunk = v; }
+  if (nchunk > T) nchunk = T > 0 ? T : 1;
+  // the side streams start after whatever the caller queued on `st`
+  CUDA_TRY(cudaEventRecord(b->ev_start, st));
+  CUDA_TRY(cudaStreamWaitEvent(b->s_up, b->ev_start, 0));
+  CUDA_TRY(cudaStreamWaitEvent(b->s_down, b->ev_start, 0));
   if (qpos0_host) {   // explicit initial joint angles: reset on the device, then continue from that state
     const size_t qb = (size_t)NV * b->n * es;
     if (!b->init_stage) CUDA_TRY(cudaMalloc(&b->init_stage, 2 * qb));
@@ -778,10 +826,34 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
     if ((rc = so101_batch_reset(b, b->init_stage, nullptr, nullptr, stream))) return rc;
     flags |= SO101_ROLL_NO_RESET;
   }
-  const size_t rb = (size_t)b->n * (T + 1) * SO101_ROW * ((flags & SO101_ROLL_ROWS_F32) ? sizeof(float) : sizeof(double));
-  if ((rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
-  if ((rc = so101_batch_rollout(b, &dspec, T, frame_skip, b->rows_stage, flags, stream))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(rows_host, b->rows_stage, rb, cudaMemcpyDeviceToHost, st));
+  // chunk c covers control steps (tb[c], tb[c+1]]; rows tb[c]+1 .. tb[c+1] (+ row 0 for the first chunk)
+  int tb[So101Batch::MAXCHUNK + 1];
+  for (int c = 0; c <= nchunk; c++) tb[c] = (int)((int64_t)T * c / nchunk);
+  if (tensor) {
+    for (int c = 0; c < nchunk; c++) {   // u_t for t in [first, tb[c+1]]: chunk c reads u at tb[c] .. tb[c+1]
+      const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
+      CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->u_stage) + first * ustep,
+                               static_cast<const char*>(spec->u) + first * ustep, (size_t)(last - first + 1) * ustep,
+                               cudaMemcpyHostToDevice, b->s_up));
+      CUDA_TRY(cudaEventRecord(b->ev_up[c], b->s_up));
+    }
+  }
+  const size_t pitch = (size_t)(T + 1) * SO101_ROW * rs;
+  for (int c = 0; c < nchunk; c++) {
+    if (tensor) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_up[c], 0));
+    const uint32_t f = c == 0 ? flags : (flags | SO101_ROLL_NO_RESET);
+    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, b->rows_stage, f, stream))) return rc;
+    CUDA_TRY(cudaEventRecord(b->ev_k[c], st));
+    CUDA_TRY(cudaStreamWaitEvent(b->s_down, b->ev_k[c], 0));
+    const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
+    const size_t off = (size_t)first * SO101_ROW * rs, width = (size_t)(last - first + 1) * SO101_ROW * rs;
+    if (nchunk == 1)
+      CUDA_TRY(cudaMemcpyAsync(rows_host, b->rows_stage, rb, cudaMemcpyDeviceToHost, b->s_down));
+    else
+      CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(rows_host) + off, pitch, static_cast<char*>(b->rows_stage) + off,
+                                 pitch, width, (size_t)b->n, cudaMemcpyDeviceToHost, b->s_down));
+  }
+  CUDA_TRY(cudaStreamSynchronize(b->s_down));
   CUDA_TRY(cudaStreamSynchronize(st));
   return SO101_OK;
 }

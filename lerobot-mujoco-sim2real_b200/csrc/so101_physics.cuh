@@ -681,11 +681,37 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
     G1 = g1a - g1b;
     G2 = T(0.5) * g2;
   }
+  T jar0[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) jar0[i] = a[i] - rw.aref_f[i];
+  // Fast path (99 % of the searches after a prox start): if the root of the FIRST piece - the zones the rows
+  // are in at alpha = 0 - is reached before any row changes zone, it is the answer.  Zones are intervals and
+  // jar moves monotonically with alpha, so "same zone at alpha = root" means no breakpoint in between; a row
+  // sitting exactly on a zone boundary takes the general path.
+  if (!rw.anylim) {
+    T d0 = G1, d1 = T(2) * G2;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const T Ds = m.fr_D[i] * sr[i];
+      if (abs_(jar0[i]) < m.fr_Rf[i]) { d0 += Ds * jar0[i]; d1 += Ds * sr[i]; }
+      else d0 += copysign_(m.fr_f[i], jar0[i]) * sr[i];
+    }
+    if (d1 <= T(0)) d1 = T(MJ_MINVAL);
+    const T root = -d0 * rcp_(d1);
+    bool same = root > T(0);
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const T x0 = jar0[i], x1 = jar0[i] + root * sr[i];
+      const bool q0 = abs_(x0) < m.fr_Rf[i], q1 = abs_(x1) < m.fr_Rf[i];
+      const bool lin_same = abs_(x0) > m.fr_Rf[i] && abs_(x1) >= m.fr_Rf[i] && (x0 > T(0)) == (x1 > T(0));
+      same &= (q0 && q1) || (!q0 && lin_same);
+    }
+    if (same) { nev_total += 1; return root; }
+  }
   // friction row i changes zone where jar0_i + alpha sr_i = -+ R_i f_i
-  T jar0[NV], blo[NV], bhi[NV];
+  T blo[NV], bhi[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) {
-    jar0[i] = a[i] - rw.aref_f[i];
     const bool moving = sr[i] != T(0);
     const T inv = rcp_(moving ? sr[i] : T(1));
     blo[i] = moving ? (-m.fr_Rf[i] - jar0[i]) * inv : inf_<T>();

@@ -310,6 +310,33 @@ def test_rollout_host_single_abi_call(tables_v):
     assert torch.equal(out, env2.rollout(T, "random", seed=5).cpu())
 
 
+@pytest.mark.parametrize("kind", ["tensor", "random", "chirp"])
+def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind):
+    """rollout_host cuts long rollouts into time chunks that overlap upload / compute / download; the rows and the
+    final state must not depend on the number of chunks (continuation launches regenerate u_t0 and skip row t0)."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    n, T = 300, 23                             # 23 control steps: uneven chunks
+    g = torch.Generator().manual_seed(9)
+    U = (torch.rand((T + 1, 5, n), generator=g, dtype=torch.float64) - 0.5).contiguous().pin_memory()
+    res = {}
+    for chunks in ("1", "2", "4"):
+        monkeypatch.setenv("SO101_HOST_CHUNKS", chunks)
+        env = _vec(tables_v, n)
+        out = torch.full((n, T + 1, 13), float("nan"), dtype=torch.float64).pin_memory()
+        env.rollout_host(T, kind, seed=21, u_host=U if kind == "tensor" else None, out_host=out,
+                         flags=T_.ROLL_GRAVCOMP_HOLD)
+        q, v, w = env.get_state()
+        res[chunks] = (out.clone(), q.clone(), v.clone(), w.clone())
+        assert env.stats()["physics_steps"] == n * T * 10
+        assert not torch.isnan(out).any()
+    for chunks in ("2", "4"):
+        for a, b in zip(res["1"], res[chunks]):
+            assert torch.equal(a, b)
+    monkeypatch.delenv("SO101_HOST_CHUNKS")
+    dev = _vec(tables_v, n).rollout(T, kind, seed=21, u=U.cuda() if kind == "tensor" else None, flags=T_.ROLL_GRAVCOMP_HOLD)
+    assert torch.equal(res["1"][0], dev.cpu())
+
+
 @pytest.mark.parametrize("n", [1, 33, 1000])
 def test_odd_batch_sizes_and_f32_rows(oracle_mod, tables_v, n):
     from lerobot_mujoco_sim2real_b200 import tables as T_
