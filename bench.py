@@ -288,14 +288,14 @@ def run_b200(args) -> None:
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     alg_bytes = env_steps_per_launch * 208.0   # fused rollout, fp64: 208 B per env-step
     roofline = {
-        "bound": "fp64_pipe", "kernel": "k_rollout<double,double>", "achieved": achieved_tf, "peak": peak64,
+        "bound": "fp64_pipe", "kernel": "k_rollout<double,double,SPLIT=true> (three-warp team kernel, batches <= 9472 envs)", "achieved": achieved_tf, "peak": peak64,
         "unit": "TFLOP/s", "frac": achieved_tf / peak64, "traffic": traffic,
         "peak_source": "register-resident DFMA loop measured in this run (so101_fma_peak), 'of measured'",
         "algorithmic_flop_per_physics_step": FLOP_PER_PHYSICS_STEP, "physics_steps_per_launch": phys_per_launch,
         "kernel_ms": kernel_ms,
         "bound_note": "neither hbm nor tensor: ~300 FLOP per byte of state/row traffic, no contraction; the limiter is "
-                      "the FP64 FMA pipe.  At this config (4096 envs = 128 warps on 592 warp schedulers) the launch is "
-                      "latency-bound; the large-batch fraction is in extra (fp64 131072: ~0.40 - the accounting budgets 2 Newton iterations, the kernels need 1.0; ncu: FP64 pipe 45 % busy)",
+                      "the FP64 FMA pipe.  At this config (4096 envs = 128 three-warp teams, one per SM, on 148 SMs) the launch is "
+                      "latency-bound: a physics step is one dependent chain of ~3.8 k instructions on the team's dynamics warp (ncu: 43 % of its samples are fixed-latency waits); the large-batch fraction is in extra (fp64 131072: ~0.40 - the accounting budgets 2 Newton iterations, the kernels need 1.0; ncu: FP64 pipe 45 % busy)",
         "hbm_sanity": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                        "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                        "algorithmic_bytes_per_env_step": 208},
@@ -371,10 +371,10 @@ def run_b200(args) -> None:
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms,
                 "path": "so101_batch_rollout_host: pinned host control tensor [T+1,5,N] + initial angles [6,N] -> "
-                        "k_reset + k_rollout (SO101_CTRL_TENSOR) -> dataset rows [N,T+1,13] to pinned host, stream sync"},
+                        "k_reset + 4 time-chunked k_rollout launches (SO101_CTRL_TENSOR) overlapped with the upload of the next chunk's controls and the download of the previous chunk's rows -> dataset rows [N,T+1,13] in pinned host memory, stream sync"},
         "gpu_launches": K,
-        "gpu_launches_note": "one k_rollout<double,double> launch per step in the device-resident region; "
-                             "the e2e region adds one k_reset launch per step",
+        "gpu_launches_note": "one k_rollout<double,double,true> launch per step in the device-resident region; "
+                             "the e2e region launches k_reset + 4 k_rollout chunks per step",
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "wall_ms_timed_region": wall_ms,
         "flags": {"envs_tripwire": n_trip, "envs_badstate": n_bad, "of": N_ENVS},

@@ -514,12 +514,13 @@ static int pick_lanes(int64_t n) {
   if (const char* ev = getenv("SO101_LANES")) { int v = atoi(ev); if (v == 32 || v == 16 || v == 8 || v == 4 || v == 2 || v == 1) return v; }
   return 32;
 }
-// Small batches (at most one team per SM: 148 x 32 envs) run the SPLIT kernels: three warps per 32 envs, 96-thread
-// blocks.  Measured on B200 (tools/split_probe.py, 100 control steps): 1024 envs 10.7 -> 6.6 ms, 4096 envs
-// 12.0 -> 9.9 ms, break-even near 7000 envs.  SO101_SPLIT=0|1 overrides (experiments, bitwise-equality test).
+// Small batches (at most two teams per SM: 148 x 64 envs) run the SPLIT kernels: three warps per 32 envs, 96-thread
+// blocks.  Measured on B200 (tools/split_probe.py, f64, ms per 100 control steps, one-warp -> team): 1024 envs
+// 11.3 -> 7.0, 4096 envs 11.9 -> 7.3, 9472 envs 13.1 -> 9.6; with three teams per SM (14208 envs) the team kernels
+// lose (16.3 -> 17.6).  SO101_SPLIT=0|1 overrides (experiments, bitwise-equality test).
 static bool pick_split(int64_t n) {
   if (const char* ev = getenv("SO101_SPLIT")) return atoi(ev) != 0;
-  return n <= (int64_t)148 * 32;
+  return n <= (int64_t)148 * 64;
 }
 template <typename T> static StateView<T> step_view(const So101Batch* b, int& blk, unsigned& grid, bool& split) {
   StateView<T> v = view<T>(b);

@@ -659,6 +659,47 @@ SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV
 // counts (CPU test `test_exact_line_search_is_equivalent` under tests/), below the CUDA-vs-CPU
 // differences of the smooth dynamics.
 // ------------------------------------------------------------------------------------------
+// mj_passive, mj_fwdActuation, right-hand side of mj_fwdAcceleration, and the constraint rows of this step
+// (mj_instantiateLimit + mj_makeImpedance + mj_referenceConstraint for the limit rows)
+template <typename T>
+SO101_DEV void build_rows(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], const T (&bias)[NV], T (&fsm)[NV],
+                          Rows<T>& rw, Counters& cnt) {
+  rw.anylim = false;
+  uint32_t near = 0;   // joints inside the margin of one of their limits
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T passive = -m.damping[i] * e.qd[i];
+    if (m.any_stiffness) passive = -m.stiffness[i] * (e.q[i] - m.qspring[i]) - m.damping[i] * e.qd[i];
+    T c = ctrl[i];
+    if (m.ctrllim_mask >> i & 1) c = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], c));
+    T force = m.act_gain[i] * c + m.act_b0[i] + m.act_b1[i] * (m.act_gear[i] * e.q[i]) +
+              m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
+    if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
+    fsm[i] = passive - bias[i] + e.fa[i] + m.act_gear[i] * force;
+    rw.aref_f[i] = -m.fr_B[i] * e.qd[i];
+    if ((m.limited_mask >> i & 1) &&
+        (e.q[i] - m.lim_lo[i] < m.lim_margin[i] || m.lim_hi[i] - e.q[i] < m.lim_margin[i])) near |= 1u << i;
+  }
+  if (near) {   // rare: the row arrays are only ever read when rw.anylim is set
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      rw.side[i] = T(0); rw.aref_l[i] = T(0); rw.D_l[i] = T(0);
+      if (!(near >> i & 1)) continue;
+      T dlo = e.q[i] - m.lim_lo[i], dhi = m.lim_hi[i] - e.q[i];
+      bool lo = dlo < m.lim_margin[i];
+      T side = lo ? T(1) : T(-1), pos = lo ? dlo : dhi;
+      T imp = limit_impedance(m.lim_imp[i], pos, m.lim_margin[i]);
+      T R = max_(T(MJ_MINVAL), (T(1) - imp) * m.lim_invw[i] / imp);
+      rw.side[i] = side;
+      rw.D_l[i] = T(1) / R;
+      rw.aref_l[i] = -m.lim_B[i] * (side * e.qd[i]) - m.lim_K[i] * imp * (pos - m.lim_margin[i]);
+    }
+    rw.anylim = true;
+    e.flags |= SO101_FLAG_LIMIT;
+    cnt.limsteps++;
+  }
+}
+
 template <typename T> SO101_DEV T inf_();
 template <> SO101_DEV double inf_<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> SO101_DEV float inf_<float>() { return __int_as_float(0x7f800000); }
@@ -801,44 +842,11 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 #pragma unroll
     for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
   }
-  // mj_passive, mj_fwdActuation, mj_fwdAcceleration (right-hand side)
   T fsm[NV], x[NV], dd[NV];
   Rows<T> rw;
-  rw.anylim = false;
+  build_rows(m, e, ctrl, bias, fsm, rw, cnt);
 #pragma unroll
-  for (int i = 0; i < NV; i++) {
-    T passive = -m.damping[i] * e.qd[i];
-    if (m.any_stiffness) passive = -m.stiffness[i] * (e.q[i] - m.qspring[i]) - m.damping[i] * e.qd[i];
-    T c = ctrl[i];
-    if (m.ctrllim_mask >> i & 1) c = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], c));
-    T force = m.act_gain[i] * c + m.act_b0[i] + m.act_b1[i] * (m.act_gear[i] * e.q[i]) +
-              m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
-    if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
-    fsm[i] = passive - bias[i] + e.fa[i] + m.act_gear[i] * force;
-    x[i] = fsm[i];
-    dd[i] = T(0);
-    rw.aref_f[i] = -m.fr_B[i] * e.qd[i];
-    rw.side[i] = T(0); rw.aref_l[i] = T(0); rw.D_l[i] = T(0);
-  }
-  // mj_instantiateLimit + mj_makeImpedance + mj_referenceConstraint for the limit rows
-  if (m.limited_mask) {
-#pragma unroll 1
-    for (int i = 0; i < NV; i++) {
-      if (!(m.limited_mask >> i & 1)) continue;
-      T dlo = e.q[i] - m.lim_lo[i], dhi = m.lim_hi[i] - e.q[i];
-      bool lo = dlo < m.lim_margin[i], hi = dhi < m.lim_margin[i];
-      if (lo || hi) {
-        T side = lo ? T(1) : T(-1), pos = lo ? dlo : dhi;
-        T imp = limit_impedance(m.lim_imp[i], pos, m.lim_margin[i]);
-        T R = max_(T(MJ_MINVAL), (T(1) - imp) * m.lim_invw[i] / imp);
-        rw.side[i] = side;
-        rw.D_l[i] = T(1) / R;
-        rw.aref_l[i] = -m.lim_B[i] * (side * e.qd[i]) - m.lim_K[i] * imp * (pos - m.lim_margin[i]);
-        rw.anylim = true;
-      }
-    }
-  }
-  if (rw.anylim) { e.flags |= SO101_FLAG_LIMIT; cnt.limsteps++; }
+  for (int i = 0; i < NV; i++) { x[i] = fsm[i]; dd[i] = T(0); }
   const bool constrained = m.nfriction != 0 || rw.anylim;
 
   enum { PH_SMOOTH, PH_NEWTON, PH_EULER, PH_DONE };
@@ -997,8 +1005,8 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 //   warp 0 "dynamics" : sincos(q0,q1) | RNEA bias forces, actuation, constraint rows | Newton solve, Euler step
 //   warp 1 "geometry" : sincos(q2,q3) | CRBA mass matrix, LDL^T of M (qacc_smooth) and of M + h B (implicit Euler)
 //   warp 2 "lookout"  : sincos(q4,q5) | contact tripwire, observation site
-// Exchange through shared memory at three block barriers per step: (S) sin/cos, (A) M + factors + flags + site,
-// (B) the new (qpos, qvel).  Every value is produced by the same expression as in physics_step, so the result is
+// Exchange through shared memory at four block barriers per step: (S) sin/cos, (A) M + its factors + flags + site,
+// (E) factors of M + h B, (B) the new (qpos, qvel).  Every value is produced by the same expression as in physics_step, so the result is
 // bit-identical to the one-warp path (GPU test `test_split_team_is_bitwise_identical`): which kernel a batch size
 // selects never changes a trajectory.
 // ------------------------------------------------------------------------------------------
@@ -1058,12 +1066,13 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   for (int i = 0; i < 15; i++) x.L1[i][lane] = Ls[i];
 #pragma unroll
   for (int i = 0; i < NV; i++) x.D1inv[i][lane] = Dinv[i];
-  ldl6_factor(M, hB, Ls, Dinv);
+  __syncthreads();   // (A) M and its factors published
+  ldl6_factor(M, hB, Ls, Dinv);      // needed only by the Euler step: overlaps the constraint solve
 #pragma unroll
   for (int i = 0; i < 15; i++) x.L2[i][lane] = Ls[i];
 #pragma unroll
   for (int i = 0; i < NV; i++) x.D2inv[i][lane] = Dinv[i];
-  __syncthreads();   // (A) M and factors published
+  __syncthreads();   // (E) factors of M + h B published
   __syncthreads();   // (B) new state published by the dynamics warp
 #pragma unroll
   for (int i = 0; i < NV; i++) { q[i] = x.q[i][lane]; qd[i] = x.qd[i][lane]; }
@@ -1090,6 +1099,7 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
     for (int c = 0; c < 3; c++) x.site[c][lane] = p[c];
   }
   __syncthreads();   // (A)
+  __syncthreads();   // (E)
   __syncthreads();   // (B)
 #pragma unroll
   for (int i = 0; i < NV; i++) { q[i] = x.q[i][lane]; qd[i] = x.qd[i][lane]; }
@@ -1119,39 +1129,9 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
   T fsm[NV], asm_[NV];
   Rows<T> rw;
-  rw.anylim = false;
+  build_rows(m, e, ctrl, bias, fsm, rw, cnt);
 #pragma unroll
-  for (int i = 0; i < NV; i++) {
-    T passive = -m.damping[i] * e.qd[i];
-    if (m.any_stiffness) passive = -m.stiffness[i] * (e.q[i] - m.qspring[i]) - m.damping[i] * e.qd[i];
-    T c = ctrl[i];
-    if (m.ctrllim_mask >> i & 1) c = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], c));
-    T force = m.act_gain[i] * c + m.act_b0[i] + m.act_b1[i] * (m.act_gear[i] * e.q[i]) +
-              m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
-    if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
-    fsm[i] = passive - bias[i] + e.fa[i] + m.act_gear[i] * force;
-    asm_[i] = fsm[i];
-    rw.aref_f[i] = -m.fr_B[i] * e.qd[i];
-    rw.side[i] = T(0); rw.aref_l[i] = T(0); rw.D_l[i] = T(0);
-  }
-  if (m.limited_mask) {
-#pragma unroll 1
-    for (int i = 0; i < NV; i++) {
-      if (!(m.limited_mask >> i & 1)) continue;
-      T dlo = e.q[i] - m.lim_lo[i], dhi = m.lim_hi[i] - e.q[i];
-      bool lo = dlo < m.lim_margin[i], hi = dhi < m.lim_margin[i];
-      if (lo || hi) {
-        T side = lo ? T(1) : T(-1), pos = lo ? dlo : dhi;
-        T imp = limit_impedance(m.lim_imp[i], pos, m.lim_margin[i]);
-        T R = max_(T(MJ_MINVAL), (T(1) - imp) * m.lim_invw[i] / imp);
-        rw.side[i] = side;
-        rw.D_l[i] = T(1) / R;
-        rw.aref_l[i] = -m.lim_B[i] * (side * e.qd[i]) - m.lim_K[i] * imp * (pos - m.lim_margin[i]);
-        rw.anylim = true;
-      }
-    }
-  }
-  if (rw.anylim) { e.flags |= SO101_FLAG_LIMIT; cnt.limsteps++; }
+  for (int i = 0; i < NV; i++) asm_[i] = fsm[i];
   const bool constrained = m.nfriction != 0 || rw.anylim;
 
   __syncthreads();   // (A) wait for the geometry and lookout warps
@@ -1249,6 +1229,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     cnt.newton += iter;
     if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
   }
+  __syncthreads();   // (E) factors of M + h B
   // mj_checkAcc, mj_Euler
   bool bad = false;
 #pragma unroll
