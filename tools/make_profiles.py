@@ -12,7 +12,7 @@ d = out["f64_4096_T100_rows (bench workload)"]
 def val(k):
     v, u = d[k]
     return float(v) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1}.get(u, 1)
-json.dump({"kernel": "k_rollout<double,double>", "config": "4096 envs x 100 control steps x 10 sub-steps, rows written (bench workload)",
+json.dump({"kernel": "k_rollout<double,double,SPLIT=true> (team kernel)", "config": "4096 envs x 100 control steps x 10 sub-steps, rows written (bench workload)",
            "dram_bytes_per_launch_config1": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
            "dram_read": val("dram__bytes_read.sum"), "dram_write": val("dram__bytes_write.sum"),
            "algorithmic_bytes_per_launch": 4096 * 100 * 208, "source": "ncu --set full, profiles/r1_ncu_full_summary.json"},
