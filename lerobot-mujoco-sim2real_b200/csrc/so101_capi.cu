@@ -216,13 +216,25 @@ SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t
 // instantiation fits 128 registers with few spills: 16 warps per SM as ONE 512-thread block, so that all
 // of them share the instruction stream between the block barriers (+5-16 % for 16 warps, +17 % more
 // for the single block; stall_no_instruction was the top f32 stall with two independent blocks).
-template <typename T> struct LBThreads { static constexpr int value = 256; };
-template <> struct LBThreads<float> { static constexpr int value = 512; };
+#ifndef SO101_F64_THREADS
+#define SO101_F64_THREADS 256
+#endif
+#ifndef SO101_F32_THREADS
+#define SO101_F32_THREADS 512
+#endif
+template <typename T> struct LBThreads { static constexpr int value = SO101_F64_THREADS; };
+template <> struct LBThreads<float> { static constexpr int value = SO101_F32_THREADS; };
 #define SO101_LB_THREADS LBThreads<T>::value
 #define SO101_LB_BLOCKS 1
+// Resident teams per SM that the register allocation of the team kernels must allow.  f64: 1 (255 registers, two
+// teams fit; a 168-register build is 12 % slower at 4096 envs).  f32: 3 (161 registers, no spills, as fast as the
+// unconstrained 194-register build and four teams fit per SM).
+template <typename T> struct TeamMinBlocks { static constexpr int value = 1; };
+template <> struct TeamMinBlocks<float> { static constexpr int value = 3; };
+#define SO101_TEAM_MINBLOCKS TeamMinBlocks<T>::value
 #define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 #define SO101_STEP_KERNEL(T) \
-  template <typename T, bool SPLIT> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SO101_LB_BLOCKS)
+  template <typename T, bool SPLIT> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
 
 // reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
 //   mode 0: qpos0/qvel0 [6][N] (nullable)   mode 1: qpos[0:5] ~ U(lo,hi) from Philox
@@ -318,7 +330,7 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
 template <typename T, typename ROW, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SO101_LB_BLOCKS)
+__global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
           ROW* rows, uint32_t rflags, unsigned long long* stats) {
   // control steps (t0, t1] of a rollout of Tn steps; t0 > 0 continues a previous launch (row t0 is already written,
@@ -514,17 +526,18 @@ static int pick_lanes(int64_t n) {
   if (const char* ev = getenv("SO101_LANES")) { int v = atoi(ev); if (v == 32 || v == 16 || v == 8 || v == 4 || v == 2 || v == 1) return v; }
   return 32;
 }
-// Small batches (at most two teams per SM: 148 x 64 envs) run the SPLIT kernels: three warps per 32 envs, 96-thread
-// blocks.  Measured on B200 (tools/split_probe.py, f64, ms per 100 control steps, one-warp -> team): 1024 envs
-// 11.3 -> 7.0, 4096 envs 11.9 -> 7.3, 9472 envs 13.1 -> 9.6; with three teams per SM (14208 envs) the team kernels
-// lose (16.3 -> 17.6).  SO101_SPLIT=0|1 overrides (experiments, bitwise-equality test).
-static bool pick_split(int64_t n) {
+// Small batches run the SPLIT kernels: three warps per 32 envs, 96-thread blocks - f64 up to two teams per SM
+// (148 x 64 envs), f32 up to four (148 x 128 envs).  Measured on B200 (tools/split_probe.py, ms per 100 control steps,
+// one-warp -> team): f64 1024 envs 11.3 -> 7.0, 4096 envs 11.9 -> 7.3, 9472 envs 13.1 -> 9.5, 14208 envs (three teams
+// per SM do not fit 255 registers) 16.3 -> 17.6; f32 4096 envs 9.8 -> 5.9, 9472 envs 10.8 -> 6.7, 18944 envs
+// 11.4 -> 7.7, 23680 envs 13.6 -> 14.5.  SO101_SPLIT=0|1 overrides (experiments, bitwise-equality test).
+static bool pick_split(int64_t n, bool f32) {
   if (const char* ev = getenv("SO101_SPLIT")) return atoi(ev) != 0;
-  return n <= (int64_t)148 * 64;
+  return n <= (int64_t)148 * (f32 ? 128 : 64);
 }
 template <typename T> static StateView<T> step_view(const So101Batch* b, int& blk, unsigned& grid, bool& split) {
   StateView<T> v = view<T>(b);
-  split = pick_lanes(b->n) == 32 && pick_split(b->n);
+  split = pick_lanes(b->n) == 32 && pick_split(b->n, sizeof(T) == 4);
   if (split) {
     blk = 32 * TEAM_WARPS;
     grid = (unsigned)((b->n + 31) / 32);
@@ -533,7 +546,7 @@ template <typename T> static StateView<T> step_view(const So101Batch* b, int& bl
   v.lanes = pick_lanes(b->n);
   blk = v.lanes == 32 ? pick_block(b->n) : 128;
   if (sizeof(T) == 4 && blk == 256 && b->n >= (int64_t)148 * 512) blk = 512;
-  if (const char* ev = getenv("SO101_BLK")) { int x = atoi(ev); if (x >= 32 && x <= 512 && x % 32 == 0) blk = x; }
+  if (const char* ev = getenv("SO101_BLK")) { int x = atoi(ev); if (x >= 32 && x <= 1024 && x % 32 == 0) blk = x; }
   const int64_t warps = (b->n + v.lanes - 1) / v.lanes;
   grid = (unsigned)((warps * 32 + blk - 1) / blk);
   return v;

@@ -16,6 +16,9 @@
 namespace so101 {
 
 #define SO101_DEV __device__ __forceinline__
+#ifndef SO101_ONEWARP_ROLLED
+#define SO101_ONEWARP_ROLLED 0
+#endif
 #define MJ_MINVAL 1e-15
 #define MJ_MAXVAL 1e10
 
@@ -832,11 +835,24 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   T M[21], bias[NV];
+#if SO101_ONEWARP_ROLLED   // experiment: the compact link loops of the team kernels in the one-warp kernels (see profiles/README.md)
+  {
+    T sn[NV], cs[NV], lq[NV], lqd[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) { lq[i] = e.q[i]; lqd[i] = e.qd[i]; }
+    joint_sincos_range(m, lq, 1, sn, cs, 1, 0, NV);
+    rnea_bias(m, sn, cs, 1, lqd, 1, bias);
+    crba_mass(m, sn, cs, 1, M, 1);
+    if (trip) tripwire_all(m, sn, cs, 1, lq, 1, e.flags);
+    if (want_site) site_from_trig(m, sn, cs, 1, site);
+  }
+#else
   {
     T sn[NV], cs[NV];
     joint_sincos(m, e.q, sn, cs);
     smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags);
   }
+#endif
   if (SYNC) __syncthreads();
   if (gravcomp_capture) {
 #pragma unroll
