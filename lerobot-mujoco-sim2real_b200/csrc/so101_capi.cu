@@ -478,7 +478,7 @@ struct So101Batch {
   void* rows_stage;   // [n][T+1][13] dataset rows (rollout_host)
   size_t rows_stage_bytes;
   // rollout_host pipeline: upload / download streams and per-chunk events
-  static constexpr int MAXCHUNK = 4;
+  static constexpr int MAXCHUNK = 8;
   bool pipe_ready;
   cudaStream_t s_up, s_down;
   cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
@@ -787,7 +787,7 @@ static int grow(void** buf, size_t* have, size_t need) {
   return SO101_OK;
 }
 
-// Host-buffer rollout, pipelined over time: the rollout is cut into up to 4 chunks of control steps; the control
+// Host-buffer rollout, pipelined over time: the rollout is cut into up to 8 chunks of control steps; the control
 // tensor of chunk c+1 is uploaded (stream up) and the rows of chunk c-1 are downloaded (stream down, strided copy into
 // the caller's [N][T+1][13] layout) while chunk c computes on the caller's stream.  Only the first upload and the last
 // download are exposed.
@@ -826,7 +826,11 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   if ((rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
   // chunking: worth it only when there is something to overlap
   int nchunk = 1;
-  if (T >= 8 && rb >= ((size_t)4 << 20)) nchunk = So101Batch::MAXCHUNK;
+  if (T >= 8 && rb >= ((size_t)4 << 20)) {   // >= 2 MB of rows per chunk
+    nchunk = (int)(rb >> 21);
+    if (nchunk > So101Batch::MAXCHUNK) nchunk = So101Batch::MAXCHUNK;
+    if (nchunk < 2) nchunk = 2;
+  }
   if (const char* ev = getenv("SO101_HOST_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= So101Batch::MAXCHUNK) nchunk = v; }
   if (nchunk > T) nchunk = T > 0 ? T : 1;
   // the side streams start after whatever the caller queued on `st`
