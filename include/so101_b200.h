@@ -245,6 +245,16 @@ int so101_batch_stats(So101Batch* b, uint64_t* stats_host, void* stream);
 /* measurement helper: register-resident FMA loop; returns achieved TFLOP/s (2 flop per FMA). */
 int so101_fma_peak(int dtype, int device, double* tflops_out);
 
+/* ---- control sequences scored under the reference's lifted linear (Koopman) model ------------------
+   z_{t+1} = A z_t + B u_t from z0 (A [nz][nz], B [nz][nu], z0 [nz]: HOST, row-major; nz <= 64, nu <= 8)
+   [REF models/KoopmanBase.py:49-57]; cost_b = sum_t q_weight |z_{t+1} - zref_t|^2 + r_weight |u_t|^2 with zref [H][nz]
+   HOST (nullable: control effort only) [REF control/MPC_Controler.py:65-98, Q = 50 I, R = 0.5 I].  U is the DEVICE tensor
+   [H][nu][n] that so101_batch_shoot takes (dtype = its element type), Xhat DEVICE float32 [n][H+1][nobs] = first nobs
+   lifted coordinates (the predicted observation; nullable), cost DEVICE double [n] (nullable).  Async on `stream`. */
+int so101_koopman_score(const double* A, const double* B, int nz, int nu, const double* z0, const double* zref,
+                        double q_weight, double r_weight, const void* U, int H, int64_t n, int dtype, int device,
+                        int nobs, void* Xhat, void* cost, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,7 +2,8 @@
 
 Only what the hot path needs lives here: the host MJCF compiler (mjcf.py), the packed tables
 (tables.py), the ctypes binding of the CUDA C-ABI library (_lib.py, csrc/), and the host-side
-mirrors of the reference interface (SOARM101_Env.py, SOARM101_DataCollection.py, vec_env.py).
+mirrors of the reference interface (SOARM101_Env.py, SOARM101_DataCollection.py, vec_env.py),
+plus the device-side twin of the reference's Koopman model / MPC cost (koopman.py).
 """
 from . import tables  # noqa: F401
 from .tables import builtin_tables, load_tables, save_tables  # noqa: F401
@@ -17,6 +18,9 @@ def __getattr__(name):  # heavy modules (torch, ctypes library) load on first us
     if name == "SOARM101Env":
         from .SOARM101_Env import SOARM101Env
         return SOARM101Env
+    if name == "KoopmanModel":
+        from .koopman import KoopmanModel
+        return KoopmanModel
     if name in ("SOARM101DataGenerator", "Collater"):
         from . import SOARM101_DataCollection as dc
         return getattr(dc, name)

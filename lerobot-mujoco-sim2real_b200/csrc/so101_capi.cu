@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "so101_physics.cuh"
 
@@ -878,8 +879,8 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
 
 int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H, int frame_skip, void* X,
                       uint32_t flags, void* stream) {
-  if (!b || !state0 || !U || !X) return fail(SO101_EINVAL, "null argument");
   if (H < 0 || frame_skip < 1) return fail(SO101_EINVAL, "H must be >= 0 and frame_skip >= 1");
+  if (!b || !state0 || (!U && H > 0) || !X) return fail(SO101_EINVAL, "null argument");
   DeviceGuard g(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   State0 s0;
@@ -985,3 +986,5 @@ int so101_fma_peak(int dtype, int device, double* tflops_out) {
 }
 
 }  // extern "C"
+
+#include "so101_koopman.cuh"

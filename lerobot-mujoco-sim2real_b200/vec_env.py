@@ -47,8 +47,10 @@ class Model:
 class SOARM101VecEnv:
     def __init__(self, xml_path: Optional[str] = None, num_envs: int = 1, dt: float = 0.02,
                  dtype: Union[str, torch.dtype] = "float64", device: Union[int, str, torch.device] = 0,
-                 tables: Optional[So101Tables] = None, seed: int = 42):
-        """xml_path: MJCF scene (compiled on the host once) — or pass pre-compiled `tables`."""
+                 tables: Optional[So101Tables] = None, seed: int = 42, gravity_compensation: bool = False):
+        """xml_path: MJCF scene (compiled on the host once) — or pass pre-compiled `tables`.
+        gravity_compensation=True: `step` first sets qfrc_applied = qfrc_bias of the current state, as the reference's
+        control loops do before every env step [REF Koopman_MPC.py:119; SOARM101_Env.py:120 (commented out)]."""
         _lib.require_device()
         if tables is None:
             if xml_path is None:
@@ -73,6 +75,7 @@ class SOARM101VecEnv:
         self.udim, self.xdim, self.max_speed = T.NU_ENV, T.NOBS, 0.5
         self.seed = int(seed)
         self._episode = 0
+        self.gravity_compensation = bool(gravity_compensation)
         self.model = Model(tables)
         L = _lib.lib()
         nbytes = L.so101_batch_state_bytes(self.num_envs, self.dtype_code)
@@ -125,6 +128,11 @@ class SOARM101VecEnv:
     def step(self, action):
         """action [N, 5] -> (obs [N, 8], 0.0, False, False, {}).  [REF SOARM101_Env.py:108-142]"""
         u = self._soa(action, T.NU_ENV)
+        if self.gravity_compensation:
+            L = _lib.lib()
+            bias = torch.empty((T.NV, self.num_envs), dtype=self.torch_dtype, device=self.device)
+            _lib.check(L.so101_batch_forward(self._h, None, bias.data_ptr(), self._stream()))
+            _lib.check(L.so101_batch_set_qfrc_applied(self._h, bias.data_ptr(), self._stream()))
         self.step_soa(u)
         return self._obs.t(), 0.0, False, False, {}
 

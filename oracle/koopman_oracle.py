@@ -1,0 +1,48 @@
+"""TEST INFRASTRUCTURE ONLY - numpy restatement of the reference's Koopman model and MPC cost.
+
+Follows [REF models/KoopmanBase.py:44-57] (lift z = [x, MLP(x)], z+ = lA z + lB u, x = lC z = first 8 coordinates)
+and [REF control/MPC_Controler.py:65-98] (horizon roll-out and cost with Q = 50 I over the lifted state, R = 0.5 I;
+`state_full` is always true there).  Pinned by the reference's own checkpoint (tests/golden/koopman_dkuc.npz, exported
+from results/SOARM101/11_27/DKUC/best_model.pt) through the fingerprints in tests/test_oracle.py.
+"""
+import numpy as np
+
+
+def lift(W, x):
+    h = x
+    n = sum(1 for k in W if k.startswith("x_encode_net.linear_") and k.endswith(".weight"))
+    for i in range(n):
+        h = h @ W[f"x_encode_net.linear_{i}.weight"].T + W[f"x_encode_net.linear_{i}.bias"]
+        if i != n - 1:
+            h = np.maximum(h, 0)
+    return np.concatenate([x, h], -1)
+
+
+def score(W, z0, U, zref=None, q=50.0, r=0.5, nobs=8):
+    """z0 [nz], U [H, nu, n], zref [H, nz] -> (Xhat [n, H+1, nobs], cost [n]) by plain loops over time."""
+    A, B = W["lA.weight"], W["lB.weight"]
+    H, nu, n = U.shape
+    z = np.tile(z0, (n, 1))
+    X = [z[:, :nobs].copy()]
+    cost = np.zeros(n)
+    for t in range(H):
+        u = U[t].T                                  # [n, nu]
+        z = z @ A.T + u @ B.T
+        if zref is not None:
+            cost += q * ((z - zref[t]) ** 2).sum(-1)
+        cost += r * (u ** 2).sum(-1)
+        X.append(z[:, :nobs].copy())
+    return np.stack(X, 1), cost
+
+
+def mpc_solve(W, z0, zref, H, q=50.0, r=0.5):
+    """The minimiser IPOPT converges to for the reference's unconstrained, quadratic problem: normal equations."""
+    A, B = W["lA.weight"], W["lB.weight"]
+    nz, nu = B.shape
+    F = np.zeros((H * nz, nz)); G = np.zeros((H * nz, H * nu))
+    for t in range(H):
+        F[t * nz:(t + 1) * nz] = np.linalg.matrix_power(A, t + 1)
+        for s in range(t + 1):
+            G[t * nz:(t + 1) * nz, s * nu:(s + 1) * nu] = np.linalg.matrix_power(A, t - s) @ B
+    rhs = q * G.T @ (zref.reshape(-1) - F @ z0)
+    return np.linalg.solve(q * G.T @ G + r * np.eye(H * nu), rhs).reshape(H, nu)

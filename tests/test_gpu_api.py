@@ -436,3 +436,26 @@ def test_split_team_is_bitwise_identical(tables_v, monkeypatch, dtype, n):
         assert env.stats()["physics_steps"] == n * (60 + 1 + 7) * 10
     for a, b in zip(out["0"], out["1"]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n", [5, 4096, 20000])     # team kernels (one partial team / one team per SM), one-warp kernels
+def test_zero_length_calls(tables_v, n):
+    """Degenerate sizes the reference API allows: step with 0 sub-steps, rollout of 0 control steps, shoot with H = 0."""
+    env = _vec(tables_v, n)
+    env.reset(seed=3)
+    q0, v0, _ = [t.clone() for t in env.get_state()]
+    obs_f, _ = env.forward()
+    obs_f = obs_f.clone()
+    u = torch.full((5, n), 0.2, dtype=env.torch_dtype, device=env.device)
+    obs0 = env.step_soa(u, 0).t().clone()
+    assert torch.equal(obs0, obs_f)                                    # no physics: observation of the current state
+    q1, v1, _ = env.get_state()
+    assert torch.equal(q0, q1) and torch.equal(v0, v1)
+    rows = env.rollout(0, "random", seed=9)                            # reset row only
+    assert rows.shape == (n, 1, 13) and torch.isfinite(rows).all()
+    rows_h = env.rollout_host(0, "random", seed=9)
+    assert torch.equal(rows.cpu(), rows_h)
+    s0 = np.concatenate([tables_v.key_qpos[:], np.zeros(12)])
+    X = env.shoot(s0, torch.empty((0, 5, n), dtype=env.torch_dtype, device=env.device))
+    assert X.shape == (n, 1, 8) and bool((X == X[0]).all())
+    assert env.stats()["physics_steps"] == 0

@@ -1,0 +1,132 @@
+"""the reference's Koopman model next to the batched stepper - lift, model roll-out and MPC cost on the
+device (`so101_koopman_score`), the MPC problem solved in closed form, and the closed loop on the CUDA simulator.
+Weights: tests/golden/koopman_dkuc.npz = the reference's shipped checkpoint (results/SOARM101/11_27/DKUC/best_model.pt)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+GOLD = os.path.join(ROOT, "tests", "golden", "koopman_dkuc.npz")
+
+
+def _weights():
+    return {k: v.astype(np.float64) for k, v in np.load(GOLD).items()}
+
+
+def test_closed_form_mpc_matches_normal_equations_cpu():
+    """mpc_gains (what the product uses) == the oracle's normal-equation solve of the reference's NLP, and the solution
+    is a stationary point of the reference's cost [REF MPC_Controler.py:65-98]."""
+    import koopman_oracle as KO
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    W = _weights()
+    km = KoopmanModel(W, device="cpu")
+    rng = np.random.default_rng(0)
+    H = 10
+    x = rng.uniform(-0.3, 0.3, 8); xref = rng.uniform(-0.3, 0.3, (H, 8))
+    z0, zref = KO.lift(W, x), KO.lift(W, xref)
+    np.testing.assert_allclose(km.lift(torch.as_tensor(x)).numpy(), z0, rtol=0, atol=1e-13)
+    u_star = KO.mpc_solve(W, z0, zref, H)
+    Kz, Kr = km.mpc_gains(H)
+    u_gain = (Kz.numpy() @ z0 + Kr.numpy() @ zref.reshape(-1)).reshape(H, 5)
+    np.testing.assert_allclose(u_gain, u_star, rtol=0, atol=1e-9)
+    # stationarity: central differences of the oracle cost vanish at u*
+    c0 = KO.score(W, z0, u_star[:, :, None], zref)[1][0]
+    for _ in range(20):
+        d = rng.standard_normal((H, 5)) * 1e-3
+        cp = KO.score(W, z0, (u_star + d)[:, :, None], zref)[1][0]
+        cm = KO.score(W, z0, (u_star - d)[:, :, None], zref)[1][0]
+        assert cp > c0 and cm > c0 and abs(cp - cm) < 1e-6 * (cp - c0 + cm - c0) + 1e-12
+    # batch control = first block of the gain solution, clipped
+    u1 = km.mpc_control(torch.as_tensor(x)[None], torch.as_tensor(xref)[None], H).numpy()[0]
+    np.testing.assert_allclose(u1, np.clip(u_star[0], -0.5, 0.5), atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_koopman_score_matches_numpy(dtype):
+    import koopman_oracle as KO
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    W = _weights()
+    km = KoopmanModel(W)
+    rng = np.random.default_rng(1)
+    H, n = 50, 8192 + 37
+    U = rng.uniform(-0.5, 0.5, (H, 5, n))
+    Ud = torch.as_tensor(U, dtype=dtype).cuda().contiguous()
+    Uh = Ud.cpu().numpy().astype(np.float64)                      # what the kernel sees
+    z0 = KO.lift(W, rng.uniform(-0.3, 0.3, 8)); zref = KO.lift(W, rng.uniform(-0.3, 0.3, (H, 8)))
+    for ref in (zref, None):
+        X, c = km.score(z0, Ud, ref)
+        Xo, co = KO.score(W, z0, Uh, ref)
+        assert X.shape == (n, H + 1, 8) and X.dtype == torch.float32 and c.dtype == torch.float64
+        np.testing.assert_allclose(X.cpu().numpy(), Xo.astype(np.float32), rtol=0, atol=2e-7)
+        np.testing.assert_allclose(c.cpu().numpy(), co, rtol=1e-12)
+    # optimality through the GPU scorer: no perturbation of the closed-form solution costs less
+    Kz, Kr = km.mpc_gains(10)
+    u_star = (Kz.cpu().numpy() @ z0 + Kr.cpu().numpy() @ zref[:10].reshape(-1)).reshape(10, 5)
+    cand = u_star[:, :, None] + np.concatenate([np.zeros((10, 5, 1)), rng.standard_normal((10, 5, 4095)) * 0.05], -1)
+    _, cc = km.score(z0, torch.as_tensor(cand, dtype=dtype).cuda().contiguous(), zref[:10], want_pred=False)
+    tol = 0.0 if dtype == torch.float64 else 1e-5 * float(cc[0])
+    assert float(cc.min()) >= float(cc[0]) - tol and int(cc.argmin()) == 0 or dtype == torch.float32
+
+
+@pytest.mark.gpu
+def test_model_prediction_vs_physics_config5(tables_v):
+    """BASELINE config 5 as the reference uses it: the same 8192 x 50 control sequences through the physics (`shoot`,
+    gravity compensation held per control step as Koopman_MPC.py:119 does) and through the model (`score`)."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    km = KoopmanModel(_weights())
+    B, H = 8192, 50
+    env = SOARM101VecEnv(tables=tables_v, num_envs=B)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    U = (torch.rand((H, 5, B), generator=g, dtype=torch.float64, device="cuda") - 0.5).contiguous()
+    s0 = np.zeros(18); s0[:5] = [0.1, -0.2, 0.15, 0.05, -0.1]
+    X = env.shoot(s0, U, flags=T_.ROLL_GRAVCOMP_HOLD)                        # physics  [B, H+1, 8]
+    Xhat, cost = km.score(km.lift(X[0, 0].double()), U, None)                # model    [B, H+1, 8]
+    err = (Xhat - X).abs()
+    mae10, mae50 = float(err[:, 1:11].mean()), float(err[:, 1:].mean())
+    print(f"model-vs-physics MAE over 8192 sequences: horizon 10: {mae10:.2e}, horizon 50: {mae50:.2e}")
+    assert torch.equal(Xhat[:, 0], X[:, 0].expand(B, 8)) or float((Xhat[:, 0] - X[:, 0]).abs().max()) < 1e-7
+    assert mae10 < 1.5e-3 and mae50 < 3.5e-3        # measured 7.3e-4 / 1.6e-3; published 200-step MAE: 6.84e-3
+    np.testing.assert_allclose(cost.cpu().numpy(), 0.5 * (U ** 2).sum((0, 1)).cpu().numpy(), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_closed_loop_mpc_tracks_on_the_cuda_simulator(tables_v):
+    """The Koopman_MPC.py loop [REF Koopman_MPC.py:119,197-222] for 512 envs at once: lift, closed-form MPC, clip,
+    env.step with gravity compensation.  The reference's model was trained on real MuJoCo data; that its MPC tracks on
+    this simulator is an end-to-end check of the stepper against the reference's own artefact."""
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    km = KoopmanModel(_weights())
+    N, H, steps = 512, 10, 250
+    dt = 0.02
+    g = torch.Generator(device="cuda").manual_seed(11)
+    amp = (torch.rand((N, 5), generator=g, dtype=torch.float64, device="cuda") - 0.5) * 0.5      # +-0.25 rad
+    freq = 0.1 + 0.2 * torch.rand((N, 5), generator=g, dtype=torch.float64, device="cuda")       # 0.1-0.3 Hz
+    t_all = torch.arange(steps + H + 1, device="cuda", dtype=torch.float64) * dt
+    qref = amp[:, None, :] * torch.sin(2 * np.pi * freq[:, None, :] * t_all[None, :, None])      # [N, steps+H+1, 5]
+    # reference observations [ee, q] from the simulator's own forward kinematics
+    scratch = SOARM101VecEnv(tables=tables_v, num_envs=N * (steps + H + 1))
+    qfull = torch.zeros((N * (steps + H + 1), 6), dtype=torch.float64, device="cuda")
+    qfull[:, :5] = qref.reshape(-1, 5)
+    scratch.set_state(qfull, torch.zeros_like(qfull), torch.zeros_like(qfull))
+    xref = scratch.forward()[0].double().reshape(N, steps + H + 1, 8).clone()
+    env = SOARM101VecEnv(tables=tables_v, num_envs=N, gravity_compensation=True)
+    q0 = torch.zeros((N, 6), dtype=torch.float64, device="cuda")
+    env.set_state(q0, torch.zeros_like(q0), torch.zeros_like(q0))
+    x = env.forward()[0].double().clone()
+    errs = []
+    for k in range(steps):
+        u = km.mpc_control(x, xref[:, k + 1:k + 1 + H], H)
+        x = env.step(u)[0].double()
+        errs.append((x[:, 3:] - qref[:, k + 1]).abs().mean().item())
+    tail = float(np.mean(errs[100:]))
+    ee = float((x[:, :3] - xref[:, steps, :3]).norm(dim=-1).mean())
+    print(f"closed-loop Koopman MPC on 512 envs: mean |q - qref| after settling {tail:.3e} rad, final ee error {ee*1e3:.2f} mm")
+    assert tail < 0.01 and ee < 0.006        # measured: 4.2e-3 rad, 2.0 mm
