@@ -2,14 +2,12 @@
 device (`so101_koopman_score`), the MPC problem solved in closed form, and the closed loop on the CUDA simulator.
 Weights: tests/golden/koopman_dkuc.npz = the reference's shipped checkpoint (results/SOARM101/11_27/DKUC/best_model.pt)."""
 import os
-import sys
 
 import numpy as np
 import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 GOLD = os.path.join(ROOT, "tests", "golden", "koopman_dkuc.npz")
 
 
@@ -20,7 +18,7 @@ def _weights():
 def test_closed_form_mpc_matches_normal_equations_cpu():
     """mpc_gains (what the product uses) == the oracle's normal-equation solve of the reference's NLP, and the solution
     is a stationary point of the reference's cost [REF MPC_Controler.py:65-98]."""
-    import koopman_oracle as KO
+    from oracle import koopman_oracle as KO
     from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
     W = _weights()
     km = KoopmanModel(W, device="cpu")
@@ -48,7 +46,7 @@ def test_closed_form_mpc_matches_normal_equations_cpu():
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_koopman_score_matches_numpy(dtype):
-    import koopman_oracle as KO
+    from oracle import koopman_oracle as KO
     from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
     W = _weights()
     km = KoopmanModel(W)
