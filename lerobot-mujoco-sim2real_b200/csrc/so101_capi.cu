@@ -846,8 +846,24 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
     flags |= SO101_ROLL_NO_RESET;
   }
   // chunk c covers control steps (tb[c], tb[c+1]]; rows tb[c]+1 .. tb[c+1] (+ row 0 for the first chunk)
+  // Boundaries: a short first chunk (its control upload is the only exposed upload), then chunks that halve towards
+  // the end (the download of the last chunk is the only exposed download); SO101_HOST_EVEN=1: equal chunks.
   int tb[So101Batch::MAXCHUNK + 1];
-  for (int c = 0; c <= nchunk; c++) tb[c] = (int)((int64_t)T * c / nchunk);
+  if (nchunk >= 4 && !getenv("SO101_HOST_EVEN")) {
+    int k = 0;
+    tb[k++] = 0;
+    tb[k++] = T < 2 ? T : 2;
+    const int rest = T - tb[1];
+    for (int sh = 1; k < nchunk && tb[k - 1] < T; sh++) {
+      const int t = T - (rest >> sh);
+      if (t > tb[k - 1]) tb[k++] = t;
+      if ((rest >> sh) == 0) break;
+    }
+    if (tb[k - 1] < T) tb[k++] = T;
+    nchunk = k - 1;
+  } else {
+    for (int c = 0; c <= nchunk; c++) tb[c] = (int)((int64_t)T * c / nchunk);
+  }
   if (tensor) {
     for (int c = 0; c < nchunk; c++) {   // u_t for t in [first, tb[c+1]]: chunk c reads u at tb[c] .. tb[c+1]
       const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
