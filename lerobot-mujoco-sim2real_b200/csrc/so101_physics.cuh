@@ -707,11 +707,12 @@ template <typename T> SO101_DEV T inf_();
 template <> SO101_DEV double inf_<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> SO101_DEV float inf_<float>() { return __int_as_float(0x7f800000); }
 
-// Returns alpha; Mv = M * sr out.
+// Returns alpha; Mv = M * sr out; exact = the step ends inside the piece it started in (see newton_exact_finish).
 template <typename T>
 SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[21], const T (&a)[NV],
                         const T (&Ma)[NV], const T (&fsm)[NV], const T (&sr)[NV], T (&Mv)[NV],
-                        uint32_t& nev_total) {
+                        uint32_t& nev_total, bool& exact) {
+  exact = false;
   T ss = T(0);
 #pragma unroll
   for (int i = 0; i < NV; i++) ss += sr[i] * sr[i];
@@ -750,7 +751,7 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
       const bool lin_same = abs_(x0) > m.fr_Rf[i] && abs_(x1) >= m.fr_Rf[i] && (x0 > T(0)) == (x1 > T(0));
       same &= (q0 && q1) || (!q0 && lin_same);
     }
-    if (same) { nev_total += 1; return root; }
+    if (same) { nev_total += 1; exact = true; return root; }
   }
   // friction row i changes zone where jar0_i + alpha sr_i = -+ R_i f_i
   T blo[NV], bhi[NV];
@@ -808,6 +809,39 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
   }
   nev_total += nev;
   return result;
+}
+
+// Minimiser of the per-dof problem 0.5 M_ii (a - as)^2 + huber_i(a - ar) (the Newton start, see physics_step).
+// Quadratic zone |a - ar| < R f: a = (M_ii as + D ar) / (M_ii + D), i.e. a - ar = M_ii (as - ar) / (M_ii + D), so the
+// zone test needs no division; linear zones: a = as -+ f / M_ii if that lands beyond the zone, else the zone edge.
+// One reciprocal per dof, no divergent branch.
+template <typename T> SO101_DEV T prox_point(const DevModel<T>& m, int i, T Mii, T as, T ar) {
+  const T d = as - ar;
+  const bool quad = abs_(Mii * d) < m.fr_Rf[i] * (Mii + m.fr_D[i]);
+  const T inv = rcp_(quad ? Mii + m.fr_D[i] : Mii);
+  const T aq = (Mii * as + m.fr_D[i] * ar) * inv;
+  const T df = m.fr_f[i] * inv;
+  const T ap = as - df, an = as + df;
+  const T edge = ar + copysign_(m.fr_Rf[i], d);
+  const T al = (ap - ar >= m.fr_Rf[i]) ? ap : ((an - ar <= -m.fr_Rf[i]) ? an : edge);
+  return quad ? aq : al;
+}
+
+// A Newton step whose line search ended inside the quadratic piece it started in (line_search fast path) lands on
+// the exact minimiser of that piece, and the cost is convex: it is the solution.  MuJoCo would evaluate the cost once
+// more, find improvement / gradient below tolerance and stop with the same iterate; here only the constraint force
+// of the new point is formed (same expressions as cost_update) and the solver stops - the second cost evaluation,
+// M a and the gradient norm are skipped.
+template <typename T>
+SO101_DEV void newton_exact_finish(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV], T (&qc)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    T jar = a[i] - rw.aref_f[i];
+    bool lin = abs_(jar) >= m.fr_Rf[i];
+    T fs = copysign_(m.fr_f[i], jar);
+    T Dj = m.fr_D[i] * jar;
+    qc[i] = lin ? -fs : -Dj;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -896,16 +930,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
         if (!rw.anylim) {
 #pragma unroll
           for (int i = 0; i < NV; i++) {
-            const T Mii = M[tri(i, i)], as = asm_[i], ar = rw.aref_f[i];
-            const T aq = (Mii * as + m.fr_D[i] * ar) * rcp_(Mii + m.fr_D[i]);   // quadratic zone
-            const T df = m.fr_f[i] * rcp_(Mii);                                 // linear zones: as -+ f / M_ii
-            const T ap = as - df, an = as + df;
-            T ai;
-            if (abs_(aq - ar) < m.fr_Rf[i]) ai = aq;
-            else if (ap - ar >= m.fr_Rf[i]) ai = ap;
-            else if (an - ar <= -m.fr_Rf[i]) ai = an;
-            else ai = ar + copysign_(m.fr_Rf[i], as - ar);
-            a[i] = ai;
+            a[i] = prox_point(m, i, M[tri(i, i)], asm_[i], rw.aref_f[i]);
           }
           symv6(M, a, Ma);
           cost = cost_update(m, rw, a, Ma, fsm, asm_, qc, hd);
@@ -939,8 +964,15 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
       bool stop = iter >= m.iterations;
       if (!stop) {
         T Mv[NV];
-        T alpha = line_search(m, rw, M, a, Ma, fsm, sr, Mv, cnt.lsevals);
+        bool exact;
+        T alpha = line_search(m, rw, M, a, Ma, fsm, sr, Mv, cnt.lsevals, exact);
         if (alpha == T(0)) {
+          stop = true;
+        } else if (exact) {
+#pragma unroll
+          for (int i = 0; i < NV; i++) a[i] += alpha * sr[i];
+          newton_exact_finish(m, rw, a, qc);
+          iter++;
           stop = true;
         } else {
 #pragma unroll
@@ -1173,16 +1205,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     if (!rw.anylim) {   // prox start (see physics_step)
 #pragma unroll
       for (int i = 0; i < NV; i++) {
-        const T Mii = M[tri(i, i)], as = asm_[i], ar = rw.aref_f[i];
-        const T aq = (Mii * as + m.fr_D[i] * ar) * rcp_(Mii + m.fr_D[i]);
-        const T df = m.fr_f[i] * rcp_(Mii);
-        const T ap = as - df, an = as + df;
-        T ai;
-        if (abs_(aq - ar) < m.fr_Rf[i]) ai = aq;
-        else if (ap - ar >= m.fr_Rf[i]) ai = ap;
-        else if (an - ar <= -m.fr_Rf[i]) ai = an;
-        else ai = ar + copysign_(m.fr_Rf[i], as - ar);
-        a[i] = ai;
+        a[i] = prox_point(m, i, M[tri(i, i)], asm_[i], rw.aref_f[i]);
       }
       symv6(M, a, Ma);
       cost = cost_update(m, rw, a, Ma, fsm, asm_, qc, hd);
@@ -1219,8 +1242,16 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
       }
 #pragma unroll
       for (int i = 0; i < NV; i++) sr[i] = -sr[i];
-      T alpha = line_search(m, rw, M, a, Ma, fsm, sr, Mv, cnt.lsevals);
+      bool exact;
+      T alpha = line_search(m, rw, M, a, Ma, fsm, sr, Mv, cnt.lsevals, exact);
       if (alpha == T(0)) break;
+      if (exact) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] += alpha * sr[i];
+        newton_exact_finish(m, rw, a, qc);
+        iter++;
+        break;
+      }
 #pragma unroll
       for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
       T oldcost = cost;
