@@ -169,6 +169,10 @@ def run_b200(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         # stdout carries exactly one JSON line: NCCL's own version / debug lines go to stderr
+        # (NCCL_DEBUG=VERSION makes NCCL printf its version to stdout; INFO and above honour NCCL_DEBUG_FILE)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+            sys.stderr.write("bench.py: NCCL_DEBUG=VERSION -> WARN (keeps stdout to one JSON line)\n")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     else:
