@@ -75,6 +75,10 @@ def test_no_cpu_fallback(tables_v):
         SOARM101VecEnv(tables=tables_v, num_envs=4)
     out = C.c_double()
     assert L.so101_fma_peak(T.F64, 0, C.byref(out)) == -4
+    import numpy as np
+    A, B, z0 = np.eye(4), np.zeros((4, 2)), np.zeros(4)
+    assert L.so101_koopman_score(A.ctypes.data, B.ctypes.data, 4, 2, z0.ctypes.data, None, 1.0, 1.0, None, 0, 1,
+                                 T.F64, 0, 0, None, None, None) == -4
 
 
 def test_product_never_imports_the_oracle():
