@@ -189,3 +189,38 @@ def test_free_running_against_joint_limits_scene_b(oracle_mod, tables_p):
     assert frac_lim > 0.5 and st["limit_steps"] > 0.3 * st["physics_steps"]
     assert int((env.flags() & T.FLAG_LIMIT).ne(0).sum()) > 0.9 * n
     assert eq < 1e-9 and ev < 1e-8
+
+
+@pytest.mark.parametrize("variant", ["frictionless", "undamped", "mixed", "heavy"])
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_model_variants_teacher_forced(oracle_mod, tables_v, monkeypatch, variant, split):
+    """Paths the two reference scenes never take: no friction rows at all (unconstrained unless a limit is active), no
+    joint damping (explicit Euler), friction / damping on some dofs only, other inertial constants - one teacher-forced
+    step from 4000 random states against the oracle, in both kernel families."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    O = oracle_mod
+    t = T_.tables_from_dict(T_.tables_to_dict(tables_v))
+    if variant == "frictionless":
+        for k in range(6): t.dof_frictionloss[k] = 0.0
+    elif variant == "undamped":
+        for k in range(6): t.dof_damping[k] = 0.0
+    elif variant == "mixed":
+        for k in (0, 2, 4): t.dof_frictionloss[k] = 0.0
+        t.dof_damping[1] = 0.0; t.dof_damping[3] = 2.0
+    else:
+        for k in range(6): t.dof_armature[k] = 0.005 + 0.01 * k
+        for b in range(2, 8): t.body_mass[b] *= 1.7
+        t.gravity[0], t.gravity[2] = 1.0, -5.0
+    monkeypatch.setenv("SO101_SPLIT", split)
+    rng = np.random.default_rng(3)
+    n = 4000
+    state = np.zeros((n, 18))
+    state[:, :5] = rng.uniform(-0.6, 0.6, (n, 5)); state[:, 5] = rng.uniform(-0.1, 1.0, n)
+    state[:, 6:12] = rng.uniform(-1.0, 1.0, (n, 6))
+    ctrl = np.zeros((n, 6)); ctrl[:, :5] = rng.uniform(-0.5, 0.5, (n, 5))
+    state, _, _ = O.step_batch(t, state, ctrl, 3)          # three oracle steps: realistic qacc_warmstart
+    ref, _, _ = O.step_batch(t, state, ctrl, 1)
+    out, _, env = _gpu_step(t, state, ctrl, 1)
+    err = _rel(out, ref)
+    print(f"{variant} split={split}: qpos {err[:, :6].max():.2e} qvel {err[:, 6:12].max():.2e} qacc {err[:, 12:].max():.2e}")
+    assert err[:, :6].max() < 1e-12 and err[:, 6:12].max() < 1e-9 and np.quantile(err[:, 12:], 0.99) < 1e-9
