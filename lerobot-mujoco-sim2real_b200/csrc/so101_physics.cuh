@@ -19,6 +19,9 @@ namespace so101 {
 #ifndef SO101_ONEWARP_ROLLED
 #define SO101_ONEWARP_ROLLED 0
 #endif
+#ifndef SO101_RNEA_UNROLL
+#define SO101_RNEA_UNROLL 1   // link-loop unroll factor of the compact RNEA (team kernels)
+#endif
 #ifndef SO101_CRBA_BRANCHLESS
 #define SO101_CRBA_BRANCHLESS 1
 #endif
@@ -467,6 +470,7 @@ SO101_DEV void joint_sincos_range(const DevModel<T>& m, const T* q, int qst, T* 
   }
 }
 
+constexpr int RNEA_UNROLL = SO101_RNEA_UNROLL;
 // qfrc_bias by RNEA (flg_acc = 0): forward pass over the links (velocity, bias acceleration, link force),
 // backward pass accumulating the forces down the chain
 template <typename T>
@@ -475,7 +479,7 @@ SO101_DEV void rnea_bias(const DevModel<T>& m, const T* sn, const T* cs, int st,
   {
     T v[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
     T a[6] = {T(0), T(0), T(0), m.accg[0], m.accg[1], m.accg[2]};
-#pragma unroll 1
+#pragma unroll (RNEA_UNROLL)
     for (int k = 0; k < NV; k++) {
       T R[9];
       make_R(m.E[k], cs[k * st], sn[k * st], R);
@@ -483,7 +487,7 @@ SO101_DEV void rnea_bias(const DevModel<T>& m, const T* sn, const T* cs, int st,
     }
   }
   T fs[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // accumulated force in the current frame
-#pragma unroll 1
+#pragma unroll (RNEA_UNROLL)
   for (int k = NV - 1; k >= 0; k--) {
 #pragma unroll
     for (int c = 0; c < 6; c++) fs[c] = add_(fs[c], f[k][c]);
