@@ -834,6 +834,46 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
   return result;
 }
 
+// ------------------------------------------------------------------------------------------
+// Direct active-set solve (friction rows only).  The solver's objective is strictly convex and piecewise quadratic:
+// on the piece where row i is in zone z_i (0: quadratic, |jar| < R f; +-1: saturated at -+f) its minimiser solves
+//   (M + diag(D_i [z_i = 0])) a = qfrc_smooth + D_i aref_i [z_i = 0] - z_i f_i [z_i != 0],
+// and a point that solves this AND lies in the piece it assumed is the global minimiser (KKT).  The zones are guessed
+// from the per-dof problem 0.5 M_ii (a - qacc_smooth_i)^2 + huber_i(a - aref_i), whose minimiser is in the
+// quadratic zone iff |M_ii (qacc_smooth_i - aref_i)| < R f M_ii + f and saturated with the sign of that quantity
+// otherwise (no division).  M is armature dominated: the guess is right in ~99 % of the steps; then ONE factorisation
+// gives MuJoCo's converged Newton iterate without cost evaluations, gradients or a line search.  Otherwise the
+// general Newton path below runs from the prox point.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+SO101_DEV void active_set_guess(const DevModel<T>& m, const Rows<T>& rw, const T (&M)[21], const T (&asm_)[NV],
+                                const T (&fsm)[NV], T (&zone)[NV], T (&rhs)[NV], T (&hd)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const T Mii = M[tri(i, i)], ar = rw.aref_f[i];
+    const T t = Mii * (asm_[i] - ar);
+    const bool quad = abs_(t) < m.fr_Rf[i] * Mii + m.fr_f[i];
+    const T z = quad ? T(0) : copysign_(T(1), t);
+    zone[i] = z;
+    hd[i] = quad ? m.fr_D[i] : T(0);
+    rhs[i] = fsm[i] + (quad ? m.fr_D[i] * ar : -z * m.fr_f[i]);
+  }
+}
+// KKT check of the direct solve at a, and the constraint force there (same values as cost_update's)
+template <typename T>
+SO101_DEV bool active_set_accept(const DevModel<T>& m, const Rows<T>& rw, const T (&zone)[NV], const T (&a)[NV],
+                                 T (&qc)[NV]) {
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const T jar = a[i] - rw.aref_f[i];
+    const bool quad = zone[i] == T(0);
+    ok &= quad ? (abs_(jar) < m.fr_Rf[i]) : (zone[i] * jar > m.fr_Rf[i] || m.fr_f[i] == T(0));
+    qc[i] = quad ? -m.fr_D[i] * jar : -zone[i] * m.fr_f[i];
+  }
+  return ok;
+}
+
 // Minimiser of the per-dof problem 0.5 M_ii (a - as)^2 + huber_i(a - ar) (the Newton start, see physics_step).
 // Quadratic zone |a - ar| < R f: a = (M_ii as + D ar) / (M_ii + D), i.e. a - ar = M_ii (as - ar) / (M_ii + D), so the
 // zone test needs no division; linear zones: a = as -+ f / M_ii if that lands beyond the zone, else the zone edge.
@@ -922,10 +962,11 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   for (int i = 0; i < NV; i++) { x[i] = fsm[i]; dd[i] = T(0); }
   const bool constrained = m.nfriction != 0 || rw.anylim;
 
-  enum { PH_SMOOTH, PH_NEWTON, PH_EULER, PH_DONE };
+  enum { PH_SMOOTH, PH_DIRECT, PH_NEWTON, PH_EULER, PH_DONE };
   int phase = PH_SMOOTH, iter = 0;
-  T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV];
+  T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV], zone[NV];
   T cost = T(0);
+  bool need_setup = false;
   while (phase != PH_DONE) {
     {
       T A[21];
@@ -936,12 +977,31 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
       ldl6_factor_solve(A, x);
     }
     bool to_euler = false;
-    if (phase == PH_SMOOTH) {
+    const int ph = phase;   // the phase whose solve has just been done
+    if (ph == PH_SMOOTH) {
 #pragma unroll
       for (int i = 0; i < NV; i++) { asm_[i] = x[i]; a[i] = x[i]; qc[i] = T(0); hd[i] = T(0); }
       if (!constrained) {
         to_euler = true;  // nefc == 0: qacc = qacc_smooth
+      } else if (!rw.anylim) {
+        active_set_guess(m, rw, M, asm_, fsm, zone, x, dd);   // next pass of the loop solves (M + diag(dd)) x = rhs
+        phase = PH_DIRECT;
       } else {
+        need_setup = true;
+      }
+    } else if (ph == PH_DIRECT) {
+      if (active_set_accept(m, rw, zone, x, qc)) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) a[i] = x[i];
+        cnt.newton += 1;
+        to_euler = true;
+      } else {
+        need_setup = true;
+      }
+    }
+    if (need_setup) {
+      need_setup = false;
+      {
         // Starting point.  MuJoCo starts Newton from the cheaper of qacc_warmstart and qacc_smooth and then
         // needs 3 iterations in ~43 % of this scene's steps.  The cost is strictly convex (unique minimiser), so
         // the start only decides how many iterations are needed: start from the closed-form minimiser of the
@@ -981,7 +1041,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
         for (int i = 0; i < NV; i++) { x[i] = Ma[i] - fsm[i] - qc[i]; dd[i] = hd[i]; }
         phase = PH_NEWTON;
       }
-    } else if (phase == PH_NEWTON) {
+    } else if (ph == PH_NEWTON) {
 #pragma unroll
       for (int i = 0; i < NV; i++) sr[i] = -x[i];
       bool stop = iter >= m.iterations;
@@ -1026,7 +1086,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
         if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
         to_euler = true;
       }
-    } else {  // PH_EULER: x = (M + h B)^-1 (qfrc_smooth + qfrc_constraint)
+    } else if (ph == PH_EULER) {  // x = (M + h B)^-1 (qfrc_smooth + qfrc_constraint)
 #pragma unroll
       for (int i = 0; i < NV; i++) {
         e.qd[i] += m.h * x[i];
@@ -1223,7 +1283,26 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   T a[NV], Ma[NV], qc[NV], hd[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); hd[i] = T(0); }
-  if (constrained) {
+  bool solved = !constrained;
+  if (constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
+    T zone[NV], xs[NV], dh[NV];
+    active_set_guess(m, rw, M, asm_, fsm, zone, xs, dh);
+    {
+      T A[21];
+#pragma unroll
+      for (int i = 0; i < 21; i++) A[i] = M[i];
+#pragma unroll
+      for (int i = 0; i < NV; i++) A[tri(i, i)] += dh[i];
+      ldl6_factor_solve(A, xs);
+    }
+    if (active_set_accept(m, rw, zone, xs, qc)) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) a[i] = xs[i];
+      cnt.newton += 1;
+      solved = true;
+    }
+  }
+  if (!solved) {
     T cost;
     if (!rw.anylim) {   // prox start (see physics_step)
 #pragma unroll
