@@ -855,7 +855,7 @@ static void fwdAcceleration(OracleData* d) {
  * that the first Newton step is already exact.  The cost is strictly convex, the minimiser unique: same result up
  * to rounding.  so101o_set_solver_start(1) switches the oracle to it (tests/test_oracle.py).
  */
-static int g_solver_start = 0;   /* 0: MuJoCo's warm start (default)   1: prox start */
+static int g_solver_start = 0;   /* 0: MuJoCo's warm start (default)   1: prox start   2: direct active set, prox fallback */
 void so101o_set_solver_start(int mode) { g_solver_start = mode; }
 
 static void proxStart(OracleData* d) {
@@ -877,6 +877,43 @@ static void proxStart(OracleData* d) {
   }
 }
 
+/* Alternative under test: the direct active-set solve of the CUDA kernels (csrc/so101_physics.cuh active_set_guess /
+ * active_set_accept).  Zones of the friction rows guessed from the per-dof problem, ONE solve of
+ * (M + J'DJ restricted to the quadratic rows) a = qfrc_smooth + ..., accepted iff every row lies in the zone it was
+ * assumed in (KKT on a strictly convex piecewise-quadratic cost => global minimiser).  Only without limit rows;
+ * returns 0 if not applicable / rejected.  so101o_set_solver_start(2) enables it (tests/test_oracle.py). */
+static int directActiveSet(OracleData* d) {
+  if (d->nefc != d->nf) return 0;                        /* limit rows present */
+  double Mf[NV * NV], H[NV * NV], rhs[NV], zone[MAXEFC];
+  fullM(d, Mf, d->qM);
+  memcpy(H, Mf, sizeof H);
+  memcpy(rhs, d->qfrc_smooth, sizeof rhs);
+  for (int i = 0; i < d->nf; i++) {
+    int dof = d->efc_id[i];
+    double Mii = Mf[dof * NV + dof], ar = d->efc_aref[i], f = d->efc_frictionloss[i], D = d->efc_D[i];
+    double t = Mii * (d->qacc_smooth[dof] - ar);
+    int quad = fabs(t) < d->efc_R[i] * f * Mii + f;
+    zone[i] = quad ? 0.0 : (t >= 0 ? 1.0 : -1.0);
+    if (quad) { H[dof * NV + dof] += D; rhs[dof] += D * ar; }
+    else rhs[dof] -= zone[i] * f;
+  }
+  double a[NV];
+  cholFactor(H, NV);
+  cholSolve(a, H, rhs, NV);
+  for (int i = 0; i < d->nf; i++) {
+    int dof = d->efc_id[i];
+    double jar = a[dof] - d->efc_aref[i], Rf = d->efc_R[i] * d->efc_frictionloss[i];
+    if (zone[i] == 0.0 ? !(fabs(jar) < Rf) : !(zone[i] * jar > Rf)) return 0;
+  }
+  memcpy(d->qacc, a, sizeof a);
+  double jarv[MAXEFC], cost;
+  for (int i = 0; i < d->nefc; i++) jarv[i] = dotn(d->efc_J[i], d->qacc, NV) - d->efc_aref[i];
+  constraintUpdate(d, jarv, &cost, 1);                   /* efc_force, qfrc_constraint at the solution */
+  d->solver_niter = 1;
+  d->solver_nls = 0;
+  return 1;
+}
+
 /* mj_fwdConstraint (warmstart + Newton) */
 static void fwdConstraint(const So101Tables* m, OracleData* d) {
   if (!d->nefc) {
@@ -896,6 +933,10 @@ static void fwdConstraint(const So101Tables* m, OracleData* d) {
   constraintUpdate(d, d->efc_b, &cost_smooth, 0);
   d->used_warmstart = 1;
   if (cost_warm > cost_smooth) { memcpy(d->qacc, d->qacc_smooth, sizeof d->qacc); d->used_warmstart = 0; }
+  if (g_solver_start == 2) {
+    if (directActiveSet(d)) return;
+    proxStart(d);
+  }
   if (g_solver_start == 1) proxStart(d);
   solNewton(m, d);
 }

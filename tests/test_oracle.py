@@ -277,6 +277,42 @@ def test_prox_start_is_equivalent(oracle_mod, tables_v, tables_p, scene):
     assert np.quantile(rel[:, 12:], 0.999) < 1e-10 and rel[:, 12:].max() < 1e-7
 
 
+@pytest.mark.parametrize("scene", ["v", "p"])
+def test_direct_active_set_is_equivalent(oracle_mod, tables_v, tables_p, scene):
+    """The CUDA kernels first try a direct active-set solve (zones of the friction rows guessed per dof, one
+    factorisation, KKT check) and only fall back to Newton from the prox point if the check fails
+    (csrc/so101_physics.cuh active_set_guess / active_set_accept).  On the CPU, everything else identical: accepted in
+    > 98 % of the steps without limit rows, and the step result equals the literal MuJoCo solver's to ~1e-13."""
+    O = oracle_mod
+    t = tables_v if scene == "v" else tables_p
+    rng = np.random.default_rng(2)
+    n = 256
+    state = np.zeros((n, 18)); state[:, :5] = rng.uniform(-0.3, 0.3, (n, 5))
+    S, U = [], []
+    for s in range(300):
+        if s % 10 == 0:
+            ctrl = np.zeros((n, 6))
+            ctrl[:, :5] = rng.uniform(-0.5, 0.5, (n, 5)) if scene == "v" else state[:, :5] + rng.uniform(-0.3, 0.3, (n, 5))
+        if s % 50 == 0 and s:
+            state[: n // 8, 2] = t.jnt_range[2][1] + rng.uniform(-1e-3, 5e-3, n // 8)
+        S.append(state); U.append(ctrl)
+        state, _, _ = O.step_batch(t, state, ctrl, 1)
+    S, U = np.concatenate(S[20:]), np.concatenate(U[20:])
+    ref, _, aux = O.step_batch(t, S, U, 1)
+    try:
+        O.set_line_search(1); O.set_solver_start(2)
+        alt, _, aux2 = O.step_batch(t, S, U, 1)
+    finally:
+        O.set_line_search(0); O.set_solver_start(0)
+    free = aux[:, 2] == 6                                   # no limit row active
+    direct = free & (aux2[:, 0] == 1) & (aux2[:, 1] == 0)   # accepted: one "iteration", no line search
+    assert (~free).sum() > 100 and direct.sum() > 0.98 * free.sum()
+    rel = np.abs(alt - ref) / (1e-3 + np.abs(ref))
+    assert rel[:, :6].max() < 1e-13
+    assert np.quantile(rel[:, 6:12], 0.999) < 2e-12 and rel[:, 6:12].max() < 1e-10
+    assert np.quantile(rel[:, 12:], 0.999) < 1e-10 and rel[:, 12:].max() < 1e-7
+
+
 def test_step_batch_matches_single_env(oracle_mod, tables_v):
     O, t = oracle_mod, tables_v
     rng = np.random.default_rng(0)
