@@ -841,22 +841,40 @@ SO101_DEV T line_search(const DevModel<T>& m, const Rows<T>& rw, const T (&Mm)[2
 // and a point that solves this AND lies in the piece it assumed is the global minimiser (KKT).  The zones are guessed
 // from the per-dof problem 0.5 M_ii (a - qacc_smooth_i)^2 + huber_i(a - aref_i), whose minimiser is in the
 // quadratic zone iff |M_ii (qacc_smooth_i - aref_i)| < R f M_ii + f and saturated with the sign of that quantity
-// otherwise (no division).  M is armature dominated: the guess is right in ~99 % of the steps; then ONE factorisation
-// gives MuJoCo's converged Newton iterate without cost evaluations, gradients or a line search.  Otherwise the
-// general Newton path below runs from the prox point.
+// otherwise (no division).  M is armature dominated: the guess is right in 99.8 % of the steps; then ONE factorisation
+// gives MuJoCo's converged Newton iterate without cost evaluations, gradients or a line search.  A rejected candidate
+// gets one more attempt with the zones it lies in (99.97 % accepted after that; a warp of 32 envs: 93 % -> 99 %);
+// what is left takes the general Newton path below from the prox point.
 // ------------------------------------------------------------------------------------------
 template <typename T>
 SO101_DEV void active_set_guess(const DevModel<T>& m, const Rows<T>& rw, const T (&M)[21], const T (&asm_)[NV],
-                                const T (&fsm)[NV], T (&zone)[NV], T (&rhs)[NV], T (&hd)[NV]) {
+                                T (&zone)[NV]) {
 #pragma unroll
   for (int i = 0; i < NV; i++) {
-    const T Mii = M[tri(i, i)], ar = rw.aref_f[i];
-    const T t = Mii * (asm_[i] - ar);
+    const T Mii = M[tri(i, i)];
+    const T t = Mii * (asm_[i] - rw.aref_f[i]);
     const bool quad = abs_(t) < m.fr_Rf[i] * Mii + m.fr_f[i];
-    const T z = quad ? T(0) : copysign_(T(1), t);
-    zone[i] = z;
+    zone[i] = quad ? T(0) : copysign_(T(1), t);
+  }
+}
+// second attempt: the zones the rejected candidate lies in (one step of an active-set iteration)
+template <typename T>
+SO101_DEV void active_set_zones_at(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV], T (&zone)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const T jar = a[i] - rw.aref_f[i];
+    zone[i] = abs_(jar) < m.fr_Rf[i] ? T(0) : copysign_(T(1), jar);
+  }
+}
+// right-hand side and Hessian diagonal of the piece given by the zones
+template <typename T>
+SO101_DEV void active_set_system(const DevModel<T>& m, const Rows<T>& rw, const T (&zone)[NV], const T (&fsm)[NV],
+                                 T (&rhs)[NV], T (&hd)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    const bool quad = zone[i] == T(0);
     hd[i] = quad ? m.fr_D[i] : T(0);
-    rhs[i] = fsm[i] + (quad ? m.fr_D[i] * ar : -z * m.fr_f[i]);
+    rhs[i] = fsm[i] + (quad ? m.fr_D[i] * rw.aref_f[i] : -zone[i] * m.fr_f[i]);
   }
 }
 // KKT check of the direct solve at a, and the constraint force there (same values as cost_update's)
@@ -984,18 +1002,24 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
       if (!constrained) {
         to_euler = true;  // nefc == 0: qacc = qacc_smooth
       } else if (!rw.anylim) {
-        active_set_guess(m, rw, M, asm_, fsm, zone, x, dd);   // next pass of the loop solves (M + diag(dd)) x = rhs
+        active_set_guess(m, rw, M, asm_, zone);
+        active_set_system(m, rw, zone, fsm, x, dd);   // next pass of the loop solves (M + diag(dd)) x = rhs
         phase = PH_DIRECT;
       } else {
         need_setup = true;
       }
     } else if (ph == PH_DIRECT) {
+      iter++;
       if (active_set_accept(m, rw, zone, x, qc)) {
 #pragma unroll
         for (int i = 0; i < NV; i++) a[i] = x[i];
-        cnt.newton += 1;
+        cnt.newton += iter;
         to_euler = true;
+      } else if (iter == 1) {
+        active_set_zones_at(m, rw, x, zone);
+        active_set_system(m, rw, zone, fsm, x, dd);
       } else {
+        iter = 0;
         need_setup = true;
       }
     }
@@ -1286,20 +1310,26 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   bool solved = !constrained;
   if (constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     T zone[NV], xs[NV], dh[NV];
-    active_set_guess(m, rw, M, asm_, fsm, zone, xs, dh);
-    {
-      T A[21];
+    active_set_guess(m, rw, M, asm_, zone);
+#pragma unroll 1
+    for (int pass = 1; pass <= 2; pass++) {
+      active_set_system(m, rw, zone, fsm, xs, dh);
+      {
+        T A[21];
 #pragma unroll
-      for (int i = 0; i < 21; i++) A[i] = M[i];
+        for (int i = 0; i < 21; i++) A[i] = M[i];
 #pragma unroll
-      for (int i = 0; i < NV; i++) A[tri(i, i)] += dh[i];
-      ldl6_factor_solve(A, xs);
-    }
-    if (active_set_accept(m, rw, zone, xs, qc)) {
+        for (int i = 0; i < NV; i++) A[tri(i, i)] += dh[i];
+        ldl6_factor_solve(A, xs);
+      }
+      if (active_set_accept(m, rw, zone, xs, qc)) {
 #pragma unroll
-      for (int i = 0; i < NV; i++) a[i] = xs[i];
-      cnt.newton += 1;
-      solved = true;
+        for (int i = 0; i < NV; i++) a[i] = xs[i];
+        cnt.newton += pass;
+        solved = true;
+        break;
+      }
+      active_set_zones_at(m, rw, xs, zone);
     }
   }
   if (!solved) {

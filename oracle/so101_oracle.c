@@ -881,7 +881,11 @@ static void proxStart(OracleData* d) {
  * active_set_accept).  Zones of the friction rows guessed from the per-dof problem, ONE solve of
  * (M + J'DJ restricted to the quadratic rows) a = qfrc_smooth + ..., accepted iff every row lies in the zone it was
  * assumed in (KKT on a strictly convex piecewise-quadratic cost => global minimiser).  Only without limit rows;
- * returns 0 if not applicable / rejected.  so101o_set_solver_start(2) enables it (tests/test_oracle.py). */
+ * returns 0 if not applicable / rejected.  so101o_set_solver_start(2) enables it (tests/test_oracle.py);
+ * so101o_set_direct_retries(1) adds the kernels' second attempt (zones of the rejected candidate). */
+static int g_direct_retries = 0;
+static long g_direct_retry_count = 0;
+void so101o_set_direct_retries(int n) { g_direct_retries = n; }
 static int directActiveSet(OracleData* d) {
   if (d->nefc != d->nf) return 0;                        /* limit rows present */
   double Mf[NV * NV], H[NV * NV], rhs[NV], zone[MAXEFC];
@@ -900,11 +904,34 @@ static int directActiveSet(OracleData* d) {
   double a[NV];
   cholFactor(H, NV);
   cholSolve(a, H, rhs, NV);
+  int ok = 1;
   for (int i = 0; i < d->nf; i++) {
     int dof = d->efc_id[i];
     double jar = a[dof] - d->efc_aref[i], Rf = d->efc_R[i] * d->efc_frictionloss[i];
-    if (zone[i] == 0.0 ? !(fabs(jar) < Rf) : !(zone[i] * jar > Rf)) return 0;
+    if (zone[i] == 0.0 ? !(fabs(jar) < Rf) : !(zone[i] * jar > Rf)) ok = 0;
   }
+  for (int retry = 0; !ok && retry < g_direct_retries; retry++) {
+    /* active-set iteration: zones of the rejected candidate, solve again */
+    memcpy(H, Mf, sizeof H);
+    memcpy(rhs, d->qfrc_smooth, sizeof rhs);
+    for (int i = 0; i < d->nf; i++) {
+      int dof = d->efc_id[i];
+      double ar = d->efc_aref[i], f = d->efc_frictionloss[i], D = d->efc_D[i], jar = a[dof] - ar, Rf = d->efc_R[i] * f;
+      zone[i] = fabs(jar) < Rf ? 0.0 : (jar > 0 ? 1.0 : -1.0);
+      if (zone[i] == 0.0) { H[dof * NV + dof] += D; rhs[dof] += D * ar; }
+      else rhs[dof] -= zone[i] * f;
+    }
+    cholFactor(H, NV);
+    cholSolve(a, H, rhs, NV);
+    ok = 1;
+    for (int i = 0; i < d->nf; i++) {
+      int dof = d->efc_id[i];
+      double jar = a[dof] - d->efc_aref[i], Rf = d->efc_R[i] * d->efc_frictionloss[i];
+      if (zone[i] == 0.0 ? !(fabs(jar) < Rf) : !(zone[i] * jar > Rf)) ok = 0;
+    }
+    g_direct_retry_count++;
+  }
+  if (!ok) return 0;
   memcpy(d->qacc, a, sizeof a);
   double jarv[MAXEFC], cost;
   for (int i = 0; i < d->nefc; i++) jarv[i] = dotn(d->efc_J[i], d->qacc, NV) - d->efc_aref[i];
