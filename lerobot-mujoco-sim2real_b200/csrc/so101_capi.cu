@@ -309,6 +309,7 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   T u[NV], site[3] = {T(0), T(0), T(0)};
 #pragma unroll
   for (int k = 0; k < NV; k++) u[k] = (ctrl && k < n_ctrl) ? ctrl[k * s.n + i] : T(0);
+  clamp_ctrl(m, u);
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
 #pragma unroll 1
@@ -372,6 +373,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
 #pragma unroll
     for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
+    clamp_ctrl(m, uc);   // rows keep the unclamped u, as the reference's dataset does
     if (rows && active && (t > t0 || t0 == 0)) {
       ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
 #pragma unroll
@@ -414,6 +416,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
     if (t > 0) {
 #pragma unroll
       for (int k = 0; k < 5; k++) uc[k] = U[((int64_t)(t - 1) * 5 + k) * s.n + i];
+      clamp_ctrl(m, uc);
 #pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++)
         step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);

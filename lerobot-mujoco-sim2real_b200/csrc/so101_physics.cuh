@@ -685,6 +685,13 @@ SO101_DEV T cost_update(const DevModel<T>& m, const Rows<T>& rw, const T (&a)[NV
 // counts (CPU test `test_exact_line_search_is_equivalent` under tests/), below the CUDA-vs-CPU
 // differences of the smooth dynamics.
 // ------------------------------------------------------------------------------------------
+// ctrlrange clamp of mj_fwdActuation, hoisted out of the sub-step loop: the control is constant over a control step
+template <typename T> SO101_DEV void clamp_ctrl(const DevModel<T>& m, T (&ctrl)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; i++)
+    if (m.ctrllim_mask >> i & 1) ctrl[i] = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], ctrl[i]));
+}
+
 // mj_passive, mj_fwdActuation, right-hand side of mj_fwdAcceleration, and the constraint rows of this step
 // (mj_instantiateLimit + mj_makeImpedance + mj_referenceConstraint for the limit rows)
 template <typename T>
@@ -696,8 +703,7 @@ SO101_DEV void build_rows(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], 
   for (int i = 0; i < NV; i++) {
     T passive = -m.damping[i] * e.qd[i];
     if (m.any_stiffness) passive = -m.stiffness[i] * (e.q[i] - m.qspring[i]) - m.damping[i] * e.qd[i];
-    T c = ctrl[i];
-    if (m.ctrllim_mask >> i & 1) c = max_(m.ctrl_lo[i], min_(m.ctrl_hi[i], c));
+    const T c = ctrl[i];   // already clamped to ctrlrange (clamp_ctrl, once per control step)
     T force = m.act_gain[i] * c + m.act_b0[i] + m.act_b1[i] * (m.act_gear[i] * e.q[i]) +
               m.act_b2[i] * (m.act_gear[i] * e.qd[i]);
     if (m.frclim_mask >> i & 1) force = max_(m.frc_lo[i], min_(m.frc_hi[i], force));
