@@ -57,7 +57,7 @@ SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps,
   for (int k = 0; k < NV; k++) { q[k] = x.q[k][lane]; qd[k] = x.qd[k][lane]; }
   if (role == 1) {
 #pragma unroll 1
-    for (int64_t n = 0; n < nsteps; n++) split_geometry_step(m, x, lane, q, qd);
+    for (int64_t n = 0; n < nsteps; n++) split_geometry_step(m, x, lane, q, qd, n);
   } else {
     int ss = 0;
 #pragma unroll 1

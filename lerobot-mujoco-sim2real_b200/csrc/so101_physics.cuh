@@ -986,7 +986,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   for (int i = 0; i < NV; i++) { x[i] = fsm[i]; dd[i] = T(0); }
   const bool constrained = m.nfriction != 0 || rw.anylim;
 
-  enum { PH_SMOOTH, PH_DIRECT, PH_NEWTON, PH_EULER, PH_DONE };
+  enum { PH_SMOOTH, PH_DIRECT, PH_NEWTON, PH_POLISH, PH_EULER, PH_DONE };
   int phase = PH_SMOOTH, iter = 0;
   T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV], zone[NV];
   T cost = T(0);
@@ -1114,8 +1114,24 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
       if (stop) {
         cnt.newton += iter;
         if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
-        to_euler = true;
+        if (!rw.anylim) {
+          // Polish: Newton stopped on its tolerance; solve the piece its iterate lies in exactly, so that a step
+          // that needed the general path ends on the same bits as one the direct solve accepted - whichever zone
+          // guess a kernel family used (the team kernels guess with a lagged factor of M).
+          active_set_zones_at(m, rw, a, zone);
+          active_set_system(m, rw, zone, fsm, x, dd);
+          phase = PH_POLISH;
+        } else {
+          to_euler = true;
+        }
       }
+    } else if (ph == PH_POLISH) {
+      T pq[NV];
+      if (active_set_accept(m, rw, zone, x, pq)) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) { a[i] = x[i]; qc[i] = pq[i]; }
+      }
+      to_euler = true;
     } else if (ph == PH_EULER) {  // x = (M + h B)^-1 (qfrc_smooth + qfrc_constraint)
 #pragma unroll
       for (int i = 0; i < NV; i++) {
@@ -1176,7 +1192,7 @@ template <typename T>
 struct SplitXch {      // shared memory of one team, structure-of-arrays over the 32 lanes
   T sn[NV][32], cs[NV][32];
   T M[21][32];
-  T L1[15][32], D1inv[NV][32];   // M       = L1 D1 L1^T
+  T L1[2][15][32], D1inv[2][NV][32];   // M = L1 D1 L1^T, double buffered: step n reads the factor of M_(n-1) (see split_geometry_step)
   T L2[15][32], D2inv[NV][32];   // M + h B = L2 D2 L2^T
   T site[3][32];
   uint32_t trip[32];
@@ -1211,9 +1227,16 @@ SO101_DEV void team_sincos(const DevModel<T>& m, SplitXch<T>& x, int lane, int r
   __syncthreads();   // (S)
 }
 
+// f64 teams guess the zones with the factor of the previous step's M (off the critical path).  In f32 a row lands
+// within rounding of a zone boundary often enough (a few times in 10^7 row-steps) that a different guess can end on a
+// neighbouring piece and on different bits than the one-warp kernels: f32 teams keep the exact, up-front factor.
+template <typename T> struct LaggedGuess { static constexpr bool value = true; };
+template <> struct LaggedGuess<float> { static constexpr bool value = false; };
+
 // geometry warp: M(q) and the two factorisations -> shared memory
 template <typename T>
-SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV]) {
+SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
+                                    int64_t n) {
   team_check_state(m, q, qd);
   team_sincos(m, x, lane, 1, q);
   crba_mass(m, &x.sn[0][lane], &x.cs[0][lane], 32, &x.M[0][lane], 32);
@@ -1222,12 +1245,25 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   for (int i = 0; i < NV; i++) { zero[i] = T(0); hB[i] = m.h * m.damping[i]; }
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
-  ldl6_factor(M, zero, Ls, Dinv);
+  // The factor of M only feeds the dynamics warp's zone guess (active_set_guess), for which the factor of the
+  // PREVIOUS step's M is as good (M moves by ~1e-3 per step): it is computed after barrier (A), off the path the
+  // dynamics warp waits on, into the buffer the next step reads.  Only the first step of a launch factors up front.
+  if (n == 0 || !LaggedGuess<T>::value) {
+    ldl6_factor(M, zero, Ls, Dinv);
 #pragma unroll
-  for (int i = 0; i < 15; i++) x.L1[i][lane] = Ls[i];
+    for (int i = 0; i < 15; i++) x.L1[0][i][lane] = Ls[i];
 #pragma unroll
-  for (int i = 0; i < NV; i++) x.D1inv[i][lane] = Dinv[i];
-  __syncthreads();   // (A) M and its factors published
+    for (int i = 0; i < NV; i++) x.D1inv[0][i][lane] = Dinv[i];
+  }
+  __syncthreads();   // (A) M published
+  if (LaggedGuess<T>::value) {
+    const int nb = (int)((n + 1) & 1);
+    ldl6_factor(M, zero, Ls, Dinv);
+#pragma unroll
+    for (int i = 0; i < 15; i++) x.L1[nb][i][lane] = Ls[i];
+#pragma unroll
+    for (int i = 0; i < NV; i++) x.D1inv[nb][i][lane] = Dinv[i];
+  }
   ldl6_factor(M, hB, Ls, Dinv);      // needed only by the Euler step: overlaps the constraint solve
 #pragma unroll
   for (int i = 0; i < 15; i++) x.L2[i][lane] = Ls[i];
@@ -1304,17 +1340,16 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
   T Ls[15], Dinv[NV];
-#pragma unroll
-  for (int i = 0; i < 15; i++) Ls[i] = x.L1[i][lane];
-#pragma unroll
-  for (int i = 0; i < NV; i++) Dinv[i] = x.D1inv[i][lane];
-  ldl6_solve(Ls, Dinv, asm_);
-
   T a[NV], Ma[NV], qc[NV], hd[NV];
-#pragma unroll
-  for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); hd[i] = T(0); }
-  bool solved = !constrained;
+  bool solved = false;
   if (constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
+    // zone guess from qacc_smooth approximated with the factor of the previous step's M (split_geometry_step)
+    const int rb = LaggedGuess<T>::value ? (int)(cnt.steps & 1u) : 0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) Ls[i] = x.L1[rb][i][lane];
+#pragma unroll
+    for (int i = 0; i < NV; i++) Dinv[i] = x.D1inv[rb][i][lane];
+    ldl6_solve(Ls, Dinv, asm_);
     T zone[NV], xs[NV], dh[NV];
     active_set_guess(m, rw, M, asm_, zone);
 #pragma unroll 1
@@ -1339,6 +1374,14 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     }
   }
   if (!solved) {
+    // general path (no friction rows, an active limit row, or the direct solve was rejected): exact qacc_smooth
+#pragma unroll
+    for (int i = 0; i < NV; i++) asm_[i] = fsm[i];
+    ldl6_factor_solve(M, asm_);
+#pragma unroll
+    for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); hd[i] = T(0); }
+  }
+  if (!solved && constrained) {
     T cost;
     if (!rw.anylim) {   // prox start (see physics_step)
 #pragma unroll
@@ -1413,6 +1456,23 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     }
     cnt.newton += iter;
     if (iter >= m.iterations) e.flags |= SO101_FLAG_MAXITER;
+    if (!rw.anylim) {   // polish (see physics_step): the exact minimiser of the piece the Newton iterate lies in
+      T zone[NV], xs[NV], dh[NV], pq[NV];
+      active_set_zones_at(m, rw, a, zone);
+      active_set_system(m, rw, zone, fsm, xs, dh);
+      {
+        T A[21];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] = M[i];
+#pragma unroll
+        for (int i = 0; i < NV; i++) A[tri(i, i)] += dh[i];
+        ldl6_factor_solve(A, xs);
+      }
+      if (active_set_accept(m, rw, zone, xs, pq)) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) { a[i] = xs[i]; qc[i] = pq[i]; }
+      }
+    }
   }
   __syncthreads();   // (E) factors of M + h B
   // mj_checkAcc, mj_Euler
