@@ -301,7 +301,7 @@ def run_b200(args) -> None:
         "kernel_ms": kernel_ms,
         "bound_note": "neither hbm nor tensor: ~300 FLOP per byte of state/row traffic, no contraction; the limiter is "
                       "the FP64 FMA pipe.  At this config (4096 envs = 128 three-warp teams, one per SM, on 148 SMs) the launch is "
-                      "latency-bound: a physics step is one dependent chain of ~3.8 k instructions on the team's dynamics warp (ncu: 43 % of its samples are fixed-latency waits); the large-batch fraction is in extra (fp64 131072: ~0.40 - the accounting budgets 2 Newton iterations, the kernels need 1.0; ncu: FP64 pipe 45 % busy)",
+                      "latency-bound: a physics step is one dependent chain of ~2.8 k instructions on the team's dynamics warp (ncu: 41 % of its samples are fixed-latency waits); the large-batch fraction is in extra (fp64 131072: ~0.50 - the accounting budgets 2 Newton iterations and a line search, the kernels need one direct solve; ncu: FP64 pipe 45 % busy)",
         "hbm_sanity": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                        "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                        "algorithmic_bytes_per_env_step": 208},
