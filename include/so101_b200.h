@@ -221,9 +221,9 @@ int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int fra
                         void* rows, uint32_t flags, void* stream);
 /* host-buffer variant (what SOARM101DataGenerator calls): spec->u (SO101_CTRL_TENSOR) and qpos0_host
    [6][N] (nullable: random reset) are HOST pointers, rows_host receives the dataset.  Work is ordered
-   after `stream`; long rollouts are cut into up to 8 time chunks whose uploads / downloads run on two
+   after `stream`; long rollouts are cut into up to 12 time chunks whose uploads / downloads run on two
    internal streams and overlap the compute (invisible in the result); everything is synchronised before
-   return.  Pinned host memory makes the copies async.  (Env. knob SO101_HOST_CHUNKS=1..8 overrides.) */
+   return.  Pinned host memory makes the copies async.  (Env. knob SO101_HOST_CHUNKS=1..12 overrides.) */
 int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const void* qpos0_host, int T,
                              int frame_skip, void* rows_host, uint32_t flags, void* stream);
 /* B = n_envs control sequences from one shared state: state0 host pointer to 18 doubles

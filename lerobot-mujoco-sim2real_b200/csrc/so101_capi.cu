@@ -482,7 +482,7 @@ struct So101Batch {
   void* rows_stage;   // [n][T+1][13] dataset rows (rollout_host)
   size_t rows_stage_bytes;
   // rollout_host pipeline: upload / download streams and per-chunk events
-  static constexpr int MAXCHUNK = 8;
+  static constexpr int MAXCHUNK = 12;
   bool pipe_ready;
   cudaStream_t s_up, s_down;
   cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
@@ -791,7 +791,7 @@ static int grow(void** buf, size_t* have, size_t need) {
   return SO101_OK;
 }
 
-// Host-buffer rollout, pipelined over time: the rollout is cut into up to 8 chunks of control steps; the control
+// Host-buffer rollout, pipelined over time: the rollout is cut into up to 12 chunks of control steps; the control
 // tensor of chunk c+1 is uploaded (stream up) and the rows of chunk c-1 are downloaded (stream down, strided copy into
 // the caller's [N][T+1][13] layout) while chunk c computes on the caller's stream.  Only the first upload and the last
 // download are exposed.
@@ -849,14 +849,17 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
     flags |= SO101_ROLL_NO_RESET;
   }
   // chunk c covers control steps (tb[c], tb[c+1]]; rows tb[c]+1 .. tb[c+1] (+ row 0 for the first chunk)
-  // Boundaries: a short first chunk (its control upload is the only exposed upload), then chunks that halve towards
-  // the end (the download of the last chunk is the only exposed download); SO101_HOST_EVEN=1: equal chunks.
+  // Boundaries: chunks that double from 2 control steps (every upload finishes while the previous, half as long
+  // chunk computes, even at a fraction of the PCIe rate - right after the caller flushed L2 uploads are ~3x slower),
+  // then chunks that halve towards the end (the download of the last chunk is the only exposed download).
+  // SO101_HOST_EVEN=1: equal chunks.
   int tb[So101Batch::MAXCHUNK + 1];
   if (nchunk >= 4 && !getenv("SO101_HOST_EVEN")) {
-    int k = 0;
+    int k = 0, pos = 0;
     tb[k++] = 0;
-    tb[k++] = T < 2 ? T : 2;
-    const int rest = T - tb[1];
+    for (int sz = 2; pos + sz < T / 2 && k < nchunk - 3; sz *= 2) { pos += sz; tb[k++] = pos; }
+    if (k == 1) { pos = T < 2 ? T : 2; tb[k++] = pos; }
+    const int rest = T - pos;
     for (int sh = 1; k < nchunk && tb[k - 1] < T; sh++) {
       const int t = T - (rest >> sh);
       if (t > tb[k - 1]) tb[k++] = t;

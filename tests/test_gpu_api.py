@@ -319,7 +319,7 @@ def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind)
     g = torch.Generator().manual_seed(9)
     U = (torch.rand((T + 1, 5, n), generator=g, dtype=torch.float64) - 0.5).contiguous().pin_memory()
     res = {}
-    for chunks in ("1", "2", "4", "8"):
+    for chunks in ("1", "2", "4", "8", "12"):
         monkeypatch.setenv("SO101_HOST_CHUNKS", chunks)
         env = _vec(tables_v, n)
         out = torch.full((n, T + 1, 13), float("nan"), dtype=torch.float64).pin_memory()
@@ -329,7 +329,7 @@ def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind)
         res[chunks] = (out.clone(), q.clone(), v.clone(), w.clone())
         assert env.stats()["physics_steps"] == n * T * 10
         assert not torch.isnan(out).any()
-    for chunks in ("2", "4", "8"):
+    for chunks in ("2", "4", "8", "12"):
         for a, b in zip(res["1"], res[chunks]):
             assert torch.equal(a, b)
     monkeypatch.delenv("SO101_HOST_CHUNKS")
