@@ -358,6 +358,25 @@ def run_b200(args) -> None:
         extra["config5_shoot_8192x50"] = {"ms": best5, "env_steps_per_s": 8192 * 50 / (best5 * 1e-3),
                                           "rollouts_per_s": 8192 / (best5 * 1e-3)}
         del e5
+        # row N3: 16384 reference curves (300 way-points each, position-only as Koopman_MPC.py runs them) -> joint tracks
+        import numpy as np
+        from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import CartesianTrajectoryGenerator, reference_curve
+        gen = CartesianTrajectoryGenerator(tables=tables, device=dev.index)
+        nik = 16384
+        base = np.stack([reference_curve(nm, ix)[0] for nm in ("Fig8", "Circle") for ix in (0, 1)])
+        xyz = torch.as_tensor(base[np.arange(nik) % 4] + np.random.default_rng(SEED).uniform(-0.03, 0.03, (nik, 1, 3)),
+                              device=dev)
+        gen.solve_tracks(xyz)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); qik, stik = gen.solve_tracks(xyz); b.record(); torch.cuda.synchronize()
+        ms_ik = a.elapsed_time(b)
+        extra["n3_ik_tracks_16384x300"] = {
+            "ms": ms_ik, "waypoints_per_s": nik * 300 / (ms_ik * 1e-3),
+            "gauss_newton_iters_per_waypoint": float((stik >> 8).double().mean().item()),
+            "success_frac": float((stik & 1).double().mean().item()),
+            "note": "k_ik_track<false>: one thread per track incl. the [n,P,3] -> [P,3,n] relayout"}
+        del gen, xyz, qik, stik
 
     # CPU baseline: bounded sample sized for ~10-20 s of CPU work
     cal_rate, _, nthr = oracle_rate(64, 1, 1)

@@ -20,6 +20,9 @@
  *                                                                   [REF SOARM101/SOARM101_DataCollection.py:108-134]
  *   so101_batch_shoot       <- batched evaluation of control sequences from one shared state
  *                              (Koopman_MPC.py:197-222 closed loop, BASELINE.json config 5)
+ *   so101_ik_track          <- the per-way-point dm_control qpos_from_site_pose loop of
+ *                              CartesianTrajectoryGenerator.generate / _solve_ik
+ *                                                                   [REF control/TrajectoryGenerator.py:81-116, 180-210]
  *
  * Conventions
  *   - plain C, no exceptions; every call returns 0 on success, <0 on error (so101_last_error()
@@ -43,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 4
+#define SO101_ABI_VERSION 5
 #define SO101_NV       6   /* hinge dofs: 5 arm joints + gripper */
 #define SO101_MAXBODY  8   /* world, fixed base, 6 links */
 #define SO101_MAXTRIP 16   /* contact-tripwire boxes (<= 3 per link) */
@@ -172,6 +175,9 @@ typedef struct So101Tables {
   double  trip_half[SO101_MAXTRIP][3];
   double  trip_plane_z;                       /* table top (world z)                       */
   double  trip_qbox[SO101_NV][2];             /* lo, hi                                    */
+  /* orientation of the observation site in its body's frame (w, x, y, z): only the inverse
+     kinematics (so101_ik_track) reads it, the stepper needs the site position alone */
+  double  site_quat[4];
 } So101Tables;
 
 typedef struct So101Model So101Model;
@@ -254,6 +260,40 @@ int so101_fma_peak(int dtype, int device, double* tflops_out);
 int so101_koopman_score(const double* A, const double* B, int nz, int nu, const double* z0, const double* zref,
                         double q_weight, double r_weight, const void* U, int H, int64_t n, int dtype, int device,
                         int nobs, void* Xhat, void* cost, void* stream);
+
+/* ---- batched site-pose inverse kinematics along Cartesian way-point tracks ------------------------
+   Replaces the loop of CartesianTrajectoryGenerator.generate [REF control/TrajectoryGenerator.py:180-210] around
+   dm_control.utils.inverse_kinematics.qpos_from_site_pose [REF control/TrajectoryGenerator.py:96-107] for n
+   independent tracks at once: track b visits way-points xyz[p][.][b], p = 0..P-1, in order; every solve starts from the
+   previous way-point's joint vector (the first one from q0, or the model's qpos0 when q0 is NULL); a failed solve
+   repeats the previous way-point's answer and restores the joint vector it started from, as the reference loop does.
+   One solve = damped/min-norm Gauss-Newton on the site pose error: err = [target - site_xpos | quat2Vel(target_quat *
+   conj(site_xquat))], err_norm = |err_pos| + rot_weight |err_rot|; success when err_norm < tol; update = (J'J + reg I)^-1
+   J'err when err_norm > reg_threshold, else the minimum-norm least-squares solution of J'J x = J'err (singular values
+   below DBL_EPSILON * largest dropped, numpy lstsq rcond=-1); stop (fail) when err_norm / |update| > progress_thresh;
+   |update| clipped to max_update_norm; q += update on the dofs of dof_mask (mj_integratePos for hinges).
+   All DEVICE buffers are double, structure-of-arrays over the tracks:
+     xyz    [P][3][n]   way-points (world frame)
+     quat   [4][n]      target orientation (w,x,y,z) held along the whole track, or NULL = position only
+     q0     [6][n]      start joint vectors, or NULL
+     q_out  [P][6][n]   joint vector stored for every way-point (all 6 dofs; the reference keeps [:num_joints])
+     status [P][n]      int32: bit 0 = success, bits 8.. = iterations used (the reference's IKResult.steps)
+     err    [P][n]      err_norm at exit (nullable)
+   Async on `stream`; the model handle comes from so101_model_create. */
+typedef struct So101IkParams {
+  double  tol;                 /* 1e-6   [REF control/TrajectoryGenerator.py:103]                  */
+  double  rot_weight;          /* 0.5    [REF :104]                                                */
+  double  reg_strength;        /* 1e-2   [REF :105]                                                */
+  double  reg_threshold;       /* 0.1    dm_control default regularization_threshold               */
+  double  max_update_norm;     /* 2.0    dm_control default                                        */
+  double  progress_thresh;     /* 20.0   dm_control default                                        */
+  int32_t max_steps;           /* 100    [REF :102]                                                */
+  int32_t dof_mask;            /* bit k = dof k may move; 0x1f = the five arm joints [REF :56]     */
+} So101IkParams;
+
+int so101_ik_track(const So101Model* model, const So101IkParams* params, const double* xyz, const double* quat,
+                   const double* q0, int P, int64_t n, int device, double* q_out, int32_t* status, double* err,
+                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from typing import Optional
 
-from .tables import So101CtrlSpec, So101Tables
+from .tables import So101CtrlSpec, So101IkParams, So101Tables
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libso101_b200.so")
 
@@ -24,7 +24,7 @@ EXPORTS = [
     "so101_batch_rollout", "so101_batch_rollout_host", "so101_batch_shoot",
     "so101_batch_get_state", "so101_batch_set_state", "so101_batch_set_qfrc_applied",
     "so101_batch_get_flags", "so101_batch_clear_flags", "so101_batch_stats",
-    "so101_fma_peak", "so101_koopman_score",
+    "so101_fma_peak", "so101_koopman_score", "so101_ik_track",
 ]
 
 
@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
     L.so101_batch_stats.argtypes = [vp, C.POINTER(u64), vp]
     L.so101_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.so101_koopman_score.argtypes = [vp, vp, i32, i32, vp, vp, C.c_double, C.c_double, vp, i32, i64, i32, i32, i32, vp, vp, vp]
+    L.so101_ik_track.argtypes = [vp, C.POINTER(So101IkParams), vp, vp, vp, i32, i64, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("so101_abi_version", "so101_device_count"):

@@ -1010,3 +1010,4 @@ int so101_fma_peak(int dtype, int device, double* tflops_out) {
 }  // extern "C"
 
 #include "so101_koopman.cuh"
+#include "so101_ik.cuh"

@@ -439,7 +439,7 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
     body_mass = [0.0]
     body_jnt = [-1]
     joints: List[dict] = []
-    sites: List[Tuple[str, int, np.ndarray]] = []
+    sites: List[Tuple[str, int, np.ndarray, np.ndarray]] = []
     geoms: List[Geom] = []
 
     def read_geoms_sites(elem: ET.Element, bid: int, childclass: Optional[str]) -> None:
@@ -455,7 +455,8 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
         for s in elem.findall("site"):
             a = dict(cls_of(s, childclass).site)
             a.update(s.attrib)
-            sites.append((a.get("name", ""), bid, _floats(a.get("pos", "0 0 0"), 3)))
+            sites.append((a.get("name", ""), bid, _floats(a.get("pos", "0 0 0"), 3),
+                          _frame_quat(a, angle_scale, comp["eulerseq"])))
 
     def visit_body(elem: ET.Element, parent: int, childclass: Optional[str]) -> None:
         a = elem.attrib
@@ -636,6 +637,7 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
     sid = site_names.index(site_name)
     t.site_body = sites[sid][1]
     t.site_pos[:] = list(sites[sid][2])
+    t.site_quat[:] = list(sites[sid][3])
 
     # ---- derived constants (engine_setconst.c): M(qpos0), invweight0, meaninertia, dampratio ------
     M0 = mass_matrix_numpy(t, np.array([j["ref"] for j in joints]))
