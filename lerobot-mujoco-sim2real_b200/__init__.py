@@ -3,7 +3,9 @@
 Only what the hot path needs lives here: the host MJCF compiler (mjcf.py), the packed tables
 (tables.py), the ctypes binding of the CUDA C-ABI library (_lib.py, csrc/), and the host-side
 mirrors of the reference interface (SOARM101_Env.py, SOARM101_DataCollection.py, vec_env.py),
-plus the device-side twin of the reference's Koopman model / MPC cost (koopman.py).
+plus the device-side twin of the reference's Koopman model / MPC cost (koopman.py), its Cartesian
+trajectory generator with the per-way-point inverse kinematics as one launch (TrajectoryGenerator.py, N3) and the
+control loop of Koopman_MPC.py over a batch of curves (Koopman_MPC.py).
 """
 from . import tables  # noqa: F401
 from .tables import builtin_tables, load_tables, save_tables  # noqa: F401
@@ -21,6 +23,12 @@ def __getattr__(name):  # heavy modules (torch, ctypes library) load on first us
     if name == "KoopmanModel":
         from .koopman import KoopmanModel
         return KoopmanModel
+    if name == "CartesianTrajectoryGenerator":
+        from .TrajectoryGenerator import CartesianTrajectoryGenerator
+        return CartesianTrajectoryGenerator
+    if name == "BatchedKoopmanMPC":
+        from .Koopman_MPC import BatchedKoopmanMPC
+        return BatchedKoopmanMPC
     if name in ("SOARM101DataGenerator", "Collater"):
         from . import SOARM101_DataCollection as dc
         return getattr(dc, name)

@@ -338,3 +338,79 @@ def test_cartesian_trajectory_generator_drop_in(tables_v, tables_p):
     dist = np.linalg.norm(ee[:, 20:] - xb[:, 20:P - 1].cpu().numpy(), axis=2)
     print(f"servo tracking of the IK joint track: mean {dist.mean() * 1e3:.2f} mm, max {dist.max() * 1e3:.2f} mm")
     assert dist.mean() < 0.03
+
+
+def _mpc_loop_oracle(tables, W, cp, ja, frames, H=10):
+    """CPU restatement of the reference loop [REF Koopman_MPC.py:83-90, 109-126, 197-222] for ONE curve: C-oracle
+    physics, numpy Koopman lift, the MPC's NLP solved by normal equations.  -> (actions [frames,5], actual [frames,8])."""
+    from oracle import koopman_oracle as KO
+    from oracle import oracle as O
+    o = O.Oracle(tables)
+    o.reset()
+    q = np.zeros(6); q[:5] = ja[0]
+    o.set("qpos", q); o.forward()                                    # runBefore
+    ref = np.hstack([cp, ja])
+    state = ref[0].copy()
+    nz = W["lA.weight"].shape[0]
+    acts, actual = [], []
+    for k in range(frames):
+        o.set("qfrc_applied", np.array(o.arr("qfrc_bias")))          # gravity compensation (:119)
+        seg = ref[k + 1:k + H + 1]
+        zref = np.zeros((H, nz))
+        if len(seg):
+            zref[:len(seg)] = KO.lift(W, seg)
+        a = np.clip(KO.mpc_solve(W, KO.lift(W, state), zref, H)[0], -0.5, 0.5)
+        ctrl = np.zeros(6); ctrl[:5] = a
+        o.set("ctrl", ctrl)
+        o.step(10)                                                   # env.step: frame_skip x mj_step
+        state = np.concatenate([o.arr("site_xpos"), o.arr("qpos")[:5]]).astype(np.float32).astype(np.float64)
+        o.forward()                                                  # mj_forward (:126)
+        acts.append(a); actual.append(state)
+    return np.array(acts), np.array(actual)
+
+
+@pytest.mark.gpu
+def test_koopman_mpc_loop_follows_ik_tracks(tables_v):
+    """Rows N3 + N4 on the stepper: the reference's Koopman_MPC.py loop for 64 curves at once — curve -> IK joint track
+    (one launch) -> reference states [ee | q] -> closed-form MPC on the reference's shipped model -> env.step with
+    gravity compensation.  The first frames are checked against a CPU restatement of the loop (scene A is chaotic
+    beyond ~100 physics steps, F3); over the whole curve the end effector must follow the Cartesian reference."""
+    import torch
+    from lerobot_mujoco_sim2real_b200.Koopman_MPC import BatchedKoopmanMPC
+    from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import CartesianTrajectoryGenerator, reference_curve
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    W = {k: v.astype(np.float64) for k, v in np.load(os.path.join(ROOT, "tests", "golden", "koopman_dkuc.npz")).items()}
+    km = KoopmanModel(W)
+    gen = CartesianTrajectoryGenerator(tables=tables_v)
+    rng = np.random.default_rng(21)
+    n = 64
+    base = [reference_curve(nm, ix)[0] for nm in ("Fig8", "Circle") for ix in (1, 0)]
+    xyz = np.stack([base[b % 4] + (rng.uniform(-0.02, 0.02, 3) if b >= 4 else 0.0) for b in range(n)])
+    q, st = gen.solve_tracks(xyz)
+    assert (st & 1).all()
+    cp, ja = torch.as_tensor(xyz).cuda(), q[:, :, :5].contiguous()
+    env = SOARM101VecEnv(tables=tables_v, num_envs=n, gravity_compensation=True)
+    loop = BatchedKoopmanMPC(env, km, cp, ja, H=10)
+    actual = loop.run().cpu().numpy()                                # [n, 300, 8]
+    assert actual.shape == (n, 300, 8) and loop.traj_index == 300
+    # (a) the first frames against the CPU restatement, curve by curve
+    frames = 8
+    for b in (0, 3, 17):
+        acts_o, actual_o = _mpc_loop_oracle(tables_v, W, xyz[b], ja[b].cpu().numpy(), frames)
+        d = np.abs(actual[b, :frames] - actual_o).max()
+        assert d < 5e-6, (b, d)                                      # float32 observations, <= 80 physics steps
+    # (b) tracking: frame k has applied the control computed for reference k+1
+    ee_err = np.linalg.norm(actual[:, 20:299, :3] - xyz[:, 21:300], axis=2)
+    q_err = np.abs(actual[:, 20:299, 3:] - ja[:, 21:300].cpu().numpy())
+    fam = np.arange(n) % 4
+    names = ["Fig8/idx1", "Fig8/idx0", "Circle/idx1", "Circle/idx0"]
+    for f in range(4):
+        print(f"Koopman_MPC loop, {names[f]:12s}: ee error mean {ee_err[fam == f].mean() * 1e3:6.2f} mm, "
+              f"p99 {np.quantile(ee_err[fam == f], 0.99) * 1e3:6.2f} mm; |q - q_ref| mean {q_err[fam == f].mean():.2e} rad; "
+              f"|q_ref| max {np.abs(ja[fam == f].cpu().numpy()).max():.2f} rad")
+    # idx = 1 (the y-z plane, what Koopman_MPC.py:246 runs) keeps the joints inside the model's training range
+    # (|q| < ~0.4 rad); the x-y plane curves swing the arm to +-1.4 rad, where the shipped model extrapolates
+    yz = (fam == 0) | (fam == 2)
+    assert ee_err[yz].mean() < 0.01
+    assert np.isfinite(actual).all()
