@@ -16,7 +16,8 @@
 //     equations.  (J'J + reg I)^-1 J' = J'(JJ' + reg I)^-1 and pinv(J'J) J' = pinv(J) = J' pinv(JJ') hold exactly and
 //     J'J, JJ' share their non-zero spectrum, so numpy's `lstsq(J'J, J'err, rcond=-1)` cut (singular values
 //     <= DBL_EPSILON * largest are dropped) is the same cut on either side;
-//   * the pseudo-inverse is a cyclic Jacobi eigen-decomposition of that symmetric matrix (3x3 or 6x6, unrolled).
+//   * the pseudo-inverse is the plain inverse (LDL') whenever every pivot is far above the cut, and a cyclic Jacobi
+//     eigen-decomposition of that symmetric matrix (3x3 or 6x6, unrolled) otherwise.
 // Included at the end of so101_capi.cu (same translation unit: shares fail()/CUDA_TRY/DeviceGuard/So101Model).
 #pragma once
 
@@ -74,17 +75,19 @@ __device__ __forceinline__ void rot_error(const double* tq, const double* sq, do
   e[0] = x * speed; e[1] = y * speed; e[2] = z * speed;
 }
 
-// x = (G + diag(add))^-1 b for a symmetric positive definite N x N system (LDL', unrolled)
+// x = (G + diag(add))^-1 b for a symmetric positive definite N x N system (LDL', unrolled).  Returns the smallest pivot.
 template <int N>
-__device__ __forceinline__ void spd_solve(const double (&G)[N][N], const double (&add)[N], const double (&b)[N],
-                                          double (&x)[N]) {
+__device__ __forceinline__ double spd_solve(const double (&G)[N][N], const double (&add)[N], const double (&b)[N],
+                                            double (&x)[N]) {
   double L[N][N], d[N];
+  double dmin = 1e300;
 #pragma unroll
   for (int j = 0; j < N; j++) {
     double s = G[j][j] + add[j];
 #pragma unroll
     for (int k = 0; k < j; k++) s -= L[j][k] * L[j][k] * d[k];
     d[j] = s;
+    dmin = fmin(dmin, s);
     const double inv = 1 / s;
 #pragma unroll
     for (int i = j + 1; i < N; i++) {
@@ -110,6 +113,28 @@ __device__ __forceinline__ void spd_solve(const double (&G)[N][N], const double 
     for (int k = i + 1; k < N; k++) t -= L[k][i] * x[k];
     x[i] = t;
   }
+  return dmin;
+}
+
+// x = G^+ b with numpy's rcond=-1 cut.  When every LDL' pivot is far above the cut (WELL * largest diagonal entry; the
+// cut itself is 2.2e-16 * lambda_max) no eigenvalue can be dropped, the pseudo-inverse IS the inverse and the
+// factorisation's answer is returned (the usual case: ~100 instructions instead of ~1500 for the eigen-decomposition);
+// otherwise - near a kinematic singularity, or masked-out dofs in the 6 x 6 case - the Jacobi path decides which
+// directions exist.
+template <int N>
+__device__ __forceinline__ void sym_pinv_apply(double (&A)[N][N], const double (&b)[N], double (&x)[N]);
+// `pad[i]` = 1 for rows/columns that are identically zero by construction (dofs that may not move): they are given a
+// unit diagonal for the factorisation, which leaves x_i = 0 and the other unknowns untouched.
+template <int N>
+__device__ __forceinline__ void sym_solve_or_pinv(double (&G)[N][N], const double (&pad)[N], const double (&b)[N],
+                                                  double (&x)[N]) {
+  constexpr double WELL = 1e-6;
+  double gmax = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) gmax = fmax(gmax, G[i][i]);
+  const double dmin = spd_solve<N>(G, pad, b, x);
+  if (dmin > WELL * gmax) return;       // false for NaN pivots too
+  sym_pinv_apply<N>(G, b, x);
 }
 
 // x = G^+ b for symmetric G, eigenvalues with |lambda| <= DBL_EPSILON * max|lambda| dropped (numpy lstsq, rcond=-1).
@@ -287,7 +312,8 @@ k_ik_track(const __grid_constant__ IkModel m, const So101IkParams prm, const dou
             const double add[3] = {prm.reg_strength, prm.reg_strength, prm.reg_strength};
             ik::spd_solve<3>(G, add, e3, y);
           } else {
-            ik::sym_pinv_apply<3>(G, e3, y);
+            const double pad[3] = {0, 0, 0};
+            ik::sym_solve_or_pinv<3>(G, pad, e3, y);
           }
 #pragma unroll
           for (int k = 0; k < NV; k++) upd[k] = J[0][k] * y[0] + J[1][k] * y[1] + J[2][k] * y[2];
@@ -307,15 +333,12 @@ k_ik_track(const __grid_constant__ IkModel m, const So101IkParams prm, const dou
               G[i][j] = t;
             }
           }
-          if (reg) {
-            double add[NV];
+          double add[NV];
 #pragma unroll
-            for (int k = 0; k < NV; k++)
-              add[k] = (((prm.dof_mask >> k) & 1) && k <= m.site_link) ? prm.reg_strength : 1.0;
-            ik::spd_solve<NV>(G, add, g, upd);
-          } else {
-            ik::sym_pinv_apply<NV>(G, g, upd);
-          }
+          for (int k = 0; k < NV; k++)
+            add[k] = (((prm.dof_mask >> k) & 1) && k <= m.site_link) ? (reg ? prm.reg_strength : 0.0) : 1.0;
+          if (reg) ik::spd_solve<NV>(G, add, g, upd);
+          else ik::sym_solve_or_pinv<NV>(G, add, g, upd);
         }
         double un = 0;
 #pragma unroll
@@ -347,8 +370,9 @@ extern "C" int so101_ik_track(const So101Model* model, const So101IkParams* para
                               const double* quat, const double* q0, int P, int64_t n, int device, double* q_out,
                               int32_t* status, double* err, void* stream) {
   using namespace so101;
-  if (!model || !params || !q_out || !status || (!xyz && P > 0 && n > 0)) return fail(SO101_EINVAL, "null argument");
+  if (!model || !params) return fail(SO101_EINVAL, "null argument");
   if (P < 0 || n < 0) return fail(SO101_EINVAL, "ik_track: negative size");
+  if (P > 0 && n > 0 && (!q_out || !status || !xyz)) return fail(SO101_EINVAL, "null argument");
   if (params->max_steps < 1 || !(params->tol >= 0)) return fail(SO101_EINVAL, "ik_track: need max_steps >= 1, tol >= 0");
   if ((params->dof_mask & ~((1 << NV) - 1)) != 0) return fail(SO101_EINVAL, "ik_track: dof_mask has bits beyond dof 5");
   if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible: this library has no CPU fallback");

@@ -113,3 +113,32 @@ class KoopmanModel:
         zref = self.lift(xref.reshape(N * H, -1)).reshape(N, H * self.nz)
         u = z0 @ Kz[:self.nu].t() + zref @ Kr[:self.nu].t()
         return torch.clamp(u, -clip, clip)
+
+    # ---- sampling MPC through the physics ("replaces IPOPT with sampling MPC") -----------------------
+    def shooting_mpc(self, shooter, state0, x: torch.Tensor, xref: torch.Tensor, sigma: float = 0.05,
+                     clip: float = 0.5, q_weight: float = 50.0, r_weight: float = 0.5, flags: int = 0,
+                     seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """One sampling-MPC step: B = shooter.num_envs candidate control sequences [H, nu] are rolled through the
+        PHYSICS from the shared physics state `state0` (18 doubles: qpos, qvel, qacc_warmstart) in one `k_shoot` launch
+        (BASELINE config 5) and costed with the reference's MPC cost on the lifted outcome,
+            sum_t q |psi(x_{t+1}) - psi(xref_t)|^2 + r |u_t|^2          [REF control/MPC_Controler.py:65-98],
+        candidate 0 = the closed-form minimiser under the Koopman MODEL (what `mpc_control` applies), the others =
+        that sequence plus N(0, sigma^2) noise, all clipped to +-clip.  x [8] = current observation, xref [H, 8].
+        -> (U_best [H, nu], costs [B] (physics-evaluated), index of the best).  The best candidate can only improve on
+        the model's answer as judged by the true dynamics."""
+        H = int(xref.shape[0])
+        B = shooter.num_envs
+        dev, dt = shooter.device, shooter.torch_dtype
+        Kz, Kr = self.mpc_gains(H, q_weight, r_weight)
+        z0 = self.lift(x.reshape(1, -1))                                        # [1, nz]
+        zref = self.lift(xref)                                                  # [H, nz]
+        u_model = (z0 @ Kz.t() + zref.reshape(1, -1) @ Kr.t()).reshape(H, self.nu)
+        g = torch.Generator(device=dev).manual_seed(int(seed))
+        noise = torch.randn((H, self.nu, B), generator=g, dtype=torch.float64, device=dev) * sigma
+        noise[:, :, 0] = 0.0
+        U = torch.clamp(u_model[:, :, None] + noise, -clip, clip).to(dt).contiguous()          # [H, nu, B]
+        X = shooter.shoot(state0, U, flags=flags)                                # [B, H+1, 8] float32, physics
+        Z = self.lift(X[:, 1:].reshape(B * H, -1).double()).reshape(B, H, self.nz)
+        costs = q_weight * ((Z - zref[None]) ** 2).sum(dim=(1, 2)) + r_weight * (U.double() ** 2).sum(dim=(0, 1))
+        best = int(torch.argmin(costs).item())
+        return U[:, :, best].double(), costs, best

@@ -253,6 +253,29 @@ def test_ik_kernel_matches_live_oracle_batched(tables_v):
 
 
 @pytest.mark.gpu
+def test_ik_empty_and_single_inputs(tables_v):
+    """Edge cases: no tracks, no way-points, one track with one way-point, a start vector per track."""
+    import torch
+    from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import CartesianTrajectoryGenerator
+    gen = CartesianTrajectoryGenerator(tables=tables_v)
+    q, st = gen.solve_tracks(torch.empty((0, 7, 3), dtype=torch.float64))
+    assert tuple(q.shape) == (0, 7, 6) and tuple(st.shape) == (0, 7)
+    q, st = gen.solve_tracks(torch.empty((5, 0, 3), dtype=torch.float64))
+    assert tuple(q.shape) == (5, 0, 6) and tuple(st.shape) == (5, 0)
+    tgt = np.array([0.35, 0.05, 0.18])
+    q, st, err = gen.solve_tracks(tgt.reshape(1, 1, 3), return_err=True)
+    assert int(st[0, 0]) & 1 and float(err[0, 0]) < 1e-6
+    # already on target: zero iterations, the start vector comes back untouched (gripper dof included)
+    q0 = q[0, 0].clone(); q0[5] = 0.3
+    q2, st2 = gen.solve_tracks(tgt.reshape(1, 1, 3), q0=q0)
+    assert int(st2[0, 0]) == 1 and torch.equal(q2[0, 0], q0)
+    with pytest.raises(ValueError):
+        gen.solve_tracks(np.zeros((2, 3, 2)))
+    with pytest.raises(ValueError):
+        gen.solve_tracks(np.zeros((2, 3, 3)), target_quat=np.zeros((3, 4)))
+
+
+@pytest.mark.gpu
 def test_ik_full_size_properties(tables_v):
     """16384 reference curves (random plane, scale, centre; P = 300 way-points = the reference's 60 s x 5 Hz) in one
     launch: every successful way-point is hit within tol (float64 FK on a sample, the stepper's own site on all final

@@ -128,3 +128,55 @@ def test_closed_loop_mpc_tracks_on_the_cuda_simulator(tables_v):
     ee = float((x[:, :3] - xref[:, steps, :3]).norm(dim=-1).mean())
     print(f"closed-loop Koopman MPC on 512 envs: mean |q - qref| after settling {tail:.3e} rad, final ee error {ee*1e3:.2f} mm")
     assert tail < 0.01 and ee < 0.006        # measured: 4.2e-3 rad, 2.0 mm
+
+
+@pytest.mark.gpu
+def test_shooting_mpc_improves_on_the_model_solution(tables_v):
+    """Sampling MPC through the physics: 8192 candidates around the closed-form (model) solution in one k_shoot
+    launch, costed with the reference's MPC cost on the simulated outcome.  Candidate 0 IS the model's solution, so
+    the winner is never worse; re-shooting the winner alone reproduces its trajectory and cost (determinism,
+    batch-position invariance); in closed loop the sampled controls track at least as well as the model's."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    km = KoopmanModel(_weights())
+    B, H = 8192, 10
+    shooter = SOARM101VecEnv(tables=tables_v, num_envs=B)
+    plant = SOARM101VecEnv(tables=tables_v, num_envs=2, gravity_compensation=True)     # env 0: sampled, env 1: model
+    q0 = torch.zeros((2, 6), dtype=torch.float64, device="cuda")
+    q0[:, :5] = torch.tensor([0.1, -0.2, 0.15, 0.05, -0.1], dtype=torch.float64)
+    plant.set_state(q0, torch.zeros_like(q0), torch.zeros_like(q0))
+    x = plant.forward()[0].double().clone()                                          # [2, 8]
+    # reference: joints swing sinusoidally; reference observations from the simulator's own kinematics
+    steps = 40
+    t = torch.arange(steps + H + 1, dtype=torch.float64, device="cuda") * 0.02
+    qref = q0[0, :5][None] + 0.2 * torch.sin(2 * np.pi * 0.4 * t)[:, None] * torch.tensor([1.0, -0.7, 0.5, 0.8, -1.0],
+                                                                                         dtype=torch.float64, device="cuda")
+    scratch = SOARM101VecEnv(tables=tables_v, num_envs=steps + H + 1)
+    qf = torch.zeros((steps + H + 1, 6), dtype=torch.float64, device="cuda"); qf[:, :5] = qref
+    scratch.set_state(qf, torch.zeros_like(qf), torch.zeros_like(qf))
+    xref = scratch.forward()[0].double().clone()                                     # [steps+H+1, 8]
+    err_s, err_m, gains = [], [], []
+    for k in range(steps):
+        qp, qv, qw = plant.get_state()
+        s0 = torch.cat([qp[0], qv[0], qw[0]]).cpu().numpy()
+        Ub, costs, best = km.shooting_mpc(shooter, s0, x[0], xref[k + 1:k + 1 + H], sigma=0.05,
+                                          flags=T_.ROLL_GRAVCOMP_HOLD, seed=k)
+        assert float(costs[best]) <= float(costs[0])
+        gains.append(1.0 - float(costs[best]) / float(costs[0]))
+        if k == 0:
+            # the winner re-shot in another batch position: same observations, same cost
+            U1 = Ub[:, :, None].expand(H, 5, B).contiguous()
+            X1 = shooter.shoot(s0, U1, flags=T_.ROLL_GRAVCOMP_HOLD)
+            assert torch.equal(X1[0], X1[B - 1])
+            Z = km.lift(X1[0, 1:].double())
+            c1 = 50.0 * ((Z - km.lift(xref[1:1 + H])) ** 2).sum() + 0.5 * (Ub ** 2).sum()
+            assert abs(float(c1) - float(costs[best])) <= 1e-9 * float(c1)
+        u_model = km.mpc_control(x[1:2], xref[None, k + 1:k + 1 + H], H)[0]
+        x = plant.step(torch.stack([Ub[0], u_model]))[0].double().clone()
+        err_s.append(float((x[0, 3:] - qref[k + 1]).abs().mean()))
+        err_m.append(float((x[1, 3:] - qref[k + 1]).abs().mean()))
+    print(f"shooting MPC (8192 candidates x {H} steps through the physics): mean cost reduction vs the model's solution "
+          f"{100 * np.mean(gains):.1f} %; closed-loop |q - qref| {np.mean(err_s[10:]):.2e} rad (sampled) vs "
+          f"{np.mean(err_m[10:]):.2e} rad (model)")
+    assert np.mean(err_s[10:]) < 1.25 * np.mean(err_m[10:]) + 1e-3
