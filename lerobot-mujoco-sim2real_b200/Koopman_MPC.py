@@ -50,10 +50,12 @@ class BatchedKoopmanMPC:
         n = self.env.num_envs
         init = torch.cat([self.state_all_ref[:, 0, 3:8], torch.zeros((n, 5), dtype=torch.float64,
                                                                     device=self.env.device)], dim=1)
-        self.env.reset(options={"initial_state": init})                      # qpos[:5] = joint_angle_traj[0]; mj_forward
+        obs0 = self.env.reset(options={"initial_state": init})[0]            # qpos[:5] = joint_angle_traj[0]; mj_forward
+        self.obs0 = obs0.to(torch.float64).clone()
         self.state_tensor = self.state_all_ref[:, 0].clone()
         self.traj_index = 0
         self.actual_traj = []
+        self.applied = []
 
     def runMPC(self) -> torch.Tensor:
         """One frame [REF Koopman_MPC.py:197-222] -> the applied control a [n, 5]."""
@@ -69,6 +71,7 @@ class BatchedKoopmanMPC:
         s_next = self.env.step(a)[0]
         self.state_tensor = s_next.to(torch.float64).clone()
         self.actual_traj.append(self.state_tensor)
+        self.applied.append(a)
         self.traj_index += 1
         return a
 
@@ -78,3 +81,13 @@ class BatchedKoopmanMPC:
         for _ in range(self.total_frames if frames is None else int(frames)):
             self.runMPC()
         return torch.stack(self.actual_traj, dim=1)
+
+    def dataset_rows(self) -> torch.Tensor:
+        """The closed-loop run as Koopman training data in the layout of `generate_physics_based_data`
+        [REF SOARM101/SOARM101_DataCollection.py:108-134]: rows [n, frames, 13] float64 = [u_i (5) | ee_i (3) | q_i (5)]
+        with u_i the control applied FROM observation i (s_0 = the observation after runBefore's reset, s_{i+1} =
+        step(u_i)) - on-policy data along the Cartesian curves, consumable by the reference's `Collater`."""
+        if not self.applied:
+            raise RuntimeError("run() first")
+        states = torch.stack([self.obs0] + self.actual_traj[:-1], dim=1)     # s_0 .. s_{frames-1}
+        return torch.cat([torch.stack(self.applied, dim=1), states], dim=2).contiguous()

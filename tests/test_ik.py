@@ -419,6 +419,26 @@ def test_koopman_mpc_loop_follows_ik_tracks(tables_v):
     loop = BatchedKoopmanMPC(env, km, cp, ja, H=10)
     actual = loop.run().cpu().numpy()                                # [n, 300, 8]
     assert actual.shape == (n, 300, 8) and loop.traj_index == 300
+    # the run as a dataset in the reference's row layout [u | ee | q]: re-stepping row i's control from row i's state is
+    # not possible from observations alone, but the bookkeeping is: states are the run's observations shifted by one,
+    # controls are clipped, and the first state is the reset observation of the first IK way-point
+    rows = loop.dataset_rows().cpu().numpy()
+    assert rows.shape == (n, 300, 13) and rows.dtype == np.float64
+    assert np.array_equal(rows[:, 1:, 5:], actual[:, :-1]) and np.abs(rows[:, :, :5]).max() <= 0.5
+    assert np.abs(rows[:, 0, 5:8] - xyz[:, 0]).max() < 2e-6 and np.abs(rows[:, 0, 8:] - ja[:, 0].cpu().numpy()).max() < 1e-6
+    # the reference's trained model on this on-policy data, one step ahead (informational: the curves move slowly and
+    # reach |q| = 0.6, outside the random-control training distribution, so the margin over persistence is small here;
+    # the fingerprint proper is on random-control data, tests/test_oracle.py / test_gpu_api.py)
+    A, Bm = torch.as_tensor(km.A).cuda(), torch.as_tensor(km.B).cuda()
+    rt = torch.as_tensor(rows).cuda()
+    z = km.lift(rt[:, :-1, 5:].reshape(-1, 8))
+    pred = (z @ A.t() + rt[:, :-1, :5].reshape(-1, 5) @ Bm.t())[:, :8].reshape(n, 299, 8)
+    fam_t = torch.arange(n, device="cuda") % 4
+    yz_t = (fam_t == 0) | (fam_t == 2)
+    mse = float(((pred - rt[:, 1:, 5:]) ** 2)[yz_t].mean())
+    pers = float(((rt[:, :-1, 5:] - rt[:, 1:, 5:]) ** 2)[yz_t].mean())
+    print(f"one-step prediction of the shipped model on the closed-loop rows (y-z curves): MSE {mse:.2e}, persistence {pers:.2e}")
+    assert mse < 1e-5 and mse < pers
     # (a) the first frames against the CPU restatement, curve by curve
     frames = 8
     for b in (0, 3, 17):
