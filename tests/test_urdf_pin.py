@@ -33,6 +33,9 @@ def test_compiled_tables_match_the_urdf(tables_v, tables_p):
     bodies = _bodies()
     assert abs(sum(g["link_mass"]) - 0.632006) < 1e-9
     for t in (tables_v, tables_p):
+        # joint ranges (the limit rows' geometry): MJCF and URDF print them to 6 digits
+        rng_mjcf = np.array([list(t.jnt_range[k]) for k in range(6)])
+        assert all(t.jnt_limited[k] for k in range(6)) and np.abs(rng_mjcf - g["joint_limits"]).max() < 5e-6
         for n, m in zip(g["link_names"], g["link_mass"]):
             assert t.body_mass[bodies.index(LINK_TO_BODY[str(n)])] == pytest.approx(m, abs=1e-12)
         for i, q in enumerate(g["q"]):

@@ -63,8 +63,10 @@ class Urdf:
             xyz, R = origin(J)
             ax = J.find("axis")
             a = np.array([float(v) for v in ax.get("xyz").split()]) if ax is not None else np.zeros(3)
+            lim = J.find("limit")
             self.joints[J.get("name")] = dict(type=J.get("type"), parent=J.find("parent").get("link"),
-                                              child=J.find("child").get("link"), xyz=xyz, R=R, axis=a)
+                                              child=J.find("child").get("link"), xyz=xyz, R=R, axis=a,
+                                              limit=(float(lim.get("lower")), float(lim.get("upper"))) if lim is not None else None)
         children = {j["child"] for j in self.joints.values()}
         self.root = [n for n in self.links if n not in children][0]
 
@@ -136,7 +138,8 @@ def main():
         names = sorted(coms)
         ee.append(e); com.append([coms[n] for n in names]); Ms.append(M)
     out = dict(q=Q, ee=np.array(ee), com=np.array(com), M=np.array(Ms), link_names=np.array(names),
-               link_mass=np.array([masses[n] for n in names]), source=np.array("SOARM101/SO101/so101_new_calib.urdf"))
+               link_mass=np.array([masses[n] for n in names]),
+               joint_limits=np.array([u.joints[j]["limit"] for j in JOINTS]), source=np.array("SOARM101/SO101/so101_new_calib.urdf"))
     path = os.path.join(ROOT, "tests", "golden", "urdf_kinematics.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "links", names, "total mass", sum(masses.values()))
