@@ -132,15 +132,44 @@ class CartesianTrajectoryGenerator:
         out = (q_out.permute(2, 0, 1), status.t())
         return out + (err.t(),) if return_err else out
 
+    def curves_on_device(self, traj_names: Sequence[str], idx: Optional[Sequence[int]] = None,
+                         traj_scale: Optional[Sequence[float]] = None, centers=None, radius: float = 0.1) -> torch.Tensor:
+        """`reference_curve` for n tracks at once as device tensor ops (no per-track host loop, nothing uploaded but
+        the per-track parameters): -> xyz [n, P, 3] float64.  Same formulas; sin/cos come from the device math library,
+        so way-points agree with the numpy version to ~1e-16, not bitwise."""
+        n = len(traj_names)
+        dev = self.device
+        for nm in traj_names:
+            if nm not in ("Fig8", "Circle"):
+                raise ValueError(f"未知的轨迹名称: {nm}")   # reference text
+        fig8 = torch.tensor([nm == "Fig8" for nm in traj_names], device=dev)[:, None]
+        ix = torch.as_tensor(self.idx if idx is None else idx, device=dev).expand(n) if idx is None \
+            else torch.as_tensor(idx, device=dev)
+        yz = (ix == 1)[:, None]
+        sc = torch.full((n,), float(self.traj_scale), dtype=torch.float64, device=dev) if traj_scale is None \
+            else torch.as_tensor(traj_scale, dtype=torch.float64, device=dev)
+        default_c = torch.where(yz, torch.tensor([[0.4, 0.0, 0.2]], dtype=torch.float64, device=dev),
+                                torch.tensor([[0.3, 0.0, 0.2]], dtype=torch.float64, device=dev))
+        c = default_c if centers is None else torch.as_tensor(centers, dtype=torch.float64, device=dev)
+        P = int(self.time_steps_per_sec * self.time_horizon)
+        t = 1.6 + 0.02 * torch.linspace(0, self.time_horizon * 5, P, dtype=torch.float64, device=dev)[None]   # [1, P]
+        s_, c_ = torch.sin(t), torch.cos(t)
+        den = 1 + s_ ** 2
+        a = (0.2 * sc)[:, None]
+        u, v = 2 * a * s_ * c_ / den, a * c_ / den          # Fig8: (long in-plane axis, y)
+        # Circle: y-z plane -> y = r cos, z = r sin; x-y plane -> x = r cos, y = r sin
+        cu = radius * c_.expand(n, P)
+        su = radius * s_.expand(n, P)
+        x = torch.where(yz, c[:, 0:1].expand(n, P), c[:, 0:1] + torch.where(fig8, u, cu))
+        y = c[:, 1:2] + torch.where(fig8, v, torch.where(yz, cu, su))
+        z = torch.where(yz, c[:, 2:3] + torch.where(fig8, u, su), c[:, 2:3].expand(n, P))
+        return torch.stack([x, y, z], dim=2).contiguous()
+
     def generate_batch(self, traj_names: Sequence[str], idx: Optional[Sequence[int]] = None,
                        traj_scale: Optional[Sequence[float]] = None, centers=None, target_orientation=None):
         """One reference curve per entry (name, plane, scale, centre) -> (xyz [n,P,3], q [n,P,num_joints], status [n,P])
-        as device tensors; all tracks are solved in one launch."""
-        n = len(traj_names)
-        pts = [reference_curve(traj_names[i], self.idx if idx is None else idx[i], self.time_horizon,
-                               self.time_steps_per_sec, self.traj_scale if traj_scale is None else traj_scale[i],
-                               None if centers is None else centers[i])[0] for i in range(n)]
-        xyz = torch.as_tensor(np.stack(pts), device=self.device)
+        as device tensors; way-points are built on the device and all tracks are solved in one launch."""
+        xyz = self.curves_on_device(traj_names, idx, traj_scale, centers)
         q, status = self.solve_tracks(xyz, target_orientation)
         return xyz, q[:, :, :self.num_joints], status
 

@@ -351,6 +351,12 @@ def test_cartesian_trajectory_generator_drop_in(tables_v, tables_p):
     # batch of curves -> control tensor of the position-servo scene: the arm follows the curve
     xb, qb, sb = gen.generate_batch(["Fig8", "Circle", "Fig8", "Circle"], idx=[1, 1, 0, 0])
     assert (sb & 1).all()
+    from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import reference_curve
+    for b, (nm, ix) in enumerate((("Fig8", 1), ("Circle", 1), ("Fig8", 0), ("Circle", 0))):
+        assert np.abs(xb[b].cpu().numpy() - reference_curve(nm, ix)[0]).max() < 1e-15      # way-points built on the device
+    xs = gen.curves_on_device(["Fig8", "Circle"], idx=[0, 1], traj_scale=[0.7, 0.5], centers=[(0.31, 0.01, 0.2), (0.4, 0, 0.21)])
+    assert np.abs(xs[0].cpu().numpy() - reference_curve("Fig8", 0, traj_scale=0.7, center=(0.31, 0.01, 0.2))[0]).max() < 1e-15
+    assert np.abs(xs[1].cpu().numpy() - reference_curve("Circle", 1, center=(0.4, 0, 0.21))[0]).max() < 1e-15
     n, P = qb.shape[0], qb.shape[1]
     env = SOARM101VecEnv(tables=tables_p, num_envs=n, dtype="float64")
     env.reset(options={"initial_state": torch.cat([qb[:, 0], torch.zeros((n, 5), device=qb.device,

@@ -36,6 +36,10 @@ def test_compiled_tables_match_the_urdf(tables_v, tables_p):
         # joint ranges (the limit rows' geometry): MJCF and URDF print them to 6 digits
         rng_mjcf = np.array([list(t.jnt_range[k]) for k in range(6)])
         assert all(t.jnt_limited[k] for k in range(6)) and np.abs(rng_mjcf - g["joint_limits"]).max() < 5e-6
+        # servo constants as the reference's stand-alone SO101/joints_properties.xml states them for class sts3215
+        # (damping 0.60, frictionloss 0.052, armature 0.028): a second reference-owned source for the dof tables
+        for k in range(6):
+            assert (t.dof_damping[k], t.dof_frictionloss[k], t.dof_armature[k]) == (0.6, 0.052, 0.028)
         for n, m in zip(g["link_names"], g["link_mass"]):
             assert t.body_mass[bodies.index(LINK_TO_BODY[str(n)])] == pytest.approx(m, abs=1e-12)
         for i, q in enumerate(g["q"]):
