@@ -375,7 +375,9 @@ extern "C" int so101_ik_track(const So101Model* model, const So101IkParams* para
   if (P > 0 && n > 0 && (!q_out || !status || !xyz)) return fail(SO101_EINVAL, "null argument");
   if (params->max_steps < 1 || !(params->tol >= 0)) return fail(SO101_EINVAL, "ik_track: need max_steps >= 1, tol >= 0");
   if ((params->dof_mask & ~((1 << NV) - 1)) != 0) return fail(SO101_EINVAL, "ik_track: dof_mask has bits beyond dof 5");
-  if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible: this library has no CPU fallback");
+  const int ndev = so101_device_count();
+  if (ndev <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SO101_EINVAL, "device index out of range");
   if (P == 0 || n == 0) return SO101_OK;
   DeviceGuard g(device);
   if (!g.ok) return fail(SO101_ECUDA, "cudaSetDevice failed");
