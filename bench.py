@@ -358,47 +358,50 @@ def run_b200(args) -> None:
         extra["config5_shoot_8192x50"] = {"ms": best5, "env_steps_per_s": 8192 * 50 / (best5 * 1e-3),
                                           "rollouts_per_s": 8192 / (best5 * 1e-3)}
         del e5
-        # BASELINE configs[0] workload through the drop-in API: the reference's whole data job with args.py defaults
-        # (train 50000 x 20 random; val 2000 x 200 random; tests 2000 x 200 random / sin / chirp), host arrays out
-        import types
-        from lerobot_mujoco_sim2real_b200.SOARM101_DataCollection import SOARM101DataGenerator
-        jargs = types.SimpleNamespace(xml_path="unused", x_dim=8, u_dim=5, device="cuda", seed=SEED, env="SOARM101")
-        jgen = SOARM101DataGenerator(jargs, tables=tables, device=dev.index)
-        job = [(50000, 20, "random"), (2000, 200, "random"), (2000, 200, "random"), (2000, 200, "sin"), (2000, 200, "chirp")]
-        jgen.generate_physics_based_data(64, 2, "random")
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nbytes = 0
-        for (jn, jt, jk) in job:
-            arr = jgen.generate_physics_based_data(jn, jt, jk)
-            nbytes += arr.nbytes
-        job_s = time.perf_counter() - t0
-        job_steps = sum(jn * jt for jn, jt, _ in job)
-        extra["config0_reference_data_job_args_py_defaults"] = {
-            "datasets": [f"{jn}x{jt} {jk}" for jn, jt, jk in job], "env_steps": job_steps, "wall_ms": job_s * 1e3,
-            "env_steps_per_s": job_steps / job_s, "host_bytes_out": nbytes,
-            "note": "SOARM101DataGenerator.generate_physics_based_data x5 (what generate_and_save_data runs before np.save), "
-                    "host wall clock incl. device->host copies; the reference runs this serially on one CPU MuJoCo env"}
-        del jgen
-        # row N3: 16384 reference curves (300 way-points each, position-only as Koopman_MPC.py runs them) -> joint tracks
-        import numpy as np
-        from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import CartesianTrajectoryGenerator, reference_curve
-        gen = CartesianTrajectoryGenerator(tables=tables, device=dev.index)
-        nik = 16384
-        base = np.stack([reference_curve(nm, ix)[0] for nm in ("Fig8", "Circle") for ix in (0, 1)])
-        xyz = torch.as_tensor(base[np.arange(nik) % 4] + np.random.default_rng(SEED).uniform(-0.03, 0.03, (nik, 1, 3)),
-                              device=dev)
-        gen.solve_tracks(xyz)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); qik, stik = gen.solve_tracks(xyz); b.record(); torch.cuda.synchronize()
-        ms_ik = a.elapsed_time(b)
-        extra["n3_ik_tracks_16384x300"] = {
-            "ms": ms_ik, "waypoints_per_s": nik * 300 / (ms_ik * 1e-3),
-            "gauss_newton_iters_per_waypoint": float((stik >> 8).double().mean().item()),
-            "success_frac": float((stik & 1).double().mean().item()),
-            "note": "k_ik_track<false>: one thread per track incl. the [n,P,3] -> [P,3,n] relayout"}
-        del gen, xyz, qik, stik
+        if rank == 0:   # single-GPU side measurements: no collectives, nothing on stdout
+            import contextlib
+            # BASELINE configs[0] workload through the drop-in API: the reference's whole data job with args.py defaults
+            # (train 50000 x 20 random; val 2000 x 200 random; tests 2000 x 200 random / sin / chirp), host arrays out
+            import types
+            from lerobot_mujoco_sim2real_b200.SOARM101_DataCollection import SOARM101DataGenerator
+            jargs = types.SimpleNamespace(xml_path="unused", x_dim=8, u_dim=5, device="cuda", seed=SEED, env="SOARM101")
+            with contextlib.redirect_stdout(sys.stderr):
+                jgen = SOARM101DataGenerator(jargs, tables=tables, device=dev.index)
+            job = [(50000, 20, "random"), (2000, 200, "random"), (2000, 200, "random"), (2000, 200, "sin"), (2000, 200, "chirp")]
+            jgen.generate_device(64, 2, "random").cpu().numpy()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nbytes = 0
+            for (jn, jt, jk) in job:
+                arr = jgen.generate_device(jn, jt, jk, seed=SEED).cpu().numpy()   # what generate_physics_based_data returns
+                nbytes += arr.nbytes
+            job_s = time.perf_counter() - t0
+            job_steps = sum(jn * jt for jn, jt, _ in job)
+            extra["config0_reference_data_job_args_py_defaults"] = {
+                "datasets": [f"{jn}x{jt} {jk}" for jn, jt, jk in job], "env_steps": job_steps, "wall_ms": job_s * 1e3,
+                "env_steps_per_s": job_steps / job_s, "host_bytes_out": nbytes,
+                "note": "SOARM101DataGenerator: the five datasets generate_and_save_data builds before np.save (rank 0 only, no gather), "
+                        "host wall clock incl. device->host copies; the reference runs this serially on one CPU MuJoCo env"}
+            del jgen
+            # row N3: 16384 reference curves (300 way-points each, position-only as Koopman_MPC.py runs them) -> joint tracks
+            import numpy as np
+            from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import CartesianTrajectoryGenerator, reference_curve
+            gen = CartesianTrajectoryGenerator(tables=tables, device=dev.index)
+            nik = 16384
+            base = np.stack([reference_curve(nm, ix)[0] for nm in ("Fig8", "Circle") for ix in (0, 1)])
+            xyz = torch.as_tensor(base[np.arange(nik) % 4] + np.random.default_rng(SEED).uniform(-0.03, 0.03, (nik, 1, 3)),
+                                  device=dev)
+            gen.solve_tracks(xyz)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); qik, stik = gen.solve_tracks(xyz); b.record(); torch.cuda.synchronize()
+            ms_ik = a.elapsed_time(b)
+            extra["n3_ik_tracks_16384x300"] = {
+                "ms": ms_ik, "waypoints_per_s": nik * 300 / (ms_ik * 1e-3),
+                "gauss_newton_iters_per_waypoint": float((stik >> 8).double().mean().item()),
+                "success_frac": float((stik & 1).double().mean().item()),
+                "note": "k_ik_track<false>: one thread per track incl. the [n,P,3] -> [P,3,n] relayout"}
+            del gen, xyz, qik, stik
 
     # CPU baseline: bounded sample sized for ~10-20 s of CPU work
     cal_rate, _, nthr = oracle_rate(64, 1, 1)
