@@ -44,6 +44,7 @@ class BatchedKoopmanMPC:
         self.actual_traj = []
         self.state_tensor: Optional[torch.Tensor] = None
         self.Kz, self.Kr = model.mpc_gains(self.H)
+        self._zwin: Optional[torch.Tensor] = None
 
     def runBefore(self) -> None:
         """[REF Koopman_MPC.py:83-90]"""
@@ -56,17 +57,35 @@ class BatchedKoopmanMPC:
         self.traj_index = 0
         self.actual_traj = []
         self.applied = []
+        self._zwin = None
+
+    def _lift_ref_row(self, j: int) -> torch.Tensor:
+        """Lifted reference row j of every curve, ZERO past the end of the trajectory (the reference fills a
+        zero-initialised array, [REF Koopman_MPC.py:199-203])."""
+        if j < self.total_frames:
+            return self.model.lift(self.state_all_ref[:, j])
+        return torch.zeros((self.env.num_envs, self.model.nz), dtype=torch.float64, device=self.env.device)
 
     def runMPC(self) -> torch.Tensor:
-        """One frame [REF Koopman_MPC.py:197-222] -> the applied control a [n, 5]."""
+        """One frame [REF Koopman_MPC.py:197-222] -> the applied control a [n, 5].
+
+        Consecutive windows [k+1, k+H] overlap in H-1 rows, so the lifted window lives in a circular buffer: each frame
+        lifts ONE new reference row per curve (the reference re-lifts all H) and the matching column blocks of the
+        reference gain are rotated instead of the data."""
         n, H, nz, nu = self.env.num_envs, self.H, self.model.nz, self.model.nu
         k = self.traj_index
-        seg = self.state_all_ref[:, k + 1:k + H + 1]                         # [n, <=H, 8]
-        lifted_ref = torch.zeros((n, H, nz), dtype=torch.float64, device=self.env.device)
-        if seg.shape[1] > 0:
-            lifted_ref[:, :seg.shape[1]] = self.model.lift(seg.reshape(-1, 8)).reshape(n, seg.shape[1], nz)
+        if self._zwin is None:
+            self._zwin = torch.empty((n, H, nz), dtype=torch.float64, device=self.env.device)
+            for j in range(H):
+                self._zwin[:, (k + j) % H] = self._lift_ref_row(k + 1 + j)
+        else:
+            self._zwin[:, (k - 1) % H] = self._lift_ref_row(k + H)     # the slot of row k (just consumed) <- row k+H
+        # slot s holds row k+1+((s - k) mod H): window position j = (s - k) mod H  <=>  s = (k + j) mod H
+        order = [(k + j) % H for j in range(H)]
+        Kr_rot = torch.empty((nu, H, nz), dtype=torch.float64, device=self.env.device)
+        Kr_rot[:, order] = self.Kr[:nu].reshape(nu, H, nz)
         z0 = self.model.lift(self.state_tensor)
-        u = z0 @ self.Kz[:nu].t() + lifted_ref.reshape(n, H * nz) @ self.Kr[:nu].t()
+        u = z0 @ self.Kz[:nu].t() + self._zwin.reshape(n, H * nz) @ Kr_rot.reshape(nu, H * nz).t()
         a = torch.clamp(u, -self.clip, self.clip)                            # get_control [REF MPC_Controler.py:149]
         s_next = self.env.step(a)[0]
         self.state_tensor = s_next.to(torch.float64).clone()
