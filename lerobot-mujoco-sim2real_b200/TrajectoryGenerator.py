@@ -134,15 +134,19 @@ class CartesianTrajectoryGenerator:
 
     def curves_on_device(self, traj_names: Sequence[str], idx: Optional[Sequence[int]] = None,
                          traj_scale: Optional[Sequence[float]] = None, centers=None, radius: float = 0.1) -> torch.Tensor:
-        """`reference_curve` for n tracks at once as device tensor ops (no per-track host loop, nothing uploaded but
+        """traj_names: sequence of 'Fig8' / 'Circle', or a bool array (True = Fig8).
+        `reference_curve` for n tracks at once as device tensor ops (no per-track host loop, nothing uploaded but
         the per-track parameters): -> xyz [n, P, 3] float64.  Same formulas; sin/cos come from the device math library,
         so way-points agree with the numpy version to ~1e-16, not bitwise."""
         n = len(traj_names)
         dev = self.device
-        for nm in traj_names:
-            if nm not in ("Fig8", "Circle"):
-                raise ValueError(f"未知的轨迹名称: {nm}")   # reference text
-        fig8 = torch.tensor([nm == "Fig8" for nm in traj_names], device=dev)[:, None]
+        if isinstance(traj_names, (np.ndarray, torch.Tensor)) and traj_names.dtype in (np.bool_, torch.bool):
+            fig8 = torch.as_tensor(traj_names, device=dev)[:, None]          # True = Fig8, False = Circle (large batches)
+        else:
+            for nm in traj_names:
+                if nm not in ("Fig8", "Circle"):
+                    raise ValueError(f"未知的轨迹名称: {nm}")   # reference text
+            fig8 = torch.tensor([nm == "Fig8" for nm in traj_names], device=dev)[:, None]
         ix = torch.as_tensor(self.idx if idx is None else idx, device=dev).expand(n) if idx is None \
             else torch.as_tensor(idx, device=dev)
         yz = (ix == 1)[:, None]

@@ -40,7 +40,7 @@ def curve_params(lo, hi):
     i = np.arange(lo, hi, dtype=np.uint64)
     h = (i * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(11)
     u = [((h >> np.uint64(8 * k)) & np.uint64(0xFF)).astype(np.float64) / 255.0 for k in range(4)]
-    names = ["Fig8" if x < 0.5 else "Circle" for x in u[0]]
+    names = u[0] < 0.5                                                  # True = Fig8, False = Circle
     centers = np.stack([0.4 + 0 * u[1], 0.03 * (u[1] - 0.5), 0.2 + 0.03 * (u[2] - 0.5)], axis=1)    # y-z plane (idx = 1)
     return names, centers, 0.4 + 0.2 * u[3]
 
@@ -51,7 +51,7 @@ def run_shard(lo, hi, frames):
     names, centers, scale = curve_params(lo, hi)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
-    xyz, q, st = gen.generate_batch(names, idx=[1] * n, traj_scale=scale, centers=centers)
+    xyz, q, st = gen.generate_batch(names, idx=np.ones(n, dtype=np.int64), traj_scale=scale, centers=centers)
     ev[1].record()
     env = SOARM101VecEnv(tables=tables, num_envs=n, dtype="float64", device=local, gravity_compensation=True)
     loop = BatchedKoopmanMPC(env, km, xyz, q, H=10)
