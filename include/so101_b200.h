@@ -277,7 +277,9 @@ int so101_koopman_score(const double* A, const double* B, int nz, int nu, const 
      quat   [4][n]      target orientation (w,x,y,z) held along the whole track, or NULL = position only
      q0     [6][n]      start joint vectors, or NULL
      q_out  [P][6][n]   joint vector stored for every way-point (all 6 dofs; the reference keeps [:num_joints])
-     status [P][n]      int32: bit 0 = success, bits 8.. = iterations used (the reference's IKResult.steps)
+     status [P][n]      int32: bit 0 = success, bit 1 = track aborted (its FIRST way-point could not be solved: the
+                        reference raises RuntimeError there; the track stays at its start vector), bits 8.. =
+                        iterations used (the reference's IKResult.steps)
      err    [P][n]      err_norm at exit (nullable)
    Async on `stream`; the model handle comes from so101_model_create. */
 typedef struct So101IkParams {
