@@ -368,12 +368,12 @@ def run_b200(args) -> None:
             with contextlib.redirect_stdout(sys.stderr):
                 jgen = SOARM101DataGenerator(jargs, tables=tables, device=dev.index)
             job = [(50000, 20, "random"), (2000, 200, "random"), (2000, 200, "random"), (2000, 200, "sin"), (2000, 200, "chirp")]
-            jgen.generate_device(64, 2, "random").cpu().numpy()
+            jgen.generate_device(64, 2, "random")[0].cpu().numpy()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             nbytes = 0
             for (jn, jt, jk) in job:
-                arr = jgen.generate_device(jn, jt, jk, seed=SEED).cpu().numpy()   # what generate_physics_based_data returns
+                arr = jgen.generate_device(jn, jt, jk, seed=SEED)[0].cpu().numpy()   # what generate_physics_based_data returns
                 nbytes += arr.nbytes
             job_s = time.perf_counter() - t0
             job_steps = sum(jn * jt for jn, jt, _ in job)

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 5
+#define SO101_ABI_VERSION 6
 #define SO101_NV       6   /* hinge dofs: 5 arm joints + gripper */
 #define SO101_MAXBODY  8   /* world, fixed base, 6 links */
 #define SO101_MAXTRIP 16   /* contact-tripwire boxes (<= 3 per link) */
@@ -202,6 +202,17 @@ int  so101_batch_create(const So101Model* model, int64_t n_envs, int dtype, int 
                         void* state_buf, So101Batch** out);
 void so101_batch_destroy(So101Batch* batch);
 
+/* Explicit experiment options of a batch (profiling sweeps, the kernel-family equality test).  The library never reads
+   the environment: a stray variable cannot change which kernel runs.  value 0 = automatic for every option. */
+enum {
+  SO101_OPT_KERNEL_FAMILY = 0,  /* SO101_FAMILY_*: force the one-warp or the three-warp team kernels           */
+  SO101_OPT_BLOCK         = 1,  /* threads per block of the one-warp kernels (multiple of 32, <= launch bound)  */
+  SO101_OPT_HOST_CHUNKS   = 2,  /* pipeline depth of so101_batch_rollout_host, 1..12                            */
+  SO101_OPT_HOST_EVEN     = 3   /* 1: equal time chunks in so101_batch_rollout_host                             */
+};
+enum { SO101_FAMILY_AUTO = 0, SO101_FAMILY_ONEWARP = 1, SO101_FAMILY_TEAM = 2 };
+int so101_batch_set_option(So101Batch* b, int option, int value);
+
 /* mj_resetData, then qpos[0:nq] <- qpos0[j][N] (NULL: model qpos0), qvel likewise (NULL: 0),
    then mj_forward; obs (nullable) receives float32 [8][N]. */
 int so101_batch_reset(So101Batch* b, const void* qpos0, const void* qvel0, void* obs, void* stream);
@@ -214,9 +225,10 @@ int so101_batch_forward(So101Batch* b, void* obs, void* qfrc_bias, void* stream)
    n_substeps x mj_step; obs float32 [8][N] with the reference's one-sub-step ee lag. */
 int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps, void* obs, void* stream);
 /* host-buffer variants: pinned or pageable host pointers, H2D + kernel + D2H on `stream`,
-   stream synchronised before return.  These are what SOARM101Env.step()/reset() call. */
+   stream synchronised before return.  These are what SOARM101Env.step()/reset() call.
+   flags_host (nullable): receives the per-env status words [N] with the observation (one sync). */
 int so101_batch_step_host(So101Batch* b, const void* ctrl_host, int n_ctrl, int n_substeps,
-                          void* obs_host, void* stream);
+                          void* obs_host, uint32_t* flags_host, void* stream);
 int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qvel0_host,
                            void* obs_host, void* stream);
 
@@ -247,6 +259,20 @@ int so101_batch_clear_flags(So101Batch* b, void* stream);
 /* solver statistics accumulated since the last call: [0]=physics steps, [1]=Newton iterations,
    [2]=line-search evaluations, [3]=steps with an active limit row (host pointer, 4 x uint64). */
 int so101_batch_stats(So101Batch* b, uint64_t* stats_host, void* stream);
+
+/* ---- the dataset gather without a collective ------------------------------------------------------------
+   The only inter-GPU exchange of this path is the gather of the row shards [N/G][T+1][13] to rank 0
+   (what np.save needs, [REF SOARM101/SOARM101_DataCollection.py:156]).  Rank 0 allocates the full [N][T+1][13] buffer
+   with so101_shared_alloc and passes the 64-byte handle to the other ranks of the node (any host channel); they map it
+   with so101_shared_open and hand `ptr + first_row_of_my_shard` to so101_batch_rollout as `rows`: the row writer of
+   k_rollout then stores straight into rank 0's HBM over NVLink while the simulation runs - the transfer is fused into
+   the kernel, nothing is staged, copied or concatenated afterwards.  Writers synchronise their stream, then all ranks
+   meet at a host barrier before rank 0 reads.  One process per GPU; handles are valid on the same node only. */
+#define SO101_IPC_HANDLE_BYTES 64
+int so101_shared_alloc(int device, size_t bytes, void** ptr, unsigned char* handle /* [64] out */);
+int so101_shared_open(int device, const unsigned char* handle /* [64] */, void** ptr);
+int so101_shared_close(int device, void* ptr);
+int so101_shared_free(int device, void* ptr);
 
 /* measurement helper: register-resident FMA loop; returns achieved TFLOP/s (2 flop per FMA). */
 int so101_fma_peak(int dtype, int device, double* tflops_out);

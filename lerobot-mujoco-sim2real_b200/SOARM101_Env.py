@@ -192,7 +192,7 @@ class SOARM101Env(_EnvBase):
                                       "(use the reference env for rendering)")
         from . import mjcf
         self._compiled = mjcf.compile_mjcf(xml_path)   # raises FileNotFoundError like the reference
-        mjcf.attach_tripwire(self._compiled, xml_path)
+        self.contact_tables = mjcf.attach_tripwire(self._compiled, xml_path)   # "none": contacts go unnoticed (stderr says why)
         t = self._compiled.tables
         self._vec = SOARM101VecEnv(tables=t, num_envs=1, dt=dt, dtype=dtype, device=device)
         self.frame_skip = self._vec.frame_skip
@@ -219,6 +219,7 @@ class SOARM101Env(_EnvBase):
         self._last_ee = np.zeros(3)
         self._time = 0.0
         self._obs_host = np.zeros((T.NOBS, 1), dtype=np.float32)
+        self._flags_host = np.zeros(1, dtype=np.uint32)
 
     # ---- internals ------------------------------------------------------------------------------
     def _set_ctrl(self, a) -> None:
@@ -264,9 +265,13 @@ class SOARM101Env(_EnvBase):
         self._ctrl[: self.udim] = target_velocity          # ctrl[5] keeps its value (0 after reset)
         u = np.ascontiguousarray(self._ctrl.reshape(T.NV, 1), dtype=self._np_dtype)
         _lib.check(_lib.lib().so101_batch_step_host(self._vec._h, u.ctypes.data, T.NV, self.frame_skip,
-                                                    self._obs_host.ctypes.data, self._vec._stream()))
+                                                    self._obs_host.ctypes.data, self._flags_host.ctypes.data,
+                                                    self._vec._stream()))
         self._time += self.dt
-        return self._obs(), 0.0, False, False, {}
+        # the reference returns an empty info dict; here it carries the env's status word whenever it is not clean
+        # (tables.FLAG_*: a contact the simulator does not model, a state blow-up that mj_step would have reset, ...)
+        fl = int(self._flags_host[0])
+        return self._obs(), 0.0, False, False, ({"flags": fl} if fl & T.FLAG_ABNORMAL else {})
 
     def forward(self) -> np.ndarray:
         """mujoco.mj_forward(model, data) for callers that invoke it explicitly

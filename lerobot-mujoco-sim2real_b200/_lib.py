@@ -23,7 +23,8 @@ EXPORTS = [
     "so101_batch_step", "so101_batch_step_host", "so101_batch_reset_host",
     "so101_batch_rollout", "so101_batch_rollout_host", "so101_batch_shoot",
     "so101_batch_get_state", "so101_batch_set_state", "so101_batch_set_qfrc_applied",
-    "so101_batch_get_flags", "so101_batch_clear_flags", "so101_batch_stats",
+    "so101_batch_get_flags", "so101_batch_clear_flags", "so101_batch_stats", "so101_batch_set_option",
+    "so101_shared_alloc", "so101_shared_open", "so101_shared_close", "so101_shared_free",
     "so101_fma_peak", "so101_koopman_score", "so101_ik_track",
 ]
 
@@ -72,7 +73,7 @@ def lib() -> C.CDLL:
     L.so101_batch_reset_random.argtypes = [vp, u64, i64, C.c_double, C.c_double, vp, vp]
     L.so101_batch_forward.argtypes = [vp, vp, vp, vp]
     L.so101_batch_step.argtypes = [vp, vp, i32, i32, vp, vp]
-    L.so101_batch_step_host.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.so101_batch_step_host.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.so101_batch_reset_host.argtypes = [vp, vp, vp, vp, vp]
     L.so101_batch_rollout.argtypes = [vp, C.POINTER(So101CtrlSpec), i32, i32, vp, u32, vp]
     L.so101_batch_rollout_host.argtypes = [vp, C.POINTER(So101CtrlSpec), vp, i32, i32, vp, u32, vp]
@@ -83,6 +84,11 @@ def lib() -> C.CDLL:
     L.so101_batch_get_flags.argtypes = [vp, vp, vp]
     L.so101_batch_clear_flags.argtypes = [vp, vp]
     L.so101_batch_stats.argtypes = [vp, C.POINTER(u64), vp]
+    L.so101_batch_set_option.argtypes = [vp, i32, i32]
+    L.so101_shared_alloc.argtypes = [i32, C.c_size_t, C.POINTER(vp), C.c_char_p]
+    L.so101_shared_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
+    L.so101_shared_close.argtypes = [i32, vp]
+    L.so101_shared_free.argtypes = [i32, vp]
     L.so101_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.so101_koopman_score.argtypes = [vp, vp, i32, i32, vp, vp, C.c_double, C.c_double, vp, i32, i64, i32, i32, i32, vp, vp, vp]
     L.so101_ik_track.argtypes = [vp, C.POINTER(So101IkParams), vp, vp, vp, i32, i64, i32, vp, vp, vp, vp]

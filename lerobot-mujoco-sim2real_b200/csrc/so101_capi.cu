@@ -28,12 +28,10 @@ struct StateView {
   T* base;
   uint32_t* flags;
   int64_t n;
-  int lanes;   // env lanes used per warp (32, or fewer for small batches: see pick_lanes)
 };
 
-// thread -> env for the stepping kernels.  A warp carries `lanes` envs; its other lanes shadow
-// them (same instruction stream, same data, no extra divergence) and never store.  Idle lanes and
-// tail threads are clamped to a valid env so that every thread reaches the block barriers.
+// thread -> env for the stepping kernels.  Tail threads are clamped to a valid env (they shadow it and never
+// store) so that every thread reaches the block barriers.
 // SPLIT kernels (small batches): a 96-thread block is a TEAM of three warps on the same 32 envs, warp 0 = dynamics
 // role (owns the env, loads and stores), warps 1, 2 = geometry and lookout roles (see so101_physics.cuh, SplitXch).
 template <typename T> SO101_DEV int64_t env_of_pair(const StateView<T>& s, bool& active) {
@@ -81,10 +79,8 @@ SO101_DEV void step_env(const DevModel<T>& m, SplitXch<T>& x, Env<T>& e, const T
 }
 
 template <typename T> SO101_DEV int64_t env_of_thread(const StateView<T>& s, bool& active) {
-  const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int64_t i = (gthread >> 5) * s.lanes + (lane & (s.lanes - 1));
-  active = lane < s.lanes && i < s.n;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  active = i < s.n;
   return i < s.n ? i : s.n - 1;
 }
 
@@ -486,6 +482,8 @@ struct So101Batch {
   bool pipe_ready;
   cudaStream_t s_up, s_down;
   cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
+  // explicit experiment options (so101_batch_set_option); 0 = automatic.  Nothing on this path reads the environment.
+  int opt_family, opt_block, opt_host_chunks, opt_host_even;
 };
 
 struct DeviceGuard {
@@ -506,7 +504,6 @@ static size_t elem_size(int dtype) { return dtype == SO101_F64 ? sizeof(double) 
 // block size: big batches use 256-thread blocks (8 warps share the instruction stream of a step,
 // see physics_step SYNC); small batches use smaller blocks so that every SM gets work
 static int pick_block(int64_t n) {
-  if (const char* ev = getenv("SO101_BLK")) { int v = atoi(ev); if (v >= 32 && v <= 256 && v % 32 == 0) return v; }
   if (n >= (int64_t)148 * 256) return 256;
   if (n >= (int64_t)148 * 128) return 128;
   if (n >= (int64_t)148 * 64) return 64;
@@ -519,39 +516,30 @@ template <typename T> static StateView<T> view(const So101Batch* b) {
   v.base = static_cast<T*>(b->state);
   v.flags = reinterpret_cast<uint32_t*>(static_cast<char*>(b->state) + (size_t)NROWS * b->n * sizeof(T));
   v.n = b->n;
-  v.lanes = 32;
   return v;
-}
-// Experiment knob (SO101_LANES=16|8|4...): spread a small batch over more, partially filled warps.
-// Measured on B200: no gain (4096 envs f64: 172 -> 175 M physics-steps/s with 8 lanes) - the per-warp
-// critical path is set by the hard solver steps, which nearly every group of 8 envs contains too.
-// The default therefore stays at full warps.
-static int pick_lanes(int64_t n) {
-  if (const char* ev = getenv("SO101_LANES")) { int v = atoi(ev); if (v == 32 || v == 16 || v == 8 || v == 4 || v == 2 || v == 1) return v; }
-  return 32;
 }
 // Small batches run the SPLIT kernels: three warps per 32 envs, 96-thread blocks - f64 up to two teams per SM
 // (148 x 64 envs), f32 up to four (148 x 128 envs).  Measured on B200 (tools/split_probe.py, ms per 100 control steps,
 // one-warp -> team): f64 1024 envs 11.3 -> 7.0, 4096 envs 11.9 -> 7.3, 9472 envs 13.1 -> 9.5, 14208 envs (three teams
 // per SM do not fit 255 registers) 16.3 -> 17.6; f32 4096 envs 9.8 -> 5.9, 9472 envs 10.8 -> 6.7, 18944 envs
-// 11.4 -> 7.7, 23680 envs 13.6 -> 14.5.  SO101_SPLIT=0|1 overrides (experiments, bitwise-equality test).
-static bool pick_split(int64_t n, bool f32) {
-  if (const char* ev = getenv("SO101_SPLIT")) return atoi(ev) != 0;
-  return n <= (int64_t)148 * (f32 ? 128 : 64);
+// 11.4 -> 7.7, 23680 envs 13.6 -> 14.5.  SO101_OPT_KERNEL_FAMILY forces one family (experiments, bitwise-equality test).
+static bool pick_split(const So101Batch* b, bool f32) {
+  if (b->opt_family == SO101_FAMILY_ONEWARP) return false;
+  if (b->opt_family == SO101_FAMILY_TEAM) return true;
+  return b->n <= (int64_t)148 * (f32 ? 128 : 64);
 }
 template <typename T> static StateView<T> step_view(const So101Batch* b, int& blk, unsigned& grid, bool& split) {
   StateView<T> v = view<T>(b);
-  split = pick_lanes(b->n) == 32 && pick_split(b->n, sizeof(T) == 4);
+  split = pick_split(b, sizeof(T) == 4);
   if (split) {
     blk = 32 * TEAM_WARPS;
     grid = (unsigned)((b->n + 31) / 32);
     return v;
   }
-  v.lanes = pick_lanes(b->n);
-  blk = v.lanes == 32 ? pick_block(b->n) : 128;
+  blk = pick_block(b->n);
   if (sizeof(T) == 4 && blk == 256 && b->n >= (int64_t)148 * 512) blk = 512;
-  if (const char* ev = getenv("SO101_BLK")) { int x = atoi(ev); if (x >= 32 && x <= 1024 && x % 32 == 0) blk = x; }
-  const int64_t warps = (b->n + v.lanes - 1) / v.lanes;
+  if (b->opt_block) blk = b->opt_block;                 // validated against the launch bounds in so101_batch_set_option
+  const int64_t warps = (b->n + 31) / 32;
   grid = (unsigned)((warps * 32 + blk - 1) / blk);
   return v;
 }
@@ -633,6 +621,31 @@ void so101_batch_destroy(So101Batch* b) {
   delete b;
 }
 
+int so101_batch_set_option(So101Batch* b, int option, int value) {
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  switch (option) {
+    case SO101_OPT_KERNEL_FAMILY:
+      if (value < SO101_FAMILY_AUTO || value > SO101_FAMILY_TEAM) return fail(SO101_EINVAL, "kernel family must be 0 (auto), 1 (one-warp) or 2 (team)");
+      b->opt_family = value;
+      return SO101_OK;
+    case SO101_OPT_BLOCK: {
+      const int lim = b->dtype == SO101_F64 ? SO101_F64_THREADS : SO101_F32_THREADS;   // the kernels' __launch_bounds__
+      if (value != 0 && (value < 32 || value > lim || value % 32)) return fail(SO101_EINVAL, "block size must be 0 (auto) or a multiple of 32 up to the launch bound (256 f64 / 512 f32)");
+      b->opt_block = value;
+      return SO101_OK;
+    }
+    case SO101_OPT_HOST_CHUNKS:
+      if (value < 0 || value > So101Batch::MAXCHUNK) return fail(SO101_EINVAL, "host pipeline chunks must be 0 (auto) .. 12");
+      b->opt_host_chunks = value;
+      return SO101_OK;
+    case SO101_OPT_HOST_EVEN:
+      b->opt_host_even = value != 0;
+      return SO101_OK;
+    default:
+      return fail(SO101_EINVAL, "unknown option");
+  }
+}
+
 #define DISPATCH(b, CALL_D, CALL_F)              \
   do {                                           \
     if ((b)->dtype == SO101_F64) { CALL_D; }     \
@@ -706,7 +719,7 @@ static int ensure_stage(So101Batch* b) {
 }
 
 int so101_batch_step_host(So101Batch* b, const void* ctrl_host, int n_ctrl, int n_substeps, void* obs_host,
-                          void* stream) {
+                          uint32_t* flags_host, void* stream) {
   if (!b) return fail(SO101_EINVAL, "null batch");
   if (n_ctrl < 0 || n_ctrl > NV) return fail(SO101_EINVAL, "n_ctrl must be 0..6");
   DeviceGuard g(b->device);
@@ -721,6 +734,9 @@ int so101_batch_step_host(So101Batch* b, const void* ctrl_host, int n_ctrl, int 
   if (obs_host)
     CUDA_TRY(cudaMemcpyAsync(obs_host, b->obs_stage, (size_t)SO101_NOBS * b->n * sizeof(float),
                              cudaMemcpyDeviceToHost, st));
+  if (flags_host)
+    CUDA_TRY(cudaMemcpyAsync(flags_host, static_cast<char*>(b->state) + (size_t)NROWS * b->n * elem_size(b->dtype),
+                             (size_t)b->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return SO101_OK;
 }
@@ -835,26 +851,36 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
     if (nchunk > So101Batch::MAXCHUNK) nchunk = So101Batch::MAXCHUNK;
     if (nchunk < 2) nchunk = 2;
   }
-  if (const char* ev = getenv("SO101_HOST_CHUNKS")) { int v = atoi(ev); if (v >= 1 && v <= So101Batch::MAXCHUNK) nchunk = v; }
+  if (b->opt_host_chunks) nchunk = b->opt_host_chunks;
   if (nchunk > T) nchunk = T > 0 ? T : 1;
+  // An error return inside the pipeline must not leave copies in flight that touch the caller's host buffers.
+  auto drain = [&]() { cudaStreamSynchronize(b->s_up); cudaStreamSynchronize(b->s_down); cudaStreamSynchronize(st); };
+#define PIPE_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t err__ = (expr);                                                                     \
+    if (err__ != cudaSuccess) {                                                                     \
+      drain();                                                                                      \
+      return fail(SO101_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));              \
+    }                                                                                               \
+  } while (0)
   // the side streams start after whatever the caller queued on `st`
-  CUDA_TRY(cudaEventRecord(b->ev_start, st));
-  CUDA_TRY(cudaStreamWaitEvent(b->s_up, b->ev_start, 0));
-  CUDA_TRY(cudaStreamWaitEvent(b->s_down, b->ev_start, 0));
+  PIPE_TRY(cudaEventRecord(b->ev_start, st));
+  PIPE_TRY(cudaStreamWaitEvent(b->s_up, b->ev_start, 0));
+  PIPE_TRY(cudaStreamWaitEvent(b->s_down, b->ev_start, 0));
   if (qpos0_host) {   // explicit initial joint angles: reset on the device, then continue from that state
     const size_t qb = (size_t)NV * b->n * es;
-    if (!b->init_stage) CUDA_TRY(cudaMalloc(&b->init_stage, 2 * qb));
-    CUDA_TRY(cudaMemcpyAsync(b->init_stage, qpos0_host, qb, cudaMemcpyHostToDevice, st));
-    if ((rc = so101_batch_reset(b, b->init_stage, nullptr, nullptr, stream))) return rc;
+    if (!b->init_stage) PIPE_TRY(cudaMalloc(&b->init_stage, 2 * qb));
+    PIPE_TRY(cudaMemcpyAsync(b->init_stage, qpos0_host, qb, cudaMemcpyHostToDevice, st));
+    if ((rc = so101_batch_reset(b, b->init_stage, nullptr, nullptr, stream))) { drain(); return rc; }
     flags |= SO101_ROLL_NO_RESET;
   }
   // chunk c covers control steps (tb[c], tb[c+1]]; rows tb[c]+1 .. tb[c+1] (+ row 0 for the first chunk)
   // Boundaries: chunks that double from 2 control steps (every upload finishes while the previous, half as long
   // chunk computes, even at a fraction of the PCIe rate - right after the caller flushed L2 uploads are ~3x slower),
   // then chunks that halve towards the end (the download of the last chunk is the only exposed download).
-  // SO101_HOST_EVEN=1: equal chunks.
+  // SO101_OPT_HOST_EVEN: equal chunks.
   int tb[So101Batch::MAXCHUNK + 1];
-  if (nchunk >= 4 && !getenv("SO101_HOST_EVEN")) {
+  if (nchunk >= 4 && !b->opt_host_even) {
     int k = 0, pos = 0;
     tb[k++] = 0;
     for (int sz = 2; pos + sz < T / 2 && k < nchunk - 3; sz *= 2) { pos += sz; tb[k++] = pos; }
@@ -873,27 +899,28 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   if (tensor) {
     for (int c = 0; c < nchunk; c++) {   // u_t for t in [first, tb[c+1]]: chunk c reads u at tb[c] .. tb[c+1]
       const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
-      CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(b->u_stage) + first * ustep,
+      PIPE_TRY(cudaMemcpyAsync(static_cast<char*>(b->u_stage) + first * ustep,
                                static_cast<const char*>(spec->u) + first * ustep, (size_t)(last - first + 1) * ustep,
                                cudaMemcpyHostToDevice, b->s_up));
-      CUDA_TRY(cudaEventRecord(b->ev_up[c], b->s_up));
+      PIPE_TRY(cudaEventRecord(b->ev_up[c], b->s_up));
     }
   }
   const size_t pitch = (size_t)(T + 1) * SO101_ROW * rs;
   for (int c = 0; c < nchunk; c++) {
-    if (tensor) CUDA_TRY(cudaStreamWaitEvent(st, b->ev_up[c], 0));
+    if (tensor) PIPE_TRY(cudaStreamWaitEvent(st, b->ev_up[c], 0));
     const uint32_t f = c == 0 ? flags : (flags | SO101_ROLL_NO_RESET);
-    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, b->rows_stage, f, stream))) return rc;
-    CUDA_TRY(cudaEventRecord(b->ev_k[c], st));
-    CUDA_TRY(cudaStreamWaitEvent(b->s_down, b->ev_k[c], 0));
+    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, b->rows_stage, f, stream))) { drain(); return rc; }
+    PIPE_TRY(cudaEventRecord(b->ev_k[c], st));
+    PIPE_TRY(cudaStreamWaitEvent(b->s_down, b->ev_k[c], 0));
     const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
     const size_t off = (size_t)first * SO101_ROW * rs, width = (size_t)(last - first + 1) * SO101_ROW * rs;
     if (nchunk == 1)
-      CUDA_TRY(cudaMemcpyAsync(rows_host, b->rows_stage, rb, cudaMemcpyDeviceToHost, b->s_down));
+      PIPE_TRY(cudaMemcpyAsync(rows_host, b->rows_stage, rb, cudaMemcpyDeviceToHost, b->s_down));
     else
-      CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(rows_host) + off, pitch, static_cast<char*>(b->rows_stage) + off,
+      PIPE_TRY(cudaMemcpy2DAsync(static_cast<char*>(rows_host) + off, pitch, static_cast<char*>(b->rows_stage) + off,
                                  pitch, width, (size_t)b->n, cudaMemcpyDeviceToHost, b->s_down));
   }
+#undef PIPE_TRY
   CUDA_TRY(cudaStreamSynchronize(b->s_down));
   CUDA_TRY(cudaStreamSynchronize(st));
   return SO101_OK;
@@ -972,6 +999,45 @@ int so101_batch_stats(So101Batch* b, uint64_t* stats_host, void* stream) {
   CUDA_TRY(cudaMemcpyAsync(stats_host, b->stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemsetAsync(b->stats, 0, 4 * sizeof(uint64_t), st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  return SO101_OK;
+}
+
+// ---- dataset buffer shared between the ranks of one node (CUDA IPC) -----------------------------------------------
+int so101_shared_alloc(int device, size_t bytes, void** ptr, unsigned char* handle) {
+  if (!ptr || !handle || bytes == 0) return fail(SO101_EINVAL, "bad argument");
+  if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SO101_ECUDA, "cudaSetDevice failed");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SO101_IPC_HANDLE_BYTES, "handle size");
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(SO101_ECUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  std::memcpy(handle, &h, sizeof h);
+  *ptr = p;
+  return SO101_OK;
+}
+int so101_shared_open(int device, const unsigned char* handle, void** ptr) {
+  if (!ptr || !handle) return fail(SO101_EINVAL, "bad argument");
+  if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SO101_ECUDA, "cudaSetDevice failed");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof h);
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SO101_OK;
+}
+int so101_shared_close(int device, void* ptr) {
+  if (!ptr) return SO101_OK;
+  DeviceGuard g(device);
+  CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return SO101_OK;
+}
+int so101_shared_free(int device, void* ptr) {
+  if (!ptr) return SO101_OK;
+  DeviceGuard g(device);
+  CUDA_TRY(cudaFree(ptr));
   return SO101_OK;
 }
 

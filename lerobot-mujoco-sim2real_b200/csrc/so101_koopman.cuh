@@ -76,20 +76,27 @@ extern "C" int so101_koopman_score(const double* A, const double* B, int nz, int
   if (zref) std::memcpy(&host[o], zref, sizeof(double) * H * nz);
   double* pack = nullptr;
   CUDA_TRY(cudaMallocAsync(&pack, bytes, st));
-  // pageable source: the copy is staged before the call returns, `host` may go out of scope afterwards
-  CUDA_TRY(cudaMemcpyAsync(pack, host.data(), bytes, cudaMemcpyHostToDevice, st));
+  // every exit below releases `pack` (stream ordered)
+  cudaError_t err = cudaMemcpyAsync(pack, host.data(), bytes, cudaMemcpyHostToDevice, st);   // pageable source: staged before return
   const int blk = 128;
   const unsigned grid = (unsigned)((n + blk - 1) / blk);
-  if (dtype == SO101_F64) {
-    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_koopman_score<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    k_koopman_score<double><<<grid, blk, bytes, st>>>(pack, nz, nu, H, zref != nullptr, q_weight, r_weight,
-                                                      (const double*)U, n, nobs, (float*)Xhat, (double*)cost);
-  } else {
-    if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_koopman_score<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    k_koopman_score<float><<<grid, blk, bytes, st>>>(pack, nz, nu, H, zref != nullptr, q_weight, r_weight,
-                                                     (const float*)U, n, nobs, (float*)Xhat, (double*)cost);
+  if (err == cudaSuccess && bytes > 48 * 1024)
+    err = dtype == SO101_F64
+              ? cudaFuncSetAttribute(k_koopman_score<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+              : cudaFuncSetAttribute(k_koopman_score<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (err == cudaSuccess) {
+    if (dtype == SO101_F64)
+      k_koopman_score<double><<<grid, blk, bytes, st>>>(pack, nz, nu, H, zref != nullptr, q_weight, r_weight,
+                                                        (const double*)U, n, nobs, (float*)Xhat, (double*)cost);
+    else
+      k_koopman_score<float><<<grid, blk, bytes, st>>>(pack, nz, nu, H, zref != nullptr, q_weight, r_weight,
+                                                       (const float*)U, n, nobs, (float*)Xhat, (double*)cost);
+    err = cudaGetLastError();
   }
-  CUDA_TRY(cudaGetLastError());
+  if (err != cudaSuccess) {
+    cudaFreeAsync(pack, st);
+    return fail(SO101_ECUDA, std::string("koopman_score: ") + cudaGetErrorString(err));
+  }
   CUDA_TRY(cudaFreeAsync(pack, st));
   return SO101_OK;
 }

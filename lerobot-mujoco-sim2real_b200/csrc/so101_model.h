@@ -119,6 +119,7 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
   if (t.abi_version != SO101_ABI_VERSION) return "tables ABI version mismatch";
   if (t.nv != NV || t.nu != NV) return "model must have exactly 6 hinge dofs and 6 actuators";
   if (t.nbody < NV + 1 || t.nbody > SO101_MAXBODY) return "unsupported body count";
+  if (t.ntrip < 0 || t.ntrip > SO101_MAXTRIP) return "ntrip exceeds SO101_MAXTRIP: a truncated tripwire could miss a contact";
   // ---- chain check: link k = jnt_body[k]; parent(link k) == link k-1; link 0 hangs off fixed bodies
   int link[NV];
   for (int k = 0; k < NV; k++) {

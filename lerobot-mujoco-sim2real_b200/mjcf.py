@@ -343,13 +343,14 @@ def _principal(full6: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 _TRIP_FIELDS = ("ntrip", "trip_body", "trip_center", "trip_axes", "trip_half", "trip_plane_z", "trip_qbox")
 
 
-def attach_tripwire(cm: "CompiledModel", xml_path: str) -> str:
+def attach_tripwire(cm: "CompiledModel", xml_path: str, required: bool = False) -> str:
     """Fill the contact-tripwire tables of a freshly compiled model.
 
     Fast path: the scene is one of the built-in ones and compiles to the committed tables bit for bit
     -> reuse their precomputed tripwire.  Otherwise build it from the collision meshes (tripwire.py,
     needs scipy and the STL files, ~15 s).  Returns how it was obtained; "none" leaves the tripwire
-    disabled (no env is ever flagged) and says why on stderr."""
+    disabled (no env is ever flagged) and says why on stderr; with `required` (the data generator) that is an error:
+    the scene has contacts enabled and trajectories that reach one must be recognisable."""
     import ctypes
     import sys
     key = os.path.basename(xml_path)
@@ -369,6 +370,9 @@ def attach_tripwire(cm: "CompiledModel", xml_path: str) -> str:
         tripwire.fill_tripwire(cm)
         return "meshes"
     except Exception as exc:   # scipy or meshes missing: stepping still works, contact is just not flagged
+        if required:
+            raise MjcfError(f"contact tables for {xml_path} could not be built ({exc}); without them trajectories that "
+                            "touch the table would be written to the dataset unnoticed") from exc
         print(f"[so101] contact tripwire disabled for {xml_path}: {exc}", file=sys.stderr)
         return "none"
 

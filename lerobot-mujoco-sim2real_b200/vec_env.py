@@ -113,7 +113,8 @@ class SOARM101VecEnv:
             self.seed, self._episode = int(seed), 0
         if options and "initial_state" in options:
             init = torch.as_tensor(options["initial_state"]).to(self.device, self.torch_dtype).reshape(self.num_envs, -1)
-            q = torch.zeros((T.NV, self.num_envs), dtype=self.torch_dtype, device=self.device)
+            q = torch.as_tensor(list(self.tables.qpos0), dtype=self.torch_dtype, device=self.device)
+            q = q.reshape(T.NV, 1).repeat(1, self.num_envs)      # mj_resetData: qpos = qpos0 (the gripper keeps it)
             v = torch.zeros_like(q)
             q[:5] = init[:, :5].t()
             v[:5] = init[:, 5:10].t()
@@ -165,18 +166,24 @@ class SOARM101VecEnv:
 
     def rollout(self, steps: int, input_type: str = "random", seed: Optional[int] = None, env_offset: int = 0,
                 u: Optional[torch.Tensor] = None, flags: int = 0, out: Optional[torch.Tensor] = None,
-                frame_skip: Optional[int] = None) -> torch.Tensor:
+                frame_skip: Optional[int] = None, out_ptr: Optional[int] = None) -> Optional[torch.Tensor]:
         """One launch = `generate_physics_based_data(num_envs, steps, input_type)`
-        [REF SOARM101_DataCollection.py:90-136].  -> rows [N, steps+1, 13] float64 on device."""
+        [REF SOARM101_DataCollection.py:90-136].  -> rows [N, steps+1, 13] float64 on device.
+        out_ptr: raw device address the rows are written to instead of a torch tensor - e.g. this rank's slice of the
+        dataset buffer that lives on another GPU of the node (`sharding.SharedRows`); returns None then."""
         row_dtype = torch.float32 if flags & T.ROLL_ROWS_F32 else torch.float64
-        if out is None:
-            out = torch.empty((self.num_envs, steps + 1, T.ROW), dtype=row_dtype, device=self.device)
-        assert out.is_contiguous() and out.dtype == row_dtype and out.shape == (self.num_envs, steps + 1, T.ROW)
+        if out_ptr is None:
+            if out is None:
+                out = torch.empty((self.num_envs, steps + 1, T.ROW), dtype=row_dtype, device=self.device)
+            assert out.is_contiguous() and out.dtype == row_dtype and out.shape == (self.num_envs, steps + 1, T.ROW)
+            out_ptr = out.data_ptr()
+        else:
+            assert out is None, "give out or out_ptr, not both"
         if u is not None:
             assert u.is_contiguous() and u.dtype == self.torch_dtype and u.shape == (steps + 1, T.NU_ENV, self.num_envs)
         spec = self.make_spec(input_type, seed, env_offset, u)
         _lib.check(_lib.lib().so101_batch_rollout(self._h, C.byref(spec), steps, frame_skip or self.frame_skip,
-                                                  out.data_ptr(), flags, self._stream()))
+                                                  out_ptr, flags, self._stream()))
         return out
 
     def rollout_host(self, steps: int, input_type: str = "random", seed: Optional[int] = None, env_offset: int = 0,
@@ -247,6 +254,11 @@ class SOARM101VecEnv:
 
     def clear_flags(self) -> None:
         _lib.check(_lib.lib().so101_batch_clear_flags(self._h, self._stream()))
+
+    def set_option(self, option: int, value: int) -> None:
+        """Explicit experiment options (tables.OPT_*): kernel family, block size, host pipeline depth.  The library
+        never reads environment variables."""
+        _lib.check(_lib.lib().so101_batch_set_option(self._h, int(option), int(value)))
 
     def stats(self) -> Dict[str, int]:
         """Counters since the last call: physics steps, Newton iterations, line-search evals, limit steps."""

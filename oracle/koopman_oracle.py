@@ -46,3 +46,29 @@ def mpc_solve(W, z0, zref, H, q=50.0, r=0.5):
             G[t * nz:(t + 1) * nz, s * nu:(s + 1) * nu] = np.linalg.matrix_power(A, t - s) @ B
     rhs = q * G.T @ (zref.reshape(-1) - F @ z0)
     return np.linalg.solve(q * G.T @ G + r * np.eye(H * nu), rhs).reshape(H, nu)
+
+
+def k_linear_loss(W, x, u, start_idx, gamma=0.99, pre_length=5):
+    """The reference's training loss [REF models/losses.py:54-129] for the linear model (loss_name "mse"): from
+    x0 = x[:, start_idx] the lifted state is rolled `pre_length` steps under z+ = lA z + lB u (u_encoder is the
+    identity) and compared, gamma-weighted, (i) in lifted space with the lift of the true next state (koopman_loss),
+    (ii) after decoding with lC (pred_loss), (iii) recon_loss = mse(lC lift(x1), x1); total = their sum; all divided
+    by the sum of the weights.  stable_Loss = 1e-3 * sum(max(|eig(lA)| - 1, 0)) [REF :18-21, :117].
+    x [n, steps, 8], u [n, steps, 5] -> dict of floats."""
+    A, B, Cm = W["lA.weight"], W["lB.weight"], W["lC.weight"]
+    mse = lambda a, b: float(((a - b) ** 2).mean())
+    z = lift(W, x[:, start_idx])
+    out = dict(koopman_loss=0.0, pred_loss=0.0, recon_loss=0.0, total_loss=0.0)
+    beta, cont = 1.0, 0.0
+    for i in range(start_idx, start_idx + pre_length):
+        z = z @ A.T + u[:, i] @ B.T
+        x1 = x[:, i + 1]
+        z1 = lift(W, x1)
+        k, p, r = mse(z, z1), mse(z @ Cm.T, x1), mse(z1 @ Cm.T, x1)
+        out["koopman_loss"] += beta * k; out["pred_loss"] += beta * p; out["recon_loss"] += beta * r
+        out["total_loss"] += beta * (k + p + r)
+        cont += beta
+        beta *= gamma
+    out = {k: v / cont for k, v in out.items()}
+    out["stable_Loss"] = 1e-3 * float(np.clip(np.abs(np.linalg.eigvals(A)) - 1.0, 0.0, None).sum())
+    return out

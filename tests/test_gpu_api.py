@@ -240,6 +240,62 @@ def test_data_generator_drop_in(oracle_mod, tables_v, tmp_path):
     assert (d / "train_data_300_4.npy").stat().st_mtime_ns == before
 
 
+def test_data_generator_never_returns_flagged_trajectories(tables_v, tmp_path):
+    """The scene has contacts enabled: a trajectory that reaches a contact the simulator does not model is not MuJoCo
+    data.  Default policy: such trajectories are replaced by fresh flag-free ones (deterministically, same shape);
+    'keep' returns them with the mask (and generate_and_save_data writes the mask file); 'raise' raises."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    from lerobot_mujoco_sim2real_b200.SOARM101_DataCollection import ContactError, SOARM101DataGenerator
+    d = tmp_path / "data"
+    args = types.SimpleNamespace(
+        xml_path="unused", x_dim=8, u_dim=5, device="cuda", seed=42, env="SOARM101",
+        train_samples=64, train_steps=2, test_samples=400, test_steps=200, batch_size=32, eval_batch_size=16,
+        data_dir_save=str(d), data_dir_load_train=str(d / "train_data_64_2.npy"),
+        data_dir_load_val=str(d / "val_data_400_200.npy"))
+    BAD = SOARM101DataGenerator.BAD_FLAGS
+    keep = SOARM101DataGenerator(args, tables=tables_v, on_contact="keep")
+    raw = keep.generate_physics_based_data(400, 200, "chirp", seed=5)          # long chirp runs do leave the safe region
+    flags = keep.last_flags.copy()
+    nbad = int(np.count_nonzero(flags & BAD))
+    assert flags.shape == (400,) and nbad > 0, "test premise: some chirp trajectories are flagged"
+    gen = SOARM101DataGenerator(args, tables=tables_v)                         # default: regenerate
+    data = gen.generate_physics_based_data(400, 200, "chirp", seed=5)
+    assert data.shape == raw.shape and gen.last_replaced == nbad
+    good = (flags & BAD) == 0
+    np.testing.assert_array_equal(data[good], raw[good])                       # untouched where nothing was flagged
+    assert not np.array_equal(data[~good], raw[~good])
+    # every replacement is a flag-free trajectory of a fresh env index, in order
+    env_flags = []
+    cand, f = gen.generate_device(nbad + nbad // 4 + 32, 200, "chirp", seed=5, env_offset=400)
+    okc = cand[(f & BAD) == 0][:nbad].cpu().numpy()
+    if len(okc) == nbad:
+        np.testing.assert_array_equal(data[~good], okc)
+    np.testing.assert_array_equal(gen.generate_physics_based_data(400, 200, "chirp", seed=5), data)   # deterministic
+    with pytest.raises(ContactError):
+        SOARM101DataGenerator(args, tables=tables_v, on_contact="raise").generate_physics_based_data(400, 200, "chirp", seed=5)
+    keep.generate_and_save_data()
+    masks = sorted(p.name for p in d.iterdir() if p.name.endswith(".flags.npy"))
+    assert masks, "on_contact='keep' must write the mask next to a dataset that contains flagged trajectories"
+    for name in masks:
+        m = np.load(d / name)
+        assert m.shape[0] == np.load(d / name.replace(".flags.npy", ".npy")).shape[0]
+
+
+def test_env_step_reports_abnormal_flags_in_info(tables_v):
+    """SOARM101Env.step returns {} like the reference while the env is clean, and the status word once it is not."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    import ctypes as C
+    from lerobot_mujoco_sim2real_b200 import _lib
+    env = SOARM101VecEnv(tables=tables_v, num_envs=2)
+    q = np.zeros((2, 6)); q[1, :5] = [0.0, 1.2, 1.2, 0.0, 0.0]                  # env 1 far outside the safe joint box
+    env.set_state(q, np.zeros((2, 6)), np.zeros((2, 6)))
+    obs = np.zeros((8, 2), dtype=np.float32); fl = np.zeros(2, dtype=np.uint32); u = np.zeros((6, 2))
+    _lib.check(_lib.lib().so101_batch_step_host(env._h, u.ctypes.data, 6, 1, obs.ctypes.data, fl.ctypes.data, env._stream()))
+    assert fl[0] & T_.FLAG_ABNORMAL == 0 and fl[1] & T_.FLAG_ABNORMAL != 0
+    assert np.array_equal(fl.astype(np.int32), env.flags().cpu().numpy())
+
+
 def test_fp32_free_running_scene_b(oracle_mod, tables_p):
     """fp32 mode, stated tolerance: 1000 physics steps on the contractive scene within 5e-6 rad / 1e-4 rad/s
     (measured 3.5e-7 / 4.1e-6)."""
@@ -320,8 +376,8 @@ def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind)
     U = (torch.rand((T + 1, 5, n), generator=g, dtype=torch.float64) - 0.5).contiguous().pin_memory()
     res = {}
     for chunks in ("1", "2", "4", "8", "12"):
-        monkeypatch.setenv("SO101_HOST_CHUNKS", chunks)
         env = _vec(tables_v, n)
+        env.set_option(T_.OPT_HOST_CHUNKS, int(chunks))
         out = torch.full((n, T + 1, 13), float("nan"), dtype=torch.float64).pin_memory()
         env.rollout_host(T, kind, seed=21, u_host=U if kind == "tensor" else None, out_host=out,
                          flags=T_.ROLL_GRAVCOMP_HOLD)
@@ -332,7 +388,6 @@ def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind)
     for chunks in ("2", "4", "8", "12"):
         for a, b in zip(res["1"], res[chunks]):
             assert torch.equal(a, b)
-    monkeypatch.delenv("SO101_HOST_CHUNKS")
     dev = _vec(tables_v, n).rollout(T, kind, seed=21, u=U.cuda() if kind == "tensor" else None, flags=T_.ROLL_GRAVCOMP_HOLD)
     assert torch.equal(res["1"][0], dev.cpu())
 
@@ -416,6 +471,20 @@ def test_reference_published_eval_metric_reproduced_on_gpu(tables_v, dtype):
     assert 5.5e-3 < mae < 8.5e-3
 
 
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_reference_training_loss_fingerprints_on_gpu(tables_v, dtype):
+    """koopman_loss / pred_loss / recon_loss / train_total_loss of the reference's best epoch
+    [REF results/SOARM101/11_27/DKUC/best_scores.json:3-8] on the reference's train-shaped job (50000 x 20 'random')
+    generated by the CUDA rollout: four more statistics that have seen real MuJoCo output of this path."""
+    import os
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    from tests.test_oracle import check_training_loss_fingerprints
+    W = {k: v.astype(np.float64) for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "koopman_dkuc.npz")).items()}
+    env = _vec(tables_v, 50000, dtype=dtype)
+    rows = env.rollout(20, "random", seed=99, flags=T_.ROLL_GRAVCOMP_HOLD).cpu().numpy()
+    check_training_loss_fingerprints(W, rows[:, :, 5:], rows[:, :, :5], f"CUDA {dtype}:")
+
+
 # ------------------------------------------------------------------------------------------------
 # small batches run the three-warp "team" kernels (so101_physics.cuh, SplitXch): same bits as the one-warp kernels,
 # so the batch size (and with it the shard a rank holds) never changes a trajectory
@@ -424,9 +493,10 @@ def test_reference_published_eval_metric_reproduced_on_gpu(tables_v, dtype):
 @pytest.mark.parametrize("n", [1, 300, 4096])
 def test_split_team_is_bitwise_identical(tables_v, monkeypatch, dtype, n):
     out = {}
+    from lerobot_mujoco_sim2real_b200 import tables as T_
     for split in ("0", "1"):
-        monkeypatch.setenv("SO101_SPLIT", split)
         env = _vec(tables_v, n, dtype)
+        env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_TEAM if split == "1" else T_.FAMILY_ONEWARP)
         rows = env.rollout(100, "random", seed=7, env_offset=5)          # 1000 chaotic physics steps
         q, v, w = env.get_state()
         obs = env.step(torch.full((n, 5), 0.3, dtype=env.torch_dtype, device=env.device))   # k_step path

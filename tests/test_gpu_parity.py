@@ -35,10 +35,12 @@ def _oracle_traj(O, tables, n, steps, seed, ctrl_hold=10, qscale=0.3, uscale=0.5
     return np.stack(states), np.stack(ctrls)   # [steps+1, n, 18], [steps, n, 6]
 
 
-def _gpu_step(tables, state, ctrl, nsub=1, dtype="float64"):
+def _gpu_step(tables, state, ctrl, nsub=1, dtype="float64", family=0):
+    from lerobot_mujoco_sim2real_b200 import tables as T_
     from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
     n = state.shape[0]
     env = SOARM101VecEnv(tables=tables, num_envs=n, dtype=dtype)
+    env.set_option(T_.OPT_KERNEL_FAMILY, family)
     env.set_state(state[:, :6], state[:, 6:12], state[:, 12:18])
     u = torch.as_tensor(ctrl.T.copy(), dtype=env.torch_dtype, device=env.device).contiguous()
     obs = env.step_soa(u, nsub).t().cpu().numpy()
@@ -211,7 +213,6 @@ def test_model_variants_teacher_forced(oracle_mod, tables_v, monkeypatch, varian
         for k in range(6): t.dof_armature[k] = 0.005 + 0.01 * k
         for b in range(2, 8): t.body_mass[b] *= 1.7
         t.gravity[0], t.gravity[2] = 1.0, -5.0
-    monkeypatch.setenv("SO101_SPLIT", split)
     rng = np.random.default_rng(3)
     n = 4000
     state = np.zeros((n, 18))
@@ -220,7 +221,7 @@ def test_model_variants_teacher_forced(oracle_mod, tables_v, monkeypatch, varian
     ctrl = np.zeros((n, 6)); ctrl[:, :5] = rng.uniform(-0.5, 0.5, (n, 5))
     state, _, _ = O.step_batch(t, state, ctrl, 3)          # three oracle steps: realistic qacc_warmstart
     ref, _, _ = O.step_batch(t, state, ctrl, 1)
-    out, _, env = _gpu_step(t, state, ctrl, 1)
+    out, _, env = _gpu_step(t, state, ctrl, 1, family=T_.FAMILY_TEAM if split == "1" else T_.FAMILY_ONEWARP)
     err = _rel(out, ref)
     print(f"{variant} split={split}: qpos {err[:, :6].max():.2e} qvel {err[:, 6:12].max():.2e} qacc {err[:, 12:].max():.2e}")
     assert err[:, :6].max() < 1e-12 and err[:, 6:12].max() < 1e-9 and np.quantile(err[:, 12:], 0.99) < 1e-9

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Block-size sweep for the one-warp kernels (SO101_BLK knob): wave quantisation vs warps per SM."""
+"""Block-size sweep for the one-warp kernels (SO101_OPT_BLOCK option): wave quantisation vs warps per SM."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lerobot_mujoco_sim2real_b200 import builtin_tables
+from lerobot_mujoco_sim2real_b200 import builtin_tables, tables as T_
 from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
 tables = builtin_tables()
 cases = [("float64", 131072, [256, 224, 192]), ("float64", 65536, [256, 224, 192]), ("float64", 32768, [256, 224, 192, 128]),
@@ -13,8 +13,9 @@ if len(sys.argv) > 1:
     cases = eval(sys.argv[1])
 for dtype, n, blks in cases:
     for blk in blks:
-        os.environ["SO101_BLK"] = str(blk)
         env = SOARM101VecEnv(tables=tables, num_envs=n, dtype=dtype)
+        env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_ONEWARP)
+        env.set_option(T_.OPT_BLOCK, blk)
         T = 40
         env.rollout_discard(2, "random"); torch.cuda.synchronize()
         best = 1e30
@@ -25,4 +26,3 @@ for dtype, n, blks in cases:
         warps = (n + 31) // 32; blocks = (warps * 32 + blk - 1) // blk
         print(f"{dtype} n={n:7d} blk={blk:4d} blocks={blocks:5d} ({blocks/148:.2f}/SM): {best:8.3f} ms  {n*T*10/best/1e6:8.1f} G/1000 physics-steps/s", flush=True)
         del env
-os.environ.pop("SO101_BLK", None)

@@ -23,8 +23,7 @@ print("device rollout(tensor U resident, rows to device):", timed(lambda: env.ro
 print("H2D U only:", timed(lambda: Ud.copy_(U, non_blocking=True)))
 print("D2H rows only (contiguous):", timed(lambda: rows.copy_(rows_d, non_blocking=True)))
 for ch in ("1", "2", "4", "8"):
-    os.environ["SO101_HOST_CHUNKS"] = ch
+    env.set_option(T.OPT_HOST_CHUNKS, int(ch))
     for even in (False, True):
-        if even: os.environ["SO101_HOST_EVEN"] = "1"
-        else: os.environ.pop("SO101_HOST_EVEN", None)
+        env.set_option(T.OPT_HOST_EVEN, int(even))
         print(f"rollout_host chunks={ch} even={even}:", timed(lambda: env.rollout_host(TC, "tensor", u_host=U, qpos0_host=q0, out_host=rows)))

@@ -13,10 +13,10 @@ for n in (1, 32, 256, 1024, 4096):
     env.reset()
     L = _lib.lib()
     for _ in range(20):
-        L.so101_batch_step_host(env._h, u.ctypes.data, 6, 10, obs.ctypes.data, env._stream())
+        L.so101_batch_step_host(env._h, u.ctypes.data, 6, 10, obs.ctypes.data, None, env._stream())
     t0 = time.perf_counter()
     K = 200
     for _ in range(K):
-        L.so101_batch_step_host(env._h, u.ctypes.data, 6, 10, obs.ctypes.data, env._stream())
+        L.so101_batch_step_host(env._h, u.ctypes.data, 6, 10, obs.ctypes.data, None, env._stream())
     dt = (time.perf_counter() - t0) / K
     print(f"n={n:5d}: step_host (10 sub-steps, H2D+kernel+D2H+sync) {dt*1e6:8.1f} us  -> {n/dt/1e3:9.1f} k env-steps/s")

@@ -3,7 +3,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lerobot_mujoco_sim2real_b200 import builtin_tables
+from lerobot_mujoco_sim2real_b200 import builtin_tables, tables as T_
 from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
 
 tables = builtin_tables()
@@ -12,8 +12,8 @@ for dtype in ("float64", "float32"):
     for n in sizes:
         res = {}
         for split in ("0", "1"):
-            os.environ["SO101_SPLIT"] = split
             env = SOARM101VecEnv(tables=tables, num_envs=n, dtype=dtype)
+            env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_TEAM if split == "1" else T_.FAMILY_ONEWARP)
             env.rollout_discard(2, "random")
             torch.cuda.synchronize()
             best = 1e30
@@ -30,4 +30,3 @@ for dtype in ("float64", "float32"):
         dq = (res["0"][1] - res["1"][1]).abs().max().item()
         print(f"{dtype} n={n:6d}: one-warp {res['0'][0]:8.3f} ms  split {res['1'][0]:8.3f} ms  "
               f"speedup {res['0'][0]/res['1'][0]:.3f}  bitwise_equal={same} max|dq|={dq:.3e}", flush=True)
-os.environ.pop("SO101_SPLIT", None)

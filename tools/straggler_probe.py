@@ -3,7 +3,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, ctypes as C
-from lerobot_mujoco_sim2real_b200 import builtin_tables
+from lerobot_mujoco_sim2real_b200 import builtin_tables, tables as T_
 from lerobot_mujoco_sim2real_b200 import _lib
 from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
 
@@ -11,8 +11,8 @@ tables = builtin_tables()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 for dtype in ("float64",):
     for split in ("0", "1"):
-        os.environ["SO101_SPLIT"] = split
         env = SOARM101VecEnv(tables=tables, num_envs=32, dtype=dtype)
+        env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_TEAM if split == "1" else T_.FAMILY_ONEWARP)
         ts, lim, newt = [], [], []
         for off in range(0, N, 32):
             spec = env.make_spec("random", 7, off)
@@ -30,4 +30,3 @@ for dtype in ("float64",):
               f"max {ts.max():.3f}; limit-steps/warp median {np.median(lim):.0f} max {lim.max()}  corr(t,lim)={np.corrcoef(ts,lim)[0,1]:.2f}")
         order = np.argsort(ts)[-5:]
         print("   slowest:", [(int(o), round(float(ts[o]), 3), int(lim[o]), round(newt[o], 3)) for o in order])
-os.environ.pop("SO101_SPLIT", None)
