@@ -478,7 +478,7 @@ def test_reference_training_loss_fingerprints_on_gpu(tables_v, dtype):
     generated by the CUDA rollout: four more statistics that have seen real MuJoCo output of this path."""
     import os
     from lerobot_mujoco_sim2real_b200 import tables as T_
-    from tests.test_oracle import check_training_loss_fingerprints
+    from oracle.koopman_oracle import check_training_loss_fingerprints
     W = {k: v.astype(np.float64) for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "koopman_dkuc.npz")).items()}
     env = _vec(tables_v, 50000, dtype=dtype)
     rows = env.rollout(20, "random", seed=99, flags=T_.ROLL_GRAVCOMP_HOLD).cpu().numpy()

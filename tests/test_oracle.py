@@ -209,30 +209,7 @@ def test_koopman_long_horizon_fingerprint(oracle_mod, tables_v):
 
 
 
-PUBLISHED_TRAIN = dict(koopman_loss=4.1822929293272153e-07, pred_loss=9.377657459082502e-07,
-                       recon_loss=4.393824788019431e-09, total_loss=1.360388863313245e-06,
-                       stable_Loss=1.9319259122283284e-06)   # [REF results/SOARM101/11_27/DKUC/best_scores.json:3-8]
-
-
-def check_training_loss_fingerprints(W, x, u, label=""):
-    """Four more statistics the reference holds from REAL MuJoCo data of this path: the epoch-429 means of its training
-    loss terms [REF results/.../best_scores.json:3-8], recomputed with `k_linear_loss` [REF models/losses.py:54-129]
-    restated in oracle/koopman_oracle.py on train-shaped data (21-row 'random' trajectories, float32 like the
-    reference's TensorDataset) averaged over all 15 window starts (the reference draws one per batch).  A model that
-    fitted its own training set scores a little better there than on fresh data, hence the one-sided bands."""
-    from oracle import koopman_oracle as KO
-    x = x.astype(np.float32).astype(np.float64); u = u.astype(np.float32).astype(np.float64)
-    acc = {}
-    for s in range(x.shape[1] - 5 - 1 + 1):                   # random.randint(0, steps - pre_length - 1) is inclusive
-        for k, v in KO.k_linear_loss(W, x, u, s).items():
-            acc.setdefault(k, []).append(v)
-    got = {k: float(np.mean(v)) for k, v in acc.items()}
-    print(label, {k: f"{got[k]:.3e} (published {PUBLISHED_TRAIN[k]:.3e})" for k in got})
-    for k in ("koopman_loss", "pred_loss", "total_loss"):
-        assert 0.9 * PUBLISHED_TRAIN[k] < got[k] < 1.3 * PUBLISHED_TRAIN[k], (k, got[k])
-    assert 0.8 * PUBLISHED_TRAIN["recon_loss"] < got["recon_loss"] < 1.2 * PUBLISHED_TRAIN["recon_loss"]
-    assert abs(got["stable_Loss"] / PUBLISHED_TRAIN["stable_Loss"] - 1) < 0.02     # model-only statistic
-    return got
+from oracle.koopman_oracle import PUBLISHED_TRAIN, check_training_loss_fingerprints  # noqa: E402
 
 
 def test_training_loss_fingerprints(oracle_mod, tables_v):
