@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 6
+#define SO101_ABI_VERSION 7
 #define SO101_NV       6   /* hinge dofs: 5 arm joints + gripper */
 #define SO101_MAXBODY  8   /* world, fixed base, 6 links */
 #define SO101_MAXTRIP 16   /* contact-tripwire boxes (<= 3 per link) */
@@ -68,11 +68,14 @@ enum {
 /* per-env status bits (so101_batch_get_flags) */
 enum {
   SO101_FLAG_BADSTATE   = 1u << 0,  /* qpos/qvel/qacc NaN or |x|>1e10 (mj_checkPos/Vel/Acc) */
-  SO101_FLAG_TRIP_TABLE = 1u << 1,  /* a collision bounding box crossed the table plane    */
+  SO101_FLAG_TRIP_TABLE = 1u << 1,  /* a table contact that is NOT simulated occurred: no hull data loaded, more than
+                                       SO101_MAXCON simultaneous contacts, or a contact beyond the table's footprint */
   SO101_FLAG_TRIP_SELF  = 1u << 2,  /* joint vector left the self-collision-free box       */
   SO101_FLAG_LIMIT      = 1u << 3,  /* a joint-limit row was active at least once (info)   */
-  SO101_FLAG_MAXITER    = 1u << 4   /* Newton hit opt.iterations (info)                    */
+  SO101_FLAG_MAXITER    = 1u << 4,  /* Newton hit opt.iterations (info)                    */
+  SO101_FLAG_CONTACT    = 1u << 5   /* table-plane contact rows were active at least once (info; simulated) */
 };
+#define SO101_MAXCON 6   /* simultaneous table contacts per env the kernels simulate (one per colliding geom) */
 
 /* rollout / shoot option bits */
 enum {
@@ -178,7 +181,34 @@ typedef struct So101Tables {
   /* orientation of the observation site in its body's frame (w, x, y, z): only the inverse
      kinematics (so101_ik_track) reads it, the stepper needs the site position alone */
   double  site_quat[4];
+  /* table-plane contact (the scene enables contacts, scene_with_table_v.xml:28,31): colliding geom i
+     (i < ntrip, same order as the tripwire boxes; its convex hull comes through so101_model_set_hulls) against the
+     top face z = trip_plane_z of the static table box.  One condim-3 contact per geom (MuJoCo's convex-convex
+     routine returns one), pyramidal cone -> 4 rows. */
+  double  body_invweight0[SO101_MAXBODY][2];  /* mjModel.body_invweight0: translational, rotational              */
+  double  con_friction[3];                    /* contact friction: elementwise max of the two geoms' friction    */
+  double  con_solref[2];                      /* contact solref / solimp (solmix-weighted mean of the geoms')    */
+  double  con_solimp[5];
+  double  con_margin;                         /* includemargin = max margin - max gap                            */
+  double  con_box[4];                         /* footprint of the table's top face: x_lo, x_hi, y_lo, y_hi       */
+  int32_t con_enabled;                        /* 0: no contact tables (tripwire flags only)                      */
+  int32_t con_condim;                         /* 3                                                               */
 } So101Tables;
+
+/* Convex hulls of the colliding geoms, one per tripwire box and in the same order (host pointers; copied). */
+typedef struct So101Hulls {
+  int32_t ngeom;               /* == So101Tables.ntrip                                                   */
+  int32_t nvert;               /* total number of hull vertices                                          */
+  int32_t nadj;                /* total number of adjacency entries                                      */
+  int32_t cube_res;            /* G: resolution of the direction -> start-vertex cube map                */
+  const int32_t* vert_start;   /* [ngeom + 1] first vertex of every geom                                 */
+  const double*  vert;         /* [nvert][3] hull vertices in the frame of the geom's BODY               */
+  const int32_t* adj_start;    /* [nvert + 1] CSR over the hull's edge graph                             */
+  const int32_t* adj;          /* [nadj] neighbour vertex ids (global)                                   */
+  const int32_t* cube;         /* [ngeom][6][G][G] a hull vertex (global id) near the support point of the direction
+                                  whose largest component is +-x, +-y, +-z (faces 0..5) and whose other two components,
+                                  divided by it, fall into cell (iu, iv) of [-1, 1]^2: the hill climb's start  */
+} So101Hulls;
 
 typedef struct So101Model So101Model;
 typedef struct So101Batch So101Batch;
@@ -191,6 +221,11 @@ int         so101_device_count(void);
 /* ---- model ---------------------------------------------------------------------------- */
 int  so101_model_create(const So101Tables* tables, So101Model** out);
 void so101_model_destroy(So101Model* model);
+/* Attach the convex hulls of the colliding geoms: from then on batches created from this model SIMULATE table-plane
+   contacts (exact support point of the hull by hill climbing on its edge graph where the bounding box dips below the
+   table top -> contact rows in a general dense Newton path taken only by envs in contact) instead of only flagging
+   them.  Without hulls SO101_FLAG_TRIP_TABLE marks such envs and their dynamics stay contact-free. */
+int  so101_model_set_hulls(So101Model* model, const So101Hulls* hulls);
 
 /* ---- batch ---------------------------------------------------------------------------- */
 /* bytes of per-env state for n_envs (SoA rows: qpos[6] qvel[6] qacc_warmstart[6]

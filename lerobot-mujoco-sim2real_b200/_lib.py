@@ -10,14 +10,14 @@ import ctypes as C
 import os
 from typing import Optional
 
-from .tables import So101CtrlSpec, So101IkParams, So101Tables
+from .tables import So101CtrlSpec, So101Hulls, So101IkParams, So101Tables
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libso101_b200.so")
 
 #: every symbol include/so101_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "so101_last_error", "so101_abi_version", "so101_tables_sizeof", "so101_device_count",
-    "so101_model_create", "so101_model_destroy",
+    "so101_model_create", "so101_model_destroy", "so101_model_set_hulls",
     "so101_batch_state_bytes", "so101_batch_create", "so101_batch_destroy",
     "so101_batch_reset", "so101_batch_reset_random", "so101_batch_forward",
     "so101_batch_step", "so101_batch_step_host", "so101_batch_reset_host",
@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
     L.so101_tables_sizeof.restype = C.c_size_t
     L.so101_device_count.restype = i32
     L.so101_model_create.argtypes = [C.POINTER(So101Tables), C.POINTER(vp)]
+    L.so101_model_set_hulls.argtypes = [vp, C.POINTER(So101Hulls)]
     L.so101_model_destroy.argtypes = [vp]
     L.so101_model_destroy.restype = None
     L.so101_batch_state_bytes.argtypes = [i64, i32]

@@ -461,6 +461,10 @@ struct So101Model {
   So101Tables tables;
   DevModel<double> d;
   DevModel<float> f;
+  // convex hulls of the colliding geoms (so101_model_set_hulls), vertices already in link frames; empty: none
+  std::vector<double> hull_vert;
+  std::vector<int32_t> hull_vstart, hull_adj_start, hull_adj, hull_cube;
+  int hull_res = 0;
 };
 
 struct So101Batch {
@@ -469,6 +473,9 @@ struct So101Batch {
   int dtype, device;
   void* state;        // NROWS*n elements + n uint32 flags
   bool owns_state;
+  DevModel<double> dm_d;      // the model's constants with this batch's device pointers patched in (hull data)
+  DevModel<float> dm_f;
+  void* hull_dev[4];          // vert, adj_start, adj, cube on b->device (null: no hulls -> tripwire flags only)
   unsigned long long* stats;  // device, 4 counters
   void* ctrl_stage;   // [6][n] batch dtype (host variants)
   float* obs_stage;   // [8][n]
@@ -567,6 +574,40 @@ int so101_model_create(const So101Tables* tables, So101Model** out) {
 }
 void so101_model_destroy(So101Model* m) { delete m; }
 
+int so101_model_set_hulls(So101Model* m, const So101Hulls* h) {
+  if (!m || !h) return fail(SO101_EINVAL, "null argument");
+  const So101Tables& t = m->tables;
+  if (!t.con_enabled) return fail(SO101_EMODEL, "the tables carry no contact parameters (con_enabled = 0)");
+  if (h->ngeom != t.ntrip || h->nvert <= 0 || h->nadj <= 0 || h->cube_res <= 0 || !h->vert_start || !h->vert ||
+      !h->adj_start || !h->adj || !h->cube)
+    return fail(SO101_EINVAL, "hulls: need one hull per tripwire box and all five arrays");
+  if (h->vert_start[0] != 0 || h->vert_start[h->ngeom] != h->nvert || h->adj_start[0] != 0 || h->adj_start[h->nvert] != h->nadj)
+    return fail(SO101_EINVAL, "hulls: inconsistent offsets");
+  std::vector<double> vert((size_t)3 * h->nvert);
+  for (int g = 0; g < h->ngeom; g++) {
+    if (h->vert_start[g + 1] <= h->vert_start[g]) return fail(SO101_EINVAL, "hulls: empty hull");
+    for (int i = h->vert_start[g]; i < h->vert_start[g + 1]; i++) {
+      if (!hostbuild::hull_to_link(t, t.trip_body[g], h->vert + 3 * i, &vert[3 * (size_t)i]))
+        return fail(SO101_EMODEL, "hulls: geom on a body without a joint");
+      for (int e = h->adj_start[i]; e < h->adj_start[i + 1]; e++)
+        if (h->adj[e] < h->vert_start[g] || h->adj[e] >= h->vert_start[g + 1])
+          return fail(SO101_EINVAL, "hulls: an edge leaves its hull");
+    }
+  }
+  const size_t ncube = (size_t)h->ngeom * 6 * h->cube_res * h->cube_res;
+  for (size_t i = 0; i < ncube; i++) {
+    const int g = (int)(i / ((size_t)6 * h->cube_res * h->cube_res));
+    if (h->cube[i] < h->vert_start[g] || h->cube[i] >= h->vert_start[g + 1]) return fail(SO101_EINVAL, "hulls: cube map entry outside its hull");
+  }
+  m->hull_vert.swap(vert);
+  m->hull_vstart.assign(h->vert_start, h->vert_start + h->ngeom + 1);
+  m->hull_adj_start.assign(h->adj_start, h->adj_start + h->nvert + 1);
+  m->hull_adj.assign(h->adj, h->adj + h->nadj);
+  m->hull_cube.assign(h->cube, h->cube + ncube);
+  m->hull_res = h->cube_res;
+  return SO101_OK;
+}
+
 size_t so101_batch_state_bytes(int64_t n, int dtype) {
   if (n <= 0) return 0;
   return (size_t)NROWS * n * elem_size(dtype) + (size_t)n * sizeof(uint32_t);
@@ -593,9 +634,28 @@ int so101_batch_create(const So101Model* model, int64_t n, int dtype, int device
   cudaError_t e = cudaMalloc(&b->stats, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(b->stats, 0, 4 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemset(b->state, 0, bytes);
+  // the model's constants, with the hull data of this device patched in (contact path on) or contact off
+  b->dm_d = model->d;
+  b->dm_d.con_enabled = 0;
+  if (e == cudaSuccess && model->tables.con_enabled && !model->hull_vert.empty()) {
+    const void* src[4] = {model->hull_vert.data(), model->hull_adj_start.data(), model->hull_adj.data(), model->hull_cube.data()};
+    const size_t nb[4] = {model->hull_vert.size() * sizeof(double), model->hull_adj_start.size() * sizeof(int32_t),
+                          model->hull_adj.size() * sizeof(int32_t), model->hull_cube.size() * sizeof(int32_t)};
+    for (int k = 0; k < 4 && e == cudaSuccess; k++) {
+      e = cudaMalloc(&b->hull_dev[k], nb[k]);
+      if (e == cudaSuccess) e = cudaMemcpy(b->hull_dev[k], src[k], nb[k], cudaMemcpyHostToDevice);
+      const uint64_t w = (uint64_t)(uintptr_t)b->hull_dev[k];
+      b->dm_d.hull_ptr[2 * k] = (int32_t)(uint32_t)(w & 0xffffffffu);
+      b->dm_d.hull_ptr[2 * k + 1] = (int32_t)(uint32_t)(w >> 32);
+    }
+    b->dm_d.hull_res = model->hull_res;
+    b->dm_d.con_enabled = 1;
+  }
+  hostbuild::convert<float>(b->dm_d, b->dm_f);
   if (e != cudaSuccess) {
     if (b->owns_state) cudaFree(b->state);
     cudaFree(b->stats);
+    for (int k = 0; k < 4; k++) cudaFree(b->hull_dev[k]);
     delete b;
     return fail(SO101_ECUDA, std::string("batch init: ") + cudaGetErrorString(e));
   }
@@ -607,6 +667,7 @@ void so101_batch_destroy(So101Batch* b) {
   DeviceGuard g(b->device);
   if (b->owns_state) cudaFree(b->state);
   cudaFree(b->stats);
+  for (int k = 0; k < 4; k++) cudaFree(b->hull_dev[k]);
   cudaFree(b->ctrl_stage);
   cudaFree(b->obs_stage);
   cudaFree(b->init_stage);
@@ -658,9 +719,9 @@ int so101_batch_reset(So101Batch* b, const void* qpos0, const void* qvel0, void*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int blk = pick_block(b->n);
   DISPATCH(b,
-    (k_reset<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), (const double*)qpos0,
+    (k_reset<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->dm_d, view<double>(b), (const double*)qpos0,
         (const double*)qvel0, 0, 0, 0, 0.0, 0.0, (float*)obs)),
-    (k_reset<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), (const float*)qpos0,
+    (k_reset<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->dm_f, view<float>(b), (const float*)qpos0,
         (const float*)qvel0, 0, 0, 0, 0.0, 0.0, (float*)obs)));
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -673,9 +734,9 @@ int so101_batch_reset_random(So101Batch* b, uint64_t seed, int64_t env_offset, d
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int blk = pick_block(b->n);
   DISPATCH(b,
-    (k_reset<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), nullptr, nullptr, 1, seed,
+    (k_reset<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->dm_d, view<double>(b), nullptr, nullptr, 1, seed,
         env_offset, lo, hi, (float*)obs)),
-    (k_reset<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), nullptr, nullptr, 1, seed,
+    (k_reset<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->dm_f, view<float>(b), nullptr, nullptr, 1, seed,
         env_offset, lo, hi, (float*)obs)));
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -687,8 +748,8 @@ int so101_batch_forward(So101Batch* b, void* obs, void* qfrc_bias, void* stream)
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int blk = pick_block(b->n);
   DISPATCH(b,
-    (k_forward<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->d, view<double>(b), (float*)obs, (double*)qfrc_bias)),
-    (k_forward<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->model->f, view<float>(b), (float*)obs, (float*)qfrc_bias)));
+    (k_forward<double><<<grid_for(b->n, blk), blk, 0, st>>>(b->dm_d, view<double>(b), (float*)obs, (double*)qfrc_bias)),
+    (k_forward<float><<<grid_for(b->n, blk), blk, 0, st>>>(b->dm_f, view<float>(b), (float*)obs, (float*)qfrc_bias)));
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
 }
@@ -701,12 +762,12 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
   int blk; unsigned grid; bool split;
   if (b->dtype == SO101_F64) {
     StateView<double> v = step_view<double>(b, blk, grid, split);
-    if (split) k_step<double, true><<<grid, blk, 0, st>>>(b->model->d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
-    else k_step<double, false><<<grid, blk, 0, st>>>(b->model->d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    if (split) k_step<double, true><<<grid, blk, 0, st>>>(b->dm_d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    else k_step<double, false><<<grid, blk, 0, st>>>(b->dm_d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
   } else {
     StateView<float> v = step_view<float>(b, blk, grid, split);
-    if (split) k_step<float, true><<<grid, blk, 0, st>>>(b->model->f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
-    else k_step<float, false><<<grid, blk, 0, st>>>(b->model->f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    if (split) k_step<float, true><<<grid, blk, 0, st>>>(b->dm_f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+    else k_step<float, false><<<grid, blk, 0, st>>>(b->dm_f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
   }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -937,12 +998,12 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
   int blk; unsigned grid; bool split;
   if (b->dtype == SO101_F64) {
     StateView<double> v = step_view<double>(b, blk, grid, split);
-    if (split) k_shoot<double, true><<<grid, blk, 0, st>>>(b->model->d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
-    else k_shoot<double, false><<<grid, blk, 0, st>>>(b->model->d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
+    if (split) k_shoot<double, true><<<grid, blk, 0, st>>>(b->dm_d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
+    else k_shoot<double, false><<<grid, blk, 0, st>>>(b->dm_d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
   } else {
     StateView<float> v = step_view<float>(b, blk, grid, split);
-    if (split) k_shoot<float, true><<<grid, blk, 0, st>>>(b->model->f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
-    else k_shoot<float, false><<<grid, blk, 0, st>>>(b->model->f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
+    if (split) k_shoot<float, true><<<grid, blk, 0, st>>>(b->dm_f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
+    else k_shoot<float, false><<<grid, blk, 0, st>>>(b->dm_f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
   }
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;

@@ -1,0 +1,362 @@
+// so101_contact.cuh — table-plane contact: the path of an env whose collision bounding box dipped
+// below the table top.  Reference: the scene enables contacts [REF SOARM101/SO101/scene_with_table_v.xml:28,31;
+// so101_new_calib_v.xml:53-117]; mj_step then runs mj_collision (mesh hull vs box: mjc_Convex, one contact per geom
+// pair), mj_instantiateContact (condim 3, pyramidal: rows J_n +- mu J_t), mj_makeImpedance and solves all rows with
+// the Newton solver.  Restated for CPU in oracle/so101_oracle.c (collision, makeConstraint).
+//
+// This file is the RARE path (a few % of the envs of a long chirp rollout, none of a short random one): everything
+// is rolled loops over local-memory arrays in ONE out-of-line function, so that the hot instruction stream of
+// physics_step does not grow.  Steps:
+//   1. world frames of the links from the joint angles (the hot path never forms them);
+//   2. for every hull whose box tripped: exact support vertex in direction -z by steepest ascent on the hull's edge
+//      graph, started from a direction cube map (mean < 1 step) -> penetration depth, contact point, Jacobian rows
+//      from the world hinge axes / anchors;
+//   3. a general dense Newton solve over friction rows (Huber), joint-limit rows and contact rows (one-sided), with
+//      MuJoCo's warm-start pick, termination tests and the exact piecewise-quadratic line search of line_search().
+// Returns false when no hull actually touches the plane (the box test is conservative): the caller continues on the
+// fast path.
+#pragma once
+
+namespace so101 {
+
+constexpr int MAXCON = SO101_MAXCON;
+constexpr int MAXONE = NV + 4 * MAXCON;     // one-sided rows: joint limits + pyramid rows
+
+template <typename T> SO101_DEV uint64_t hull_word_(const DevModel<T>& m, int which) {
+  return ((uint64_t)(uint32_t)m.hull_ptr[2 * which + 1] << 32) | (uint64_t)(uint32_t)m.hull_ptr[2 * which];
+}
+
+// support vertex of hull `g` for direction d (link frame): cube-map start, then steepest ascent on the edge graph
+template <typename T>
+SO101_DEV int hull_support(const DevModel<T>& m, int g, const T (&d)[3], T (&v)[3]) {
+  const double* vert = reinterpret_cast<const double*>(hull_word_(m, 0));
+  const int32_t* adj_start = reinterpret_cast<const int32_t*>(hull_word_(m, 1));
+  const int32_t* adj = reinterpret_cast<const int32_t*>(hull_word_(m, 2));
+  const int32_t* cube = reinterpret_cast<const int32_t*>(hull_word_(m, 3));
+  const int res = m.hull_res;
+  int ax = 0;
+  if (abs_(d[1]) > abs_(d[ax])) ax = 1;
+  if (abs_(d[2]) > abs_(d[ax])) ax = 2;
+  const T dm = abs_(d[ax]);
+  const T inv = dm > T(0) ? T(1) / dm : T(0);
+  const T u = d[(ax + 1) % 3] * inv, w = d[(ax + 2) % 3] * inv;
+  int iu = (int)((u + T(1)) * T(0.5) * T(res)), iw = (int)((w + T(1)) * T(0.5) * T(res));
+  iu = iu < 0 ? 0 : (iu >= res ? res - 1 : iu);
+  iw = iw < 0 ? 0 : (iw >= res ? res - 1 : iw);
+  const int face = 2 * ax + (d[ax] < T(0) ? 1 : 0);
+  int cur = cube[((g * 6 + face) * res + iu) * res + iw];
+  T best = d[0] * (T)vert[3 * cur] + d[1] * (T)vert[3 * cur + 1] + d[2] * (T)vert[3 * cur + 2];
+#pragma unroll 1
+  for (int it = 0; it < 4096; it++) {
+    int nxt = -1;
+    const int e1 = adj_start[cur + 1];
+#pragma unroll 1
+    for (int e = adj_start[cur]; e < e1; e++) {
+      const int c = adj[e];
+      const T val = d[0] * (T)vert[3 * c] + d[1] * (T)vert[3 * c + 1] + d[2] * (T)vert[3 * c + 2];
+      if (val > best) { best = val; nxt = c; }
+    }
+    if (nxt < 0) break;
+    cur = nxt;
+  }
+  v[0] = (T)vert[3 * cur]; v[1] = (T)vert[3 * cur + 1]; v[2] = (T)vert[3 * cur + 2];
+  return cur;
+}
+
+template <typename T>
+struct OneSided {        // one-sided rows (active when jar < 0): joint limits first, then 4 pyramid rows per contact
+  int n;
+  T J[MAXONE][NV], aref[MAXONE], D[MAXONE];
+};
+
+// cost, constraint force and Hessian activity of all rows at acceleration a (mj_constraintUpdate + Gauss term)
+template <typename T>
+SO101_DEV T contact_cost(const DevModel<T>& m, const T* aref_f, const OneSided<T>& os, const T* a, const T* Ma,
+                         const T* fsm, const T* asm_, T* qc, T* hd, uint32_t& active) {
+  T s = T(0);
+#pragma unroll 1
+  for (int i = 0; i < NV; i++) {
+    const T jar = a[i] - aref_f[i];
+    if (m.fr_f[i] == T(0)) { qc[i] = T(0); hd[i] = T(0); continue; }
+    if (abs_(jar) >= m.fr_Rf[i]) {
+      const T fs = copysign_(m.fr_f[i], jar);
+      s += fs * jar - m.fr_hRff[i]; qc[i] = -fs; hd[i] = T(0);
+    } else {
+      const T Dj = m.fr_D[i] * jar;
+      s += T(0.5) * Dj * jar; qc[i] = -Dj; hd[i] = m.fr_D[i];
+    }
+  }
+  active = 0;
+#pragma unroll 1
+  for (int r = 0; r < os.n; r++) {
+    T jar = -os.aref[r];
+#pragma unroll 1
+    for (int j = 0; j < NV; j++) jar += os.J[r][j] * a[j];
+    if (jar < T(0)) {
+      s += T(0.5) * os.D[r] * jar * jar;
+      const T f = -os.D[r] * jar;
+#pragma unroll 1
+      for (int j = 0; j < NV; j++) qc[j] += os.J[r][j] * f;
+      active |= 1u << r;
+    }
+  }
+  T g = T(0);
+#pragma unroll 1
+  for (int i = 0; i < NV; i++) g += T(0.5) * (Ma[i] - fsm[i]) * (a[i] - asm_[i]);
+  return s + g;
+}
+
+// exact line search over friction (Huber) and one-sided rows: the root of the piecewise-linear slope (see line_search)
+template <typename T>
+SO101_DEV T contact_line_search(const DevModel<T>& m, const T* aref_f, const OneSided<T>& os, const T* Mm, const T* a,
+                                const T* Ma, const T* fsm, const T* sr, T* Mv, uint32_t& nev_total) {
+  T ss = T(0);
+#pragma unroll 1
+  for (int i = 0; i < NV; i++) ss += sr[i] * sr[i];
+  if (sqrt_(ss) < T(MJ_MINVAL)) return T(0);
+#pragma unroll 1
+  for (int i = 0; i < NV; i++) {
+    T s = T(0);
+#pragma unroll 1
+    for (int j = 0; j < NV; j++) s += Mm[i >= j ? tri(i, j) : tri(j, i)] * sr[j];
+    Mv[i] = s;
+  }
+  T G1 = T(0), G2 = T(0);
+#pragma unroll 1
+  for (int i = 0; i < NV; i++) { G1 += sr[i] * Ma[i] - fsm[i] * sr[i]; G2 += sr[i] * Mv[i]; }
+  G2 *= T(0.5);
+  T jar1[MAXONE], jv1[MAXONE];
+#pragma unroll 1
+  for (int r = 0; r < os.n; r++) {
+    T x = -os.aref[r], v = T(0);
+#pragma unroll 1
+    for (int j = 0; j < NV; j++) { x += os.J[r][j] * a[j]; v += os.J[r][j] * sr[j]; }
+    jar1[r] = x; jv1[r] = v;
+  }
+  T alpha = T(0), result = T(0);
+  uint32_t nev = 0;
+#pragma unroll 1
+  for (int it = 0; it < 3 * NV + MAXONE + 2; it++) {
+    T nb = inf_<T>();
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      if (sr[i] == T(0) || m.fr_f[i] == T(0)) continue;
+      const T x0 = a[i] - aref_f[i];
+      const T b0 = (-m.fr_Rf[i] - x0) / sr[i], b1 = (m.fr_Rf[i] - x0) / sr[i];
+      if (b0 > alpha) nb = min_(nb, b0);
+      if (b1 > alpha) nb = min_(nb, b1);
+    }
+#pragma unroll 1
+    for (int r = 0; r < os.n; r++) {
+      if (jv1[r] == T(0)) continue;
+      const T b = -jar1[r] / jv1[r];
+      if (b > alpha) nb = min_(nb, b);
+    }
+    const bool last = !(nb < inf_<T>());
+    const T mid = last ? alpha + T(1) : T(0.5) * (alpha + nb);
+    T d0 = G1 + T(2) * G2 * mid, d1 = T(2) * G2;
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      if (m.fr_f[i] == T(0)) continue;
+      const T x = a[i] - aref_f[i] + mid * sr[i];
+      const T Ds = m.fr_D[i] * sr[i];
+      if (abs_(x) < m.fr_Rf[i]) { d0 += Ds * x; d1 += Ds * sr[i]; }
+      else d0 += copysign_(m.fr_f[i], x) * sr[i];
+    }
+#pragma unroll 1
+    for (int r = 0; r < os.n; r++) {
+      const T x = jar1[r] + mid * jv1[r];
+      if (x < T(0)) { d0 += os.D[r] * x * jv1[r]; d1 += os.D[r] * jv1[r] * jv1[r]; }
+    }
+    nev++;
+    if (d1 <= T(0)) d1 = T(MJ_MINVAL);
+    const T root = mid - d0 / d1;
+    if (root <= nb || last) { result = max_(root, alpha); break; }
+    alpha = nb;
+    result = nb;
+  }
+  nev_total += nev;
+  return result;
+}
+
+// Returns true when at least one hull touches the table: then a = qacc and qc = qfrc_constraint of the full problem
+// (friction + limit + contact rows) are set and the caller goes straight to mj_checkAcc / mj_Euler.
+template <typename T>
+__device__ __noinline__ bool contact_solve(const DevModel<T>& m, const T* q, const T* qd, uint32_t hits, const T* Mm,
+                                           const T* fsm, const T* aref_f, const T* lim_side, const T* lim_aref,
+                                           const T* lim_D, bool anylim, const T* warm, T* a, T* qc, uint32_t& flags,
+                                           Counters& cnt) {
+  OneSided<T> os;
+  os.n = 0;
+  if (anylim) {
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      if (lim_side[i] == T(0)) continue;
+      const int r = os.n++;
+#pragma unroll 1
+      for (int j = 0; j < NV; j++) os.J[r][j] = T(0);
+      os.J[r][i] = lim_side[i];
+      os.aref[r] = lim_aref[i];
+      os.D[r] = lim_D[i];
+    }
+  }
+  // ---- world frames and contacts -----------------------------------------------------------------------------------
+  T axw[NV][3], anw[NV][3];            // hinge axes and anchors in the world frame
+  T Rw[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, ow[3] = {T(0), T(0), T(0)};
+  int ncon = 0;
+#pragma unroll 1
+  for (int k = 0; k < NV; k++) {
+    T s_, c_, R[9], Rn[9], o[3];
+    sincos_(q[k] - m.qpos0[k], &s_, &c_);
+    make_R(m.E[k], c_, s_, R);
+    rot(Rw, m.r[k], o);
+    ow[0] += o[0]; ow[1] += o[1]; ow[2] += o[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rw[3 * i] * R[j] + Rw[3 * i + 1] * R[3 + j] + Rw[3 * i + 2] * R[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
+    axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
+    anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
+#pragma unroll 1
+    for (int b = 0; b < m.trip_n[k]; b++) {
+      if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
+      // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
+      // ordered deterministically (same rule as the oracle's collision())
+      const T d[3] = {m.con_tilt[k][0] - Rw[6], m.con_tilt[k][1] - Rw[7], m.con_tilt[k][2] - Rw[8]};
+      T v[3];
+      hull_support(m, m.trip_geom[k][b], d, v);
+      const T zmin = ow[2] + (Rw[6] * v[0] + Rw[7] * v[1] + Rw[8] * v[2]);
+      const T dist = zmin - m.trip_z;
+      if (!(dist < m.con_margin)) continue;
+      T p[3];
+      rot(Rw, v, p);
+      p[0] += ow[0]; p[1] += ow[1]; p[2] = zmin - T(0.5) * dist;
+      if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
+        flags |= SO101_FLAG_TRIP_TABLE;                  // an edge of the table, or more contacts than rows: not simulated
+        continue;
+      }
+      ncon++;
+      // translational Jacobian of the contact point: column j = axis_j x (p - anchor_j), j <= k
+      T Jn[NV], Jy[NV], Jx[NV];
+#pragma unroll 1
+      for (int j = 0; j < NV; j++) {
+        Jn[j] = Jy[j] = Jx[j] = T(0);
+        if (j > k) continue;
+        const T rx = p[0] - anw[j][0], ry = p[1] - anw[j][1], rz = p[2] - anw[j][2];
+        Jx[j] = axw[j][1] * rz - axw[j][2] * ry;
+        Jy[j] = axw[j][2] * rx - axw[j][0] * rz;
+        Jn[j] = axw[j][0] * ry - axw[j][1] * rx;
+      }
+      const T imp = limit_impedance(m.con_imp, dist, m.con_margin);
+      const T mu = m.con_mu;
+      const T R1 = max_(T(MJ_MINVAL), (T(1) - imp) * (m.con_tran[k] + mu * mu * m.con_tran[k]) / imp);
+      const T Dp = T(1) / (T(2) * mu * mu * R1);
+      // contact frame: normal +z, tangents (0,1,0) and (-1,0,0) (mju_makeFrame); rows J_n +- mu J_t
+#pragma unroll 1
+      for (int e = 0; e < 4; e++) {
+        const int r = os.n++;
+        const T sg = (e & 1) ? -mu : mu;
+        T vel = T(0);
+#pragma unroll 1
+        for (int j = 0; j < NV; j++) {
+          const T Jt = e < 2 ? Jy[j] : -Jx[j];
+          os.J[r][j] = Jn[j] + sg * Jt;
+          vel += os.J[r][j] * qd[j];
+        }
+        os.D[r] = Dp;
+        os.aref[r] = -m.con_B * vel - m.con_K * imp * (dist - m.con_margin);
+      }
+    }
+  }
+  if (ncon == 0) return false;
+  flags |= SO101_FLAG_CONTACT;
+
+  // ---- Newton over all rows (mj_solPrimal, Newton flavour) ---------------------------------------------------------
+  T asm_[NV], Ma[NV], hd[NV], cost;
+  uint32_t active = 0;
+  {
+    T A[21];
+#pragma unroll
+    for (int i = 0; i < 21; i++) A[i] = Mm[i];
+#pragma unroll
+    for (int i = 0; i < NV; i++) asm_[i] = fsm[i];
+    ldl6_factor_solve(A, asm_);
+  }
+  {  // warm start: the cheaper of qacc_warmstart and qacc_smooth
+    T cbest = T(0);
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+      T ca[NV], cMa[NV], cqc[NV], chd[NV];
+      uint32_t cact;
+#pragma unroll 1
+      for (int i = 0; i < NV; i++) ca[i] = c ? asm_[i] : warm[i];
+#pragma unroll 1
+      for (int i = 0; i < NV; i++) {
+        T s = T(0);
+#pragma unroll 1
+        for (int j = 0; j < NV; j++) s += Mm[i >= j ? tri(i, j) : tri(j, i)] * ca[j];
+        cMa[i] = s;
+      }
+      const T cc = contact_cost(m, aref_f, os, ca, cMa, fsm, asm_, cqc, chd, cact);
+      if (c == 0 || cbest > cc) {
+#pragma unroll 1
+        for (int i = 0; i < NV; i++) { a[i] = ca[i]; Ma[i] = cMa[i]; qc[i] = cqc[i]; hd[i] = chd[i]; }
+        cost = cc; active = cact;
+      }
+      if (c == 0) cbest = cc;
+    }
+  }
+  int iter = 0;
+#pragma unroll 1
+  while (iter < m.iterations) {
+    T sr[NV], Mv[NV];
+    {  // H = M + diag(friction quadratic) + sum_active D J'J ; search = -H^-1 grad
+      T H[21];
+#pragma unroll
+      for (int i = 0; i < 21; i++) H[i] = Mm[i];
+#pragma unroll
+      for (int i = 0; i < NV; i++) { H[tri(i, i)] += hd[i]; sr[i] = Ma[i] - fsm[i] - qc[i]; }
+#pragma unroll 1
+      for (int r = 0; r < os.n; r++) {
+        if (!(active >> r & 1u)) continue;
+#pragma unroll 1
+        for (int i = 0; i < NV; i++) {
+          const T di = os.D[r] * os.J[r][i];
+          if (di == T(0)) continue;
+#pragma unroll 1
+          for (int j = 0; j <= i; j++) H[tri(i, j)] += di * os.J[r][j];
+        }
+      }
+      ldl6_factor_solve(H, sr);
+#pragma unroll
+      for (int i = 0; i < NV; i++) sr[i] = -sr[i];
+    }
+    const T alpha = contact_line_search(m, aref_f, os, Mm, a, Ma, fsm, sr, Mv, cnt.lsevals);
+    if (alpha == T(0)) break;
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
+    const T oldcost = cost;
+    cost = contact_cost(m, aref_f, os, a, Ma, fsm, asm_, qc, hd, active);
+    T gg = T(0), nn = T(0);
+#pragma unroll 1
+    for (int i = 0; i < NV; i++) {
+      const T g = Ma[i] - fsm[i] - qc[i];
+      gg += g * g;
+      if (Noise<T>::on) nn += fsm[i] * fsm[i] + qc[i] * qc[i];
+    }
+    T tol_i = m.tolerance, tol_g = m.tolerance;
+    if (Noise<T>::on) {
+      tol_i += T(Noise<T>::eps) * m.scale * abs_(cost);
+      tol_g += T(Noise<T>::eps) * m.scale * sqrt_(nn);
+    }
+    iter++;
+    if (m.scale * (oldcost - cost) < tol_i || m.scale * sqrt_(gg) < tol_g) break;
+  }
+  cnt.newton += iter;
+  if (iter >= m.iterations) flags |= SO101_FLAG_MAXITER;
+  return true;
+}
+
+}  // namespace so101

@@ -52,7 +52,16 @@ struct DevModel {
   T trip_c[NV][TRIP_PER_LINK][3], trip_ax[NV][TRIP_PER_LINK][9], trip_half[NV][TRIP_PER_LINK][3];
   T trip_rad[NV][TRIP_PER_LINK];   // |half|_2: bounding-sphere pre-check
   T trip_z, trip_qlo[NV], trip_qhi[NV];
+  // table-plane contact rows (so101_contact.cuh): sliding friction, K / B of the contact solref, impedance
+  // parameters, includemargin, translational body_invweight0 of every link, footprint of the table top
+  T con_mu, con_K, con_B, con_margin, con_imp[5], con_tran[NV], con_box[4];
+  T con_tilt[NV][3];   // tie-breaking tilt of the support direction (1e-7 * (2,3,4)/sqrt(29) in the BODY frame) in link axes
   int32_t trip_n[NV];   // <- first non-T field (see hostbuild::convert)
+  int32_t trip_geom[NV][TRIP_PER_LINK];   // hull (= tripwire box) index of slot b of link k
+  // device pointers of the hull data as (lo, hi) words - int32 so that DevModel<double> and DevModel<float> share the
+  // layout of this tail; patched per batch (so101_batch_create), 0 = no hulls: vert, adj_start, adj, cube
+  int32_t hull_ptr[8];
+  int32_t hull_res, con_enabled;
   int32_t ntrip;
   int32_t site_link;
   int32_t iterations, ls_iterations;
@@ -208,6 +217,7 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
       mv(At, c3, m.trip_c[k][slot]);
       for (int a = 0; a < 3; a++) mv(At, &t.trip_axes[i][3 * a], &m.trip_ax[k][slot][3 * a]);
       for (int c = 0; c < 3; c++) m.trip_half[k][slot][c] = t.trip_half[i][c];
+      m.trip_geom[k][slot] = i;
       m.trip_rad[k][slot] = std::sqrt(t.trip_half[i][0] * t.trip_half[i][0] + t.trip_half[i][1] * t.trip_half[i][1] +
                                       t.trip_half[i][2] * t.trip_half[i][2]) * (1 + 1e-5);  // margin covers f32 rounding of |zw|
       m.trip_n[k] = slot + 1;
@@ -229,6 +239,28 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
   m.trip_z = t.trip_plane_z;
   for (int k = 0; k < NV; k++) { m.trip_qlo[k] = t.trip_qbox[k][0]; m.trip_qhi[k] = t.trip_qbox[k][1]; }
 
+  // contact rows: K, B as mj_makeImpedance derives them from the contact's solref (refsafe), see the limit rows below
+  if (t.con_enabled) {
+    if (t.con_condim != 3) return "contact: only condim 3";
+    if (t.con_solimp[4] != 1.0 && t.con_solimp[4] != 2.0) return "contact solimp power must be 1 or 2 on the CUDA path";
+    double c0 = t.con_solref[0], c1 = t.con_solref[1], cd = t.con_solimp[1];
+    if (c0 > 0 && c0 < 2 * t.timestep) c0 = 2 * t.timestep;
+    if (c0 > 0) { m.con_K = 1 / std::fmax(1e-15, cd * cd * c0 * c0 * c1 * c1); m.con_B = 2 / std::fmax(1e-15, cd * c0); }
+    else { m.con_K = -c0 / std::fmax(1e-15, cd * cd); m.con_B = -c1 / std::fmax(1e-15, cd); }
+    m.con_mu = t.con_friction[0];
+    m.con_margin = t.con_margin;
+    for (int c = 0; c < 5; c++) m.con_imp[c] = t.con_solimp[c];
+    for (int c = 0; c < 4; c++) m.con_box[c] = t.con_box[c];
+    for (int k = 0; k < NV; k++) {
+      m.con_tran[k] = t.body_invweight0[0][0] + t.body_invweight0[link[k]][0];
+      const double tilt[3] = {2e-7 / 5.385164807134504, 3e-7 / 5.385164807134504, 4e-7 / 5.385164807134504};
+      double A[9], At[9];
+      z2vec(t.jnt_axis[k], A);
+      mt(A, At);
+      mv(At, tilt, m.con_tilt[k]);
+    }
+    m.con_enabled = 1;
+  }
   for (int c = 0; c < 3; c++) m.accg[c] = -t.gravity[c];
   m.h = t.timestep;
   m.tolerance = t.tolerance;
@@ -291,6 +323,20 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
     if (m.ctrl_of_dof[k] != k) return "actuator i must drive joint i (ctrl rows are indexed by joint)";
   }
   return "";
+}
+
+// hull vertex of a geom on body `body` (body frame) -> the frame of its link (origin = joint anchor, z = hinge axis)
+inline bool hull_to_link(const So101Tables& t, int body, const double v[3], double out[3]) {
+  for (int k = 0; k < NV; k++) {
+    if (t.jnt_body[k] != body) continue;
+    double A[9], At[9], d3[3];
+    z2vec(t.jnt_axis[k], A);
+    mt(A, At);
+    for (int c = 0; c < 3; c++) d3[c] = v[c] - t.jnt_pos[k][c];
+    mv(At, d3, out);
+    return true;
+  }
+  return false;
 }
 
 template <typename T>

@@ -232,9 +232,11 @@ SO101_DEV void rnea_link(const T (&R)[9], const T (&r)[3], const T (&I)[10], T w
 #pragma unroll
   for (int c = 0; c < 6; c++) { v[c] = vc[c]; a[c] = ac[c]; }
 }
-// contact tripwire of one link: zw = world z axis in the link frame, zo = world height of its origin
+// contact tripwire of one link: zw = world z axis in the link frame, zo = world height of its origin.
+// A box that dips below the table top sets bit k * TRIP_PER_LINK + b of `hits`: the caller either runs the contact
+// path on exactly those hulls (so101_contact.cuh) or, without hull data, raises SO101_FLAG_TRIP_TABLE.
 template <typename T, typename BOX>
-SO101_DEV void tripwire_box(const BOX& m, int k, int b, const T (&zw)[3], T zo, uint32_t& flags) {
+SO101_DEV void tripwire_box(const BOX& m, int k, int b, const T (&zw)[3], T zo, uint32_t& hits) {
   T zc0 = add_(zo, dot3_(zw[0], m.trip_c[k][b][0], zw[1], m.trip_c[k][b][1], zw[2], m.trip_c[k][b][2]));
   if (sub_(zc0, m.trip_rad[k][b]) >= m.trip_z) return;   // bounding sphere clears the plane: box does too
   T ext = T(0);
@@ -242,7 +244,7 @@ SO101_DEV void tripwire_box(const BOX& m, int k, int b, const T (&zw)[3], T zo, 
   for (int ax = 0; ax < 3; ax++)
     ext = fma_(abs_(dot3_(zw[0], m.trip_ax[k][b][3 * ax], zw[1], m.trip_ax[k][b][3 * ax + 1], zw[2],
                           m.trip_ax[k][b][3 * ax + 2])), m.trip_half[k][b][ax], ext);
-  if (sub_(zc0, ext) < m.trip_z) flags |= SO101_FLAG_TRIP_TABLE;
+  if (sub_(zc0, ext) < m.trip_z) hits |= 1u << (k * TRIP_PER_LINK + b);
 }
 template <typename T> SO101_DEV void tripwire_frame(const T (&R)[9], const T (&r)[3], T (&zw)[3], T& zo) {
   zo = add_(zo, dot3_(zw[0], r[0], zw[1], r[1], zw[2], r[2]));
@@ -366,11 +368,12 @@ template <typename T> SO101_DEV void joint_sincos(const DevModel<T>& m, const T 
 
 // contact tripwire of link k, unrolled form
 template <typename T>
-SO101_DEV void tripwire_link(const DevModel<T>& m, int k, const T (&R)[9], T qk, T (&zw)[3], T& zo, uint32_t& flags) {
+SO101_DEV void tripwire_link(const DevModel<T>& m, int k, const T (&R)[9], T qk, T (&zw)[3], T& zo, uint32_t& flags,
+                             uint32_t& hits) {
   tripwire_frame(R, m.r[k], zw, zo);
 #pragma unroll
   for (int b = 0; b < TRIP_PER_LINK; b++) {
-    if (m.trip_n[k] > b) tripwire_box(m, k, b, zw, zo, flags);
+    if (m.trip_n[k] > b) tripwire_box(m, k, b, zw, zo, hits);
   }
   if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
 }
@@ -378,7 +381,7 @@ SO101_DEV void tripwire_link(const DevModel<T>& m, int k, const T (&R)[9], T qk,
 template <typename T, bool WANT_M, bool WANT_BIAS = true>
 SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (&qd)[NV], const T (&sn)[NV],
                                const T (&cs)[NV], T (&M)[21], T (&bias)[NV], bool want_site, T (&site)[3], bool trip,
-                               uint32_t& flags) {
+                               uint32_t& flags, uint32_t& hits) {
   // ---- forward pass: velocities, accelerations, link forces --------------------------------
   T f[NV][6];
   if (WANT_BIAS) {
@@ -391,7 +394,7 @@ SO101_DEV void smooth_dynamics(const DevModel<T>& m, const T (&q)[NV], const T (
       T R[9];
       make_R(m.E[k], cs[k], sn[k], R);
       rnea_link(R, m.r[k], m.I[k], qd[k], v, a, f[k]);
-      if (trip) tripwire_link(m, k, R, q[k], zw, zo, flags);
+      if (trip) tripwire_link(m, k, R, q[k], zw, zo, flags, hits);
     }
   }
 
@@ -562,7 +565,7 @@ SO101_DEV void crba_mass(const DevModel<T>& m, const T* sn, const T* cs, int st,
 // contact tripwire over all links (flags only)
 template <typename T>
 SO101_DEV void tripwire_all(const DevModel<T>& m, const T* sn, const T* cs, int st, const T* q, int qst,
-                            uint32_t& flags) {
+                            uint32_t& flags, uint32_t& hits) {
   T zw[3] = {T(0), T(0), T(1)};  // world z axis in the current frame
   T zo = T(0);                   // world height of the current frame origin
 #pragma unroll 1
@@ -571,7 +574,7 @@ SO101_DEV void tripwire_all(const DevModel<T>& m, const T* sn, const T* cs, int 
     make_R(m.E[k], cs[k * st], sn[k * st], R);
     tripwire_frame(R, m.r[k], zw, zo);
 #pragma unroll 1
-    for (int b = 0; b < m.trip_n[k]; b++) tripwire_box(m, k, b, zw, zo, flags);
+    for (int b = 0; b < m.trip_n[k]; b++) tripwire_box(m, k, b, zw, zo, hits);
     const T qk = q[k * qst];
     if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
   }
@@ -931,6 +934,10 @@ SO101_DEV void newton_exact_finish(const DevModel<T>& m, const Rows<T>& rw, cons
   }
 }
 
+}  // namespace so101
+#include "so101_contact.cuh"
+namespace so101 {
+
 // ------------------------------------------------------------------------------------------
 // one physics step.  After the smooth dynamics every lane runs the same small phase machine
 //   SMOOTH (qacc_smooth = M^-1 qfrc_smooth) -> NEWTON x n -> EULER ((M + hB)^-1 ...)
@@ -956,6 +963,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   T M[21], bias[NV];
+  uint32_t hits = 0;   // tripwire boxes below the table top
 #if SO101_ONEWARP_ROLLED   // experiment: the compact link loops of the team kernels in the one-warp kernels (see profiles/README.md)
   {
     T sn[NV], cs[NV], lq[NV], lqd[NV];
@@ -964,14 +972,14 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     joint_sincos_range(m, lq, 1, sn, cs, 1, 0, NV);
     rnea_bias(m, sn, cs, 1, lqd, 1, bias);
     crba_mass(m, sn, cs, 1, M, 1);
-    if (trip) tripwire_all(m, sn, cs, 1, lq, 1, e.flags);
+    if (trip) tripwire_all(m, sn, cs, 1, lq, 1, e.flags, hits);
     if (want_site) site_from_trig(m, sn, cs, 1, site);
   }
 #else
   {
     T sn[NV], cs[NV];
     joint_sincos(m, e.q, sn, cs);
-    smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags);
+    smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags, hits);
   }
 #endif
   if (SYNC) __syncthreads();
@@ -991,6 +999,41 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV], zone[NV];
   T cost = T(0);
   bool need_setup = false;
+  if (hits) {
+    // a collision box is below the table top: exact hull test and, if a hull does touch, the full constraint solve with
+    // contact rows - out of line (so101_contact.cuh); the phase machine then only runs its Euler solve
+    bool in_contact = false;
+    if (m.con_enabled)
+      in_contact = contact_solve<T>(m, e.q, e.qd, hits, M, fsm, rw.aref_f, rw.side, rw.aref_l, rw.D_l, rw.anylim, e.warm,
+                                    a, qc, e.flags, cnt);
+    else
+      e.flags |= SO101_FLAG_TRIP_TABLE;   // no hull data: the env is only marked, its dynamics stay contact-free
+    if (in_contact) {
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < NV; i++) bad |= bad_(a[i]);
+      if (bad) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
+        e.time = T(0);
+        e.flags |= SO101_FLAG_BADSTATE;
+        phase = PH_DONE;
+      } else if (m.any_damping) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) { dd[i] = m.h * m.damping[i]; x[i] = fsm[i] + qc[i]; }
+        phase = PH_EULER;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+          e.qd[i] += m.h * a[i];
+          e.q[i] += m.h * e.qd[i];
+          e.warm[i] = a[i];
+        }
+        e.time += m.h;
+        phase = PH_DONE;
+      }
+    }
+  }
   while (phase != PH_DONE) {
     {
       T A[21];
@@ -1195,7 +1238,7 @@ struct SplitXch {      // shared memory of one team, structure-of-arrays over th
   T L1[2][15][32], D1inv[2][NV][32];   // M = L1 D1 L1^T, double buffered: step n reads the factor of M_(n-1) (see split_geometry_step)
   T L2[15][32], D2inv[NV][32];   // M + h B = L2 D2 L2^T
   T site[3][32];
-  uint32_t trip[32];
+  uint32_t trip[32], hits[32];   // TRIP_SELF flag / tripwire boxes below the table top (lookout warp)
   T q[NV][32], qd[NV][32];       // state handed back by the dynamics warp
 };
 
@@ -1281,14 +1324,15 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
                                   bool want_site, bool trip) {
   team_check_state(m, q, qd);
   team_sincos(m, x, lane, 2, q);
-  uint32_t fl = 0;
+  uint32_t fl = 0, hits = 0;
   if (trip) {
     T lq[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) lq[i] = q[i];
-    tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl);
+    tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
   }
   x.trip[lane] = fl;
+  x.hits[lane] = hits;
   if (want_site) {
     T p[3];
     site_from_trig(m, &x.sn[0][lane], &x.cs[0][lane], 32, p);
@@ -1342,7 +1386,14 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   T Ls[15], Dinv[NV];
   T a[NV], Ma[NV], qc[NV], hd[NV];
   bool solved = false;
-  if (constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
+  if (trip && x.hits[lane]) {        // table contact (see physics_step)
+    if (m.con_enabled)
+      solved = contact_solve<T>(m, e.q, e.qd, x.hits[lane], M, fsm, rw.aref_f, rw.side, rw.aref_l, rw.D_l, rw.anylim,
+                                e.warm, a, qc, e.flags, cnt);
+    else
+      e.flags |= SO101_FLAG_TRIP_TABLE;
+  }
+  if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     // zone guess from qacc_smooth approximated with the factor of the previous step's M (split_geometry_step)
     const int rb = LaggedGuess<T>::value ? (int)(cnt.steps & 1u) : 0;
 #pragma unroll

@@ -277,6 +277,15 @@ class Geom:
     mesh: Optional[str]
     contype: int
     conaffinity: int
+    # contact parameters (MuJoCo defaults: friction "1 0.005 0.0001", solref "0.02 1", solimp "0.9 0.95 0.001 0.5 2")
+    friction: np.ndarray = None
+    solref: np.ndarray = None
+    solimp: np.ndarray = None
+    margin: float = 0.0
+    gap: float = 0.0
+    condim: int = 3
+    priority: int = 0
+    solmix: float = 1.0
 
 
 @dataclass
@@ -295,6 +304,7 @@ class CompiledModel:
     meshdir: str
     xml_dir: str
     M0: np.ndarray
+    hulls: Optional[dict] = None     # convex hulls of the colliding geoms (tripwire.build_hulls); None: the built-in ones
 
     def joint_id(self, name: str) -> int:
         return self.joint_names.index(name)
@@ -340,7 +350,8 @@ def _principal(full6: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return w, mat_q(V)
 
 
-_TRIP_FIELDS = ("ntrip", "trip_body", "trip_center", "trip_axes", "trip_half", "trip_plane_z", "trip_qbox")
+_TRIP_FIELDS = ("ntrip", "trip_body", "trip_center", "trip_axes", "trip_half", "trip_plane_z", "trip_qbox",
+                "con_friction", "con_solref", "con_solimp", "con_margin", "con_box", "con_enabled", "con_condim")
 
 
 def attach_tripwire(cm: "CompiledModel", xml_path: str, required: bool = False) -> str:
@@ -368,6 +379,7 @@ def attach_tripwire(cm: "CompiledModel", xml_path: str, required: bool = False) 
     try:
         from . import tripwire
         tripwire.fill_tripwire(cm)
+        cm.hulls = tripwire.build_hulls(cm)
         return "meshes"
     except Exception as exc:   # scipy or meshes missing: stepping still works, contact is just not flagged
         if required:
@@ -455,7 +467,12 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
                 size=_floats(a.get("size", "0 0 0")),
                 pos=_floats(a.get("pos", "0 0 0"), 3), quat=_frame_quat(a, angle_scale, comp["eulerseq"]),
                 mesh=a.get("mesh"), contype=int(a.get("contype", "1")),
-                conaffinity=int(a.get("conaffinity", "1"))))
+                conaffinity=int(a.get("conaffinity", "1")),
+                friction=_pad(_floats(a.get("friction", "1 0.005 0.0001")), [1.0, 0.005, 0.0001]),
+                solref=_pad(_floats(a.get("solref", "0.02 1")), [0.02, 1.0]),
+                solimp=_pad_solimp(_floats(a.get("solimp", "0.9 0.95 0.001 0.5 2"))),
+                margin=float(a.get("margin", "0")), gap=float(a.get("gap", "0")), condim=int(a.get("condim", "3")),
+                priority=int(a.get("priority", "0")), solmix=float(a.get("solmix", "1"))))
         for s in elem.findall("site"):
             a = dict(cls_of(s, childclass).site)
             a.update(s.attrib)
@@ -650,6 +667,22 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
         t.dof_M0[k] = M0[k, k]
         t.dof_invweight0[k] = Minv[k, k]
     t.meaninertia = float(np.mean(np.diag(M0)))
+    # body_invweight0 (engine_setconst.c set0): mean translational / rotational diagonal of J M^-1 J' with J the
+    # Jacobian of the body's centre of mass at qpos0; bodies without dofs above them get 0
+    q0 = np.array([j["ref"] for j in joints])
+    xpos0, xmat0, anchor0, axis0 = fk_numpy(t, q0)
+    for b in range(1, nbody):
+        com = xpos0[b] + xmat0[b] @ np.array(t.body_ipos[b][:])
+        Jp, Jr = np.zeros((3, nv)), np.zeros((3, nv))
+        a = b
+        while a > 0:
+            k = t.body_jnt[a]
+            if k >= 0:
+                Jp[:, k] = np.cross(axis0[k], com - anchor0[k])
+                Jr[:, k] = axis0[k]
+            a = t.body_parent[a]
+        t.body_invweight0[b][0] = float(np.trace(Jp @ Minv @ Jp.T) / 3.0)
+        t.body_invweight0[b][1] = float(np.trace(Jr @ Minv @ Jr.T) / 3.0)
     for k, a in enumerate(acts):
         gain, b = t.act_gain[k], t.act_bias[k]
         if gain == -b[1] and b[2] > 0:   # position-like actuator carrying a damping ratio
@@ -680,6 +713,12 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
         actuator_names=actuator_names, site_names=site_names, site_body=[s[1] for s in sites],
         site_pos=[s[2] for s in sites], key_names=key_names, geoms=geoms, mesh_files=mesh_files,
         meshdir=os.path.join(xml_dir, comp.get("meshdir", "")), xml_dir=xml_dir, M0=M0)
+
+
+def _pad(v: np.ndarray, full) -> np.ndarray:
+    out = np.array(full, dtype=np.float64)
+    out[: v.size] = v
+    return out
 
 
 def _pad_solimp(v: np.ndarray) -> np.ndarray:

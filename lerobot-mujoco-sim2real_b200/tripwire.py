@@ -152,15 +152,13 @@ def fill_tripwire(cm: mjcf.CompiledModel, with_self_box: bool = True) -> None:
     xpos0, xmat0, _, axis0 = mjcf.fk_numpy(t, np.array(t.qpos0[:]))
     first = t.jnt_body[0]
     vertical_first = abs(abs(axis0[0][2]) - 1.0) < 1e-9
-    boxes = []
     for b, name, pts in geom_hulls(cm):
-        if t.body_jnt[b] < 0:
-            continue
         if b == first and vertical_first:
             zmin = float((xpos0[b] + pts @ xmat0[b].T)[:, 2].min())
             if zmin <= plane:
                 raise mjcf.MjcfError(f"geom {name!r} of the first link is in permanent contact with the support plane")
-            continue
+    boxes = []
+    for b, name, pts in _contact_geoms(cm):
         c, ax, half = obb(pts)
         boxes.append((b, c, ax, half))
     if len(boxes) > T.MAXTRIP:
@@ -172,10 +170,123 @@ def fill_tripwire(cm: mjcf.CompiledModel, with_self_box: bool = True) -> None:
         t.trip_axes[i][:] = list(ax.reshape(-1))
         t.trip_half[i][:] = list(half)
     t.trip_plane_z = plane
+    fill_contact_params(cm)
     if with_self_box:
         box = self_collision_box(cm, body_hulls(cm))
         for k in range(t.nv):
             t.trip_qbox[k][0], t.trip_qbox[k][1] = float(box[k, 0]), float(box[k, 1])
+
+
+CUBE_RES = 16
+
+
+def _contact_geoms(cm: mjcf.CompiledModel):
+    """The colliding geoms that get a tripwire box / a hull, in table order (fill_tripwire's order), with hull
+    vertices in the body frame.  Geoms of a first link that turns about a vertical axis are left out (their height
+    above the plane never changes; fill_tripwire checks them once)."""
+    t = cm.tables
+    _, _, _, axis0 = mjcf.fk_numpy(t, np.array(t.qpos0[:]))
+    first = t.jnt_body[0]
+    vertical_first = abs(abs(axis0[0][2]) - 1.0) < 1e-9
+    return [(b, name, pts) for b, name, pts in geom_hulls(cm)
+            if t.body_jnt[b] >= 0 and not (b == first and vertical_first)]
+
+
+def fill_contact_params(cm: mjcf.CompiledModel) -> None:
+    """Contact parameters of (static support box, colliding geom) pairs as mj_contactParam mixes them; the CUDA
+    contact path handles ONE parameter set, condim 3, and the top face of ONE axis-aligned box."""
+    t = cm.tables
+    t.con_enabled = 0
+    boxes = [g for g in cm.geoms if g.body == 0 and (g.contype or g.conaffinity) and g.type == "box"]
+    planes = [g for g in cm.geoms if g.body == 0 and (g.contype or g.conaffinity) and g.type == "plane"]
+    if len(boxes) != 1 or t.ntrip == 0:
+        return
+    box = boxes[0]
+    if abs(abs(mjcf.q_norm(box.quat)[0]) - 1.0) > 1e-12:
+        raise mjcf.MjcfError("contact: the support box must be axis aligned")
+    if any(p.pos[2] >= box.pos[2] + box.size[2] for p in planes):
+        raise mjcf.MjcfError("contact: a static plane above the table top is not handled")
+    movers = [g for g in cm.geoms if g.body != 0 and (g.contype or g.conaffinity)]
+    params = set()
+    for g in movers:
+        if not ((g.contype & box.conaffinity) or (box.contype & g.conaffinity)):
+            raise mjcf.MjcfError("contact: a colliding geom that does not collide with the table is not handled")
+        if g.priority != box.priority:
+            src = g if g.priority > box.priority else box
+            fr, sr, si = src.friction, src.solref, src.solimp
+        else:
+            w = box.solmix / (box.solmix + g.solmix) if box.solmix + g.solmix > 0 else 0.5
+            fr = np.maximum(box.friction, g.friction)
+            sr, si = w * box.solref + (1 - w) * g.solref, w * box.solimp + (1 - w) * g.solimp
+        params.add((tuple(fr), tuple(sr), tuple(si), max(box.margin, g.margin) - max(box.gap, g.gap),
+                    max(box.condim, g.condim)))
+    if len(params) != 1:
+        raise mjcf.MjcfError("contact: the colliding geoms must share one contact parameter set")
+    fr, sr, si, margin, condim = next(iter(params))
+    if condim != 3:
+        raise mjcf.MjcfError("contact: only condim 3 is handled")
+    t.con_friction[:] = list(fr)
+    t.con_solref[:] = list(sr)
+    t.con_solimp[:] = list(si)
+    t.con_margin = float(margin)
+    t.con_condim = int(condim)
+    t.con_box[:] = [box.pos[0] - box.size[0], box.pos[0] + box.size[0], box.pos[1] - box.size[1], box.pos[1] + box.size[1]]
+    t.con_enabled = 1
+
+
+def build_hulls(cm: mjcf.CompiledModel, res: int = CUBE_RES) -> Dict[str, np.ndarray]:
+    """Hull vertices (body frame), their edge graph (CSR) and a direction -> start-vertex cube map per colliding geom,
+    in tripwire-box order: what `so101_model_set_hulls` takes.  Convex hulls by qhull (scipy), as MuJoCo builds them
+    for mesh collision.  The edge graph contains every polytope edge (plus diagonals of triangulated flat faces), so a
+    steepest-ascent walk on it ends on the support vertex of any direction."""
+    from scipy.spatial import ConvexHull
+    t = cm.tables
+    verts, vstart, adj_rows = [], [0], []
+    cube = []
+    for b, name, pts in _contact_geoms(cm):
+        hull = ConvexHull(pts)
+        keep = np.sort(hull.vertices)
+        remap = -np.ones(len(pts), dtype=np.int64)
+        remap[keep] = np.arange(len(keep))
+        v = pts[keep]
+        nbr = [set() for _ in range(len(v))]
+        for tri in remap[hull.simplices]:
+            for a_, b_ in ((0, 1), (1, 2), (0, 2)):
+                nbr[tri[a_]].add(int(tri[b_])); nbr[tri[b_]].add(int(tri[a_]))
+        base = vstart[-1]
+        for n in nbr:
+            adj_rows.append(sorted(base + x for x in n))
+        # cube map: support vertex of the direction through the centre of every cell
+        c = (np.arange(res) + 0.5) / res * 2 - 1
+        uu, vv = np.meshgrid(c, c, indexing="ij")
+        faces = []
+        for face in range(6):
+            ax, sgn = face // 2, (1.0 if face % 2 == 0 else -1.0)
+            d = np.zeros((res, res, 3))
+            d[..., ax] = sgn
+            d[..., (ax + 1) % 3] = uu * sgn if False else uu
+            d[..., (ax + 2) % 3] = vv
+            faces.append(base + np.argmax(d.reshape(-1, 3) @ v.T, axis=1).reshape(res, res))
+        cube.append(np.stack(faces))
+        verts.append(v)
+        vstart.append(base + len(v))
+    adj_start = np.zeros(vstart[-1] + 1, dtype=np.int32)
+    adj_start[1:] = np.cumsum([len(r) for r in adj_rows])
+    return {
+        "vert_start": np.asarray(vstart, dtype=np.int32), "vert": np.ascontiguousarray(np.concatenate(verts), dtype=np.float64),
+        "adj_start": adj_start, "adj": np.asarray([x for r in adj_rows for x in r], dtype=np.int32),
+        "cube": np.ascontiguousarray(np.stack(cube), dtype=np.int32), "cube_res": np.int32(res),
+        "trip_center": np.ctypeslib.as_array(t.trip_center)[:t.ntrip].copy(),
+        "trip_body": np.ctypeslib.as_array(t.trip_body)[:t.ntrip].copy(),
+    }
+
+
+def support_numpy(h: Dict[str, np.ndarray], g: int, d: np.ndarray) -> Tuple[int, float]:
+    """Brute-force support vertex (global id, value) of geom g for direction d (body frame): the check for the walk."""
+    lo, hi = h["vert_start"][g], h["vert_start"][g + 1]
+    vals = h["vert"][lo:hi] @ d
+    k = int(np.argmax(vals))
+    return lo + k, float(vals[k])
 
 
 def table_clearance_numpy(t: T.So101Tables, q: np.ndarray) -> float:

@@ -32,10 +32,25 @@ def _dtype_code(dtype: Union[str, torch.dtype]) -> Tuple[int, torch.dtype]:
 class Model:
     """Owns a `So101Model*` (compiled tables uploaded as kernel-parameter constants)."""
 
-    def __init__(self, tables: So101Tables):
+    def __init__(self, tables: So101Tables, hulls="auto"):
+        """hulls: dict of hull arrays (tripwire.build_hulls), "auto" = the built-in ones when the tables carry the
+        built-in scenes' contact geometry, None = none.  With hulls the batch SIMULATES table-plane contact; without,
+        envs that would touch the table are only flagged (SO101_FLAG_TRIP_TABLE)."""
         self.tables = tables
         self._h = C.c_void_p()
         _lib.check(_lib.lib().so101_model_create(C.byref(tables), C.byref(self._h)))
+        if isinstance(hulls, str):
+            hulls = T.hulls_for(tables)
+        self.has_contact = False
+        if hulls is not None and tables.con_enabled:
+            arrs = [np.ascontiguousarray(hulls["vert_start"], dtype=np.int32), np.ascontiguousarray(hulls["vert"], dtype=np.float64),
+                    np.ascontiguousarray(hulls["adj_start"], dtype=np.int32), np.ascontiguousarray(hulls["adj"], dtype=np.int32),
+                    np.ascontiguousarray(hulls["cube"], dtype=np.int32)]
+            h = T.So101Hulls()
+            h.ngeom, h.nvert, h.nadj, h.cube_res = len(arrs[0]) - 1, arrs[1].shape[0], arrs[3].shape[0], int(hulls["cube_res"])
+            h.vert_start, h.vert, h.adj_start, h.adj, h.cube = [a.ctypes.data for a in arrs]
+            _lib.check(_lib.lib().so101_model_set_hulls(self._h, C.byref(h)))     # copied by the library
+            self.has_contact = True
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -47,7 +62,8 @@ class Model:
 class SOARM101VecEnv:
     def __init__(self, xml_path: Optional[str] = None, num_envs: int = 1, dt: float = 0.02,
                  dtype: Union[str, torch.dtype] = "float64", device: Union[int, str, torch.device] = 0,
-                 tables: Optional[So101Tables] = None, seed: int = 42, gravity_compensation: bool = False):
+                 tables: Optional[So101Tables] = None, seed: int = 42, gravity_compensation: bool = False,
+                 hulls="auto"):
         """xml_path: MJCF scene (compiled on the host once) — or pass pre-compiled `tables`.
         gravity_compensation=True: `step` first sets qfrc_applied = qfrc_bias of the current state, as the reference's
         control loops do before every env step [REF Koopman_MPC.py:119; SOARM101_Env.py:120 (commented out)]."""
@@ -59,6 +75,8 @@ class SOARM101VecEnv:
             self.compiled = compile_mjcf(xml_path)
             attach_tripwire(self.compiled, xml_path)
             tables = self.compiled.tables
+            if isinstance(hulls, str) and self.compiled.hulls is not None:
+                hulls = self.compiled.hulls
         else:
             self.compiled = None
         self.tables = tables
@@ -76,7 +94,7 @@ class SOARM101VecEnv:
         self.seed = int(seed)
         self._episode = 0
         self.gravity_compensation = bool(gravity_compensation)
-        self.model = Model(tables)
+        self.model = Model(tables, hulls)
         L = _lib.lib()
         nbytes = L.so101_batch_state_bytes(self.num_envs, self.dtype_code)
         # caller-owned state: one torch allocation, bound to the batch for its lifetime

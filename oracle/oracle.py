@@ -18,9 +18,9 @@ _ROOT = os.path.dirname(_HERE)
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from lerobot_mujoco_sim2real_b200.tables import So101CtrlSpec, So101Tables  # noqa: E402
+from lerobot_mujoco_sim2real_b200.tables import So101CtrlSpec, So101Hulls, So101Tables  # noqa: E402
 
-NV, NB, NM, MAXEFC = 6, 8, 21, 24
+NV, NB, NM, MAXEFC, MAXCON = 6, 8, 21, 64, 10
 _d, _i = C.c_double, C.c_int32
 
 
@@ -51,6 +51,9 @@ class OracleData(C.Structure):
         ("nM", _i),
         ("body_subtreemass", _d * NB),
         ("ls_evals_iter", _i * 8),
+        ("ncon", _i), ("con_unsupported", _i), ("con_geom", _i * MAXCON), ("con_vert", _i * MAXCON),
+        ("con_dist", _d * MAXCON), ("con_pos", (_d * 3) * MAXCON), ("con_frame", (_d * 9) * MAXCON),
+        ("con_gap", _d * MAXCON),
     ]
 
 
@@ -97,6 +100,8 @@ def lib() -> C.CDLL:
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.so101o_shoot.argtypes = [P(So101Tables), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                    C.c_void_p, C.c_uint32, C.c_int]
+        L.so101o_set_hulls.argtypes = [P(So101Hulls)]
+        L.so101o_contact_probe.argtypes = [P(So101Tables), C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         L.so101o_num_threads.restype = C.c_int
         L.so101o_set_line_search.argtypes = [C.c_int]
         L.so101o_set_solver_start.argtypes = [C.c_int]
@@ -139,6 +144,26 @@ class Oracle:
         out = np.zeros((NV, NV))
         lib().so101o_fullM(C.byref(self.d), out.ctypes.data_as(C.POINTER(_d)))
         return out
+
+
+def hulls_struct(h):
+    """dict of hull arrays (tripwire.build_hulls / tables.builtin_hulls) -> (So101Hulls, keep-alive list)"""
+    arrs = [np.ascontiguousarray(h["vert_start"], dtype=np.int32), np.ascontiguousarray(h["vert"], dtype=np.float64),
+            np.ascontiguousarray(h["adj_start"], dtype=np.int32), np.ascontiguousarray(h["adj"], dtype=np.int32),
+            np.ascontiguousarray(h["cube"], dtype=np.int32)]
+    s = So101Hulls()
+    s.ngeom, s.nvert, s.nadj, s.cube_res = len(arrs[0]) - 1, arrs[1].shape[0], arrs[3].shape[0], int(h["cube_res"])
+    s.vert_start, s.vert, s.adj_start, s.adj, s.cube = [a.ctypes.data for a in arrs]
+    return s, arrs
+
+
+def set_hulls(h) -> None:
+    """Load (or, with None, unload) the convex hulls: with them the oracle simulates table-plane contact."""
+    if h is None:
+        lib().so101o_set_hulls(None)
+        return
+    s, keep = hulls_struct(h)
+    lib().so101o_set_hulls(C.byref(s))
 
 
 def uniform8(seed: int, env: int, step: int, stream: int) -> np.ndarray:
@@ -198,6 +223,14 @@ def step_batch(tables: So101Tables, state: np.ndarray, ctrl: np.ndarray, nsub: i
     lib().so101o_step_batch(C.byref(tables), n, _ptr(state), _ptr(ctrl), _ptr(qfrc_applied), nsub,
                             _ptr(out), _ptr(obs), _ptr(aux), nthreads)
     return out, obs, aux
+
+
+def contact_probe(tables: So101Tables, state: np.ndarray, nthreads: int = 0) -> np.ndarray:
+    """state [n, 18] -> [n, 4] = (ncon, unsupported, smallest runner-up gap of the witness vertices, deepest dist)."""
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    out = np.empty((state.shape[0], 4))
+    lib().so101o_contact_probe(C.byref(tables), state.shape[0], _ptr(state), _ptr(out), nthreads)
+    return out
 
 
 def shoot(tables: So101Tables, state0: np.ndarray, U: np.ndarray, frame_skip: int = 10, flags: int = 0,

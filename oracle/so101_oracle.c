@@ -26,7 +26,11 @@
  * artefact in the tree that has seen real MuJoCo output: one-step MSE 7.5e-7 (training loss
  * 9.4e-7) and the published 200-step open-loop MAE (6.84e-3) reproduced at 6.8e-3
  * (tests/test_oracle.py).  No bit-level golden vector of mj_step exists, hence "unpinned".
- * Collision detection / contact rows are NOT restated.
+ * Collision detection is restated for ONE case, the one the hot-path scene reaches: the convex
+ * hull of a mesh geom against the top face of the static table box (mjc_Convex returns one contact per geom pair:
+ * normal = the face normal, dist = lowest hull point - face height, pos = midway between the two witness points),
+ * with mj_instantiateContact (condim 3, pyramidal cone: rows J_n +- mu J_t), mj_diagApprox and the pyramidal
+ * R = 2 mu^2 R[first] adjustment of mj_makeImpedance.  Mesh-mesh self collision is not restated (tripwire flag).
  *
  * Deliberately generic (body_parent tree, sparse qM in MuJoCo's dof_Madr layout, dense efc_J)
  * so that it shares no structure with the chain-specialised CUDA kernels it checks.
@@ -44,12 +48,13 @@
 #define NV SO101_NV
 #define NB SO101_MAXBODY
 #define NM 21           /* max entries of sparse qM (serial chain of 6) */
-#define MAXEFC 24       /* 6 friction + 12 limit rows, padded */
+#define MAXCON 10       /* one contact per colliding geom (SO101_MAXTRIP boxes at most; the reference scene has 10) */
+#define MAXEFC 64       /* 6 friction + 12 limit rows + 4 rows per contact, padded */
 #define mjMINVAL 1e-15
 #define mjMAXVAL 1e10
 
 enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3 };
-enum { ROW_FRICTION = 0, ROW_LIMIT = 1 };
+enum { ROW_FRICTION = 0, ROW_LIMIT = 1, ROW_CONTACT = 2 };
 
 typedef struct OracleData {
   /* state */
@@ -76,6 +81,10 @@ typedef struct OracleData {
   int32_t dof_parent[NV], dof_Madr[NV], dof_body[NV], body_root[NB], nM;
   double body_subtreemass[NB];
   int32_t ls_evals_iter[8];   /* diagnostics: PrimalEval count of the first 8 line searches of the last solve */
+  /* contacts (mj_collision for hull-vs-table-top; filled only when hulls are loaded, so101o_set_hulls) */
+  int32_t ncon, con_unsupported;            /* unsupported: a contact beyond the table's footprint */
+  int32_t con_geom[MAXCON], con_vert[MAXCON];
+  double con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_gap[MAXCON];
 } OracleData;
 
 /* ---------------------------------------------------------------------------------------- */
@@ -417,6 +426,71 @@ static double impedance(const double* solimp, double pos, double margin) {
   return solimp[0] + y * (solimp[1] - solimp[0]);
 }
 
+/* ---- convex hulls of the colliding geoms (test infrastructure: set once, read by every thread) ---- */
+static struct {
+  int ngeom, nvert;
+  int* vert_start;
+  double* vert;
+} g_hulls = {0, 0, NULL, NULL};
+void so101o_set_hulls(const So101Hulls* h) {
+  free(g_hulls.vert_start); free(g_hulls.vert);
+  g_hulls.ngeom = g_hulls.nvert = 0; g_hulls.vert_start = NULL; g_hulls.vert = NULL;
+  if (!h || h->ngeom <= 0) return;
+  g_hulls.ngeom = h->ngeom; g_hulls.nvert = h->nvert;
+  g_hulls.vert_start = (int*)malloc(sizeof(int) * (h->ngeom + 1));
+  g_hulls.vert = (double*)malloc(sizeof(double) * 3 * h->nvert);
+  memcpy(g_hulls.vert_start, h->vert_start, sizeof(int) * (h->ngeom + 1));
+  memcpy(g_hulls.vert, h->vert, sizeof(double) * 3 * h->nvert);
+}
+
+/* mj_collision, restricted to (table box top face, mesh hull) pairs: mjc_Convex gives ONE contact per pair, at the
+   deepest hull vertex (brute force over the hull's vertices; the first lowest one wins), normal +z (from the box,
+   geom1, into the mesh, geom2), dist = z_min - z_top, pos midway between the witness points.  con_gap = how much
+   higher the runner-up vertex is (ties make the witness point ambiguous; tests skip them). */
+static void collision(const So101Tables* m, OracleData* d) {
+  d->ncon = 0; d->con_unsupported = 0;
+  if (!m->con_enabled || g_hulls.ngeom != m->ntrip) return;
+  for (int g = 0; g < m->ntrip && d->ncon < MAXCON; g++) {
+    int b = m->trip_body[g];
+    const double* R = d->xmat[b];
+    /* witness vertex = support vertex of the direction "down" (world -z in the body frame).  Extruded shapes have
+       edges that stay parallel to the table whatever the joint angles (hinge axes 1-3 are horizontal): a whole edge
+       is lowest and the witness point is ambiguous (MuJoCo's answer there depends on its GJK/EPA iterates).  Rule
+       here: the direction is tilted by 1e-7 towards e = (2,3,4)/sqrt(29) in the body frame, which orders tied
+       vertices deterministically and moves the selected point by < 1e-9 m in height. */
+    static const double tilt[3] = {2e-7 / 5.385164807134504, 3e-7 / 5.385164807134504, 4e-7 / 5.385164807134504};
+    const double dsel[3] = {-R[6] + tilt[0], -R[7] + tilt[1], -R[8] + tilt[2]};
+    double sbest = -1e300, s2 = -1e300;
+    int arg = -1;
+    for (int i = g_hulls.vert_start[g]; i < g_hulls.vert_start[g + 1]; i++) {
+      const double* v = g_hulls.vert + 3 * i;
+      double sv = dsel[0] * v[0] + dsel[1] * v[1] + dsel[2] * v[2];
+      if (sv > sbest) { s2 = sbest; sbest = sv; arg = i; }
+      else if (sv > s2) s2 = sv;
+    }
+    double zmin, z2 = 0;
+    {
+      const double* v = g_hulls.vert + 3 * arg;
+      zmin = d->xpos[b][2] + (R[6] * v[0] + R[7] * v[1] + R[8] * v[2]);
+      z2 = zmin + (sbest - s2);
+    }
+    double dist = zmin - m->trip_plane_z;
+    if (!(dist < m->con_margin)) continue;
+    int c = d->ncon++;
+    const double* v = g_hulls.vert + 3 * arg;
+    double p[3];
+    mulMatVec3(p, R, v);
+    for (int k = 0; k < 3; k++) p[k] += d->xpos[b][k];
+    d->con_geom[c] = g; d->con_vert[c] = arg; d->con_dist[c] = dist; d->con_gap[c] = z2 - zmin;
+    d->con_pos[c][0] = p[0]; d->con_pos[c][1] = p[1]; d->con_pos[c][2] = p[2] - 0.5 * dist;
+    /* mju_makeFrame for the normal (0,0,1): y = (0,1,0), z = x cross y = (-1,0,0) */
+    const double frame[9] = {0, 0, 1, 0, 1, 0, -1, 0, 0};
+    memcpy(d->con_frame[c], frame, sizeof frame);
+    if (p[0] < m->con_box[0] || p[0] > m->con_box[1] || p[1] < m->con_box[2] || p[1] > m->con_box[3])
+      d->con_unsupported = 1;   /* beyond the top face: an edge contact of the box, not restated */
+  }
+}
+
 static void addRow(OracleData* d, int type, int id, int dof, double jac, double pos, double margin,
                    double floss, double diagApprox) {
   int r = d->nefc++;
@@ -442,10 +516,41 @@ static void makeConstraint(const So101Tables* m, OracleData* d) {
       if (dist < margin) addRow(d, ROW_LIMIT, i, i, -side, dist, margin, 0.0, m->dof_invweight0[i]);
     }
   }
+  /* mj_instantiateContact: condim 3, pyramidal cone.  Jacobian of the contact point on the mesh's body (the table is
+     the world: zero Jacobian) by mj_jac, rotated into the contact frame; rows J_n + mu J_tk and J_n - mu J_tk. */
+  for (int c = 0; c < d->ncon && d->nefc + 4 <= MAXEFC; c++) {
+    int b = m->trip_body[d->con_geom[c]];
+    double jacp[3][NV], off[3];
+    memset(jacp, 0, sizeof jacp);
+    for (int k = 0; k < 3; k++) off[k] = d->con_pos[c][k] - d->subtree_com[d->body_root[b]][k];
+    for (int a = b; a > 0; a = m->body_parent[a]) {
+      int j = m->body_jnt[a];
+      if (j < 0) continue;
+      double tmp[3];
+      cross3(tmp, d->cdof[j], off);                        /* cdof_ang x (point - com) + cdof_lin */
+      for (int k = 0; k < 3; k++) jacp[k][j] = tmp[k] + d->cdof[j][3 + k];
+    }
+    double Jc[3][NV];
+    for (int r3 = 0; r3 < 3; r3++)
+      for (int j = 0; j < NV; j++)
+        Jc[r3][j] = d->con_frame[c][3 * r3] * jacp[0][j] + d->con_frame[c][3 * r3 + 1] * jacp[1][j] +
+                    d->con_frame[c][3 * r3 + 2] * jacp[2][j];
+    double tran = m->body_invweight0[0][0] + m->body_invweight0[b][0];
+    for (int k = 1; k < 3; k++) {
+      double fri = m->con_friction[0];   /* mjContact.friction = (sliding, sliding, torsional, rolling, rolling) */
+      for (int sgn = 1; sgn >= -1; sgn -= 2) {
+        int r = d->nefc++;
+        for (int j = 0; j < NV; j++) d->efc_J[r][j] = Jc[0][j] + sgn * fri * Jc[k][j];
+        d->efc_type[r] = ROW_CONTACT; d->efc_id[r] = c;
+        d->efc_pos[r] = d->con_dist[c]; d->efc_margin[r] = m->con_margin; d->efc_frictionloss[r] = 0;
+        d->efc_diagApprox[r] = tran + fri * fri * tran;    /* mj_diagApprox, pyramidal, translational dims */
+      }
+    }
+  }
   for (int r = 0; r < d->nefc; r++) {
     int id = d->efc_id[r];
-    const double* solref = d->efc_type[r] == ROW_FRICTION ? m->dof_solref[id] : m->jnt_solref[id];
-    const double* solimp = d->efc_type[r] == ROW_FRICTION ? m->dof_solimp[id] : m->jnt_solimp[id];
+    const double* solref = d->efc_type[r] == ROW_FRICTION ? m->dof_solref[id] : d->efc_type[r] == ROW_LIMIT ? m->jnt_solref[id] : m->con_solref;
+    const double* solimp = d->efc_type[r] == ROW_FRICTION ? m->dof_solimp[id] : d->efc_type[r] == ROW_LIMIT ? m->jnt_solimp[id] : m->con_solimp;
     double sr0 = solref[0], sr1 = solref[1];
     if (sr0 > 0 && sr0 < 2 * m->timestep) sr0 = 2 * m->timestep; /* refsafe */
     double imp = impedance(solimp, d->efc_pos[r], d->efc_margin[r]);
@@ -461,6 +566,15 @@ static void makeConstraint(const So101Tables* m, OracleData* d) {
     }
     if (d->efc_type[r] == ROW_FRICTION) K = 0;
     d->efc_KBIP[r][0] = K; d->efc_KBIP[r][1] = B; d->efc_KBIP[r][2] = imp; d->efc_KBIP[r][3] = 0;
+  }
+  /* mj_makeImpedance, frictional contacts: every row of a pyramid gets R = 2 mu^2 R[first row] (mu = friction[0] /
+     sqrt(impratio), impratio 1) */
+  for (int r = 0; r < d->nefc; r++) {
+    if (d->efc_type[r] != ROW_CONTACT) continue;
+    double mu = m->con_friction[0];
+    double Rpy = 2 * mu * mu * d->efc_R[r];
+    for (int j = 0; j < 4; j++) { d->efc_R[r + j] = Rpy; d->efc_D[r + j] = 1 / Rpy; }
+    r += 3;
   }
 }
 
@@ -771,7 +885,7 @@ static void fwdPosition(const So101Tables* m, OracleData* d) {
   comPos(m, d);
   crb(m, d);
   factorI(d, d->qM, d->qLD, d->qLDiagInv);
-  /* mj_collision: not restated */
+  collision(m, d);
   makeConstraint(m, d);
 }
 
@@ -960,11 +1074,11 @@ static void fwdConstraint(const So101Tables* m, OracleData* d) {
   constraintUpdate(d, d->efc_b, &cost_smooth, 0);
   d->used_warmstart = 1;
   if (cost_warm > cost_smooth) { memcpy(d->qacc, d->qacc_smooth, sizeof d->qacc); d->used_warmstart = 0; }
-  if (g_solver_start == 2) {
+  if (g_solver_start == 2 && !d->ncon) {
     if (directActiveSet(d)) return;
     proxStart(d);
   }
-  if (g_solver_start == 1) proxStart(d);
+  if (g_solver_start == 1 && !d->ncon) proxStart(d);
   solNewton(m, d);
 }
 
@@ -1179,6 +1293,26 @@ void so101o_step_batch(const So101Tables* m, int64_t n, const double* state_in, 
       aux[e * 4 + 0] = d.solver_niter; aux[e * 4 + 1] = d.solver_nls;
       aux[e * 4 + 2] = d.nefc; aux[e * 4 + 3] = d.warning_bad;
     }
+  }
+}
+
+/* contact situation of n states (qpos = state_in[e][0:6]): out[e] = {ncon, unsupported, smallest runner-up gap of
+   the witness vertices (ties make MuJoCo's witness point ambiguous), deepest dist} */
+void so101o_contact_probe(const So101Tables* m, int64_t n, const double* state_in, double* out, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+#endif
+  for (int64_t e = 0; e < n; e++) {
+    OracleData d;
+    so101o_init(m, &d);
+    so101o_reset(m, &d);
+    for (int k = 0; k < NV; k++) d.qpos[k] = state_in[e * 18 + k];
+    kinematics(m, &d);
+    collision(m, &d);
+    double gap = 1e300, dist = 0;
+    for (int c = 0; c < d.ncon; c++) { gap = fmin(gap, d.con_gap[c]); dist = fmin(dist, d.con_dist[c]); }
+    out[e * 4 + 0] = d.ncon; out[e * 4 + 1] = d.con_unsupported; out[e * 4 + 2] = gap; out[e * 4 + 3] = dist;
   }
 }
 
