@@ -105,6 +105,8 @@ def oracle_rate(n_envs: int, reps: int, warm: int, threads: int = 0, t_ctrl: int
     from oracle import oracle as O
     O.build()
     tables = builtin_tables("scene_with_table_v.xml")
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    O.set_hulls(T_.builtin_hulls())      # same physics as the CUDA arm: table-plane contact simulated
     # torchrun exports OMP_NUM_THREADS=1: ask the OS for the cores this process may use instead
     nthr = threads or len(os.sched_getaffinity(0))
     times = []

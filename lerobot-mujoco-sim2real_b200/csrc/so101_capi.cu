@@ -841,7 +841,7 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
   if (b->dtype == SO101_F64) {
     StateView<double> v = step_view<double>(b, blk, grid, split);
 #define SO101_ROLL(TT, RR, SS, mdl) \
-  k_rollout<TT, RR, SS><<<grid, blk, 0, st>>>(b->model->mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats)
+  k_rollout<TT, RR, SS><<<grid, blk, 0, st>>>(b->dm_##mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats)
     if (split) { if (r32) SO101_ROLL(double, float, true, d); else SO101_ROLL(double, double, true, d); }
     else { if (r32) SO101_ROLL(double, float, false, d); else SO101_ROLL(double, double, false, d); }
   } else {

@@ -179,13 +179,28 @@ SO101_DEV T contact_line_search(const DevModel<T>& m, const T* aref_f, const One
   return result;
 }
 
-// Returns true when at least one hull touches the table: then a = qacc and qc = qfrc_constraint of the full problem
-// (friction + limit + contact rows) are set and the caller goes straight to mj_checkAcc / mj_Euler.
+// What the contact path reads and writes, copied by the caller inside its `if (hits)` branch: only these copies have
+// their address taken, the hot path's own arrays stay in registers.
 template <typename T>
-__device__ __noinline__ bool contact_solve(const DevModel<T>& m, const T* q, const T* qd, uint32_t hits, const T* Mm,
-                                           const T* fsm, const T* aref_f, const T* lim_side, const T* lim_aref,
-                                           const T* lim_D, bool anylim, const T* warm, T* a, T* qc, uint32_t& flags,
-                                           Counters& cnt) {
+struct ContactIO {
+  T q[NV], qd[NV], warm[NV], M[21], fsm[NV], aref_f[NV];
+  T lim_side[NV], lim_aref[NV], lim_D[NV];
+  uint32_t hits, anylim;
+  // out
+  T a[NV], qc[NV];
+  uint32_t flags, newton, lsevals;
+};
+
+// Returns true when at least one hull touches the table: then io.a = qacc and io.qc = qfrc_constraint of the full
+// problem (friction + limit + contact rows) are set and the caller goes straight to mj_checkAcc / mj_Euler.
+template <typename T>
+__device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& io) {
+  const T* q = io.q; const T* qd = io.qd; const T* Mm = io.M; const T* fsm = io.fsm; const T* aref_f = io.aref_f;
+  const T* lim_side = io.lim_side; const T* lim_aref = io.lim_aref; const T* lim_D = io.lim_D; const T* warm = io.warm;
+  const uint32_t hits = io.hits;
+  const bool anylim = io.anylim != 0;
+  T* a = io.a; T* qc = io.qc;
+  uint32_t& flags = io.flags;
   OneSided<T> os;
   os.n = 0;
   if (anylim) {
@@ -273,6 +288,94 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, const T* q, con
   if (ncon == 0) return false;
   flags |= SO101_FLAG_CONTACT;
 
+  // ---- direct active-set iteration ----------------------------------------------------------------------------------
+  // The objective is strictly convex and piecewise quadratic.  On the piece where friction row i is in zone z_i
+  // (0: quadratic, +-1: saturated) and the one-sided rows of the set A are active its minimiser solves
+  //   (M + diag(D_i [z_i = 0]) + sum_A D_r J_r J_r') a = qfrc_smooth + D_i aref_i [z_i = 0] - z_i f_i + sum_A D_r aref_r J_r,
+  // and a solution that lies in the piece it assumed is the global minimiser (KKT) - MuJoCo's converged Newton iterate
+  // without cost evaluations or line searches.  Pieces: first the one qacc_warmstart lies in (a persisting contact keeps
+  // its piece), then the one the rejected candidate lies in (a full Newton step), a few times; whatever is left takes
+  // the safeguarded Newton iteration below.
+  {
+    T az[NV];
+    uint32_t zq = 0, zp = 0, act = 0;      // friction zones (quadratic / saturated positive), active one-sided rows
+#pragma unroll
+    for (int i = 0; i < NV; i++) az[i] = warm[i];
+    bool done = false;
+#pragma unroll 1
+    for (int attempt = 0; attempt <= 6 && !done; attempt++) {
+      uint32_t nzq = 0, nzp = 0, nact = 0;
+      bool strict = true;
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        const T jar = az[i] - aref_f[i];
+        if (m.fr_f[i] == T(0) || abs_(jar) < m.fr_Rf[i]) nzq |= 1u << i;
+        else if (jar > T(0)) nzp |= 1u << i;
+        strict &= m.fr_f[i] == T(0) || abs_(jar) != m.fr_Rf[i];
+      }
+#pragma unroll 1
+      for (int r = 0; r < os.n; r++) {
+        T jar = -os.aref[r];
+#pragma unroll
+        for (int j = 0; j < NV; j++) jar += os.J[r][j] * az[j];
+        if (jar < T(0)) nact |= 1u << r;
+      }
+      if (attempt > 0 && nzq == zq && nzp == zp && nact == act && strict) {   // the candidate lies in its own piece
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+          a[i] = az[i];
+          const T jar = az[i] - aref_f[i];
+          qc[i] = (zq >> i & 1u) ? -m.fr_D[i] * jar : ((zp >> i & 1u) ? -m.fr_f[i] : m.fr_f[i]);
+          if (m.fr_f[i] == T(0)) qc[i] = T(0);
+        }
+#pragma unroll 1
+        for (int r = 0; r < os.n; r++) {
+          if (!(act >> r & 1u)) continue;
+          T jar = -os.aref[r];
+#pragma unroll
+          for (int j = 0; j < NV; j++) jar += os.J[r][j] * az[j];
+          const T f = -os.D[r] * jar;
+#pragma unroll
+          for (int j = 0; j < NV; j++) qc[j] += os.J[r][j] * f;
+        }
+        io.newton += attempt;
+        done = true;
+        break;
+      }
+      if (attempt == 6) break;
+      zq = nzq; zp = nzp; act = nact;
+      T H[21], rhs[NV];
+#pragma unroll
+      for (int i = 0; i < 21; i++) H[i] = Mm[i];
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        rhs[i] = fsm[i];
+        if (m.fr_f[i] == T(0)) continue;
+        if (zq >> i & 1u) { H[tri(i, i)] += m.fr_D[i]; rhs[i] += m.fr_D[i] * aref_f[i]; }
+        else rhs[i] += (zp >> i & 1u) ? -m.fr_f[i] : m.fr_f[i];
+      }
+#pragma unroll 1
+      for (int r = 0; r < os.n; r++) {
+        if (!(act >> r & 1u)) continue;
+        T Jr[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) Jr[j] = os.J[r][j];
+        const T Dr = os.D[r], Da = Dr * os.aref[r];
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+          const T di = Dr * Jr[i];
+          rhs[i] += Da * Jr[i];
+#pragma unroll
+          for (int j = 0; j <= i; j++) H[tri(i, j)] += di * Jr[j];
+        }
+      }
+      ldl6_factor_solve(H, rhs);
+#pragma unroll
+      for (int i = 0; i < NV; i++) az[i] = rhs[i];
+    }
+    if (done) return true;
+  }
+
   // ---- Newton over all rows (mj_solPrimal, Newton flavour) ---------------------------------------------------------
   T asm_[NV], Ma[NV], hd[NV], cost;
   uint32_t active = 0;
@@ -333,7 +436,7 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, const T* q, con
 #pragma unroll
       for (int i = 0; i < NV; i++) sr[i] = -sr[i];
     }
-    const T alpha = contact_line_search(m, aref_f, os, Mm, a, Ma, fsm, sr, Mv, cnt.lsevals);
+    const T alpha = contact_line_search(m, aref_f, os, Mm, a, Ma, fsm, sr, Mv, io.lsevals);
     if (alpha == T(0)) break;
 #pragma unroll 1
     for (int i = 0; i < NV; i++) { a[i] += alpha * sr[i]; Ma[i] += alpha * Mv[i]; }
@@ -354,7 +457,7 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, const T* q, con
     iter++;
     if (m.scale * (oldcost - cost) < tol_i || m.scale * sqrt_(gg) < tol_g) break;
   }
-  cnt.newton += iter;
+  io.newton += iter;
   if (iter >= m.iterations) flags |= SO101_FLAG_MAXITER;
   return true;
 }

@@ -938,6 +938,33 @@ SO101_DEV void newton_exact_finish(const DevModel<T>& m, const Rows<T>& rw, cons
 #include "so101_contact.cuh"
 namespace so101 {
 
+// the caller's side of the contact path: copies in, call, copies out (see ContactIO)
+template <typename T>
+SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, const T (&M)[21], const T (&fsm)[NV],
+                              const Rows<T>& rw, T (&a)[NV], T (&qc)[NV], Counters& cnt) {
+  ContactIO<T> io;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    io.q[i] = e.q[i]; io.qd[i] = e.qd[i]; io.warm[i] = e.warm[i]; io.fsm[i] = fsm[i]; io.aref_f[i] = rw.aref_f[i];
+    io.lim_side[i] = rw.anylim ? rw.side[i] : T(0);
+    io.lim_aref[i] = rw.anylim ? rw.aref_l[i] : T(0);
+    io.lim_D[i] = rw.anylim ? rw.D_l[i] : T(0);
+  }
+#pragma unroll
+  for (int i = 0; i < 21; i++) io.M[i] = M[i];
+  io.hits = hits; io.anylim = rw.anylim ? 1u : 0u;
+  io.flags = 0; io.newton = 0; io.lsevals = 0;
+  const bool in_contact = contact_solve<T>(m, io);
+  e.flags |= io.flags;
+  if (in_contact) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) { a[i] = io.a[i]; qc[i] = io.qc[i]; }
+    cnt.newton += io.newton;
+    cnt.lsevals += io.lsevals;
+  }
+  return in_contact;
+}
+
 // ------------------------------------------------------------------------------------------
 // one physics step.  After the smooth dynamics every lane runs the same small phase machine
 //   SMOOTH (qacc_smooth = M^-1 qfrc_smooth) -> NEWTON x n -> EULER ((M + hB)^-1 ...)
@@ -1004,8 +1031,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     // contact rows - out of line (so101_contact.cuh); the phase machine then only runs its Euler solve
     bool in_contact = false;
     if (m.con_enabled)
-      in_contact = contact_solve<T>(m, e.q, e.qd, hits, M, fsm, rw.aref_f, rw.side, rw.aref_l, rw.D_l, rw.anylim, e.warm,
-                                    a, qc, e.flags, cnt);
+      in_contact = contact_branch<T>(m, e, hits, M, fsm, rw, a, qc, cnt);
     else
       e.flags |= SO101_FLAG_TRIP_TABLE;   // no hull data: the env is only marked, its dynamics stay contact-free
     if (in_contact) {
@@ -1388,8 +1414,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   bool solved = false;
   if (trip && x.hits[lane]) {        // table contact (see physics_step)
     if (m.con_enabled)
-      solved = contact_solve<T>(m, e.q, e.qd, x.hits[lane], M, fsm, rw.aref_f, rw.side, rw.aref_l, rw.D_l, rw.anylim,
-                                e.warm, a, qc, e.flags, cnt);
+      solved = contact_branch<T>(m, e, x.hits[lane], M, fsm, rw, a, qc, cnt);
     else
       e.flags |= SO101_FLAG_TRIP_TABLE;
   }

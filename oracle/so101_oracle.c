@@ -453,6 +453,15 @@ static void collision(const So101Tables* m, OracleData* d) {
   for (int g = 0; g < m->ntrip && d->ncon < MAXCON; g++) {
     int b = m->trip_body[g];
     const double* R = d->xmat[b];
+    {   /* broadphase: the geom's bounding box (box contains hull contains mesh) clears the plane -> no contact */
+      double c[3], ext = 0;
+      mulMatVec3(c, R, m->trip_center[g]);
+      for (int ax = 0; ax < 3; ax++) {
+        const double* u = m->trip_axes[g] + 3 * ax;
+        ext += fabs(R[6] * u[0] + R[7] * u[1] + R[8] * u[2]) * m->trip_half[g][ax];
+      }
+      if (d->xpos[b][2] + c[2] - ext >= m->trip_plane_z + m->con_margin) continue;
+    }
     /* witness vertex = support vertex of the direction "down" (world -z in the body frame).  Extruded shapes have
        edges that stay parallel to the table whatever the joint angles (hinge axes 1-3 are horizontal): a whole edge
        is lowest and the witness point is ambiguous (MuJoCo's answer there depends on its GJK/EPA iterates).  Rule

@@ -37,6 +37,10 @@ def tables_p():
 
 @pytest.fixture(scope="session")
 def oracle_mod():
+    """The CPU oracle with the hull data loaded: like the CUDA path (and like MuJoCo on the reference scene) it
+    simulates table-plane contact wherever a state reaches the table."""
+    from lerobot_mujoco_sim2real_b200 import tables as T
     from oracle import oracle as O
     O.build()
+    O.set_hulls(T.builtin_hulls())
     return O

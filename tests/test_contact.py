@@ -16,9 +16,8 @@ def hulls():
 
 @pytest.fixture()
 def contact_oracle(oracle_mod, hulls):
-    oracle_mod.set_hulls(hulls)
-    yield oracle_mod
-    oracle_mod.set_hulls(None)
+    oracle_mod.set_hulls(hulls)      # the session default; stated here because these tests are about it
+    return oracle_mod
 
 
 def _sample_states(n, seed, qmax=1.0):

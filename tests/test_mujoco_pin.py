@@ -141,6 +141,15 @@ def check_model(g, t):
 
 def check_forward_oracle(g, O, t):
     """Every stage of mj_forward the oracle restates, state by state."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    O.set_hulls(None)                      # fw_*: contacts disabled
+    try:
+        return _check_forward_oracle(g, O, t)
+    finally:
+        O.set_hulls(T_.builtin_hulls())
+
+
+def _check_forward_oracle(g, O, t):
     o = O.Oracle(t)
     nb = int(g["m_nbody"])
     K = g["fw_in_qpos"].shape[0]
@@ -226,7 +235,16 @@ def check_free_running(g, step_fn, contractive: bool):
 
 
 def _oracle_step(O, t):
-    return lambda s, u: O.step_batch(t, s, u, 1)[0]
+    """contact-free oracle step (tf_* vectors are recorded with contacts disabled)"""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+
+    def step(s, u):
+        O.set_hulls(None)
+        try:
+            return O.step_batch(t, s, u, 1)[0]
+        finally:
+            O.set_hulls(T_.builtin_hulls())
+    return step
 
 
 def _gpu_step(t):
@@ -237,7 +255,7 @@ def _gpu_step(t):
     def step(s, u):
         n = s.shape[0]
         if n not in envs:
-            envs[n] = SOARM101VecEnv(tables=t, num_envs=n, dtype="float64")
+            envs[n] = SOARM101VecEnv(tables=t, num_envs=n, dtype="float64", hulls=None)   # tf_*: contacts disabled
         env = envs[n]
         env.set_state(s[:, :6], s[:, 6:12], s[:, 12:18])
         uu = torch.as_tensor(np.ascontiguousarray(u.T), dtype=torch.float64, device=env.device).contiguous()
@@ -251,7 +269,7 @@ def check_forward_gpu(g, t):
     """what the C ABI exposes of mj_forward: observation site and qfrc_bias"""
     from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
     K = g["fw_in_qpos"].shape[0]
-    env = SOARM101VecEnv(tables=t, num_envs=K, dtype="float64")
+    env = SOARM101VecEnv(tables=t, num_envs=K, dtype="float64", hulls=None)
     env.set_state(g["fw_in_qpos"], g["fw_in_qvel"], g["fw_in_warm"])
     obs, bias = env.forward()
     _close("site_xpos (f32 observation)", obs.cpu().numpy()[:, :3], g["fw_site_xpos"].astype(np.float32), 0, 1e-7)

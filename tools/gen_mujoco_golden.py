@@ -216,9 +216,17 @@ def run_mujoco(xml: str, tag: str, seed: int, E: int, S: int, K: int, K2: int) -
 # oracle backend: same schema, for exercising the test harness only
 # --------------------------------------------------------------------------------------------------------------------
 def run_oracle(tag: str, seed: int, E: int, S: int, K: int, K2: int) -> dict:
-    from lerobot_mujoco_sim2real_b200 import builtin_tables
+    from lerobot_mujoco_sim2real_b200 import builtin_tables, tables as T_
     from oracle import oracle as O
     t = builtin_tables(SCENES[tag])
+    O.set_hulls(None)            # fw_* / tf_* / sd_* are the contact-free pipeline (MuJoCo backend: mjDSBL_CONTACT)
+    try:
+        return _run_oracle(O, t, tag, seed, E, S, K, K2)
+    finally:
+        O.set_hulls(T_.builtin_hulls())
+
+
+def _run_oracle(O, t, tag: str, seed: int, E: int, S: int, K: int, K2: int) -> dict:
     out = {"meta_version": np.array("oracle"), "meta_scene": np.array(SCENES[tag]), "meta_seed": np.array(seed),
            "meta_source": np.array("oracle-selftest"), "meta_frame_skip": np.array(FRAME_SKIP)}
     arr = lambda x: np.ctypeslib.as_array(x).copy()
