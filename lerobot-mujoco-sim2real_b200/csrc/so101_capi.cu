@@ -71,11 +71,46 @@ template <typename T> SO101_DEV void publish_state(SplitXch<T>& x, const Env<T>&
   for (int k = 0; k < NV; k++) { x.q[k][lane] = e.q[k]; x.qd[k][lane] = e.qd[k]; }
   __syncthreads();   // (0)
 }
-template <typename T, bool SPLIT>
+template <typename T, bool SPLIT, int CM>
 SO101_DEV void step_env(const DevModel<T>& m, SplitXch<T>& x, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
-                        bool want_site, T (&site)[3], bool trip, Counters& cnt) {
-  if (SPLIT) split_dynamics_step(m, x, threadIdx.x & 31, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
-  else physics_step<T, true>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
+                        bool want_site, T (&site)[3], bool trip, Counters& cnt, int64_t nstep) {
+  if (SPLIT) split_dynamics_step<T, CM>(m, x, threadIdx.x & 31, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, nstep);
+  else physics_step<T, true, CM>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
+}
+
+// ---- freeze / resume (table contact, see physics_step) ---------------------------------------------------------------
+// The fast kernels (RESUME = false) freeze an env the moment one of its collision boxes dips below the table top, note
+// where it stopped (at[i] = index of the physics step to execute next) and append it to `list`; the contact kernels
+// (RESUME = true: the same kernel bodies with the contact path compiled in, one thread / team lane per LIST ENTRY)
+// carry the listed envs on from there.  Frozen envs keep SO101_FLAG_FROZEN in their stored flags until the next API
+// call clears it, so that later time chunks of the same call leave them to the contact kernels.
+struct Frz {
+  int32_t* at;
+  int32_t* list;
+  int32_t* count;        // entries appended so far
+  const int32_t* upto;   // RESUME: process entries [0, *upto)
+  int32_t clear;         // fast kernels: first launch of an API call - stale FROZEN bits are dropped at load
+};
+template <typename T, bool SPLIT, bool RESUME>
+SO101_DEV int64_t env_slot(const StateView<T>& s, const Frz& fz, bool& active, bool& exit_block) {
+  const int64_t n_eff = RESUME ? (int64_t)*fz.upto : s.n;
+  const int64_t j = SPLIT ? (int64_t)blockIdx.x * 32 + (threadIdx.x & 31) : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t first = SPLIT ? (int64_t)blockIdx.x * 32 : (int64_t)blockIdx.x * blockDim.x;
+  exit_block = first >= n_eff;                       // uniform over the block
+  if (exit_block) { active = false; return 0; }
+  active = (!SPLIT || threadIdx.x < 32) && j < n_eff;
+  const int64_t jc = j < n_eff ? j : n_eff - 1;      // tail threads shadow a valid entry and never store
+  return RESUME ? (int64_t)fz.list[jc] : jc;
+}
+// end of a fast kernel: a newly frozen env records where it stopped and joins the list
+SO101_DEV void frz_append(const Frz& fz, int64_t i, int32_t idx) {
+  fz.at[i] = idx;
+  fz.list[atomicAdd(fz.count, 1)] = (int32_t)i;
+}
+__global__ void k_snapshot(const int32_t* count, int32_t* snap) { *snap = *count; }
+__global__ void k_mask_flags(uint32_t* f, int64_t n, uint32_t mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f[i] &= mask;
 }
 
 template <typename T> SO101_DEV int64_t env_of_thread(const StateView<T>& s, bool& active) {
@@ -291,16 +326,23 @@ k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* 
 }
 
 // SOARM101Env.step: ctrl rows [n_ctrl][N] (missing rows = 0), nsub x mj_step, observation
-SO101_STEP_KERNEL(T)
+#define SO101_STEP_KERNEL2(T) \
+  template <typename T, bool SPLIT, bool RESUME> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
+SO101_STEP_KERNEL2(T)
 k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
-       unsigned long long* stats) {
+       unsigned long long* stats, Frz fz) {
+  constexpr int CM = RESUME ? CM_SOLVE : CM_FREEZE;
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
+  bool active, exit_block;
+  const int64_t i = env_slot<T, SPLIT, RESUME>(s, fz, active, exit_block);
+  if (exit_block) return;
   if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, nsub, nsub); return; }
-  bool active;
-  const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   Env<T> e;
   load_env(s, i, e);
+  if (!RESUME && fz.clear) e.flags &= ~SO101_FLAG_FROZEN;
+  const bool was_frozen = !RESUME && (e.flags & SO101_FLAG_FROZEN);
+  const int start = RESUME ? fz.at[i] : 0;     // RESUME: the sub-step at which this env froze
   if (SPLIT) publish_state(xch, e);
   T u[NV], site[3] = {T(0), T(0), T(0)};
 #pragma unroll
@@ -308,12 +350,19 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   clamp_ctrl(m, u);
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
+  int frozen_idx = -1;
 #pragma unroll 1
-  for (int ss = 0; ss < nsub; ss++) step_env<T, SPLIT>(m, xch, e, u, false, ss == nsub - 1, site, trip, cnt);
+  for (int ss = 0; ss < nsub; ss++) {
+    if (RESUME && ss == start) e.flags &= ~SO101_FLAG_FROZEN;
+    step_env<T, SPLIT, CM>(m, xch, e, u, false, ss == nsub - 1, site, trip, cnt, ss);
+    if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) frozen_idx = ss;
+  }
   if (nsub == 0) site_fk(m, e.q, site);
-  if (active) {
+  if (active && !was_frozen) {
+    if (RESUME) { e.flags |= SO101_FLAG_FROZEN; fz.at[i] = nsub; }
     store_env(s, i, e);
-    if (obs) {
+    if (!RESUME && frozen_idx >= 0) frz_append(fz, i, frozen_idx);
+    if (obs && (RESUME || frozen_idx < 0)) {
 #pragma unroll
       for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
 #pragma unroll
@@ -327,21 +376,25 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
-template <typename T, typename ROW, bool SPLIT>
+template <typename T, typename ROW, bool SPLIT, bool RESUME>
 __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
-          ROW* rows, uint32_t rflags, unsigned long long* stats) {
+          ROW* rows, uint32_t rflags, unsigned long long* stats, Frz fz) {
   // control steps (t0, t1] of a rollout of Tn steps; t0 > 0 continues a previous launch (row t0 is already written,
-  // u_t0 is regenerated: the control stream is a pure function of (seed, env, t))
+  // u_t0 is regenerated: the control stream is a pure function of (seed, env, t)).  Physics step index of sub-step ss
+  // of loop iteration t: t * frame_skip + ss (what Frz.at holds).
+  constexpr int CM = RESUME ? CM_SOLVE : CM_FREEZE;
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
+  bool active, exit_block;
+  const int64_t i = env_slot<T, SPLIT, RESUME>(s, fz, active, exit_block);
+  if (exit_block) return;
   if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)(t1 - t0) * frame_skip, frame_skip); return; }
-  bool active;
-  const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   const int64_t env = spec.env_offset + i;
   Env<T> e;
-  if (rflags & SO101_ROLL_NO_RESET) {
+  if (RESUME || (rflags & SO101_ROLL_NO_RESET)) {
     load_env(s, i, e);
+    if (!RESUME && fz.clear) e.flags &= ~SO101_FLAG_FROZEN;
   } else {
     reset_env(m, e);
     double r[5];
@@ -349,6 +402,8 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
 #pragma unroll
     for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(spec.reset_lo, spec.reset_hi - spec.reset_lo, r[k]);
   }
+  const bool was_frozen = !RESUME && (e.flags & SO101_FLAG_FROZEN);
+  const int start = RESUME ? fz.at[i] : 0;
   CtrlGen g;
   ctrl_init(spec, env, g);
   Counters cnt = {0, 0, 0, 0};
@@ -359,18 +414,26 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   if (SPLIT) publish_state(xch, e);
   double u[5];
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  int frozen_idx = -1;
+  int64_t nstep = 0;
 #pragma unroll 1
   for (int t = t0; t <= t1; t++) {
     if (t > t0) {
 #pragma unroll 1
-      for (int ss = 0; ss < frame_skip; ss++)
-        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+      for (int ss = 0; ss < frame_skip; ss++, nstep++) {
+        if (RESUME && t * frame_skip + ss == start) e.flags &= ~SO101_FLAG_FROZEN;
+        step_env<T, SPLIT, CM>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
+        if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) frozen_idx = t * frame_skip + ss;
+      }
     }
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
 #pragma unroll
     for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
     clamp_ctrl(m, uc);   // rows keep the unclamped u, as the reference's dataset does
-    if (rows && active && (t > t0 || t0 == 0)) {
+    // row t belongs to whoever executed the last sub-step of iteration t: the fast kernel while the env is not frozen,
+    // the contact kernel from the iteration in which it took over
+    const bool mine = RESUME ? (t > t0 && !(e.flags & SO101_FLAG_FROZEN)) : (!(e.flags & SO101_FLAG_FROZEN) && (t > t0 || t0 == 0));
+    if (rows && active && mine) {
       ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
 #pragma unroll
       for (int k = 0; k < 5; k++) row[k] = (ROW)u[k];
@@ -380,26 +443,37 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
       for (int k = 0; k < 5; k++) row[8 + k] = (ROW)(float)e.q[k];
     }
   }
-  if (active) store_env(s, i, e);
-  if (!active) cnt = {0, 0, 0, 0};
+  if (active && !was_frozen) {
+    if (RESUME) { e.flags |= SO101_FLAG_FROZEN; fz.at[i] = (t1 + 1) * frame_skip; }
+    store_env(s, i, e);
+    if (!RESUME && frozen_idx >= 0) frz_append(fz, i, frozen_idx);
+  }
+  if (!active || was_frozen) cnt = {0, 0, 0, 0};
   add_stats(stats, cnt);
 }
 
 struct State0 { double v[18]; };
 
 // B control sequences U[H][5][B] from one shared state; X[B][H+1][8] float32 observations
-SO101_STEP_KERNEL(T)
+SO101_STEP_KERNEL2(T)
 k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
-        int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
+        int frame_skip, float* X, uint32_t rflags, unsigned long long* stats, Frz fz) {
+  constexpr int CM = RESUME ? CM_SOLVE : CM_FREEZE;
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
+  bool active, exit_block;
+  const int64_t i = env_slot<T, SPLIT, RESUME>(s, fz, active, exit_block);
+  if (exit_block) return;
   if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)H * frame_skip, frame_skip); return; }
-  bool active;
-  const int64_t i = SPLIT ? env_of_pair(s, active) : env_of_thread(s, active);
   Env<T> e;
-  reset_env(m, e);
+  if (RESUME) {
+    load_env(s, i, e);
+  } else {
+    reset_env(m, e);
 #pragma unroll
-  for (int k = 0; k < NV; k++) { e.q[k] = (T)s0.v[k]; e.qd[k] = (T)s0.v[6 + k]; e.warm[k] = (T)s0.v[12 + k]; }
+    for (int k = 0; k < NV; k++) { e.q[k] = (T)s0.v[k]; e.qd[k] = (T)s0.v[6 + k]; e.warm[k] = (T)s0.v[12 + k]; }
+  }
+  const int start = RESUME ? fz.at[i] : 0;
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
@@ -407,6 +481,8 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   site_fk(m, e.q, site);
   if (SPLIT) publish_state(xch, e);
   T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  int frozen_idx = -1;
+  int64_t nstep = 0;
 #pragma unroll 1
   for (int t = 0; t <= H; t++) {
     if (t > 0) {
@@ -414,10 +490,14 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
       for (int k = 0; k < 5; k++) uc[k] = U[((int64_t)(t - 1) * 5 + k) * s.n + i];
       clamp_ctrl(m, uc);
 #pragma unroll 1
-      for (int ss = 0; ss < frame_skip; ss++)
-        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt);
+      for (int ss = 0; ss < frame_skip; ss++, nstep++) {
+        if (RESUME && t * frame_skip + ss == start) e.flags &= ~SO101_FLAG_FROZEN;
+        step_env<T, SPLIT, CM>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
+        if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) frozen_idx = t * frame_skip + ss;
+      }
     }
-    if (active) {
+    const bool mine = RESUME ? (t > 0 && !(e.flags & SO101_FLAG_FROZEN)) : !(e.flags & SO101_FLAG_FROZEN);
+    if (active && mine) {
       float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;
 #pragma unroll
       for (int k = 0; k < 3; k++) x[k] = (float)site[k];
@@ -425,8 +505,13 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
       for (int k = 0; k < 5; k++) x[3 + k] = (float)e.q[k];
     }
   }
-  if (active) store_env(s, i, e);
-  else cnt = {0, 0, 0, 0};
+  if (active) {
+    if (RESUME) { e.flags |= SO101_FLAG_FROZEN; fz.at[i] = (H + 1) * frame_skip; }
+    store_env(s, i, e);
+    if (!RESUME && frozen_idx >= 0) frz_append(fz, i, frozen_idx);
+  } else {
+    cnt = {0, 0, 0, 0};
+  }
   add_stats(stats, cnt);
 }
 
@@ -476,6 +561,8 @@ struct So101Batch {
   DevModel<double> dm_d;      // the model's constants with this batch's device pointers patched in (hull data)
   DevModel<float> dm_f;
   void* hull_dev[4];          // vert, adj_start, adj, cube on b->device (null: no hulls -> tripwire flags only)
+  // freeze / resume bookkeeping (struct Frz): at[n], list[n], count, snapshots of count per time chunk
+  int32_t* frz_at; int32_t* frz_list; int32_t* frz_count; int32_t* frz_snap;
   unsigned long long* stats;  // device, 4 counters
   void* ctrl_stage;   // [6][n] batch dtype (host variants)
   float* obs_stage;   // [8][n]
@@ -549,6 +636,32 @@ template <typename T> static StateView<T> step_view(const So101Batch* b, int& bl
   const int64_t warps = (b->n + 31) / 32;
   grid = (unsigned)((warps * 32 + blk - 1) / blk);
   return v;
+}
+
+// ---- freeze / resume launches ----------------------------------------------------------------------------------------
+static bool has_contact(const So101Batch* b) { return b->dm_d.con_enabled != 0; }
+// Frz of a fast launch (chunk = index of the time chunk within the API call; chunk 0 clears stale FROZEN bits)
+static Frz frz_fast(const So101Batch* b, int chunk) {
+  Frz f;
+  f.at = b->frz_at; f.list = b->frz_list; f.count = b->frz_count; f.upto = nullptr; f.clear = chunk == 0;
+  return f;
+}
+static Frz frz_resume(const So101Batch* b, int chunk) {
+  Frz f = frz_fast(b, chunk);
+  f.upto = b->frz_snap + chunk;
+  f.clear = 0;
+  return f;
+}
+// launch shape of a contact kernel: one thread (team lane) per list entry, worst case every env (blocks beyond the
+// list's end exit at once)
+static void resume_shape(const So101Batch* b, bool split, int& blk, unsigned& grid) {
+  if (split) { blk = 32 * TEAM_WARPS; grid = (unsigned)((b->n + 31) / 32); }
+  else { blk = 64; grid = (unsigned)((b->n + 63) / 64); }
+}
+// before the first fast launch of an API call: the list starts empty
+static cudaError_t frz_begin(const So101Batch* b, int chunk, cudaStream_t st) {
+  if (!has_contact(b) || chunk != 0) return cudaSuccess;
+  return cudaMemsetAsync(b->frz_count, 0, sizeof(int32_t), st);
 }
 
 extern "C" {
@@ -650,12 +763,18 @@ int so101_batch_create(const So101Model* model, int64_t n, int dtype, int device
     }
     b->dm_d.hull_res = model->hull_res;
     b->dm_d.con_enabled = 1;
+    if (e == cudaSuccess) e = cudaMalloc(&b->frz_at, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->frz_list, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&b->frz_count, (1 + So101Batch::MAXCHUNK + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemset(b->frz_count, 0, (1 + So101Batch::MAXCHUNK + 1) * sizeof(int32_t));
+    b->frz_snap = b->frz_count + 1;
   }
   hostbuild::convert<float>(b->dm_d, b->dm_f);
   if (e != cudaSuccess) {
     if (b->owns_state) cudaFree(b->state);
     cudaFree(b->stats);
     for (int k = 0; k < 4; k++) cudaFree(b->hull_dev[k]);
+    cudaFree(b->frz_at); cudaFree(b->frz_list); cudaFree(b->frz_count);
     delete b;
     return fail(SO101_ECUDA, std::string("batch init: ") + cudaGetErrorString(e));
   }
@@ -668,6 +787,7 @@ void so101_batch_destroy(So101Batch* b) {
   if (b->owns_state) cudaFree(b->state);
   cudaFree(b->stats);
   for (int k = 0; k < 4; k++) cudaFree(b->hull_dev[k]);
+  cudaFree(b->frz_at); cudaFree(b->frz_list); cudaFree(b->frz_count);
   cudaFree(b->ctrl_stage);
   cudaFree(b->obs_stage);
   cudaFree(b->init_stage);
@@ -760,16 +880,33 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
   DeviceGuard g(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int blk; unsigned grid; bool split;
-  if (b->dtype == SO101_F64) {
-    StateView<double> v = step_view<double>(b, blk, grid, split);
-    if (split) k_step<double, true><<<grid, blk, 0, st>>>(b->dm_d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
-    else k_step<double, false><<<grid, blk, 0, st>>>(b->dm_d, v, (const double*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
-  } else {
-    StateView<float> v = step_view<float>(b, blk, grid, split);
-    if (split) k_step<float, true><<<grid, blk, 0, st>>>(b->dm_f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
-    else k_step<float, false><<<grid, blk, 0, st>>>(b->dm_f, v, (const float*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats);
+  CUDA_TRY(frz_begin(b, 0, st));
+  for (int pass = 0; pass < (has_contact(b) ? 2 : 1); pass++) {
+    // pass 0: the fast kernel (freezes envs that reach the table); pass 1: the contact kernel finishes them
+    const Frz fz = pass ? frz_resume(b, 0) : frz_fast(b, 0);
+#define SO101_STEP(TT, SS, RES, mdl) \
+  k_step<TT, SS, RES><<<grid, blk, 0, st>>>(b->dm_##mdl, v, (const TT*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats, fz)
+    if (b->dtype == SO101_F64) {
+      StateView<double> v = step_view<double>(b, blk, grid, split);
+      if (pass) {
+        resume_shape(b, split, blk, grid);
+        if (split) SO101_STEP(double, true, true, d); else SO101_STEP(double, false, true, d);
+      } else {
+        if (split) SO101_STEP(double, true, false, d); else SO101_STEP(double, false, false, d);
+      }
+    } else {
+      StateView<float> v = step_view<float>(b, blk, grid, split);
+      if (pass) {
+        resume_shape(b, split, blk, grid);
+        if (split) SO101_STEP(float, true, true, f); else SO101_STEP(float, false, true, f);
+      } else {
+        if (split) SO101_STEP(float, true, false, f); else SO101_STEP(float, false, false, f);
+      }
+    }
+#undef SO101_STEP
+    CUDA_TRY(cudaGetLastError());
+    if (!pass && has_contact(b)) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
   }
-  CUDA_TRY(cudaGetLastError());
   return SO101_OK;
 }
 
@@ -799,6 +936,8 @@ int so101_batch_step_host(So101Batch* b, const void* ctrl_host, int n_ctrl, int 
     CUDA_TRY(cudaMemcpyAsync(flags_host, static_cast<char*>(b->state) + (size_t)NROWS * b->n * elem_size(b->dtype),
                              (size_t)b->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (flags_host)
+    for (int64_t i = 0; i < b->n; i++) flags_host[i] &= ~SO101_FLAG_FROZEN;   // internal book-keeping bit
   return SO101_OK;
 }
 
@@ -823,13 +962,18 @@ int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qv
   return SO101_OK;
 }
 
+// One time chunk (t0, t1] of a rollout.  `chunk` = index of the chunk within the API call.  The fast kernel runs on
+// `st`; with contact tables the contact kernel for the envs frozen so far follows - on `st`, or on `side` (then it
+// overlaps the NEXT chunk's fast kernel, which leaves frozen envs alone; the caller joins `side` at the end).
 static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t1, int T, int frame_skip, void* rows,
-                         uint32_t flags, void* stream) {
+                         uint32_t flags, void* stream, int chunk = 0, cudaStream_t side = nullptr,
+                         cudaEvent_t ev_fast = nullptr) {
   if (!b || !spec) return fail(SO101_EINVAL, "null argument");
   if (T < 0 || frame_skip < 1) return fail(SO101_EINVAL, "T must be >= 0 and frame_skip >= 1");
   if (spec->kind < SO101_CTRL_RANDOM || spec->kind > SO101_CTRL_TENSOR) return fail(SO101_EINVAL, "bad control kind");
   if (spec->kind == SO101_CTRL_TENSOR && !spec->u) return fail(SO101_EINVAL, "SO101_CTRL_TENSOR needs spec->u");
   if (spec->kind == SO101_CTRL_CHIRP && spec->t_total <= 0) return fail(SO101_EINVAL, "chirp needs t_total > 0");
+  if (chunk < 0 || chunk > So101Batch::MAXCHUNK) return fail(SO101_EINVAL, "too many time chunks");
   DeviceGuard g(b->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DevSpec ds;
@@ -838,25 +982,73 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
   ds.reset_lo = spec->reset_lo; ds.reset_hi = spec->reset_hi; ds.u = spec->u;
   int blk; unsigned grid; bool split;
   const bool r32 = flags & SO101_ROLL_ROWS_F32;
-  if (b->dtype == SO101_F64) {
-    StateView<double> v = step_view<double>(b, blk, grid, split);
-#define SO101_ROLL(TT, RR, SS, mdl) \
-  k_rollout<TT, RR, SS><<<grid, blk, 0, st>>>(b->dm_##mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats)
-    if (split) { if (r32) SO101_ROLL(double, float, true, d); else SO101_ROLL(double, double, true, d); }
-    else { if (r32) SO101_ROLL(double, float, false, d); else SO101_ROLL(double, double, false, d); }
-  } else {
-    StateView<float> v = step_view<float>(b, blk, grid, split);
-    if (split) { if (r32) SO101_ROLL(float, float, true, f); else SO101_ROLL(float, double, true, f); }
-    else { if (r32) SO101_ROLL(float, float, false, f); else SO101_ROLL(float, double, false, f); }
+  CUDA_TRY(frz_begin(b, chunk, st));
+  for (int pass = 0; pass < (has_contact(b) ? 2 : 1); pass++) {
+    const Frz fz = pass ? frz_resume(b, chunk) : frz_fast(b, chunk);
+    cudaStream_t ls = (pass && side) ? side : st;
+#define SO101_ROLL(TT, RR, SS, RES, mdl) \
+  k_rollout<TT, RR, SS, RES><<<grid, blk, 0, ls>>>(b->dm_##mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats, fz)
+#define SO101_ROLL_ROWS(TT, SS, RES, mdl) do { if (r32) SO101_ROLL(TT, float, SS, RES, mdl); else SO101_ROLL(TT, double, SS, RES, mdl); } while (0)
+    if (b->dtype == SO101_F64) {
+      StateView<double> v = step_view<double>(b, blk, grid, split);
+      if (pass) {
+        resume_shape(b, split, blk, grid);
+        if (split) SO101_ROLL_ROWS(double, true, true, d); else SO101_ROLL_ROWS(double, false, true, d);
+      } else {
+        if (split) SO101_ROLL_ROWS(double, true, false, d); else SO101_ROLL_ROWS(double, false, false, d);
+      }
+    } else {
+      StateView<float> v = step_view<float>(b, blk, grid, split);
+      if (pass) {
+        resume_shape(b, split, blk, grid);
+        if (split) SO101_ROLL_ROWS(float, true, true, f); else SO101_ROLL_ROWS(float, false, true, f);
+      } else {
+        if (split) SO101_ROLL_ROWS(float, true, false, f); else SO101_ROLL_ROWS(float, false, false, f);
+      }
+    }
+#undef SO101_ROLL_ROWS
 #undef SO101_ROLL
+    CUDA_TRY(cudaGetLastError());
+    if (!pass && has_contact(b)) {
+      k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap + chunk);
+      CUDA_TRY(cudaGetLastError());
+      if (side) {
+        CUDA_TRY(cudaEventRecord(ev_fast, st));
+        CUDA_TRY(cudaStreamWaitEvent(side, ev_fast, 0));
+      }
+    }
   }
-  CUDA_TRY(cudaGetLastError());
   return SO101_OK;
 }
 
+static int ensure_pipe(So101Batch* b);
+
 int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip, void* rows, uint32_t flags,
                         void* stream) {
-  return rollout_range(b, spec, 0, T, T, frame_skip, rows, flags, stream);
+  if (!b) return fail(SO101_EINVAL, "null batch");
+  // Small batches (team kernels: one team per SM, the launch is as long as its slowest block) with contact tables: cut
+  // the rollout into time chunks so that the contact kernel of chunk c - a handful of envs on otherwise idle SMs - runs
+  // beside the fast kernel of chunk c + 1 instead of after the whole rollout.
+  const bool team = pick_split(b, b->dtype == SO101_F32);
+  if (!(has_contact(b) && team && T >= 16)) return rollout_range(b, spec, 0, T, T, frame_skip, rows, flags, stream);
+  DeviceGuard g(b->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if ((rc = ensure_pipe(b))) return rc;
+  const int nchunk = T >= 80 ? 10 : (T >= 40 ? 5 : 2);
+  CUDA_TRY(cudaEventRecord(b->ev_start, st));
+  CUDA_TRY(cudaStreamWaitEvent(b->s_up, b->ev_start, 0));
+  for (int c = 0; c < nchunk; c++) {
+    const int t0 = (int)((int64_t)T * c / nchunk), t1 = (int)((int64_t)T * (c + 1) / nchunk);
+    const uint32_t f = c == 0 ? flags : (flags | SO101_ROLL_NO_RESET);
+    if ((rc = rollout_range(b, spec, t0, t1, T, frame_skip, rows, f, stream, c, b->s_up, b->ev_k[c]))) {
+      cudaStreamSynchronize(b->s_up);
+      return rc;
+    }
+  }
+  CUDA_TRY(cudaEventRecord(b->ev_up[0], b->s_up));      // join: the caller's stream continues after the last contact kernel
+  CUDA_TRY(cudaStreamWaitEvent(st, b->ev_up[0], 0));
+  return SO101_OK;
 }
 
 static int grow(void** buf, size_t* have, size_t need) {
@@ -970,7 +1162,7 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   for (int c = 0; c < nchunk; c++) {
     if (tensor) PIPE_TRY(cudaStreamWaitEvent(st, b->ev_up[c], 0));
     const uint32_t f = c == 0 ? flags : (flags | SO101_ROLL_NO_RESET);
-    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, b->rows_stage, f, stream))) { drain(); return rc; }
+    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, b->rows_stage, f, stream, c))) { drain(); return rc; }
     PIPE_TRY(cudaEventRecord(b->ev_k[c], st));
     PIPE_TRY(cudaStreamWaitEvent(b->s_down, b->ev_k[c], 0));
     const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
@@ -996,16 +1188,32 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
   State0 s0;
   std::memcpy(s0.v, state0, sizeof s0.v);
   int blk; unsigned grid; bool split;
-  if (b->dtype == SO101_F64) {
-    StateView<double> v = step_view<double>(b, blk, grid, split);
-    if (split) k_shoot<double, true><<<grid, blk, 0, st>>>(b->dm_d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
-    else k_shoot<double, false><<<grid, blk, 0, st>>>(b->dm_d, v, s0, (const double*)U, H, frame_skip, (float*)X, flags, b->stats);
-  } else {
-    StateView<float> v = step_view<float>(b, blk, grid, split);
-    if (split) k_shoot<float, true><<<grid, blk, 0, st>>>(b->dm_f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
-    else k_shoot<float, false><<<grid, blk, 0, st>>>(b->dm_f, v, s0, (const float*)U, H, frame_skip, (float*)X, flags, b->stats);
+  CUDA_TRY(frz_begin(b, 0, st));
+  for (int pass = 0; pass < (has_contact(b) ? 2 : 1); pass++) {
+    const Frz fz = pass ? frz_resume(b, 0) : frz_fast(b, 0);
+#define SO101_SHOOT(TT, SS, RES, mdl) \
+  k_shoot<TT, SS, RES><<<grid, blk, 0, st>>>(b->dm_##mdl, v, s0, (const TT*)U, H, frame_skip, (float*)X, flags, b->stats, fz)
+    if (b->dtype == SO101_F64) {
+      StateView<double> v = step_view<double>(b, blk, grid, split);
+      if (pass) {
+        resume_shape(b, split, blk, grid);
+        if (split) SO101_SHOOT(double, true, true, d); else SO101_SHOOT(double, false, true, d);
+      } else {
+        if (split) SO101_SHOOT(double, true, false, d); else SO101_SHOOT(double, false, false, d);
+      }
+    } else {
+      StateView<float> v = step_view<float>(b, blk, grid, split);
+      if (pass) {
+        resume_shape(b, split, blk, grid);
+        if (split) SO101_SHOOT(float, true, true, f); else SO101_SHOOT(float, false, true, f);
+      } else {
+        if (split) SO101_SHOOT(float, true, false, f); else SO101_SHOOT(float, false, false, f);
+      }
+    }
+#undef SO101_SHOOT
+    CUDA_TRY(cudaGetLastError());
+    if (!pass && has_contact(b)) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
   }
-  CUDA_TRY(cudaGetLastError());
   return SO101_OK;
 }
 
@@ -1042,8 +1250,12 @@ int so101_batch_get_flags(So101Batch* b, uint32_t* flags_dev, void* stream) {
   if (!b || !flags_dev) return fail(SO101_EINVAL, "null argument");
   DeviceGuard g(b->device);
   const char* src = static_cast<char*>(b->state) + (size_t)NROWS * b->n * elem_size(b->dtype);
-  CUDA_TRY(cudaMemcpyAsync(flags_dev, src, (size_t)b->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
-                           static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemcpyAsync(flags_dev, src, (size_t)b->n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  if (has_contact(b)) {   // the FROZEN bit is internal book-keeping
+    k_mask_flags<<<(unsigned)((b->n + 255) / 256), 256, 0, st>>>(flags_dev, b->n, ~SO101_FLAG_FROZEN);
+    CUDA_TRY(cudaGetLastError());
+  }
   return SO101_OK;
 }
 int so101_batch_clear_flags(So101Batch* b, void* stream) {

@@ -973,12 +973,20 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
 // on a barrier at the phase boundaries so that its warps stream the same instructions through
 // the instruction cache together (the step is ~50 KB of SASS; ncu: stall_no_instruction).
 // ------------------------------------------------------------------------------------------
-template <typename T, bool SYNC>
+// CM (contact mode): CM_FREEZE - the fast kernels: an env whose collision box dips below the table top is FROZEN
+// (its state stops advancing, SO101_FLAG_FROZEN) and finished by the contact kernels (k_*_resume), so that this
+// instruction stream carries no contact code at all; CM_SOLVE - the contact kernels: exact hull test and contact rows
+// in this step (so101_contact.cuh).  Without hull data (m.con_enabled == 0) both only raise SO101_FLAG_TRIP_TABLE.
+enum { CM_FREEZE = 0, CM_SOLVE = 1 };
+#define SO101_FLAG_FROZEN (1u << 31)   // internal: never leaves the library (masked by so101_batch_get_flags)
+
+template <typename T, bool SYNC, int CM>
 SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
                             bool want_site, T (&site)[3], bool trip, Counters& cnt) {
   if (SYNC) __syncthreads();
+  const bool frozen_in = (e.flags & SO101_FLAG_FROZEN) != 0;   // inert: waits for (or, there, for its turn in) the contact kernel
   // mj_checkPos / mj_checkVel
-  {
+  if (!frozen_in) {
     bool bad = false;
 #pragma unroll
     for (int i = 0; i < NV; i++) bad |= bad_(e.q[i]) | bad_(e.qd[i]);
@@ -991,6 +999,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   }
   T M[21], bias[NV];
   uint32_t hits = 0;   // tripwire boxes below the table top
+  if (!frozen_in) {
 #if SO101_ONEWARP_ROLLED   // experiment: the compact link loops of the team kernels in the one-warp kernels (see profiles/README.md)
   {
     T sn[NV], cs[NV], lq[NV], lqd[NV];
@@ -1009,7 +1018,14 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags, hits);
   }
 #endif
+  }
   if (SYNC) __syncthreads();
+  if (frozen_in) return;
+  if (CM == CM_FREEZE && hits) {
+    if (m.con_enabled) { e.flags |= SO101_FLAG_FROZEN; return; }   // nothing of this step has touched the state yet
+    e.flags |= SO101_FLAG_TRIP_TABLE;   // no hull data: the env is only marked, its dynamics stay contact-free
+    hits = 0;
+  }
   if (gravcomp_capture) {
 #pragma unroll
     for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
@@ -1026,14 +1042,14 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV], zone[NV];
   T cost = T(0);
   bool need_setup = false;
-  if (hits) {
+  if (CM == CM_SOLVE && hits) {
     // a collision box is below the table top: exact hull test and, if a hull does touch, the full constraint solve with
     // contact rows - out of line (so101_contact.cuh); the phase machine then only runs its Euler solve
     bool in_contact = false;
     if (m.con_enabled)
       in_contact = contact_branch<T>(m, e, hits, M, fsm, rw, a, qc, cnt);
     else
-      e.flags |= SO101_FLAG_TRIP_TABLE;   // no hull data: the env is only marked, its dynamics stay contact-free
+      e.flags |= SO101_FLAG_TRIP_TABLE;
     if (in_contact) {
       bool bad = false;
 #pragma unroll
@@ -1372,36 +1388,55 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
   for (int i = 0; i < NV; i++) { q[i] = x.q[i][lane]; qd[i] = x.qd[i][lane]; }
 }
 
-// dynamics warp: everything else of the step
-template <typename T>
+// dynamics warp: everything else of the step.  nstep = index of this step within the launch (same for the whole block:
+// selects the buffer of the lagged factor the geometry warp wrote).  A frozen lane (see physics_step) skips the
+// arithmetic but walks through the same barriers and re-publishes its unchanged state.
+template <typename T, int CM>
 SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lane, Env<T>& e, const T (&ctrl)[NV],
-                                   bool gravcomp_capture, bool want_site, T (&site)[3], bool trip, Counters& cnt) {
-  if (team_check_state(m, e.q, e.qd)) {
+                                   bool gravcomp_capture, bool want_site, T (&site)[3], bool trip, Counters& cnt,
+                                   int64_t nstep) {
+  bool skip = (e.flags & SO101_FLAG_FROZEN) != 0;
+  if (!skip && team_check_state(m, e.q, e.qd)) {
 #pragma unroll
     for (int i = 0; i < NV; i++) { e.warm[i] = T(0); e.fa[i] = T(0); }
     e.time = T(0);
     e.flags |= SO101_FLAG_BADSTATE;
   }
   T M[21], bias[NV];
-  {
-    team_sincos(m, x, lane, 0, e.q);
+  team_sincos(m, x, lane, 0, e.q);
+  T fsm[NV], asm_[NV];
+  Rows<T> rw;
+  rw.anylim = false;
+  bool constrained = false;
+  const uint32_t lim0 = cnt.limsteps;
+  if (!skip) {
     T lqd[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) lqd[i] = e.qd[i];
     rnea_bias(m, &x.sn[0][lane], &x.cs[0][lane], 32, lqd, 1, bias);
-  }
-  if (gravcomp_capture) {
+    if (gravcomp_capture) {
 #pragma unroll
-    for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
-  }
-  T fsm[NV], asm_[NV];
-  Rows<T> rw;
-  build_rows(m, e, ctrl, bias, fsm, rw, cnt);
+      for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
+    }
+    build_rows(m, e, ctrl, bias, fsm, rw, cnt);
 #pragma unroll
-  for (int i = 0; i < NV; i++) asm_[i] = fsm[i];
-  const bool constrained = m.nfriction != 0 || rw.anylim;
-
+    for (int i = 0; i < NV; i++) asm_[i] = fsm[i];
+    constrained = m.nfriction != 0 || rw.anylim;
+  }
   __syncthreads();   // (A) wait for the geometry and lookout warps
+  if (!skip && CM == CM_FREEZE && trip && x.hits[lane]) {
+    if (m.con_enabled) {   // freeze: the contact kernel re-executes this step (a gravity-compensation capture of this
+      e.flags |= SO101_FLAG_FROZEN;   // step is repeated there with the same result; the state proper is untouched)
+      cnt.limsteps = lim0;
+      skip = true;
+    } else {
+      e.flags |= SO101_FLAG_TRIP_TABLE;
+    }
+  }
+  T Ls[15], Dinv[NV];
+  T a[NV], Ma[NV], qc[NV], hd[NV];
+  bool solved = false;
+  if (!skip) {
   if (trip) e.flags |= x.trip[lane];
   if (want_site) {
 #pragma unroll
@@ -1409,10 +1444,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
-  T Ls[15], Dinv[NV];
-  T a[NV], Ma[NV], qc[NV], hd[NV];
-  bool solved = false;
-  if (trip && x.hits[lane]) {        // table contact (see physics_step)
+  if (CM == CM_SOLVE && trip && x.hits[lane]) {        // table contact (see physics_step)
     if (m.con_enabled)
       solved = contact_branch<T>(m, e, x.hits[lane], M, fsm, rw, a, qc, cnt);
     else
@@ -1420,7 +1452,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
   if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     // zone guess from qacc_smooth approximated with the factor of the previous step's M (split_geometry_step)
-    const int rb = LaggedGuess<T>::value ? (int)(cnt.steps & 1u) : 0;
+    const int rb = LaggedGuess<T>::value ? (int)(nstep & 1) : 0;
 #pragma unroll
     for (int i = 0; i < 15; i++) Ls[i] = x.L1[rb][i][lane];
 #pragma unroll
@@ -1550,7 +1582,9 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
       }
     }
   }
+  }   // !skip
   __syncthreads();   // (E) factors of M + h B
+  if (!skip) {
   // mj_checkAcc, mj_Euler
   bool bad = false;
 #pragma unroll
@@ -1581,6 +1615,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     e.time += m.h;
   }
   cnt.steps++;
+  }   // !skip
 #pragma unroll
   for (int i = 0; i < NV; i++) { x.q[i][lane] = e.q[i]; x.qd[i][lane] = e.qd[i]; }
   __syncthreads();   // (B) new state published
