@@ -326,12 +326,20 @@ k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* 
 }
 
 // SOARM101Env.step: ctrl rows [n_ctrl][N] (missing rows = 0), nsub x mj_step, observation
+// MODE of a stepping kernel: how table contact is handled (see struct Frz)
+//   MODE_FREEZE  large batches, pass 1: no contact code in the instruction stream; envs that reach the table are frozen
+//   MODE_RESUME  large batches, pass 2: one thread per LIST ENTRY, contact path compiled in
+//   MODE_INLINE  small batches (team kernels): contact path compiled in, nothing is frozen.  A team kernel is as long as
+//                its slowest block whatever it does, so handing its few contact envs to a second launch only adds that
+//                launch's latency.
+enum { MODE_FREEZE = 0, MODE_RESUME = 1, MODE_INLINE = 2 };
 #define SO101_STEP_KERNEL2(T) \
-  template <typename T, bool SPLIT, bool RESUME> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
+  template <typename T, bool SPLIT, int MODE> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
 SO101_STEP_KERNEL2(T)
 k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
        unsigned long long* stats, Frz fz) {
-  constexpr int CM = RESUME ? CM_SOLVE : CM_FREEZE;
+  constexpr bool RESUME = MODE == MODE_RESUME;
+  constexpr int CM = MODE == MODE_FREEZE ? CM_FREEZE : CM_SOLVE;
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
   bool active, exit_block;
@@ -376,14 +384,15 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
 
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
-template <typename T, typename ROW, bool SPLIT, bool RESUME>
+template <typename T, typename ROW, bool SPLIT, int MODE>
 __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
 k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
           ROW* rows, uint32_t rflags, unsigned long long* stats, Frz fz) {
   // control steps (t0, t1] of a rollout of Tn steps; t0 > 0 continues a previous launch (row t0 is already written,
   // u_t0 is regenerated: the control stream is a pure function of (seed, env, t)).  Physics step index of sub-step ss
   // of loop iteration t: t * frame_skip + ss (what Frz.at holds).
-  constexpr int CM = RESUME ? CM_SOLVE : CM_FREEZE;
+  constexpr bool RESUME = MODE == MODE_RESUME;
+  constexpr int CM = MODE == MODE_FREEZE ? CM_FREEZE : CM_SOLVE;
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
   bool active, exit_block;
@@ -458,7 +467,8 @@ struct State0 { double v[18]; };
 SO101_STEP_KERNEL2(T)
 k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
         int frame_skip, float* X, uint32_t rflags, unsigned long long* stats, Frz fz) {
-  constexpr int CM = RESUME ? CM_SOLVE : CM_FREEZE;
+  constexpr bool RESUME = MODE == MODE_RESUME;
+  constexpr int CM = MODE == MODE_FREEZE ? CM_FREEZE : CM_SOLVE;
   __shared__ XchStorage<T, SPLIT> xst;
   SplitXch<T>& xch = xch_of(xst);
   bool active, exit_block;
@@ -654,9 +664,9 @@ static Frz frz_resume(const So101Batch* b, int chunk) {
 }
 // launch shape of a contact kernel: one thread (team lane) per list entry, worst case every env (blocks beyond the
 // list's end exit at once)
-static void resume_shape(const So101Batch* b, bool split, int& blk, unsigned& grid) {
-  if (split) { blk = 32 * TEAM_WARPS; grid = (unsigned)((b->n + 31) / 32); }
-  else { blk = 64; grid = (unsigned)((b->n + 63) / 64); }
+static void resume_shape(const So101Batch* b, int& blk, unsigned& grid) {
+  blk = 64;
+  grid = (unsigned)((b->n + 63) / 64);
 }
 // before the first fast launch of an API call: the list starts empty
 static cudaError_t frz_begin(const So101Batch* b, int chunk, cudaStream_t st) {
@@ -881,31 +891,27 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int blk; unsigned grid; bool split;
   CUDA_TRY(frz_begin(b, 0, st));
-  for (int pass = 0; pass < (has_contact(b) ? 2 : 1); pass++) {
-    // pass 0: the fast kernel (freezes envs that reach the table); pass 1: the contact kernel finishes them
+  for (int pass = 0; pass < 2; pass++) {
+    // one-warp kernels: pass 0 freezes the envs that reach the table, pass 1 (contact kernel) finishes them;
+    // team kernels: one pass with the contact path compiled in
     const Frz fz = pass ? frz_resume(b, 0) : frz_fast(b, 0);
-#define SO101_STEP(TT, SS, RES, mdl) \
-  k_step<TT, SS, RES><<<grid, blk, 0, st>>>(b->dm_##mdl, v, (const TT*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats, fz)
+#define SO101_STEP(TT, SS, MD, mdl) \
+  k_step<TT, SS, MD><<<grid, blk, 0, st>>>(b->dm_##mdl, v, (const TT*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats, fz)
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
-      if (pass) {
-        resume_shape(b, split, blk, grid);
-        if (split) SO101_STEP(double, true, true, d); else SO101_STEP(double, false, true, d);
-      } else {
-        if (split) SO101_STEP(double, true, false, d); else SO101_STEP(double, false, false, d);
-      }
+      if (split) { SO101_STEP(double, true, MODE_INLINE, d); }
+      else if (pass) { resume_shape(b, blk, grid); SO101_STEP(double, false, MODE_RESUME, d); }
+      else SO101_STEP(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
-      if (pass) {
-        resume_shape(b, split, blk, grid);
-        if (split) SO101_STEP(float, true, true, f); else SO101_STEP(float, false, true, f);
-      } else {
-        if (split) SO101_STEP(float, true, false, f); else SO101_STEP(float, false, false, f);
-      }
+      if (split) { SO101_STEP(float, true, MODE_INLINE, f); }
+      else if (pass) { resume_shape(b, blk, grid); SO101_STEP(float, false, MODE_RESUME, f); }
+      else SO101_STEP(float, false, MODE_FREEZE, f);
     }
 #undef SO101_STEP
     CUDA_TRY(cudaGetLastError());
-    if (!pass && has_contact(b)) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
+    if (split || !has_contact(b)) break;
+    if (!pass) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
   }
   return SO101_OK;
 }
@@ -962,12 +968,10 @@ int so101_batch_reset_host(So101Batch* b, const void* qpos0_host, const void* qv
   return SO101_OK;
 }
 
-// One time chunk (t0, t1] of a rollout.  `chunk` = index of the chunk within the API call.  The fast kernel runs on
-// `st`; with contact tables the contact kernel for the envs frozen so far follows - on `st`, or on `side` (then it
-// overlaps the NEXT chunk's fast kernel, which leaves frozen envs alone; the caller joins `side` at the end).
+// One time chunk (t0, t1] of a rollout; `chunk` = index of the chunk within the API call (chunk 0 empties the list of
+// frozen envs).  One-warp kernels: the fast kernel, then the contact kernel for the envs frozen so far.
 static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t1, int T, int frame_skip, void* rows,
-                         uint32_t flags, void* stream, int chunk = 0, cudaStream_t side = nullptr,
-                         cudaEvent_t ev_fast = nullptr) {
+                         uint32_t flags, void* stream, int chunk = 0) {
   if (!b || !spec) return fail(SO101_EINVAL, "null argument");
   if (T < 0 || frame_skip < 1) return fail(SO101_EINVAL, "T must be >= 0 and frame_skip >= 1");
   if (spec->kind < SO101_CTRL_RANDOM || spec->kind > SO101_CTRL_TENSOR) return fail(SO101_EINVAL, "bad control kind");
@@ -983,72 +987,34 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
   int blk; unsigned grid; bool split;
   const bool r32 = flags & SO101_ROLL_ROWS_F32;
   CUDA_TRY(frz_begin(b, chunk, st));
-  for (int pass = 0; pass < (has_contact(b) ? 2 : 1); pass++) {
+  for (int pass = 0; pass < 2; pass++) {
     const Frz fz = pass ? frz_resume(b, chunk) : frz_fast(b, chunk);
-    cudaStream_t ls = (pass && side) ? side : st;
-#define SO101_ROLL(TT, RR, SS, RES, mdl) \
-  k_rollout<TT, RR, SS, RES><<<grid, blk, 0, ls>>>(b->dm_##mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats, fz)
-#define SO101_ROLL_ROWS(TT, SS, RES, mdl) do { if (r32) SO101_ROLL(TT, float, SS, RES, mdl); else SO101_ROLL(TT, double, SS, RES, mdl); } while (0)
+#define SO101_ROLL(TT, RR, SS, MD, mdl) \
+  k_rollout<TT, RR, SS, MD><<<grid, blk, 0, st>>>(b->dm_##mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats, fz)
+#define SO101_ROLL_ROWS(TT, SS, MD, mdl) do { if (r32) SO101_ROLL(TT, float, SS, MD, mdl); else SO101_ROLL(TT, double, SS, MD, mdl); } while (0)
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
-      if (pass) {
-        resume_shape(b, split, blk, grid);
-        if (split) SO101_ROLL_ROWS(double, true, true, d); else SO101_ROLL_ROWS(double, false, true, d);
-      } else {
-        if (split) SO101_ROLL_ROWS(double, true, false, d); else SO101_ROLL_ROWS(double, false, false, d);
-      }
+      if (split) SO101_ROLL_ROWS(double, true, MODE_INLINE, d);
+      else if (pass) { resume_shape(b, blk, grid); SO101_ROLL_ROWS(double, false, MODE_RESUME, d); }
+      else SO101_ROLL_ROWS(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
-      if (pass) {
-        resume_shape(b, split, blk, grid);
-        if (split) SO101_ROLL_ROWS(float, true, true, f); else SO101_ROLL_ROWS(float, false, true, f);
-      } else {
-        if (split) SO101_ROLL_ROWS(float, true, false, f); else SO101_ROLL_ROWS(float, false, false, f);
-      }
+      if (split) SO101_ROLL_ROWS(float, true, MODE_INLINE, f);
+      else if (pass) { resume_shape(b, blk, grid); SO101_ROLL_ROWS(float, false, MODE_RESUME, f); }
+      else SO101_ROLL_ROWS(float, false, MODE_FREEZE, f);
     }
 #undef SO101_ROLL_ROWS
 #undef SO101_ROLL
     CUDA_TRY(cudaGetLastError());
-    if (!pass && has_contact(b)) {
-      k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap + chunk);
-      CUDA_TRY(cudaGetLastError());
-      if (side) {
-        CUDA_TRY(cudaEventRecord(ev_fast, st));
-        CUDA_TRY(cudaStreamWaitEvent(side, ev_fast, 0));
-      }
-    }
+    if (split || !has_contact(b)) break;
+    if (!pass) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap + chunk); CUDA_TRY(cudaGetLastError()); }
   }
   return SO101_OK;
 }
 
-static int ensure_pipe(So101Batch* b);
-
 int so101_batch_rollout(So101Batch* b, const So101CtrlSpec* spec, int T, int frame_skip, void* rows, uint32_t flags,
                         void* stream) {
-  if (!b) return fail(SO101_EINVAL, "null batch");
-  // Small batches (team kernels: one team per SM, the launch is as long as its slowest block) with contact tables: cut
-  // the rollout into time chunks so that the contact kernel of chunk c - a handful of envs on otherwise idle SMs - runs
-  // beside the fast kernel of chunk c + 1 instead of after the whole rollout.
-  const bool team = pick_split(b, b->dtype == SO101_F32);
-  if (!(has_contact(b) && team && T >= 16)) return rollout_range(b, spec, 0, T, T, frame_skip, rows, flags, stream);
-  DeviceGuard g(b->device);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc;
-  if ((rc = ensure_pipe(b))) return rc;
-  const int nchunk = T >= 80 ? 10 : (T >= 40 ? 5 : 2);
-  CUDA_TRY(cudaEventRecord(b->ev_start, st));
-  CUDA_TRY(cudaStreamWaitEvent(b->s_up, b->ev_start, 0));
-  for (int c = 0; c < nchunk; c++) {
-    const int t0 = (int)((int64_t)T * c / nchunk), t1 = (int)((int64_t)T * (c + 1) / nchunk);
-    const uint32_t f = c == 0 ? flags : (flags | SO101_ROLL_NO_RESET);
-    if ((rc = rollout_range(b, spec, t0, t1, T, frame_skip, rows, f, stream, c, b->s_up, b->ev_k[c]))) {
-      cudaStreamSynchronize(b->s_up);
-      return rc;
-    }
-  }
-  CUDA_TRY(cudaEventRecord(b->ev_up[0], b->s_up));      // join: the caller's stream continues after the last contact kernel
-  CUDA_TRY(cudaStreamWaitEvent(st, b->ev_up[0], 0));
-  return SO101_OK;
+  return rollout_range(b, spec, 0, T, T, frame_skip, rows, flags, stream);
 }
 
 static int grow(void** buf, size_t* have, size_t need) {
@@ -1189,30 +1155,25 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
   std::memcpy(s0.v, state0, sizeof s0.v);
   int blk; unsigned grid; bool split;
   CUDA_TRY(frz_begin(b, 0, st));
-  for (int pass = 0; pass < (has_contact(b) ? 2 : 1); pass++) {
+  for (int pass = 0; pass < 2; pass++) {
     const Frz fz = pass ? frz_resume(b, 0) : frz_fast(b, 0);
-#define SO101_SHOOT(TT, SS, RES, mdl) \
-  k_shoot<TT, SS, RES><<<grid, blk, 0, st>>>(b->dm_##mdl, v, s0, (const TT*)U, H, frame_skip, (float*)X, flags, b->stats, fz)
+#define SO101_SHOOT(TT, SS, MD, mdl) \
+  k_shoot<TT, SS, MD><<<grid, blk, 0, st>>>(b->dm_##mdl, v, s0, (const TT*)U, H, frame_skip, (float*)X, flags, b->stats, fz)
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
-      if (pass) {
-        resume_shape(b, split, blk, grid);
-        if (split) SO101_SHOOT(double, true, true, d); else SO101_SHOOT(double, false, true, d);
-      } else {
-        if (split) SO101_SHOOT(double, true, false, d); else SO101_SHOOT(double, false, false, d);
-      }
+      if (split) { SO101_SHOOT(double, true, MODE_INLINE, d); }
+      else if (pass) { resume_shape(b, blk, grid); SO101_SHOOT(double, false, MODE_RESUME, d); }
+      else SO101_SHOOT(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
-      if (pass) {
-        resume_shape(b, split, blk, grid);
-        if (split) SO101_SHOOT(float, true, true, f); else SO101_SHOOT(float, false, true, f);
-      } else {
-        if (split) SO101_SHOOT(float, true, false, f); else SO101_SHOOT(float, false, false, f);
-      }
+      if (split) { SO101_SHOOT(float, true, MODE_INLINE, f); }
+      else if (pass) { resume_shape(b, blk, grid); SO101_SHOOT(float, false, MODE_RESUME, f); }
+      else SO101_SHOOT(float, false, MODE_FREEZE, f);
     }
 #undef SO101_SHOOT
     CUDA_TRY(cudaGetLastError());
-    if (!pass && has_contact(b)) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
+    if (split || !has_contact(b)) break;
+    if (!pass) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
   }
   return SO101_OK;
 }

@@ -462,4 +462,199 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
   return true;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------------
+// Fast path of the contact kernels (inline): the same problem as contact_solve, organised around the THREE Jacobian rows
+// of each contact (normal, two tangents) instead of its four pyramid rows.  With rows J_n +- mu J_y, J_n +- mu J_x'
+// (x' = -x) and activity bits a1..a4,
+//   sum_active D J_r J_r' = D [ (a1+a2+a3+a4) nn' + mu (a1-a2)(ny' + yn') + mu (a3-a4)(nx'' + x'n') + mu^2 (a1+a2) yy'
+//                              + mu^2 (a3+a4) x'x'' ],
+// so one contact costs five 6x6 symmetric rank updates whatever its rows do, and a candidate's row residuals are three
+// dot products.  The solve is the direct active-set iteration of contact_solve (pieces: qacc_warmstart's, then the
+// rejected candidate's, up to six times); a step that does not settle returns 2 and takes contact_solve's safeguarded
+// Newton.  0 = no hull touches the table.
+// ----------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Con3 {
+  T Jn[NV], Jy[NV], Jx[NV];     // contact frame: normal +z, tangents (0,1,0) and (-1,0,0): Jx holds the x' = -x row
+  T D, c0, vn, vy, vx;          // row weight, -K imp (dist - margin), J . qvel
+};
+
+template <typename T>
+SO101_DEV int contact_fast(const DevModel<T>& m, const T (&q)[NV], const T (&qd)[NV], const T (&warm)[NV], uint32_t hits,
+                           const T (&Mm)[21], const T (&fsm)[NV], const Rows<T>& rw, T (&a)[NV], T (&qc)[NV],
+                           uint32_t& flags, Counters& cnt) {
+  Con3<T> con[MAXCON];
+  int ncon = 0;
+  {
+    T axw[NV][3], anw[NV][3];
+    T Rw[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, ow[3] = {T(0), T(0), T(0)};
+#pragma unroll 1
+    for (int k = 0; k < NV; k++) {
+      T s_, c_, R[9], Rn[9], o[3];
+      sincos_(q[k] - m.qpos0[k], &s_, &c_);
+      make_R(m.E[k], c_, s_, R);
+      rot(Rw, m.r[k], o);
+      ow[0] += o[0]; ow[1] += o[1]; ow[2] += o[2];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rw[3 * i] * R[j] + Rw[3 * i + 1] * R[3 + j] + Rw[3 * i + 2] * R[6 + j];
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
+      axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
+      anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
+#pragma unroll 1
+      for (int b = 0; b < m.trip_n[k]; b++) {
+        if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
+        const T d[3] = {m.con_tilt[k][0] - Rw[6], m.con_tilt[k][1] - Rw[7], m.con_tilt[k][2] - Rw[8]};
+        T v[3];
+        hull_support(m, m.trip_geom[k][b], d, v);
+        const T zmin = ow[2] + (Rw[6] * v[0] + Rw[7] * v[1] + Rw[8] * v[2]);
+        const T dist = zmin - m.trip_z;
+        if (!(dist < m.con_margin)) continue;
+        T p[3];
+        rot(Rw, v, p);
+        p[0] += ow[0]; p[1] += ow[1]; p[2] = zmin - T(0.5) * dist;
+        if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
+          flags |= SO101_FLAG_TRIP_TABLE;
+          continue;
+        }
+        Con3<T>& c = con[ncon++];
+        c.vn = c.vy = c.vx = T(0);
+#pragma unroll 1
+        for (int j = 0; j < NV; j++) {
+          T jn = T(0), jy = T(0), jx = T(0);
+          if (j <= k) {
+            const T rx = p[0] - anw[j][0], ry = p[1] - anw[j][1], rz = p[2] - anw[j][2];
+            jx = -(axw[j][1] * rz - axw[j][2] * ry);
+            jy = axw[j][2] * rx - axw[j][0] * rz;
+            jn = axw[j][0] * ry - axw[j][1] * rx;
+          }
+          c.Jn[j] = jn; c.Jy[j] = jy; c.Jx[j] = jx;
+          c.vn += jn * qd[j]; c.vy += jy * qd[j]; c.vx += jx * qd[j];
+        }
+        const T imp = limit_impedance(m.con_imp, dist, m.con_margin);
+        const T mu = m.con_mu;
+        const T R1 = max_(T(MJ_MINVAL), (T(1) - imp) * (m.con_tran[k] + mu * mu * m.con_tran[k]) / imp);
+        c.D = T(1) / (T(2) * mu * mu * R1);
+        c.c0 = -m.con_K * imp * (dist - m.con_margin);
+      }
+    }
+  }
+  if (ncon == 0) return 0;
+  flags |= SO101_FLAG_CONTACT;
+  const T mu = m.con_mu;
+  // pieces: friction zones (quadratic / saturated positive), limit rows, 4 bits per contact
+  uint32_t zq = 0, zp = 0, zl = 0, zc = 0;
+  T az[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) az[i] = warm[i];
+#pragma unroll 1
+  for (int attempt = 0; attempt <= 6; attempt++) {
+    uint32_t nzq = 0, nzp = 0, nzl = 0, nzc = 0;
+    bool strict = true;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      const T jar = az[i] - rw.aref_f[i];
+      if (m.fr_f[i] == T(0) || abs_(jar) < m.fr_Rf[i]) nzq |= 1u << i;
+      else if (jar > T(0)) nzp |= 1u << i;
+      strict &= m.fr_f[i] == T(0) || abs_(jar) != m.fr_Rf[i];
+    }
+    if (rw.anylim) {
+#pragma unroll 1
+      for (int i = 0; i < NV; i++)
+        if (rw.side[i] != T(0) && rw.side[i] * az[i] - rw.aref_l[i] < T(0)) nzl |= 1u << i;
+    }
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
+      T jn = T(0), jy = T(0), jx = T(0);
+#pragma unroll
+      for (int j = 0; j < NV; j++) { jn += con[c].Jn[j] * az[j]; jy += con[c].Jy[j] * az[j]; jx += con[c].Jx[j] * az[j]; }
+      // jar_r = J_r a - aref_r, aref_r = -B (J_r qd) + c0
+      const T bn = jn + m.con_B * con[c].vn - con[c].c0, by = mu * (jy + m.con_B * con[c].vy), bx = mu * (jx + m.con_B * con[c].vx);
+      if (bn + by < T(0)) nzc |= 1u << (4 * c);
+      if (bn - by < T(0)) nzc |= 2u << (4 * c);
+      if (bn + bx < T(0)) nzc |= 4u << (4 * c);
+      if (bn - bx < T(0)) nzc |= 8u << (4 * c);
+    }
+    if (attempt > 0 && nzq == zq && nzp == zp && nzl == zl && nzc == zc && strict) {   // the candidate lies in its own piece
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        a[i] = az[i];
+        const T jar = az[i] - rw.aref_f[i];
+        qc[i] = (zq >> i & 1u) ? -m.fr_D[i] * jar : ((zp >> i & 1u) ? -m.fr_f[i] : m.fr_f[i]);
+        if (m.fr_f[i] == T(0)) qc[i] = T(0);
+      }
+      if (rw.anylim) {
+#pragma unroll 1
+        for (int i = 0; i < NV; i++)
+          if (zl >> i & 1u) qc[i] += rw.side[i] * (-rw.D_l[i] * (rw.side[i] * az[i] - rw.aref_l[i]));
+      }
+#pragma unroll 1
+      for (int c = 0; c < ncon; c++) {
+        T jn = T(0), jy = T(0), jx = T(0);
+#pragma unroll
+        for (int j = 0; j < NV; j++) { jn += con[c].Jn[j] * az[j]; jy += con[c].Jy[j] * az[j]; jx += con[c].Jx[j] * az[j]; }
+        const T bn = jn + m.con_B * con[c].vn - con[c].c0, by = mu * (jy + m.con_B * con[c].vy), bx = mu * (jx + m.con_B * con[c].vx);
+        const uint32_t bits = zc >> (4 * c) & 15u;
+        const T f1 = (bits & 1u) ? -con[c].D * (bn + by) : T(0), f2 = (bits & 2u) ? -con[c].D * (bn - by) : T(0);
+        const T f3 = (bits & 4u) ? -con[c].D * (bn + bx) : T(0), f4 = (bits & 8u) ? -con[c].D * (bn - bx) : T(0);
+        const T fn = f1 + f2 + f3 + f4, fy = mu * (f1 - f2), fx = mu * (f3 - f4);
+#pragma unroll
+        for (int j = 0; j < NV; j++) qc[j] += con[c].Jn[j] * fn + con[c].Jy[j] * fy + con[c].Jx[j] * fx;
+      }
+      cnt.newton += attempt;
+      return 1;
+    }
+    if (attempt == 6) break;
+    zq = nzq; zp = nzp; zl = nzl; zc = nzc;
+    T H[21], rhs[NV];
+#pragma unroll
+    for (int i = 0; i < 21; i++) H[i] = Mm[i];
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      rhs[i] = fsm[i];
+      if (m.fr_f[i] != T(0)) {
+        if (zq >> i & 1u) { H[tri(i, i)] += m.fr_D[i]; rhs[i] += m.fr_D[i] * rw.aref_f[i]; }
+        else rhs[i] += (zp >> i & 1u) ? -m.fr_f[i] : m.fr_f[i];
+      }
+    }
+    if (rw.anylim) {
+#pragma unroll 1
+      for (int i = 0; i < NV; i++)
+        if (zl >> i & 1u) { H[tri(i, i)] += rw.D_l[i]; rhs[i] += rw.D_l[i] * rw.aref_l[i] * rw.side[i]; }
+    }
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
+      const uint32_t bits = zc >> (4 * c) & 15u;
+      if (!bits) continue;
+      const T a1 = (bits & 1u) ? T(1) : T(0), a2 = (bits & 2u) ? T(1) : T(0), a3 = (bits & 4u) ? T(1) : T(0), a4 = (bits & 8u) ? T(1) : T(0);
+      const T D = con[c].D;
+      const T wnn = D * (a1 + a2 + a3 + a4), wny = D * mu * (a1 - a2), wnx = D * mu * (a3 - a4);
+      const T wyy = D * mu * mu * (a1 + a2), wxx = D * mu * mu * (a3 + a4);
+      // aref of the four rows
+      const T an = -m.con_B * con[c].vn + con[c].c0, ay = -m.con_B * mu * con[c].vy, ax = -m.con_B * mu * con[c].vx;
+      const T r1 = an + ay, r2 = an - ay, r3 = an + ax, r4 = an - ax;
+      const T gn = D * (a1 * r1 + a2 * r2 + a3 * r3 + a4 * r4), gy = D * mu * (a1 * r1 - a2 * r2), gx = D * mu * (a3 * r3 - a4 * r4);
+      T n_[NV], y_[NV], x_[NV];
+#pragma unroll
+      for (int j = 0; j < NV; j++) { n_[j] = con[c].Jn[j]; y_[j] = con[c].Jy[j]; x_[j] = con[c].Jx[j]; }
+#pragma unroll
+      for (int i = 0; i < NV; i++) {
+        rhs[i] += gn * n_[i] + gy * y_[i] + gx * x_[i];
+        const T pi = wnn * n_[i] + wny * y_[i] + wnx * x_[i];     // coefficient of n_j
+        const T qi = wny * n_[i] + wyy * y_[i];                   // coefficient of y_j
+        const T ri = wnx * n_[i] + wxx * x_[i];                   // coefficient of x_j
+#pragma unroll
+        for (int j = 0; j <= i; j++) H[tri(i, j)] += pi * n_[j] + qi * y_[j] + ri * x_[j];
+      }
+    }
+    ldl6_factor_solve(H, rhs);
+#pragma unroll
+    for (int i = 0; i < NV; i++) az[i] = rhs[i];
+  }
+  return 2;
+}
+
 }  // namespace so101

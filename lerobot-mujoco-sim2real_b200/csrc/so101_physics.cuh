@@ -942,6 +942,10 @@ namespace so101 {
 template <typename T>
 SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, const T (&M)[21], const T (&fsm)[NV],
                               const Rows<T>& rw, T (&a)[NV], T (&qc)[NV], Counters& cnt) {
+  {   // fast path: settles in a couple of active-set attempts in all but a few steps per million
+    const int r = contact_fast<T>(m, e.q, e.qd, e.warm, hits, M, fsm, rw, a, qc, e.flags, cnt);
+    if (r != 2) return r == 1;
+  }
   ContactIO<T> io;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
