@@ -90,6 +90,8 @@ struct Frz {
   int32_t* count;        // entries appended so far
   const int32_t* upto;   // RESUME: process entries [0, *upto)
   int32_t clear;         // fast kernels: first launch of an API call - stale FROZEN bits are dropped at load
+  int32_t min_n, max_n;  // RESUME: this launch handles lists with min_n < *upto <= max_n (short lists go to the
+                         // three-warp team version of the contact kernel, long ones to the one-warp version)
 };
 template <typename T, bool SPLIT, bool RESUME>
 SO101_DEV int64_t env_slot(const StateView<T>& s, const Frz& fz, bool& active, bool& exit_block) {
@@ -97,6 +99,7 @@ SO101_DEV int64_t env_slot(const StateView<T>& s, const Frz& fz, bool& active, b
   const int64_t j = SPLIT ? (int64_t)blockIdx.x * 32 + (threadIdx.x & 31) : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t first = SPLIT ? (int64_t)blockIdx.x * 32 : (int64_t)blockIdx.x * blockDim.x;
   exit_block = first >= n_eff;                       // uniform over the block
+  if (RESUME) exit_block |= n_eff <= fz.min_n || n_eff > fz.max_n;
   if (exit_block) { active = false; return 0; }
   active = (!SPLIT || threadIdx.x < 32) && j < n_eff;
   const int64_t jc = j < n_eff ? j : n_eff - 1;      // tail threads shadow a valid entry and never store
@@ -363,13 +366,12 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   for (int ss = 0; ss < nsub; ss++) {
     if (RESUME && ss == start) e.flags &= ~SO101_FLAG_FROZEN;
     step_env<T, SPLIT, CM>(m, xch, e, u, false, ss == nsub - 1, site, trip, cnt, ss);
-    if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) frozen_idx = ss;
+    if (!RESUME && frozen_idx < 0 && !was_frozen && (e.flags & SO101_FLAG_FROZEN)) { frozen_idx = ss; if (active) frz_append(fz, i, frozen_idx); }
   }
   if (nsub == 0) site_fk(m, e.q, site);
   if (active && !was_frozen) {
     if (RESUME) { e.flags |= SO101_FLAG_FROZEN; fz.at[i] = nsub; }
     store_env(s, i, e);
-    if (!RESUME && frozen_idx >= 0) frz_append(fz, i, frozen_idx);
     if (obs && (RESUME || frozen_idx < 0)) {
 #pragma unroll
       for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
@@ -398,6 +400,17 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   bool active, exit_block;
   const int64_t i = env_slot<T, SPLIT, RESUME>(s, fz, active, exit_block);
   if (exit_block) return;
+  if (RESUME) {
+    // the list is ordered by freeze time: skip the iterations before the first env of this block takes over (iteration
+    // t0' regenerates the control u_t0' and nothing else, exactly like iteration t0 of any launch)
+    __shared__ int s_first;
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    if (active) atomicMin(&s_first, fz.at[i]);
+    __syncthreads();
+    const int tb = s_first / frame_skip - 1;
+    if (tb > t0) t0 = tb;
+  }
   if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)(t1 - t0) * frame_skip, frame_skip); return; }
   const int64_t env = spec.env_offset + i;
   Env<T> e;
@@ -432,7 +445,10 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
       for (int ss = 0; ss < frame_skip; ss++, nstep++) {
         if (RESUME && t * frame_skip + ss == start) e.flags &= ~SO101_FLAG_FROZEN;
         step_env<T, SPLIT, CM>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
-        if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) frozen_idx = t * frame_skip + ss;
+        if (!RESUME && frozen_idx < 0 && !was_frozen && (e.flags & SO101_FLAG_FROZEN)) {
+          frozen_idx = t * frame_skip + ss;      // appended now: the list ends up ordered by freeze time, so the lanes of a
+          if (active) frz_append(fz, i, frozen_idx);   // contact-kernel warp start at about the same step
+        }
       }
     }
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
@@ -455,7 +471,6 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   if (active && !was_frozen) {
     if (RESUME) { e.flags |= SO101_FLAG_FROZEN; fz.at[i] = (t1 + 1) * frame_skip; }
     store_env(s, i, e);
-    if (!RESUME && frozen_idx >= 0) frz_append(fz, i, frozen_idx);
   }
   if (!active || was_frozen) cnt = {0, 0, 0, 0};
   add_stats(stats, cnt);
@@ -503,7 +518,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
       for (int ss = 0; ss < frame_skip; ss++, nstep++) {
         if (RESUME && t * frame_skip + ss == start) e.flags &= ~SO101_FLAG_FROZEN;
         step_env<T, SPLIT, CM>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
-        if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) frozen_idx = t * frame_skip + ss;
+        if (!RESUME && frozen_idx < 0 && (e.flags & SO101_FLAG_FROZEN)) { frozen_idx = t * frame_skip + ss; if (active) frz_append(fz, i, frozen_idx); }
       }
     }
     const bool mine = RESUME ? (t > 0 && !(e.flags & SO101_FLAG_FROZEN)) : !(e.flags & SO101_FLAG_FROZEN);
@@ -518,7 +533,6 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   if (active) {
     if (RESUME) { e.flags |= SO101_FLAG_FROZEN; fz.at[i] = (H + 1) * frame_skip; }
     store_env(s, i, e);
-    if (!RESUME && frozen_idx >= 0) frz_append(fz, i, frozen_idx);
   } else {
     cnt = {0, 0, 0, 0};
   }
@@ -654,19 +668,31 @@ static bool has_contact(const So101Batch* b) { return b->dm_d.con_enabled != 0; 
 static Frz frz_fast(const So101Batch* b, int chunk) {
   Frz f;
   f.at = b->frz_at; f.list = b->frz_list; f.count = b->frz_count; f.upto = nullptr; f.clear = chunk == 0;
+  f.min_n = 0; f.max_n = 0x7fffffff;
   return f;
 }
-static Frz frz_resume(const So101Batch* b, int chunk) {
+// lists up to this long are latency bound (less than one team per SM ... two per SM): the team version finishes them
+// about twice as fast per step; beyond it the one-warp version has the throughput
+constexpr int TEAM_LIST_MAX = 148 * 64;
+static Frz frz_resume(const So101Batch* b, int chunk, bool team) {
   Frz f = frz_fast(b, chunk);
   f.upto = b->frz_snap + chunk;
   f.clear = 0;
+  f.min_n = team ? 0 : TEAM_LIST_MAX;
+  f.max_n = team ? TEAM_LIST_MAX : 0x7fffffff;
   return f;
 }
 // launch shape of a contact kernel: one thread (team lane) per list entry, worst case every env (blocks beyond the
 // list's end exit at once)
-static void resume_shape(const So101Batch* b, int& blk, unsigned& grid) {
-  blk = 64;
-  grid = (unsigned)((b->n + 63) / 64);
+static void resume_shape(const So101Batch* b, bool team, int& blk, unsigned& grid) {
+  if (team) {
+    const int64_t n = b->n < TEAM_LIST_MAX ? b->n : TEAM_LIST_MAX;
+    blk = 32 * TEAM_WARPS;
+    grid = (unsigned)((n + 31) / 32);
+  } else {
+    blk = 64;
+    grid = (unsigned)((b->n + 63) / 64);
+  }
 }
 // before the first fast launch of an API call: the list starts empty
 static cudaError_t frz_begin(const So101Batch* b, int chunk, cudaStream_t st) {
@@ -891,21 +917,24 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int blk; unsigned grid; bool split;
   CUDA_TRY(frz_begin(b, 0, st));
-  for (int pass = 0; pass < 2; pass++) {
-    // one-warp kernels: pass 0 freezes the envs that reach the table, pass 1 (contact kernel) finishes them;
-    // team kernels: one pass with the contact path compiled in
-    const Frz fz = pass ? frz_resume(b, 0) : frz_fast(b, 0);
+  for (int pass = 0; pass < 3; pass++) {
+    // one-warp kernels: pass 0 freezes the envs that reach the table, passes 1 / 2 (contact kernel, team / one-warp
+    // version: the one the list length calls for does the work) finish them; team kernels: one pass, contact path inside
+    if (pass == 2 && b->n <= TEAM_LIST_MAX) break;
+    const Frz fz = pass ? frz_resume(b, 0, pass == 1) : frz_fast(b, 0);
 #define SO101_STEP(TT, SS, MD, mdl) \
   k_step<TT, SS, MD><<<grid, blk, 0, st>>>(b->dm_##mdl, v, (const TT*)ctrl, n_ctrl, n_substeps, (float*)obs, b->stats, fz)
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
       if (split) { SO101_STEP(double, true, MODE_INLINE, d); }
-      else if (pass) { resume_shape(b, blk, grid); SO101_STEP(double, false, MODE_RESUME, d); }
+      else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_STEP(double, true, MODE_RESUME, d); }
+      else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_STEP(double, false, MODE_RESUME, d); }
       else SO101_STEP(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
       if (split) { SO101_STEP(float, true, MODE_INLINE, f); }
-      else if (pass) { resume_shape(b, blk, grid); SO101_STEP(float, false, MODE_RESUME, f); }
+      else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_STEP(float, true, MODE_RESUME, f); }
+      else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_STEP(float, false, MODE_RESUME, f); }
       else SO101_STEP(float, false, MODE_FREEZE, f);
     }
 #undef SO101_STEP
@@ -987,20 +1016,23 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
   int blk; unsigned grid; bool split;
   const bool r32 = flags & SO101_ROLL_ROWS_F32;
   CUDA_TRY(frz_begin(b, chunk, st));
-  for (int pass = 0; pass < 2; pass++) {
-    const Frz fz = pass ? frz_resume(b, chunk) : frz_fast(b, chunk);
+  for (int pass = 0; pass < 3; pass++) {
+    if (pass == 2 && b->n <= TEAM_LIST_MAX) break;
+    const Frz fz = pass ? frz_resume(b, chunk, pass == 1) : frz_fast(b, chunk);
 #define SO101_ROLL(TT, RR, SS, MD, mdl) \
   k_rollout<TT, RR, SS, MD><<<grid, blk, 0, st>>>(b->dm_##mdl, v, ds, t0, t1, T, frame_skip, (RR*)rows, flags, b->stats, fz)
 #define SO101_ROLL_ROWS(TT, SS, MD, mdl) do { if (r32) SO101_ROLL(TT, float, SS, MD, mdl); else SO101_ROLL(TT, double, SS, MD, mdl); } while (0)
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
       if (split) SO101_ROLL_ROWS(double, true, MODE_INLINE, d);
-      else if (pass) { resume_shape(b, blk, grid); SO101_ROLL_ROWS(double, false, MODE_RESUME, d); }
+      else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_ROLL_ROWS(double, true, MODE_RESUME, d); }
+      else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_ROLL_ROWS(double, false, MODE_RESUME, d); }
       else SO101_ROLL_ROWS(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
       if (split) SO101_ROLL_ROWS(float, true, MODE_INLINE, f);
-      else if (pass) { resume_shape(b, blk, grid); SO101_ROLL_ROWS(float, false, MODE_RESUME, f); }
+      else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_ROLL_ROWS(float, true, MODE_RESUME, f); }
+      else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_ROLL_ROWS(float, false, MODE_RESUME, f); }
       else SO101_ROLL_ROWS(float, false, MODE_FREEZE, f);
     }
 #undef SO101_ROLL_ROWS
@@ -1155,19 +1187,22 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
   std::memcpy(s0.v, state0, sizeof s0.v);
   int blk; unsigned grid; bool split;
   CUDA_TRY(frz_begin(b, 0, st));
-  for (int pass = 0; pass < 2; pass++) {
-    const Frz fz = pass ? frz_resume(b, 0) : frz_fast(b, 0);
+  for (int pass = 0; pass < 3; pass++) {
+    if (pass == 2 && b->n <= TEAM_LIST_MAX) break;
+    const Frz fz = pass ? frz_resume(b, 0, pass == 1) : frz_fast(b, 0);
 #define SO101_SHOOT(TT, SS, MD, mdl) \
   k_shoot<TT, SS, MD><<<grid, blk, 0, st>>>(b->dm_##mdl, v, s0, (const TT*)U, H, frame_skip, (float*)X, flags, b->stats, fz)
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
       if (split) { SO101_SHOOT(double, true, MODE_INLINE, d); }
-      else if (pass) { resume_shape(b, blk, grid); SO101_SHOOT(double, false, MODE_RESUME, d); }
+      else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_SHOOT(double, true, MODE_RESUME, d); }
+      else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_SHOOT(double, false, MODE_RESUME, d); }
       else SO101_SHOOT(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
       if (split) { SO101_SHOOT(float, true, MODE_INLINE, f); }
-      else if (pass) { resume_shape(b, blk, grid); SO101_SHOOT(float, false, MODE_RESUME, f); }
+      else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_SHOOT(float, true, MODE_RESUME, f); }
+      else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_SHOOT(float, false, MODE_RESUME, f); }
       else SO101_SHOOT(float, false, MODE_FREEZE, f);
     }
 #undef SO101_SHOOT
