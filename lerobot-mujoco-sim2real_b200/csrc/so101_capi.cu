@@ -45,7 +45,7 @@ template <typename T> SO101_DEV SplitXch<T>& xch_of(XchStorage<T, true>& st) { r
 template <typename T> SO101_DEV SplitXch<T>& xch_of(XchStorage<T, false>& st) { return *reinterpret_cast<SplitXch<T>*>(&st); }
 
 // helper roles of a SPLIT kernel: pick up the initial state, then shadow `nsteps` physics steps
-template <typename T>
+template <typename T, int CM>
 SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps, int frame_skip) {
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const bool trip = m.ntrip > 0;
@@ -60,7 +60,7 @@ SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps,
     int ss = 0;
 #pragma unroll 1
     for (int64_t n = 0; n < nsteps; n++) {
-      split_lookout_step(m, x, lane, q, qd, ss == frame_skip - 1, trip);
+      split_lookout_step<T, CM>(m, x, lane, q, qd, ss == frame_skip - 1, trip);
       if (++ss == frame_skip) ss = 0;
     }
   }
@@ -348,7 +348,7 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   bool active, exit_block;
   const int64_t i = env_slot<T, SPLIT, RESUME>(s, fz, active, exit_block);
   if (exit_block) return;
-  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, nsub, nsub); return; }
+  if (SPLIT && threadIdx.x >= 32) { helper_role<T, CM>(m, xch, nsub, nsub); return; }
   Env<T> e;
   load_env(s, i, e);
   if (!RESUME && fz.clear) e.flags &= ~SO101_FLAG_FROZEN;
@@ -411,7 +411,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
     const int tb = s_first / frame_skip - 1;
     if (tb > t0) t0 = tb;
   }
-  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)(t1 - t0) * frame_skip, frame_skip); return; }
+  if (SPLIT && threadIdx.x >= 32) { helper_role<T, CM>(m, xch, (int64_t)(t1 - t0) * frame_skip, frame_skip); return; }
   const int64_t env = spec.env_offset + i;
   Env<T> e;
   if (RESUME || (rflags & SO101_ROLL_NO_RESET)) {
@@ -489,7 +489,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   bool active, exit_block;
   const int64_t i = env_slot<T, SPLIT, RESUME>(s, fz, active, exit_block);
   if (exit_block) return;
-  if (SPLIT && threadIdx.x >= 32) { helper_role(m, xch, (int64_t)H * frame_skip, frame_skip); return; }
+  if (SPLIT && threadIdx.x >= 32) { helper_role<T, CM>(m, xch, (int64_t)H * frame_skip, frame_skip); return; }
   Env<T> e;
   if (RESUME) {
     load_env(s, i, e);

@@ -480,70 +480,76 @@ struct Con3 {
   T D, c0, vn, vy, vx;          // row weight, -K imp (dist - margin), J . qvel
 };
 
+// Geometry half: world frames from the joint sines / cosines (element stride `st`: 1 = thread-local arrays, 32 = the
+// team's shared memory), exact hull test of every box in `hits`, Jacobian rows and row constants of the contacts found.
 template <typename T>
-SO101_DEV int contact_fast(const DevModel<T>& m, const T (&q)[NV], const T (&qd)[NV], const T (&warm)[NV], uint32_t hits,
-                           const T (&Mm)[21], const T (&fsm)[NV], const Rows<T>& rw, T (&a)[NV], T (&qc)[NV],
-                           uint32_t& flags, Counters& cnt) {
-  Con3<T> con[MAXCON];
+SO101_DEV int contact_geometry(const DevModel<T>& m, const T* sn, const T* cs, int st, const T (&qd)[NV], uint32_t hits,
+                               Con3<T>* con, uint32_t& flags) {
   int ncon = 0;
-  {
-    T axw[NV][3], anw[NV][3];
-    T Rw[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, ow[3] = {T(0), T(0), T(0)};
+  T axw[NV][3], anw[NV][3];
+  T Rw[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, ow[3] = {T(0), T(0), T(0)};
 #pragma unroll 1
-    for (int k = 0; k < NV; k++) {
-      T s_, c_, R[9], Rn[9], o[3];
-      sincos_(q[k] - m.qpos0[k], &s_, &c_);
-      make_R(m.E[k], c_, s_, R);
-      rot(Rw, m.r[k], o);
-      ow[0] += o[0]; ow[1] += o[1]; ow[2] += o[2];
+  for (int k = 0; k < NV; k++) {
+    T R[9], Rn[9], o[3];
+    make_R(m.E[k], cs[k * st], sn[k * st], R);
+    rot(Rw, m.r[k], o);
+    ow[0] += o[0]; ow[1] += o[1]; ow[2] += o[2];
 #pragma unroll
-      for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++)
 #pragma unroll
-        for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rw[3 * i] * R[j] + Rw[3 * i + 1] * R[3 + j] + Rw[3 * i + 2] * R[6 + j];
+      for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rw[3 * i] * R[j] + Rw[3 * i + 1] * R[3 + j] + Rw[3 * i + 2] * R[6 + j];
 #pragma unroll
-      for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
-      axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
-      anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
+    for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
+    axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
+    anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
+    if (!(hits >> (k * TRIP_PER_LINK) & 7u)) continue;
 #pragma unroll 1
-      for (int b = 0; b < m.trip_n[k]; b++) {
-        if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
-        const T d[3] = {m.con_tilt[k][0] - Rw[6], m.con_tilt[k][1] - Rw[7], m.con_tilt[k][2] - Rw[8]};
-        T v[3];
-        hull_support(m, m.trip_geom[k][b], d, v);
-        const T zmin = ow[2] + (Rw[6] * v[0] + Rw[7] * v[1] + Rw[8] * v[2]);
-        const T dist = zmin - m.trip_z;
-        if (!(dist < m.con_margin)) continue;
-        T p[3];
-        rot(Rw, v, p);
-        p[0] += ow[0]; p[1] += ow[1]; p[2] = zmin - T(0.5) * dist;
-        if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
-          flags |= SO101_FLAG_TRIP_TABLE;
-          continue;
-        }
-        Con3<T>& c = con[ncon++];
-        c.vn = c.vy = c.vx = T(0);
-#pragma unroll 1
-        for (int j = 0; j < NV; j++) {
-          T jn = T(0), jy = T(0), jx = T(0);
-          if (j <= k) {
-            const T rx = p[0] - anw[j][0], ry = p[1] - anw[j][1], rz = p[2] - anw[j][2];
-            jx = -(axw[j][1] * rz - axw[j][2] * ry);
-            jy = axw[j][2] * rx - axw[j][0] * rz;
-            jn = axw[j][0] * ry - axw[j][1] * rx;
-          }
-          c.Jn[j] = jn; c.Jy[j] = jy; c.Jx[j] = jx;
-          c.vn += jn * qd[j]; c.vy += jy * qd[j]; c.vx += jx * qd[j];
-        }
-        const T imp = limit_impedance(m.con_imp, dist, m.con_margin);
-        const T mu = m.con_mu;
-        const T R1 = max_(T(MJ_MINVAL), (T(1) - imp) * (m.con_tran[k] + mu * mu * m.con_tran[k]) / imp);
-        c.D = T(1) / (T(2) * mu * mu * R1);
-        c.c0 = -m.con_K * imp * (dist - m.con_margin);
+    for (int b = 0; b < m.trip_n[k]; b++) {
+      if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
+      // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
+      // ordered deterministically (same rule as the oracle's collision())
+      const T d[3] = {m.con_tilt[k][0] - Rw[6], m.con_tilt[k][1] - Rw[7], m.con_tilt[k][2] - Rw[8]};
+      T v[3];
+      hull_support(m, m.trip_geom[k][b], d, v);
+      const T zmin = ow[2] + (Rw[6] * v[0] + Rw[7] * v[1] + Rw[8] * v[2]);
+      const T dist = zmin - m.trip_z;
+      if (!(dist < m.con_margin)) continue;
+      T p[3];
+      rot(Rw, v, p);
+      p[0] += ow[0]; p[1] += ow[1]; p[2] = zmin - T(0.5) * dist;
+      if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
+        flags |= SO101_FLAG_TRIP_TABLE;   // an edge of the table, or more contacts than rows: not simulated
+        continue;
       }
+      Con3<T>& c = con[ncon++];
+      c.vn = c.vy = c.vx = T(0);
+#pragma unroll 1
+      for (int j = 0; j < NV; j++) {
+        T jn = T(0), jy = T(0), jx = T(0);
+        if (j <= k) {
+          const T rx = p[0] - anw[j][0], ry = p[1] - anw[j][1], rz = p[2] - anw[j][2];
+          jx = -(axw[j][1] * rz - axw[j][2] * ry);
+          jy = axw[j][2] * rx - axw[j][0] * rz;
+          jn = axw[j][0] * ry - axw[j][1] * rx;
+        }
+        c.Jn[j] = jn; c.Jy[j] = jy; c.Jx[j] = jx;
+        c.vn += jn * qd[j]; c.vy += jy * qd[j]; c.vx += jx * qd[j];
+      }
+      const T imp = limit_impedance(m.con_imp, dist, m.con_margin);
+      const T mu = m.con_mu;
+      const T R1 = max_(T(MJ_MINVAL), (T(1) - imp) * (m.con_tran[k] + mu * mu * m.con_tran[k]) / imp);
+      c.D = T(1) / (T(2) * mu * mu * R1);
+      c.c0 = -m.con_K * imp * (dist - m.con_margin);
     }
   }
-  if (ncon == 0) return 0;
-  flags |= SO101_FLAG_CONTACT;
+  return ncon;
+}
+
+// Solve half: direct active-set iteration over friction, limit and contact rows.  1 = solved (a, qc set), 2 = did not
+// settle (the caller takes contact_solve's safeguarded Newton).
+template <typename T>
+SO101_DEV int contact_active_set(const DevModel<T>& m, const Con3<T>* con, int ncon, const T (&warm)[NV], const T (&Mm)[21],
+                                 const T (&fsm)[NV], const Rows<T>& rw, T (&a)[NV], T (&qc)[NV], Counters& cnt) {
   const T mu = m.con_mu;
   // pieces: friction zones (quadratic / saturated positive), limit rows, 4 bits per contact
   uint32_t zq = 0, zp = 0, zl = 0, zc = 0;

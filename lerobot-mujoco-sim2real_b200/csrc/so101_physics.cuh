@@ -938,14 +938,21 @@ SO101_DEV void newton_exact_finish(const DevModel<T>& m, const Rows<T>& rw, cons
 #include "so101_contact.cuh"
 namespace so101 {
 
-// the caller's side of the contact path: copies in, call, copies out (see ContactIO)
+// the caller's side of the contact path.  sn / cs: joint sines / cosines (stride st); con / ncon: the contacts if the
+// geometry half has already run elsewhere (the team's lookout warp), else ncon < 0 and it runs here.  Falls back to the
+// out-of-line general solver (copies in, call, copies out: see ContactIO) when the active-set iteration does not settle.
 template <typename T>
-SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, const T (&M)[21], const T (&fsm)[NV],
-                              const Rows<T>& rw, T (&a)[NV], T (&qc)[NV], Counters& cnt) {
-  {   // fast path: settles in a couple of active-set attempts in all but a few steps per million
-    const int r = contact_fast<T>(m, e.q, e.qd, e.warm, hits, M, fsm, rw, a, qc, e.flags, cnt);
-    if (r != 2) return r == 1;
+SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, const T* sn, const T* cs, int st,
+                              Con3<T>* con, int ncon, const T (&M)[21], const T (&fsm)[NV], const Rows<T>& rw,
+                              T (&a)[NV], T (&qc)[NV], Counters& cnt) {
+  if (ncon < 0) {
+    uint32_t fl = 0;
+    ncon = contact_geometry<T>(m, sn, cs, st, e.qd, hits, con, fl);
+    e.flags |= fl;
   }
+  if (ncon == 0) return false;
+  e.flags |= SO101_FLAG_CONTACT;
+  if (contact_active_set<T>(m, con, ncon, e.warm, M, fsm, rw, a, qc, cnt) == 1) return true;
   ContactIO<T> io;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
@@ -1002,11 +1009,12 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   T M[21], bias[NV];
+  T sn[NV], cs[NV];    // joint sines / cosines (the contact path of the CM_SOLVE kernels reads them again)
   uint32_t hits = 0;   // tripwire boxes below the table top
   if (!frozen_in) {
 #if SO101_ONEWARP_ROLLED   // experiment: the compact link loops of the team kernels in the one-warp kernels (see profiles/README.md)
   {
-    T sn[NV], cs[NV], lq[NV], lqd[NV];
+    T lq[NV], lqd[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) { lq[i] = e.q[i]; lqd[i] = e.qd[i]; }
     joint_sincos_range(m, lq, 1, sn, cs, 1, 0, NV);
@@ -1017,7 +1025,6 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   }
 #else
   {
-    T sn[NV], cs[NV];
     joint_sincos(m, e.q, sn, cs);
     smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags, hits);
   }
@@ -1050,10 +1057,12 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     // a collision box is below the table top: exact hull test and, if a hull does touch, the full constraint solve with
     // contact rows - out of line (so101_contact.cuh); the phase machine then only runs its Euler solve
     bool in_contact = false;
-    if (m.con_enabled)
-      in_contact = contact_branch<T>(m, e, hits, M, fsm, rw, a, qc, cnt);
-    else
+    if (m.con_enabled) {
+      Con3<T> con[MAXCON];
+      in_contact = contact_branch<T>(m, e, hits, sn, cs, 1, con, -1, M, fsm, rw, a, qc, cnt);
+    } else {
       e.flags |= SO101_FLAG_TRIP_TABLE;
+    }
     if (in_contact) {
       bool bad = false;
 #pragma unroll
@@ -1277,6 +1286,8 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 // selects never changes a trajectory.
 // ------------------------------------------------------------------------------------------
 constexpr int TEAM_WARPS = 3;
+constexpr int XCON = 2, XCON_MANY = 255;
+constexpr int CON3_N = 3 * NV + 5;     // Con3 as a flat array: Jn, Jy, Jx, D, c0, vn, vy, vx
 template <typename T>
 struct SplitXch {      // shared memory of one team, structure-of-arrays over the 32 lanes
   T sn[NV][32], cs[NV][32];
@@ -1285,6 +1296,11 @@ struct SplitXch {      // shared memory of one team, structure-of-arrays over th
   T L2[15][32], D2inv[NV][32];   // M + h B = L2 D2 L2^T
   T site[3][32];
   uint32_t trip[32], hits[32];   // TRIP_SELF flag / tripwire boxes below the table top (lookout warp)
+  // contact kernels: the lookout warp runs the geometry half of the contact path (exact hull test, Jacobian rows) beside
+  // the dynamics warp's RNEA and hands over up to XCON contacts per env; ncon = XCON_MANY: more than that, the dynamics
+  // warp computes them itself
+  uint32_t ncon[32];
+  T con[XCON][CON3_N][32];
   T q[NV][32], qd[NV][32];       // state handed back by the dynamics warp
 };
 
@@ -1365,7 +1381,7 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 }
 
 // lookout warp: contact tripwire and (on the last substep of a control step) the observation site
-template <typename T>
+template <typename T, int CM>
 SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
                                   bool want_site, bool trip) {
   team_check_state(m, q, qd);
@@ -1376,6 +1392,27 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
 #pragma unroll
     for (int i = 0; i < NV; i++) lq[i] = q[i];
     tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
+  }
+  if (CM == CM_SOLVE) {
+    uint32_t nc = 0;
+    if (hits && m.con_enabled) {
+      Con3<T> con[MAXCON];
+      nc = (uint32_t)contact_geometry<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, qd, hits, con, fl);
+      if (nc > (uint32_t)XCON) {
+        nc = XCON_MANY;
+      } else {
+#pragma unroll 1
+        for (uint32_t c = 0; c < nc; c++) {
+#pragma unroll
+          for (int j = 0; j < NV; j++) {
+            x.con[c][j][lane] = con[c].Jn[j]; x.con[c][NV + j][lane] = con[c].Jy[j]; x.con[c][2 * NV + j][lane] = con[c].Jx[j];
+          }
+          x.con[c][3 * NV][lane] = con[c].D; x.con[c][3 * NV + 1][lane] = con[c].c0;
+          x.con[c][3 * NV + 2][lane] = con[c].vn; x.con[c][3 * NV + 3][lane] = con[c].vy; x.con[c][3 * NV + 4][lane] = con[c].vx;
+        }
+      }
+    }
+    x.ncon[lane] = nc;
   }
   x.trip[lane] = fl;
   x.hits[lane] = hits;
@@ -1449,10 +1486,27 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
   if (CM == CM_SOLVE && trip && x.hits[lane]) {        // table contact (see physics_step)
-    if (m.con_enabled)
-      solved = contact_branch<T>(m, e, x.hits[lane], M, fsm, rw, a, qc, cnt);
-    else
+    if (m.con_enabled) {
+      const uint32_t nc = x.ncon[lane];
+      if (nc) {
+        Con3<T> con[MAXCON];
+        if (nc != (uint32_t)XCON_MANY) {
+#pragma unroll 1
+          for (uint32_t c = 0; c < nc; c++) {
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+              con[c].Jn[j] = x.con[c][j][lane]; con[c].Jy[j] = x.con[c][NV + j][lane]; con[c].Jx[j] = x.con[c][2 * NV + j][lane];
+            }
+            con[c].D = x.con[c][3 * NV][lane]; con[c].c0 = x.con[c][3 * NV + 1][lane];
+            con[c].vn = x.con[c][3 * NV + 2][lane]; con[c].vy = x.con[c][3 * NV + 3][lane]; con[c].vx = x.con[c][3 * NV + 4][lane];
+          }
+        }
+        solved = contact_branch<T>(m, e, x.hits[lane], &x.sn[0][lane], &x.cs[0][lane], 32, con,
+                                   nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, a, qc, cnt);
+      }
+    } else {
       e.flags |= SO101_FLAG_TRIP_TABLE;
+    }
   }
   if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     // zone guess from qacc_smooth approximated with the factor of the previous step's M (split_geometry_step)
