@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "so101_capi.cu")
 DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("so101_physics.cuh", "so101_model.h", "so101_koopman.cuh",
-                                                        "so101_ik.cuh")] + [os.path.join(ROOT, "include", "so101_b200.h")]
+                                                        "so101_ik.cuh", "so101_contact.cuh")] + [os.path.join(ROOT, "include", "so101_b200.h")]
 LIB = os.path.join(HERE, "libso101_b200.so")
 
 

@@ -601,7 +601,7 @@ struct So101Batch {
   cudaStream_t s_up, s_down;
   cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
   // explicit experiment options (so101_batch_set_option); 0 = automatic.  Nothing on this path reads the environment.
-  int opt_family, opt_block, opt_host_chunks, opt_host_even;
+  int opt_family, opt_block, opt_host_chunks, opt_host_even, opt_contact;
 };
 
 struct DeviceGuard {
@@ -664,6 +664,11 @@ template <typename T> static StateView<T> step_view(const So101Batch* b, int& bl
 
 // ---- freeze / resume launches ----------------------------------------------------------------------------------------
 static bool has_contact(const So101Batch* b) { return b->dm_d.con_enabled != 0; }
+// one-warp kernels: contact inside the stepping kernel (default) or freeze-and-resume (SO101_OPT_CONTACT_MODE = 2); the
+// team kernels always handle it inside.  Measured on B200 (tools/contact_perf.py, profiles/README.md): in-kernel wins
+// wherever more than a handful of envs touch the table, because the contact kernel of freeze-and-resume is a small,
+// latency-bound launch that cannot overlap the fast kernel (which fills every SM's register file).
+static bool contact_inline(const So101Batch* b) { return b->opt_contact != 2; }
 // Frz of a fast launch (chunk = index of the time chunk within the API call; chunk 0 clears stale FROZEN bits)
 static Frz frz_fast(const So101Batch* b, int chunk) {
   Frz f;
@@ -858,6 +863,10 @@ int so101_batch_set_option(So101Batch* b, int option, int value) {
     case SO101_OPT_HOST_EVEN:
       b->opt_host_even = value != 0;
       return SO101_OK;
+    case SO101_OPT_CONTACT_MODE:
+      if (value < 0 || value > 2) return fail(SO101_EINVAL, "contact mode must be 0 (auto), 1 (in-kernel) or 2 (freeze and resume)");
+      b->opt_contact = value;
+      return SO101_OK;
     default:
       return fail(SO101_EINVAL, "unknown option");
   }
@@ -927,19 +936,21 @@ int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
       if (split) { SO101_STEP(double, true, MODE_INLINE, d); }
+      else if (contact_inline(b)) { SO101_STEP(double, false, MODE_INLINE, d); }
       else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_STEP(double, true, MODE_RESUME, d); }
       else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_STEP(double, false, MODE_RESUME, d); }
       else SO101_STEP(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
       if (split) { SO101_STEP(float, true, MODE_INLINE, f); }
+      else if (contact_inline(b)) { SO101_STEP(float, false, MODE_INLINE, f); }
       else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_STEP(float, true, MODE_RESUME, f); }
       else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_STEP(float, false, MODE_RESUME, f); }
       else SO101_STEP(float, false, MODE_FREEZE, f);
     }
 #undef SO101_STEP
     CUDA_TRY(cudaGetLastError());
-    if (split || !has_contact(b)) break;
+    if (split || contact_inline(b) || !has_contact(b)) break;
     if (!pass) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
   }
   return SO101_OK;
@@ -1025,12 +1036,14 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
       if (split) SO101_ROLL_ROWS(double, true, MODE_INLINE, d);
+      else if (contact_inline(b)) SO101_ROLL_ROWS(double, false, MODE_INLINE, d);
       else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_ROLL_ROWS(double, true, MODE_RESUME, d); }
       else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_ROLL_ROWS(double, false, MODE_RESUME, d); }
       else SO101_ROLL_ROWS(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
       if (split) SO101_ROLL_ROWS(float, true, MODE_INLINE, f);
+      else if (contact_inline(b)) SO101_ROLL_ROWS(float, false, MODE_INLINE, f);
       else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_ROLL_ROWS(float, true, MODE_RESUME, f); }
       else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_ROLL_ROWS(float, false, MODE_RESUME, f); }
       else SO101_ROLL_ROWS(float, false, MODE_FREEZE, f);
@@ -1038,7 +1051,7 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
 #undef SO101_ROLL_ROWS
 #undef SO101_ROLL
     CUDA_TRY(cudaGetLastError());
-    if (split || !has_contact(b)) break;
+    if (split || contact_inline(b) || !has_contact(b)) break;
     if (!pass) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap + chunk); CUDA_TRY(cudaGetLastError()); }
   }
   return SO101_OK;
@@ -1195,19 +1208,21 @@ int so101_batch_shoot(So101Batch* b, const double* state0, const void* U, int H,
     if (b->dtype == SO101_F64) {
       StateView<double> v = step_view<double>(b, blk, grid, split);
       if (split) { SO101_SHOOT(double, true, MODE_INLINE, d); }
+      else if (contact_inline(b)) { SO101_SHOOT(double, false, MODE_INLINE, d); }
       else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_SHOOT(double, true, MODE_RESUME, d); }
       else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_SHOOT(double, false, MODE_RESUME, d); }
       else SO101_SHOOT(double, false, MODE_FREEZE, d);
     } else {
       StateView<float> v = step_view<float>(b, blk, grid, split);
       if (split) { SO101_SHOOT(float, true, MODE_INLINE, f); }
+      else if (contact_inline(b)) { SO101_SHOOT(float, false, MODE_INLINE, f); }
       else if (pass == 1) { resume_shape(b, true, blk, grid); SO101_SHOOT(float, true, MODE_RESUME, f); }
       else if (pass == 2) { resume_shape(b, false, blk, grid); SO101_SHOOT(float, false, MODE_RESUME, f); }
       else SO101_SHOOT(float, false, MODE_FREEZE, f);
     }
 #undef SO101_SHOOT
     CUDA_TRY(cudaGetLastError());
-    if (split || !has_contact(b)) break;
+    if (split || contact_inline(b) || !has_contact(b)) break;
     if (!pass) { k_snapshot<<<1, 1, 0, st>>>(b->frz_count, b->frz_snap); CUDA_TRY(cudaGetLastError()); }
   }
   return SO101_OK;

@@ -44,3 +44,13 @@ def oracle_mod():
     O.build()
     O.set_hulls(T.builtin_hulls())
     return O
+
+
+@pytest.fixture()
+def contact_free(oracle_mod):
+    """For tests of the contact-free pipeline (joint limits, fp32 tolerances, round-1 tripwire semantics): the oracle
+    without hull data for the duration of the test; build the CUDA envs with `hulls=None` to match."""
+    from lerobot_mujoco_sim2real_b200 import tables as T
+    oracle_mod.set_hulls(None)
+    yield oracle_mod
+    oracle_mod.set_hulls(T.builtin_hulls())

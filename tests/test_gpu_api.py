@@ -104,9 +104,10 @@ def test_shoot_matches_oracle(oracle_mod, tables_v):
     assert np.abs(X - env.shoot(s0, torch.as_tensor(U).cuda().contiguous(), flags=0).cpu().numpy()).max() > 1e-4
 
 
-def test_joint_limits_teacher_forced(oracle_mod, tables_v):
-    """States beyond / inside the 1 mm impedance ramp of joint limits: limit rows vs the oracle."""
-    O = oracle_mod
+def test_joint_limits_teacher_forced(contact_free, tables_v):
+    """States beyond / inside the 1 mm impedance ramp of joint limits: limit rows vs the oracle (contact-free pipeline
+    on both sides: a joint at its limit puts half the arm through the table, tests/test_contact.py covers that)."""
+    O = contact_free
     from lerobot_mujoco_sim2real_b200 import tables as T_
     t = tables_v
     n = 2048
@@ -122,7 +123,7 @@ def test_joint_limits_teacher_forced(oracle_mod, tables_v):
     ctrl = rng.uniform(-2.5, 2.5, (n, 6))
     ref, _, aux = O.step_batch(t, state, ctrl, 1)
     assert (aux[:, 2] >= 7).all()
-    env = _vec(t, n)
+    env = _vec(t, n, hulls=None)
     env.set_state(state[:, :6], state[:, 6:12], state[:, 12:])
     env.step_soa(torch.as_tensor(ctrl.T.copy()).cuda().contiguous(), 1)
     q, v, w = [x.cpu().numpy() for x in env.get_state()]
@@ -253,6 +254,10 @@ def test_data_generator_never_returns_flagged_trajectories(tables_v, tmp_path):
         data_dir_save=str(d), data_dir_load_train=str(d / "train_data_64_2.npy"),
         data_dir_load_val=str(d / "val_data_400_200.npy"))
     BAD = SOARM101DataGenerator.BAD_FLAGS
+    # tables WITHOUT contact parameters: the kernels only flag table contacts (with them they are simulated and a flag
+    # is the exception: an edge of the table, the self-collision box), which gives this test plenty to replace
+    tables_v = T_.tables_from_dict(T_.tables_to_dict(tables_v))
+    tables_v.con_enabled = 0
     keep = SOARM101DataGenerator(args, tables=tables_v, on_contact="keep")
     raw = keep.generate_physics_based_data(400, 200, "chirp", seed=5)          # long chirp runs do leave the safe region
     flags = keep.last_flags.copy()
@@ -296,17 +301,17 @@ def test_env_step_reports_abnormal_flags_in_info(tables_v):
     assert np.array_equal(fl.astype(np.int32), env.flags().cpu().numpy())
 
 
-def test_fp32_free_running_scene_b(oracle_mod, tables_p):
+def test_fp32_free_running_scene_b(contact_free, tables_p):
     """fp32 mode, stated tolerance: 1000 physics steps on the contractive scene within 5e-6 rad / 1e-4 rad/s
-    (measured 3.5e-7 / 4.1e-6)."""
-    O = oracle_mod
+    (measured 3.5e-7 / 4.1e-6); contact-free pipeline on both sides."""
+    O = contact_free
     from lerobot_mujoco_sim2real_b200 import tables as T_
     n, T = 512, 100
     rng = np.random.default_rng(6)
     q0 = np.zeros((n, 6)); q0[:, :5] = rng.uniform(-0.3, 0.3, (n, 5))
     U = np.cumsum(rng.uniform(-0.05, 0.05, (T + 1, 5, n)), axis=0) + q0[:, :5].T[None]
     _, fin, _ = O.rollout(tables_p, O.make_spec(kind=3, u=np.ascontiguousarray(U)), n, T, 10, qpos0=q0, want_rows=False)
-    env = _vec(tables_p, n, dtype="float32")
+    env = _vec(tables_p, n, dtype="float32", hulls=None)
     env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
     env.rollout(T, "tensor", u=torch.as_tensor(U, dtype=torch.float32).cuda().contiguous(), flags=T_.ROLL_NO_RESET)
     q, v, _ = env.get_state()
@@ -323,15 +328,17 @@ def test_fma_peak_is_plausible():
 
 
 def test_contact_tripwire_flags(tables_v):
-    """TRIP_TABLE <=> some collision box below the table plane (numpy restatement); TRIP_SELF <=> q
-    outside the certified joint box.  Evaluated at the pose the step starts from."""
+    """Without hull data (no contact path): TRIP_TABLE <=> some collision box below the table plane (numpy
+    restatement); TRIP_SELF <=> q outside the certified joint box.  Evaluated at the pose the step starts from.  With
+    hull data the same boxes select the hulls that get the exact test, and TRIP_TABLE is left for contacts the kernels
+    cannot represent (tests/test_contact.py)."""
     from lerobot_mujoco_sim2real_b200 import tables as T_, tripwire
     t = tables_v
     n = 4096
     rng = np.random.default_rng(8)
     q = rng.uniform(-1.0, 1.0, (n, 6)); q[:, 5] = np.clip(q[:, 5], -0.17, None)
     q[: n // 4, :5] = rng.uniform(-0.3, 0.3, (n // 4, 5)); q[: n // 4, 5] = 0     # the reset box
-    env = _vec(t, n)
+    env = _vec(t, n, hulls=None)
     env.set_state(q, np.zeros((n, 6)), np.zeros((n, 6)))
     env.clear_flags()
     env.step_soa(torch.zeros((5, n), dtype=torch.float64, device="cuda"), 1)

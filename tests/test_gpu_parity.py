@@ -162,10 +162,11 @@ def test_p2_free_running_scene_a_curve(oracle_mod, tables_v):
         assert b <= max(1e-12, 100 * a), (s, a, b)
 
 
-def test_free_running_against_joint_limits_scene_b(oracle_mod, tables_p):
+def test_free_running_against_joint_limits_scene_b(contact_free, tables_p):
     """Position targets far beyond the joint ranges (ctrl clamp, force clamp, limit rows active for
-    hundreds of steps): free-running agreement with the oracle on the contractive scene."""
-    O = oracle_mod
+    hundreds of steps): free-running agreement with the oracle on the contractive scene (contact-free pipeline on both
+    sides; resting on the table under load is tests/test_contact.py's free-running case)."""
+    O = contact_free
     from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
     from lerobot_mujoco_sim2real_b200 import tables as T
     n, T_ctrl = 256, 60
@@ -175,7 +176,7 @@ def test_free_running_against_joint_limits_scene_b(oracle_mod, tables_p):
     U += rng.uniform(-0.01, 0.01, U.shape)
     spec = O.make_spec(kind=3, u=np.ascontiguousarray(U))
     _, fin, _ = O.rollout(tables_p, spec, n, T_ctrl, 10, qpos0=q0, want_rows=False)
-    env = SOARM101VecEnv(tables=tables_p, num_envs=n, dtype="float64")
+    env = SOARM101VecEnv(tables=tables_p, num_envs=n, dtype="float64", hulls=None)
     env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
     env.rollout(T_ctrl, "tensor", u=torch.as_tensor(U).cuda().contiguous(), flags=T.ROLL_NO_RESET)
     q, v, _ = env.get_state()
