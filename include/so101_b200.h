@@ -243,9 +243,7 @@ enum {
   SO101_OPT_KERNEL_FAMILY = 0,  /* SO101_FAMILY_*: force the one-warp or the three-warp team kernels           */
   SO101_OPT_BLOCK         = 1,  /* threads per block of the one-warp kernels (multiple of 32, <= launch bound)  */
   SO101_OPT_HOST_CHUNKS   = 2,  /* pipeline depth of so101_batch_rollout_host, 1..12                            */
-  SO101_OPT_HOST_EVEN     = 3,  /* 1: equal time chunks in so101_batch_rollout_host                             */
-  SO101_OPT_CONTACT_MODE  = 4   /* one-warp kernels: 1 = contact path inside the stepping kernel, 2 = freeze the envs
-                                   that reach the table and finish them in the contact kernel; 0 = the default      */
+  SO101_OPT_HOST_EVEN     = 3   /* 1: equal time chunks in so101_batch_rollout_host                             */
 };
 enum { SO101_FAMILY_AUTO = 0, SO101_FAMILY_ONEWARP = 1, SO101_FAMILY_TEAM = 2 };
 int so101_batch_set_option(So101Batch* b, int option, int value);
@@ -261,6 +259,11 @@ int so101_batch_forward(So101Batch* b, void* obs, void* qfrc_bias, void* stream)
 /* ctrl [6][N] (row 5 = gripper; NULL row pointer semantics: pass n_ctrl=5 to hold it at 0);
    n_substeps x mj_step; obs float32 [8][N] with the reference's one-sub-step ee lag. */
 int so101_batch_step(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps, void* obs, void* stream);
+/* the same with flags: SO101_ROLL_GRAVCOMP_HOLD = qfrc_applied <- qfrc_bias of the state the env step starts from, held
+   over its sub-steps - the gravity compensation line of the reference's control loops
+   [REF Koopman_MPC.py:119 `data.qfrc_applied[:] = data.qfrc_bias[:]`] fused into the step launch */
+int so101_batch_step_flags(So101Batch* b, const void* ctrl, int n_ctrl, int n_substeps, void* obs, uint32_t flags,
+                           void* stream);
 /* host-buffer variants: pinned or pageable host pointers, H2D + kernel + D2H on `stream`,
    stream synchronised before return.  These are what SOARM101Env.step()/reset() call.
    flags_host (nullable): receives the per-env status words [N] with the observation (one sync). */

@@ -20,7 +20,7 @@ EXPORTS = [
     "so101_model_create", "so101_model_destroy", "so101_model_set_hulls",
     "so101_batch_state_bytes", "so101_batch_create", "so101_batch_destroy",
     "so101_batch_reset", "so101_batch_reset_random", "so101_batch_forward",
-    "so101_batch_step", "so101_batch_step_host", "so101_batch_reset_host",
+    "so101_batch_step", "so101_batch_step_flags", "so101_batch_step_host", "so101_batch_reset_host",
     "so101_batch_rollout", "so101_batch_rollout_host", "so101_batch_shoot",
     "so101_batch_get_state", "so101_batch_set_state", "so101_batch_set_qfrc_applied",
     "so101_batch_get_flags", "so101_batch_clear_flags", "so101_batch_stats", "so101_batch_set_option",
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
     L.so101_batch_reset_random.argtypes = [vp, u64, i64, C.c_double, C.c_double, vp, vp]
     L.so101_batch_forward.argtypes = [vp, vp, vp, vp]
     L.so101_batch_step.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.so101_batch_step_flags.argtypes = [vp, vp, i32, i32, vp, u32, vp]
     L.so101_batch_step_host.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.so101_batch_reset_host.argtypes = [vp, vp, vp, vp, vp]
     L.so101_batch_rollout.argtypes = [vp, C.POINTER(So101CtrlSpec), i32, i32, vp, u32, vp]

@@ -22,6 +22,19 @@ namespace so101 {
 constexpr int MAXCON = SO101_MAXCON;
 constexpr int MAXONE = NV + 4 * MAXCON;     // one-sided rows: joint limits + pyramid rows
 
+// The active-set iteration (see contact_solve) is Newton's method with full steps on a piecewise-quadratic objective.  Where
+// it does not settle it cycles between two pieces in which one friction row is saturated with opposite signs: each
+// piece's minimiser lies beyond the row's (narrow) quadratic zone, the true minimiser inside it.  From the fourth solve on,
+// a friction row whose candidate jumped from one saturated side to the other is therefore put into its quadratic zone.
+// Measured on the oracle's contact steps of the benchmark workload (583 steps): plain iteration 2.6 % unsettled after
+// 12 solves, with this rule none after 6 (mean 2.6 solves either way).
+constexpr int ACTIVE_SET_ATTEMPTS = 10;
+SO101_DEV void active_set_unflip(uint32_t zq, uint32_t zp, uint32_t& nzq, uint32_t& nzp) {
+  const uint32_t flipped = ~zq & ~nzq & (zp ^ nzp) & ((1u << NV) - 1u);
+  nzq |= flipped;
+  nzp &= ~flipped;
+}
+
 template <typename T> SO101_DEV uint64_t hull_word_(const DevModel<T>& m, int which) {
   return ((uint64_t)(uint32_t)m.hull_ptr[2 * which + 1] << 32) | (uint64_t)(uint32_t)m.hull_ptr[2 * which];
 }
@@ -303,7 +316,7 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
     for (int i = 0; i < NV; i++) az[i] = warm[i];
     bool done = false;
 #pragma unroll 1
-    for (int attempt = 0; attempt <= 6 && !done; attempt++) {
+    for (int attempt = 0; attempt <= ACTIVE_SET_ATTEMPTS && !done; attempt++) {
       uint32_t nzq = 0, nzp = 0, nact = 0;
       bool strict = true;
 #pragma unroll
@@ -342,7 +355,8 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
         done = true;
         break;
       }
-      if (attempt == 6) break;
+      if (attempt == ACTIVE_SET_ATTEMPTS) break;
+      if (attempt >= 3) active_set_unflip(zq, zp, nzq, nzp);
       zq = nzq; zp = nzp; act = nact;
       T H[21], rhs[NV];
 #pragma unroll
@@ -557,7 +571,7 @@ SO101_DEV int contact_active_set(const DevModel<T>& m, const Con3<T>* con, int n
 #pragma unroll
   for (int i = 0; i < NV; i++) az[i] = warm[i];
 #pragma unroll 1
-  for (int attempt = 0; attempt <= 6; attempt++) {
+  for (int attempt = 0; attempt <= ACTIVE_SET_ATTEMPTS; attempt++) {
     uint32_t nzq = 0, nzp = 0, nzl = 0, nzc = 0;
     bool strict = true;
 #pragma unroll
@@ -613,7 +627,8 @@ SO101_DEV int contact_active_set(const DevModel<T>& m, const Con3<T>* con, int n
       cnt.newton += attempt;
       return 1;
     }
-    if (attempt == 6) break;
+    if (attempt == ACTIVE_SET_ATTEMPTS) break;
+    if (attempt >= 3) active_set_unflip(zq, zp, nzq, nzp);
     zq = nzq; zp = nzp; zl = nzl; zc = nzc;
     T H[21], rhs[NV];
 #pragma unroll

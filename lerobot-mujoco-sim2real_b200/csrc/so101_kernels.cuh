@@ -1,0 +1,470 @@
+// so101_kernels.cuh - the stepping kernels (k_step, k_rollout, k_shoot) and their device helpers.  Compiled once per
+// (dtype, kernel family) by so101_kernels.cu so that the four translation units build in parallel; the host side
+// (so101_capi.cu) sees only the launchers declared in so101_launch.h.
+//
+// One thread owns one environment for a whole launch: its state (qpos, qvel, qacc_warmstart,
+// qfrc_applied: 25 scalars) is loaded once from the structure-of-arrays buffer, stepped
+// n_substeps (step) or T*frame_skip (rollout, shoot) times entirely in registers, and stored
+// once.  Loads/stores are coalesced (lane i <-> env i, consecutive addresses per SoA row).
+// The path is FP64/FP32-pipe bound (about 160 FLOP per byte of state traffic); tensor cores
+// and TMA are deliberately unused (no dense contraction, 100 bytes of state per thread).
+#pragma once
+#include "so101_physics.cuh"
+#include "so101_launch.h"
+
+using namespace so101;
+
+// ==========================================================================================
+// device helpers
+// ==========================================================================================
+
+// thread -> env for the stepping kernels.  Tail threads are clamped to a valid env (they shadow it and never
+// store) so that every thread reaches the block barriers.
+// SPLIT kernels (small batches): a 96-thread block is a TEAM of three warps on the same 32 envs, warp 0 = dynamics
+// role (owns the env, loads and stores), warps 1, 2 = geometry and lookout roles (see so101_physics.cuh, SplitXch).
+template <typename T> SO101_DEV int64_t env_of_pair(const StateView<T>& s, bool& active) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  active = threadIdx.x < 32 && i < s.n;
+  return i < s.n ? i : s.n - 1;
+}
+template <typename T, bool SPLIT> struct XchStorage { char unused; };
+template <typename T> struct XchStorage<T, true> { SplitXch<T> x; };
+template <typename T> SO101_DEV SplitXch<T>& xch_of(XchStorage<T, true>& st) { return st.x; }
+template <typename T> SO101_DEV SplitXch<T>& xch_of(XchStorage<T, false>& st) { return *reinterpret_cast<SplitXch<T>*>(&st); }
+
+// helper roles of a SPLIT kernel: pick up the initial state, then shadow `nsteps` physics steps
+template <typename T>
+SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps, int frame_skip) {
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const bool trip = m.ntrip > 0;
+  T q[NV], qd[NV];
+  __syncthreads();   // (0) initial state published
+#pragma unroll
+  for (int k = 0; k < NV; k++) { q[k] = x.q[k][lane]; qd[k] = x.qd[k][lane]; }
+  if (role == 1) {
+#pragma unroll 1
+    for (int64_t n = 0; n < nsteps; n++) split_geometry_step(m, x, lane, q, qd, n);
+  } else {
+    int ss = 0;
+#pragma unroll 1
+    for (int64_t n = 0; n < nsteps; n++) {
+      split_lookout_step<T>(m, x, lane, q, qd, ss == frame_skip - 1, trip);
+      if (++ss == frame_skip) ss = 0;
+    }
+  }
+}
+template <typename T> SO101_DEV void publish_state(SplitXch<T>& x, const Env<T>& e) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < NV; k++) { x.q[k][lane] = e.q[k]; x.qd[k][lane] = e.qd[k]; }
+  __syncthreads();   // (0)
+}
+template <typename T, bool SPLIT>
+SO101_DEV void step_env(const DevModel<T>& m, SplitXch<T>& x, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
+                        bool want_site, T (&site)[3], bool trip, Counters& cnt, int64_t nstep) {
+  if (SPLIT) split_dynamics_step<T>(m, x, threadIdx.x & 31, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, nstep);
+  else physics_step<T, true>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
+}
+
+// thread -> env of a stepping kernel; `active` = this thread owns the env (loads, stores, writes rows); exit_block = the
+// whole block lies beyond the batch (uniform over the block)
+template <typename T, bool SPLIT>
+SO101_DEV int64_t env_slot(const StateView<T>& s, bool& active, bool& exit_block) {
+  const int64_t j = SPLIT ? (int64_t)blockIdx.x * 32 + (threadIdx.x & 31) : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t first = SPLIT ? (int64_t)blockIdx.x * 32 : (int64_t)blockIdx.x * blockDim.x;
+  exit_block = first >= s.n;
+  if (exit_block) { active = false; return 0; }
+  active = (!SPLIT || threadIdx.x < 32) && j < s.n;
+  return j < s.n ? j : s.n - 1;      // tail threads shadow a valid env and never store
+}
+
+template <typename T> SO101_DEV int64_t env_of_thread(const StateView<T>& s, bool& active) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  active = i < s.n;
+  return i < s.n ? i : s.n - 1;
+}
+
+template <typename T> SO101_DEV void load_env(const StateView<T>& s, int64_t i, Env<T>& e) {
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    e.q[k] = s.base[(ROW_Q + k) * s.n + i];
+    e.qd[k] = s.base[(ROW_QD + k) * s.n + i];
+    e.warm[k] = s.base[(ROW_WARM + k) * s.n + i];
+    e.fa[k] = s.base[(ROW_FA + k) * s.n + i];
+  }
+  e.time = s.base[ROW_TIME * s.n + i];
+  e.flags = s.flags[i];
+}
+template <typename T> SO101_DEV void store_env(const StateView<T>& s, int64_t i, const Env<T>& e) {
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    s.base[(ROW_Q + k) * s.n + i] = e.q[k];
+    s.base[(ROW_QD + k) * s.n + i] = e.qd[k];
+    s.base[(ROW_WARM + k) * s.n + i] = e.warm[k];
+    s.base[(ROW_FA + k) * s.n + i] = e.fa[k];
+  }
+  s.base[ROW_TIME * s.n + i] = e.time;
+  s.flags[i] = e.flags;
+}
+template <typename T> SO101_DEV void reset_env(const DevModel<T>& m, Env<T>& e) {  // mj_resetData
+#pragma unroll
+  for (int k = 0; k < NV; k++) { e.q[k] = m.qpos0[k]; e.qd[k] = T(0); e.warm[k] = T(0); e.fa[k] = T(0); }
+  e.time = T(0);
+  e.flags = 0;
+}
+
+SO101_DEV void add_stats(unsigned long long* stats, const Counters& c) {
+  // warp-reduce, one atomic per warp and counter
+  uint32_t v[4] = {c.steps, c.newton, c.lsevals, c.limsteps};
+  const unsigned mask = __activemask();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    unsigned long long x = v[k];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(mask, x, o);
+    // with a partial warp shfl_down reads inactive lanes as undefined; fall back to per-lane atomics
+    if (mask == 0xffffffffu) {
+      if ((threadIdx.x & 31) == 0) atomicAdd(&stats[k], x);
+    } else {
+      atomicAdd(&stats[k], (unsigned long long)v[k]);
+    }
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011).  Stream layout specified in DESIGN.md ("control RNG"):
+// key = seed, counter = (env_lo, env_hi, step, 2*stream + block); 32-bit lanes -> [0,1).
+SO101_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll 1
+  for (int r = 0; r < 10; r++) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+    uint32_t n0 = h1 ^ c[1] ^ k0, n2 = h0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = l1; c[2] = n2; c[3] = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+enum { STREAM_RESET = 0, STREAM_CTRL = 1, STREAM_FREQ = 2, STREAM_AMP = 3, STREAM_PHASE = 4 };
+// first 5 of the 8 uniforms of (seed, env, step, stream)
+static __device__ __noinline__ void uniform5(uint64_t seed, int64_t env, uint32_t step, uint32_t stream, double* out) {
+  uint32_t c[4] = {(uint32_t)env, (uint32_t)((uint64_t)env >> 32), step, stream * 2u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = (double)c[k] * (1.0 / 4294967296.0);
+  uint32_t d[4] = {(uint32_t)env, (uint32_t)((uint64_t)env >> 32), step, stream * 2u + 1u};
+  philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+  out[4] = (double)d[0] * (1.0 / 4294967296.0);
+}
+// a + b*c without contraction: the control stream must be bit-identical to the CPU restatement
+SO101_DEV double muladd_rn(double a, double b, double c) { return __dadd_rn(a, __dmul_rn(b, c)); }
+
+struct CtrlGen {  // per-env generator state for SO101_CTRL_SIN / CHIRP
+  double freq[5], amp[5], phase[5];
+};
+SO101_DEV void ctrl_init(const DevSpec& s, int64_t env, CtrlGen& g) {
+  if (s.kind == SO101_CTRL_SIN || s.kind == SO101_CTRL_CHIRP) {
+    double r[5];
+    uniform5(s.seed, env, 0, STREAM_FREQ, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.freq[k] = muladd_rn(s.freq_lo, s.freq_hi - s.freq_lo, r[k]);
+    uniform5(s.seed, env, 0, STREAM_AMP, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.amp[k] = muladd_rn(-s.amp, 2 * s.amp, r[k]);
+    uniform5(s.seed, env, 0, STREAM_PHASE, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) g.phase[k] = __dmul_rn(2 * 3.14159265358979323846, r[k]);
+  }
+}
+// u_t  [REF SOARM101_DataCollection.py:57-74 (sin/chirp), :115,132 (random)]
+template <typename T>
+SO101_DEV void ctrl_gen(const DevSpec& s, const CtrlGen& g, int64_t env, int64_t local, int64_t n, int t,
+                        double (&u)[5]) {
+  if (s.kind == SO101_CTRL_RANDOM) {
+    double r[5];
+    uniform5(s.seed, env, (uint32_t)t, STREAM_CTRL, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) u[k] = __dmul_rn(__dmul_rn(__dadd_rn(r[k], -0.5), 2.0), s.amp);
+  } else if (s.kind == SO101_CTRL_TENSOR) {
+    const T* ut = static_cast<const T*>(s.u);
+#pragma unroll
+    for (int k = 0; k < 5; k++) u[k] = (double)ut[((int64_t)t * 5 + k) * n + local];
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < 5; k++) {
+      double f = g.freq[k];
+      if (s.kind == SO101_CTRL_CHIRP) f = muladd_rn(g.freq[k], s.freq_hi - s.freq_lo, (double)t / (double)s.t_total);
+      double arg = __dadd_rn(__dmul_rn(__dmul_rn(2 * 3.14159265358979323846, f), (double)t), g.phase[k]);
+      u[k] = __dmul_rn(g.amp[k], sin(arg));
+    }
+  }
+}
+
+// ==========================================================================================
+// kernels
+// ==========================================================================================
+// Launch bounds, from the ncu / timing experiments in profiles/README.md.  f64 needs all 255 registers
+// (one 256-thread block = 8 warps per SM; 168- or 128-register builds lose 20-30 % to spills).  The f32
+// instantiation fits 128 registers with few spills: 16 warps per SM as ONE 512-thread block, so that all
+// of them share the instruction stream between the block barriers (+5-16 % for 16 warps, +17 % more
+// for the single block; stall_no_instruction was the top f32 stall with two independent blocks).
+#ifndef SO101_F64_THREADS
+#define SO101_F64_THREADS 256
+#endif
+#ifndef SO101_F32_THREADS
+#define SO101_F32_THREADS 512
+#endif
+template <typename T> struct LBThreads { static constexpr int value = SO101_F64_THREADS; };
+template <> struct LBThreads<float> { static constexpr int value = SO101_F32_THREADS; };
+#define SO101_LB_THREADS LBThreads<T>::value
+#define SO101_LB_BLOCKS 1
+// Resident teams per SM that the register allocation of the team kernels must allow.  f64: 1 (255 registers, two
+// teams fit; a 168-register build is 12 % slower at 4096 envs).  f32: 3 (161 registers, no spills, as fast as the
+// unconstrained 194-register build and four teams fit per SM).
+template <typename T> struct TeamMinBlocks { static constexpr int value = 1; };
+template <> struct TeamMinBlocks<float> { static constexpr int value = 3; };
+#define SO101_TEAM_MINBLOCKS TeamMinBlocks<T>::value
+#define SO101_KERNEL(T) template <typename T> __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
+#define SO101_STEP_KERNEL(T) \
+  template <typename T, bool SPLIT> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
+
+// reset: mj_resetData + qpos/qvel write + (observation part of) mj_forward
+//   mode 0: qpos0/qvel0 [6][N] (nullable)   mode 1: qpos[0:5] ~ U(lo,hi) from Philox
+SO101_KERNEL(T)
+k_reset(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* qpos0, const T* qvel0, int mode,
+        uint64_t seed, int64_t env_offset, double lo, double hi, float* obs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  Env<T> e;
+  reset_env(m, e);
+  if (mode == 1) {
+    double r[5];
+    uniform5(seed, env_offset + i, 0, STREAM_RESET, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(lo, hi - lo, r[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      if (qpos0) e.q[k] = qpos0[k * s.n + i];
+      if (qvel0) e.qd[k] = qvel0[k * s.n + i];
+    }
+  }
+  store_env(s, i, e);
+  if (obs) {
+    T site[3];
+    site_fk(m, e.q, site);
+#pragma unroll
+    for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+  }
+}
+
+// mj_forward outputs the Env shims read: observation and qfrc_bias
+SO101_KERNEL(T)
+k_forward(const __grid_constant__ DevModel<T> m, StateView<T> s, float* obs, T* qfrc_bias) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n) return;
+  Env<T> e;
+  load_env(s, i, e);
+  T M[21], bias[NV], site[3];
+  uint32_t fl = 0;
+  T sn[NV], cs[NV];
+  joint_sincos_range(m, e.q, 1, sn, cs, 1, 0, NV);
+  rnea_bias(m, sn, cs, 1, e.qd, 1, bias);
+  site_from_trig(m, sn, cs, 1, site);
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+  }
+  if (qfrc_bias) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) qfrc_bias[k * s.n + i] = bias[k];
+  }
+}
+
+// SOARM101Env.step: ctrl rows [n_ctrl][N] (missing rows = 0), nsub x mj_step, observation.  Table contact is handled
+// inside the step (so101_contact.cuh).  (A freeze-and-resume variant - fast kernels without contact code that froze an env
+// at its first table contact, contact kernels that finished the listed envs - was built and measured in round 2: never
+// faster than the in-kernel path, see profiles/README.md; removed.)
+#define SO101_STEP_KERNEL2(T) \
+  template <typename T, bool SPLIT> __global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
+SO101_STEP_KERNEL2(T)
+k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int n_ctrl, int nsub, float* obs,
+       unsigned long long* stats, uint32_t sflags) {
+  __shared__ XchStorage<T, SPLIT> xst;
+  SplitXch<T>& xch = xch_of(xst);
+  bool active, exit_block;
+  const int64_t i = env_slot<T, SPLIT>(s, active, exit_block);
+  if (exit_block) return;
+  if (SPLIT && threadIdx.x >= 32) { helper_role<T>(m, xch, nsub, nsub); return; }
+  Env<T> e;
+  load_env(s, i, e);
+  if (SPLIT) publish_state(xch, e);
+  T u[NV], site[3] = {T(0), T(0), T(0)};
+#pragma unroll
+  for (int k = 0; k < NV; k++) u[k] = (ctrl && k < n_ctrl) ? ctrl[k * s.n + i] : T(0);
+  clamp_ctrl(m, u);
+  Counters cnt = {0, 0, 0, 0};
+  const bool trip = m.ntrip > 0;
+  const bool hold = sflags & SO101_ROLL_GRAVCOMP_HOLD;   // qfrc_applied = qfrc_bias of the state the env step starts from
+#pragma unroll 1
+  for (int ss = 0; ss < nsub; ss++) step_env<T, SPLIT>(m, xch, e, u, hold && ss == 0, ss == nsub - 1, site, trip, cnt, ss);
+  if (nsub == 0) site_fk(m, e.q, site);
+  if (active) {
+    store_env(s, i, e);
+    if (obs) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) obs[k * s.n + i] = (float)site[k];
+#pragma unroll
+      for (int k = 0; k < 5; k++) obs[(3 + k) * s.n + i] = (float)e.q[k];
+    }
+  } else {
+    cnt = {0, 0, 0, 0};
+  }
+  add_stats(stats, cnt);
+}
+
+// SOARM101DataGenerator.generate_physics_based_data, one env per thread:
+// rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
+template <typename T, typename ROW, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 32 * TEAM_WARPS : SO101_LB_THREADS, SPLIT ? SO101_TEAM_MINBLOCKS : SO101_LB_BLOCKS)
+k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
+          ROW* rows, uint32_t rflags, unsigned long long* stats) {
+  // control steps (t0, t1] of a rollout of Tn steps; t0 > 0 continues a previous launch (row t0 is already written,
+  // u_t0 is regenerated: the control stream is a pure function of (seed, env, t)).
+  __shared__ XchStorage<T, SPLIT> xst;
+  SplitXch<T>& xch = xch_of(xst);
+  bool active, exit_block;
+  const int64_t i = env_slot<T, SPLIT>(s, active, exit_block);
+  if (exit_block) return;
+  if (SPLIT && threadIdx.x >= 32) { helper_role<T>(m, xch, (int64_t)(t1 - t0) * frame_skip, frame_skip); return; }
+  const int64_t env = spec.env_offset + i;
+  Env<T> e;
+  if (rflags & SO101_ROLL_NO_RESET) {
+    load_env(s, i, e);
+  } else {
+    reset_env(m, e);
+    double r[5];
+    uniform5(spec.seed, env, 0, STREAM_RESET, r);
+#pragma unroll
+    for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(spec.reset_lo, spec.reset_hi - spec.reset_lo, r[k]);
+  }
+  CtrlGen g;
+  ctrl_init(spec, env, g);
+  Counters cnt = {0, 0, 0, 0};
+  const bool trip = m.ntrip > 0;
+  const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
+  T site[3];
+  site_fk(m, e.q, site);
+  if (SPLIT) publish_state(xch, e);
+  double u[5];
+  T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  int64_t nstep = 0;
+#pragma unroll 1
+  for (int t = t0; t <= t1; t++) {
+    if (t > t0) {
+#pragma unroll 1
+      for (int ss = 0; ss < frame_skip; ss++, nstep++)
+        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
+    }
+    ctrl_gen<T>(spec, g, env, i, s.n, t, u);
+#pragma unroll
+    for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
+    clamp_ctrl(m, uc);   // rows keep the unclamped u, as the reference's dataset does
+    if (rows && active && (t > t0 || t0 == 0)) {
+      ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
+#pragma unroll
+      for (int k = 0; k < 5; k++) row[k] = (ROW)u[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) row[5 + k] = (ROW)(float)site[k];
+#pragma unroll
+      for (int k = 0; k < 5; k++) row[8 + k] = (ROW)(float)e.q[k];
+    }
+  }
+  if (active) store_env(s, i, e);
+  else cnt = {0, 0, 0, 0};
+  add_stats(stats, cnt);
+}
+
+// B control sequences U[H][5][B] from one shared state; X[B][H+1][8] float32 observations
+SO101_STEP_KERNEL2(T)
+k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,
+        int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
+  __shared__ XchStorage<T, SPLIT> xst;
+  SplitXch<T>& xch = xch_of(xst);
+  bool active, exit_block;
+  const int64_t i = env_slot<T, SPLIT>(s, active, exit_block);
+  if (exit_block) return;
+  if (SPLIT && threadIdx.x >= 32) { helper_role<T>(m, xch, (int64_t)H * frame_skip, frame_skip); return; }
+  Env<T> e;
+  reset_env(m, e);
+#pragma unroll
+  for (int k = 0; k < NV; k++) { e.q[k] = (T)s0.v[k]; e.qd[k] = (T)s0.v[6 + k]; e.warm[k] = (T)s0.v[12 + k]; }
+  Counters cnt = {0, 0, 0, 0};
+  const bool trip = m.ntrip > 0;
+  const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
+  T site[3];
+  site_fk(m, e.q, site);
+  if (SPLIT) publish_state(xch, e);
+  T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+  int64_t nstep = 0;
+#pragma unroll 1
+  for (int t = 0; t <= H; t++) {
+    if (t > 0) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) uc[k] = U[((int64_t)(t - 1) * 5 + k) * s.n + i];
+      clamp_ctrl(m, uc);
+#pragma unroll 1
+      for (int ss = 0; ss < frame_skip; ss++, nstep++)
+        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
+    }
+    if (active) {
+      float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;
+#pragma unroll
+      for (int k = 0; k < 3; k++) x[k] = (float)site[k];
+#pragma unroll
+      for (int k = 0; k < 5; k++) x[3 + k] = (float)e.q[k];
+    }
+  }
+  if (active) store_env(s, i, e);
+  else cnt = {0, 0, 0, 0};
+  add_stats(stats, cnt);
+}
+
+// ---- launchers (declared in so101_launch.h; instantiated per translation unit by so101_kernels.cu) -----------------
+template <typename T, bool SPLIT>
+cudaError_t launch_step(const DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st, const T* ctrl,
+                        int n_ctrl, int nsub, float* obs, unsigned long long* stats, uint32_t sflags) {
+  k_step<T, SPLIT><<<grid, blk, 0, st>>>(m, v, ctrl, n_ctrl, nsub, obs, stats, sflags);
+  return cudaGetLastError();
+}
+template <typename T, bool SPLIT>
+cudaError_t launch_rollout(const DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st, const DevSpec& ds,
+                           int t0, int t1, int Tn, int frame_skip, void* rows, bool rows_f32, uint32_t rflags,
+                           unsigned long long* stats) {
+  if (rows_f32) k_rollout<T, float, SPLIT><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (float*)rows, rflags, stats);
+  else k_rollout<T, double, SPLIT><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (double*)rows, rflags, stats);
+  return cudaGetLastError();
+}
+template <typename T, bool SPLIT>
+cudaError_t launch_shoot(const DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st, const State0& s0,
+                         const T* U, int H, int frame_skip, float* X, uint32_t rflags, unsigned long long* stats) {
+  k_shoot<T, SPLIT><<<grid, blk, 0, st>>>(m, v, s0, U, H, frame_skip, X, rflags, stats);
+  return cudaGetLastError();
+}
+
+// register-resident FMA loop for the roofline denominator ("of measured")
+template <typename T> __global__ void k_fma_peak(T* out, int iters, T a, T b) {
+  T x[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) x[k] = T(threadIdx.x + k) * T(1e-3);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = x[k] * a + b;
+  }
+  T s = T(0);
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += x[k];
+  if (s == T(-12345.678)) out[0] = s;  // never true; keeps the loop alive
+}
+

@@ -46,8 +46,8 @@ SO101_DEV float rcp_(float x) { return __frcp_rn(x); }
 // sin/cos by Cody-Waite reduction to [-pi/4, pi/4] + fdlibm / Cephes kernels (<= 1 ulp for the
 // joint angles of a limited hinge chain; arguments beyond 2^18 fall back to the library, which
 // keeps its large-argument reduction out of the hot instruction stream).
-__device__ __noinline__ void sincos_slow_(double x, double* sp, double* cp) { sincos(x, sp, cp); }
-__device__ __noinline__ void sincos_slow_(float x, float* sp, float* cp) { sincosf(x, sp, cp); }
+static __device__ __noinline__ void sincos_slow_(double x, double* sp, double* cp) { sincos(x, sp, cp); }
+static __device__ __noinline__ void sincos_slow_(float x, float* sp, float* cp) { sincosf(x, sp, cp); }
 SO101_DEV void sincos_(double x, double* sp, double* cp) {
   if (!(fabs(x) < 262144.0)) { sincos_slow_(x, sp, cp); return; }
   double k = rint(x * 0.63661977236758134308);
@@ -984,20 +984,12 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
 // on a barrier at the phase boundaries so that its warps stream the same instructions through
 // the instruction cache together (the step is ~50 KB of SASS; ncu: stall_no_instruction).
 // ------------------------------------------------------------------------------------------
-// CM (contact mode): CM_FREEZE - the fast kernels: an env whose collision box dips below the table top is FROZEN
-// (its state stops advancing, SO101_FLAG_FROZEN) and finished by the contact kernels (k_*_resume), so that this
-// instruction stream carries no contact code at all; CM_SOLVE - the contact kernels: exact hull test and contact rows
-// in this step (so101_contact.cuh).  Without hull data (m.con_enabled == 0) both only raise SO101_FLAG_TRIP_TABLE.
-enum { CM_FREEZE = 0, CM_SOLVE = 1 };
-#define SO101_FLAG_FROZEN (1u << 31)   // internal: never leaves the library (masked by so101_batch_get_flags)
-
-template <typename T, bool SYNC, int CM>
+template <typename T, bool SYNC>
 SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
                             bool want_site, T (&site)[3], bool trip, Counters& cnt) {
   if (SYNC) __syncthreads();
-  const bool frozen_in = (e.flags & SO101_FLAG_FROZEN) != 0;   // inert: waits for (or, there, for its turn in) the contact kernel
   // mj_checkPos / mj_checkVel
-  if (!frozen_in) {
+  {
     bool bad = false;
 #pragma unroll
     for (int i = 0; i < NV; i++) bad |= bad_(e.q[i]) | bad_(e.qd[i]);
@@ -1009,9 +1001,9 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     }
   }
   T M[21], bias[NV];
-  T sn[NV], cs[NV];    // joint sines / cosines (the contact path of the CM_SOLVE kernels reads them again)
+  T sn[NV], cs[NV];    // joint sines / cosines (the contact path reads them again)
   uint32_t hits = 0;   // tripwire boxes below the table top
-  if (!frozen_in) {
+  {
 #if SO101_ONEWARP_ROLLED   // experiment: the compact link loops of the team kernels in the one-warp kernels (see profiles/README.md)
   {
     T lq[NV], lqd[NV];
@@ -1031,12 +1023,6 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 #endif
   }
   if (SYNC) __syncthreads();
-  if (frozen_in) return;
-  if (CM == CM_FREEZE && hits) {
-    if (m.con_enabled) { e.flags |= SO101_FLAG_FROZEN; return; }   // nothing of this step has touched the state yet
-    e.flags |= SO101_FLAG_TRIP_TABLE;   // no hull data: the env is only marked, its dynamics stay contact-free
-    hits = 0;
-  }
   if (gravcomp_capture) {
 #pragma unroll
     for (int i = 0; i < NV; i++) e.fa[i] = bias[i];
@@ -1053,7 +1039,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV], zone[NV];
   T cost = T(0);
   bool need_setup = false;
-  if (CM == CM_SOLVE && hits) {
+  if (hits) {
     // a collision box is below the table top: exact hull test and, if a hull does touch, the full constraint solve with
     // contact rows - out of line (so101_contact.cuh); the phase machine then only runs its Euler solve
     bool in_contact = false;
@@ -1381,7 +1367,7 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 }
 
 // lookout warp: contact tripwire and (on the last substep of a control step) the observation site
-template <typename T, int CM>
+template <typename T>
 SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
                                   bool want_site, bool trip) {
   team_check_state(m, q, qd);
@@ -1393,7 +1379,7 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
     for (int i = 0; i < NV; i++) lq[i] = q[i];
     tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
   }
-  if (CM == CM_SOLVE) {
+  {
     uint32_t nc = 0;
     if (hits && m.con_enabled) {
       Con3<T> con[MAXCON];
@@ -1432,12 +1418,11 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
 // dynamics warp: everything else of the step.  nstep = index of this step within the launch (same for the whole block:
 // selects the buffer of the lagged factor the geometry warp wrote).  A frozen lane (see physics_step) skips the
 // arithmetic but walks through the same barriers and re-publishes its unchanged state.
-template <typename T, int CM>
+template <typename T>
 SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lane, Env<T>& e, const T (&ctrl)[NV],
                                    bool gravcomp_capture, bool want_site, T (&site)[3], bool trip, Counters& cnt,
                                    int64_t nstep) {
-  bool skip = (e.flags & SO101_FLAG_FROZEN) != 0;
-  if (!skip && team_check_state(m, e.q, e.qd)) {
+  if (team_check_state(m, e.q, e.qd)) {
 #pragma unroll
     for (int i = 0; i < NV; i++) { e.warm[i] = T(0); e.fa[i] = T(0); }
     e.time = T(0);
@@ -1449,8 +1434,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   Rows<T> rw;
   rw.anylim = false;
   bool constrained = false;
-  const uint32_t lim0 = cnt.limsteps;
-  if (!skip) {
+  {
     T lqd[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) lqd[i] = e.qd[i];
@@ -1465,19 +1449,10 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     constrained = m.nfriction != 0 || rw.anylim;
   }
   __syncthreads();   // (A) wait for the geometry and lookout warps
-  if (!skip && CM == CM_FREEZE && trip && x.hits[lane]) {
-    if (m.con_enabled) {   // freeze: the contact kernel re-executes this step (a gravity-compensation capture of this
-      e.flags |= SO101_FLAG_FROZEN;   // step is repeated there with the same result; the state proper is untouched)
-      cnt.limsteps = lim0;
-      skip = true;
-    } else {
-      e.flags |= SO101_FLAG_TRIP_TABLE;
-    }
-  }
   T Ls[15], Dinv[NV];
   T a[NV], Ma[NV], qc[NV], hd[NV];
   bool solved = false;
-  if (!skip) {
+  {
   if (trip) e.flags |= x.trip[lane];
   if (want_site) {
 #pragma unroll
@@ -1485,7 +1460,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
-  if (CM == CM_SOLVE && trip && x.hits[lane]) {        // table contact (see physics_step)
+  if (trip && x.hits[lane]) {        // table contact (see physics_step)
     if (m.con_enabled) {
       const uint32_t nc = x.ncon[lane];
       if (nc) {
@@ -1640,9 +1615,9 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
       }
     }
   }
-  }   // !skip
+  }
   __syncthreads();   // (E) factors of M + h B
-  if (!skip) {
+  {
   // mj_checkAcc, mj_Euler
   bool bad = false;
 #pragma unroll
@@ -1673,7 +1648,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     e.time += m.h;
   }
   cnt.steps++;
-  }   // !skip
+  }
 #pragma unroll
   for (int i = 0; i < NV; i++) { x.q[i][lane] = e.q[i]; x.qd[i][lane] = e.qd[i]; }
   __syncthreads();   // (B) new state published

@@ -147,20 +147,19 @@ class SOARM101VecEnv:
     def step(self, action):
         """action [N, 5] -> (obs [N, 8], 0.0, False, False, {}).  [REF SOARM101_Env.py:108-142]"""
         u = self._soa(action, T.NU_ENV)
-        if self.gravity_compensation:
-            L = _lib.lib()
-            bias = torch.empty((T.NV, self.num_envs), dtype=self.torch_dtype, device=self.device)
-            _lib.check(L.so101_batch_forward(self._h, None, bias.data_ptr(), self._stream()))
-            _lib.check(L.so101_batch_set_qfrc_applied(self._h, bias.data_ptr(), self._stream()))
         self.step_soa(u)
         return self._obs.t(), 0.0, False, False, {}
 
     def step_soa(self, ctrl_soa: torch.Tensor, n_substeps: Optional[int] = None) -> torch.Tensor:
-        """Zero-copy step: ctrl_soa [5 or 6, N] contiguous, batch dtype.  Returns obs [8, N]."""
+        """Zero-copy step: ctrl_soa [5 or 6, N] contiguous, batch dtype.  Returns obs [8, N].  With
+        gravity_compensation the launch itself sets qfrc_applied = qfrc_bias of the state it starts from (one fused
+        launch instead of forward + copy + step)."""
         assert ctrl_soa.is_contiguous() and ctrl_soa.dtype == self.torch_dtype and ctrl_soa.shape[1] == self.num_envs
         ns = self.frame_skip if n_substeps is None else n_substeps
-        _lib.check(_lib.lib().so101_batch_step(self._h, ctrl_soa.data_ptr(), ctrl_soa.shape[0], ns,
-                                               self._obs.data_ptr(), self._stream()))
+        _lib.check(_lib.lib().so101_batch_step_flags(self._h, ctrl_soa.data_ptr(), ctrl_soa.shape[0], ns,
+                                                     self._obs.data_ptr(),
+                                                     T.ROLL_GRAVCOMP_HOLD if self.gravity_compensation else 0,
+                                                     self._stream()))
         return self._obs
 
     def forward(self) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -13,9 +13,8 @@ for case in cases:
     n, Tn, kind, dtype = case.split(":")
     n, Tn = int(n), int(Tn)
     res = {}
-    for name, hulls, mode in (("off", None, 0), ("on", "auto", 0), ("inl", "auto", 1)):
+    for name, hulls in (("off", None), ("on", "auto")):
         env = SOARM101VecEnv(tables=t, num_envs=n, dtype=dtype, hulls=hulls)
-        env.set_option(T.OPT_CONTACT_MODE, mode)
         env.rollout_discard(2, kind)
         torch.cuda.synchronize()
         best = 1e30
@@ -27,4 +26,4 @@ for case in cases:
         res[name] = (best, float(((fl & T.FLAG_CONTACT) != 0).mean()), float(((fl & T.FLAG_TRIP_TABLE) != 0).mean()))
         del env
     print(f"{case}: off {res['off'][0]:.3f} ms (flagged {res['off'][2]:.4f})  on {res['on'][0]:.3f} ms (in contact {res['on'][1]:.4f}, "
-          f"unsimulated {res['on'][2]:.5f})  ratio {res['on'][0] / res['off'][0]:.3f}; in-kernel {res['inl'][0]:.3f} ms ratio {res['inl'][0] / res['off'][0]:.3f}", flush=True)
+          f"unsimulated {res['on'][2]:.5f})  ratio {res['on'][0] / res['off'][0]:.3f}", flush=True)
