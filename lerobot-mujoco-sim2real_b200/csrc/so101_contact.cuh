@@ -4,17 +4,13 @@
 // pair), mj_instantiateContact (condim 3, pyramidal: rows J_n +- mu J_t), mj_makeImpedance and solves all rows with
 // the Newton solver.  Restated for CPU in oracle/so101_oracle.c (collision, makeConstraint).
 //
-// This file is the RARE path (a few % of the envs of a long chirp rollout, none of a short random one): everything
-// is rolled loops over local-memory arrays in ONE out-of-line function, so that the hot instruction stream of
-// physics_step does not grow.  Steps:
-//   1. world frames of the links from the joint angles (the hot path never forms them);
-//   2. for every hull whose box tripped: exact support vertex in direction -z by steepest ascent on the hull's edge
-//      graph, started from a direction cube map (mean < 1 step) -> penetration depth, contact point, Jacobian rows
-//      from the world hinge axes / anchors;
-//   3. a general dense Newton solve over friction rows (Huber), joint-limit rows and contact rows (one-sided), with
-//      MuJoCo's warm-start pick, termination tests and the exact piecewise-quadratic line search of line_search().
-// Returns false when no hull actually touches the plane (the box test is conservative): the caller continues on the
-// fast path.
+// This file is the RARE path (a few % of the envs of a long chirp rollout, none of a short random one):
+//   1. contact_geometry: exact hull-vs-plane test of every hull whose bounding box tripped - support vertex in direction
+//      -z by steepest ascent on the hull's edge graph, started from the previous step's vertex or a direction cube map -
+//      and, only for hulls that do touch, world frames, contact points and the three Jacobian rows of each contact;
+//   2. contact_active_set: the direct active-set iteration over friction (Huber), joint-limit and pyramid rows (inline);
+//   3. contact_solve: the general dense Newton solve over the same rows with MuJoCo's warm-start pick, termination tests
+//      and the exact piecewise-quadratic line search (out of line; only when 2 does not settle).
 #pragma once
 
 namespace so101 {
@@ -39,35 +35,49 @@ template <typename T> SO101_DEV uint64_t hull_word_(const DevModel<T>& m, int wh
   return ((uint64_t)(uint32_t)m.hull_ptr[2 * which + 1] << 32) | (uint64_t)(uint32_t)m.hull_ptr[2 * which];
 }
 
-// support vertex of hull `g` for direction d (link frame): cube-map start, then steepest ascent on the edge graph
+// support vertex of hull `g` for direction d (link frame): steepest ascent on the hull's edge graph from `start` (the
+// support vertex of the previous step, if the caller kept it) or from a direction cube map.  The hulls are convex and the
+// direction carries a generic tilt, so the ascent ends at the one global maximiser whatever the start.  Neighbours are
+// fetched four at a time so that their loads are in flight together (the walk is a chain of dependent global loads).
 template <typename T>
-SO101_DEV int hull_support(const DevModel<T>& m, int g, const T (&d)[3], T (&v)[3]) {
+SO101_DEV int hull_support(const DevModel<T>& m, int g, const double (&d)[3], T (&v)[3], int start = -1) {
+  // The search runs in double whatever T is: the tie-breaking tilt (1e-7) is below float resolution, and without it a
+  // face lying flat on the table is a plateau on which the answer would depend on where the walk started.
   const double* vert = reinterpret_cast<const double*>(hull_word_(m, 0));
   const int32_t* adj_start = reinterpret_cast<const int32_t*>(hull_word_(m, 1));
   const int32_t* adj = reinterpret_cast<const int32_t*>(hull_word_(m, 2));
-  const int32_t* cube = reinterpret_cast<const int32_t*>(hull_word_(m, 3));
-  const int res = m.hull_res;
-  int ax = 0;
-  if (abs_(d[1]) > abs_(d[ax])) ax = 1;
-  if (abs_(d[2]) > abs_(d[ax])) ax = 2;
-  const T dm = abs_(d[ax]);
-  const T inv = dm > T(0) ? T(1) / dm : T(0);
-  const T u = d[(ax + 1) % 3] * inv, w = d[(ax + 2) % 3] * inv;
-  int iu = (int)((u + T(1)) * T(0.5) * T(res)), iw = (int)((w + T(1)) * T(0.5) * T(res));
-  iu = iu < 0 ? 0 : (iu >= res ? res - 1 : iu);
-  iw = iw < 0 ? 0 : (iw >= res ? res - 1 : iw);
-  const int face = 2 * ax + (d[ax] < T(0) ? 1 : 0);
-  int cur = cube[((g * 6 + face) * res + iu) * res + iw];
-  T best = d[0] * (T)vert[3 * cur] + d[1] * (T)vert[3 * cur + 1] + d[2] * (T)vert[3 * cur + 2];
+  int cur = start;
+  if (cur < 0) {
+    const int32_t* cube = reinterpret_cast<const int32_t*>(hull_word_(m, 3));
+    const int res = m.hull_res;
+    int ax = 0;
+    if (fabs(d[1]) > fabs(d[ax])) ax = 1;
+    if (fabs(d[2]) > fabs(d[ax])) ax = 2;
+    const double dm = fabs(d[ax]);
+    const double inv = dm > 0.0 ? 1.0 / dm : 0.0;
+    const double u = d[(ax + 1) % 3] * inv, w = d[(ax + 2) % 3] * inv;
+    int iu = (int)((u + 1.0) * 0.5 * res), iw = (int)((w + 1.0) * 0.5 * res);
+    iu = iu < 0 ? 0 : (iu >= res ? res - 1 : iu);
+    iw = iw < 0 ? 0 : (iw >= res ? res - 1 : iw);
+    const int face = 2 * ax + (d[ax] < 0.0 ? 1 : 0);
+    cur = cube[((g * 6 + face) * res + iu) * res + iw];
+  }
+  double best = dot3_(d[0], vert[3 * cur], d[1], vert[3 * cur + 1], d[2], vert[3 * cur + 2]);
 #pragma unroll 1
   for (int it = 0; it < 4096; it++) {
     int nxt = -1;
-    const int e1 = adj_start[cur + 1];
+    const int e0 = adj_start[cur], e1 = adj_start[cur + 1];
 #pragma unroll 1
-    for (int e = adj_start[cur]; e < e1; e++) {
-      const int c = adj[e];
-      const T val = d[0] * (T)vert[3 * c] + d[1] * (T)vert[3 * c + 1] + d[2] * (T)vert[3 * c + 2];
-      if (val > best) { best = val; nxt = c; }
+    for (int e = e0; e < e1; e += 4) {
+      int c[4];
+      double val[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) c[u] = adj[e + u < e1 ? e + u : e1 - 1];
+#pragma unroll
+      for (int u = 0; u < 4; u++) val[u] = dot3_(d[0], vert[3 * c[u]], d[1], vert[3 * c[u] + 1], d[2], vert[3 * c[u] + 2]);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (val[u] > best) { best = val[u]; nxt = c[u]; }
     }
     if (nxt < 0) break;
     cur = nxt;
@@ -192,25 +202,30 @@ SO101_DEV T contact_line_search(const DevModel<T>& m, const T* aref_f, const One
   return result;
 }
 
-// What the contact path reads and writes, copied by the caller inside its `if (hits)` branch: only these copies have
-// their address taken, the hot path's own arrays stay in registers.
+template <typename T>
+struct Con3 {
+  T Jn[NV], Jy[NV], Jx[NV];     // contact frame: normal +z, tangents (0,1,0) and (-1,0,0): Jx holds the x' = -x row
+  T D, c0, vn, vy, vx;          // row weight, -K imp (dist - margin), J . qvel
+};
+
+// What the general solver reads and writes, copied by the caller: only these copies have their address taken, the hot
+// path's own arrays stay in registers.
 template <typename T>
 struct ContactIO {
-  T q[NV], qd[NV], warm[NV], M[21], fsm[NV], aref_f[NV];
+  T warm[NV], M[21], fsm[NV], aref_f[NV];
   T lim_side[NV], lim_aref[NV], lim_D[NV];
-  uint32_t hits, anylim;
+  uint32_t anylim;
   // out
   T a[NV], qc[NV];
   uint32_t flags, newton, lsevals;
 };
 
-// Returns true when at least one hull touches the table: then io.a = qacc and io.qc = qfrc_constraint of the full
-// problem (friction + limit + contact rows) are set and the caller goes straight to mj_checkAcc / mj_Euler.
+// General solver over friction, limit and contact rows (the contacts as contact_geometry found them): the fallback of
+// the inline active-set iteration.  io.a = qacc and io.qc = qfrc_constraint of the full problem.
 template <typename T>
-__device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& io) {
-  const T* q = io.q; const T* qd = io.qd; const T* Mm = io.M; const T* fsm = io.fsm; const T* aref_f = io.aref_f;
+__device__ __noinline__ void contact_solve(const DevModel<T>& m, ContactIO<T>& io, const Con3<T>* con, int ncon) {
+  const T* Mm = io.M; const T* fsm = io.fsm; const T* aref_f = io.aref_f;
   const T* lim_side = io.lim_side; const T* lim_aref = io.lim_aref; const T* lim_D = io.lim_D; const T* warm = io.warm;
-  const uint32_t hits = io.hits;
   const bool anylim = io.anylim != 0;
   T* a = io.a; T* qc = io.qc;
   uint32_t& flags = io.flags;
@@ -228,78 +243,19 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
       os.D[r] = lim_D[i];
     }
   }
-  // ---- world frames and contacts -----------------------------------------------------------------------------------
-  T axw[NV][3], anw[NV][3];            // hinge axes and anchors in the world frame
-  T Rw[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, ow[3] = {T(0), T(0), T(0)};
-  int ncon = 0;
+  // contact frame: normal +z, tangents (0,1,0) and (-1,0,0) (mju_makeFrame); pyramid rows J_n +- mu J_t
 #pragma unroll 1
-  for (int k = 0; k < NV; k++) {
-    T s_, c_, R[9], Rn[9], o[3];
-    sincos_(q[k] - m.qpos0[k], &s_, &c_);
-    make_R(m.E[k], c_, s_, R);
-    rot(Rw, m.r[k], o);
-    ow[0] += o[0]; ow[1] += o[1]; ow[2] += o[2];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rw[3 * i] * R[j] + Rw[3 * i + 1] * R[3 + j] + Rw[3 * i + 2] * R[6 + j];
-#pragma unroll
-    for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
-    axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
-    anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
+  for (int c = 0; c < ncon; c++) {
 #pragma unroll 1
-    for (int b = 0; b < m.trip_n[k]; b++) {
-      if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
-      // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
-      // ordered deterministically (same rule as the oracle's collision())
-      const T d[3] = {m.con_tilt[k][0] - Rw[6], m.con_tilt[k][1] - Rw[7], m.con_tilt[k][2] - Rw[8]};
-      T v[3];
-      hull_support(m, m.trip_geom[k][b], d, v);
-      const T zmin = ow[2] + (Rw[6] * v[0] + Rw[7] * v[1] + Rw[8] * v[2]);
-      const T dist = zmin - m.trip_z;
-      if (!(dist < m.con_margin)) continue;
-      T p[3];
-      rot(Rw, v, p);
-      p[0] += ow[0]; p[1] += ow[1]; p[2] = zmin - T(0.5) * dist;
-      if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
-        flags |= SO101_FLAG_TRIP_TABLE;                  // an edge of the table, or more contacts than rows: not simulated
-        continue;
-      }
-      ncon++;
-      // translational Jacobian of the contact point: column j = axis_j x (p - anchor_j), j <= k
-      T Jn[NV], Jy[NV], Jx[NV];
+    for (int e = 0; e < 4; e++) {
+      const int r = os.n++;
+      const T sg = (e & 1) ? -m.con_mu : m.con_mu;
 #pragma unroll 1
-      for (int j = 0; j < NV; j++) {
-        Jn[j] = Jy[j] = Jx[j] = T(0);
-        if (j > k) continue;
-        const T rx = p[0] - anw[j][0], ry = p[1] - anw[j][1], rz = p[2] - anw[j][2];
-        Jx[j] = axw[j][1] * rz - axw[j][2] * ry;
-        Jy[j] = axw[j][2] * rx - axw[j][0] * rz;
-        Jn[j] = axw[j][0] * ry - axw[j][1] * rx;
-      }
-      const T imp = limit_impedance(m.con_imp, dist, m.con_margin);
-      const T mu = m.con_mu;
-      const T R1 = max_(T(MJ_MINVAL), (T(1) - imp) * (m.con_tran[k] + mu * mu * m.con_tran[k]) / imp);
-      const T Dp = T(1) / (T(2) * mu * mu * R1);
-      // contact frame: normal +z, tangents (0,1,0) and (-1,0,0) (mju_makeFrame); rows J_n +- mu J_t
-#pragma unroll 1
-      for (int e = 0; e < 4; e++) {
-        const int r = os.n++;
-        const T sg = (e & 1) ? -mu : mu;
-        T vel = T(0);
-#pragma unroll 1
-        for (int j = 0; j < NV; j++) {
-          const T Jt = e < 2 ? Jy[j] : -Jx[j];
-          os.J[r][j] = Jn[j] + sg * Jt;
-          vel += os.J[r][j] * qd[j];
-        }
-        os.D[r] = Dp;
-        os.aref[r] = -m.con_B * vel - m.con_K * imp * (dist - m.con_margin);
-      }
+      for (int j = 0; j < NV; j++) os.J[r][j] = con[c].Jn[j] + sg * (e < 2 ? con[c].Jy[j] : con[c].Jx[j]);
+      os.D[r] = con[c].D;
+      os.aref[r] = -m.con_B * (con[c].vn + sg * (e < 2 ? con[c].vy : con[c].vx)) + con[c].c0;
     }
   }
-  if (ncon == 0) return false;
-  flags |= SO101_FLAG_CONTACT;
 
   // ---- direct active-set iteration ----------------------------------------------------------------------------------
   // The objective is strictly convex and piecewise quadratic.  On the piece where friction row i is in zone z_i
@@ -387,7 +343,7 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
 #pragma unroll
       for (int i = 0; i < NV; i++) az[i] = rhs[i];
     }
-    if (done) return true;
+    if (done) return;
   }
 
   // ---- Newton over all rows (mj_solPrimal, Newton flavour) ---------------------------------------------------------
@@ -473,7 +429,6 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
   }
   io.newton += iter;
   if (iter >= m.iterations) flags |= SO101_FLAG_MAXITER;
-  return true;
 }
 
 
@@ -488,72 +443,98 @@ __device__ __noinline__ bool contact_solve(const DevModel<T>& m, ContactIO<T>& i
 // rejected candidate's, up to six times); a step that does not settle returns 2 and takes contact_solve's safeguarded
 // Newton.  0 = no hull touches the table.
 // ----------------------------------------------------------------------------------------------------------------------
-template <typename T>
-struct Con3 {
-  T Jn[NV], Jy[NV], Jx[NV];     // contact frame: normal +z, tangents (0,1,0) and (-1,0,0): Jx holds the x' = -x row
-  T D, c0, vn, vy, vx;          // row weight, -K imp (dist - margin), J . qvel
-};
 
-// Geometry half: world frames from the joint sines / cosines (element stride `st`: 1 = thread-local arrays, 32 = the
-// team's shared memory), exact hull test of every box in `hits`, Jacobian rows and row constants of the contacts found.
+// Geometry half, from the joint sines / cosines (element stride `st`: 1 = thread-local arrays, 32 = the team's shared
+// memory).  Pass 1 - every step in which a collision box is below the table top, mostly without a contact - needs no
+// world frames: the height of a hull vertex is zo + zw . v with the world z axis zw and the origin height zo carried down
+// the chain exactly as the tripwire does, so it is the exact hull test of every box in `hits` and nothing else.  Pass 2,
+// only for the hulls that do touch: world frames of the links, contact points, Jacobian rows and row constants.
+// vcache (nullable): the support vertex each hull had when it was last tested - where the next walk starts.
 template <typename T>
 SO101_DEV int contact_geometry(const DevModel<T>& m, const T* sn, const T* cs, int st, const T (&qd)[NV], uint32_t hits,
-                               Con3<T>* con, uint32_t& flags) {
-  int ncon = 0;
+                               Con3<T>* con, uint32_t& flags, int32_t* vcache = nullptr) {
+  int hk[SO101_MAXTRIP], hv[SO101_MAXTRIP];     // link and support vertex of the hulls that touch
+  T hdist[SO101_MAXTRIP], hz[SO101_MAXTRIP];
+  int nhit = 0;
+  {
+    T zw[3] = {T(0), T(0), T(1)}, zo = T(0);
+#pragma unroll 1
+    for (int k = 0; k < NV; k++) {
+      if (!(hits >> (k * TRIP_PER_LINK))) break;            // no box further down the chain
+      T R[9];
+      make_R(m.E[k], cs[k * st], sn[k * st], R);
+      tripwire_frame(R, m.r[k], zw, zo);
+      if (!(hits >> (k * TRIP_PER_LINK) & 7u)) continue;
+#pragma unroll 1
+      for (int b = 0; b < m.trip_n[k]; b++) {
+        if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
+        // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
+        // ordered deterministically (same rule as the oracle's collision())
+        const double d[3] = {sub_((double)m.con_tilt[k][0], (double)zw[0]), sub_((double)m.con_tilt[k][1], (double)zw[1]),
+                             sub_((double)m.con_tilt[k][2], (double)zw[2])};
+        const int g = m.trip_geom[k][b];
+        T v[3];
+        const int vi = hull_support(m, g, d, v, vcache ? vcache[g] : -1);
+        if (vcache) vcache[g] = vi;
+        const T zmin = add_(zo, dot3_(zw[0], v[0], zw[1], v[1], zw[2], v[2]));
+        const T dist = sub_(zmin, m.trip_z);
+        if (!(dist < m.con_margin)) continue;
+        hk[nhit] = k; hv[nhit] = vi; hdist[nhit] = dist; hz[nhit] = zmin;
+        nhit++;
+      }
+    }
+  }
+  if (nhit == 0) return 0;
+  const double* vert = reinterpret_cast<const double*>(hull_word_(m, 0));
+  int ncon = 0, h = 0;
   T axw[NV][3], anw[NV][3];
   T Rw[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)}, ow[3] = {T(0), T(0), T(0)};
 #pragma unroll 1
-  for (int k = 0; k < NV; k++) {
+  for (int k = 0; k < NV && h < nhit; k++) {
     T R[9], Rn[9], o[3];
     make_R(m.E[k], cs[k * st], sn[k * st], R);
     rot(Rw, m.r[k], o);
-    ow[0] += o[0]; ow[1] += o[1]; ow[2] += o[2];
+    ow[0] = add_(ow[0], o[0]); ow[1] = add_(ow[1], o[1]); ow[2] = add_(ow[2], o[2]);
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rw[3 * i] * R[j] + Rw[3 * i + 1] * R[3 + j] + Rw[3 * i + 2] * R[6 + j];
+      for (int j = 0; j < 3; j++) Rn[3 * i + j] = dot3_(Rw[3 * i], R[j], Rw[3 * i + 1], R[3 + j], Rw[3 * i + 2], R[6 + j]);
 #pragma unroll
     for (int i = 0; i < 9; i++) Rw[i] = Rn[i];
     axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
     anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
-    if (!(hits >> (k * TRIP_PER_LINK) & 7u)) continue;
 #pragma unroll 1
-    for (int b = 0; b < m.trip_n[k]; b++) {
-      if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
-      // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
-      // ordered deterministically (same rule as the oracle's collision())
-      const T d[3] = {m.con_tilt[k][0] - Rw[6], m.con_tilt[k][1] - Rw[7], m.con_tilt[k][2] - Rw[8]};
-      T v[3];
-      hull_support(m, m.trip_geom[k][b], d, v);
-      const T zmin = ow[2] + (Rw[6] * v[0] + Rw[7] * v[1] + Rw[8] * v[2]);
-      const T dist = zmin - m.trip_z;
-      if (!(dist < m.con_margin)) continue;
+    for (; h < nhit && hk[h] == k; h++) {
+      const T dist = hdist[h];
+      const T v[3] = {(T)vert[3 * hv[h]], (T)vert[3 * hv[h] + 1], (T)vert[3 * hv[h] + 2]};
       T p[3];
       rot(Rw, v, p);
-      p[0] += ow[0]; p[1] += ow[1]; p[2] = zmin - T(0.5) * dist;
+      p[0] = add_(p[0], ow[0]); p[1] = add_(p[1], ow[1]); p[2] = fma_(T(-0.5), dist, hz[h]);
       if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
         flags |= SO101_FLAG_TRIP_TABLE;   // an edge of the table, or more contacts than rows: not simulated
         continue;
       }
       Con3<T>& c = con[ncon++];
-      c.vn = c.vy = c.vx = T(0);
+      T vn = T(0), vy = T(0), vx = T(0);
 #pragma unroll 1
       for (int j = 0; j < NV; j++) {
         T jn = T(0), jy = T(0), jx = T(0);
         if (j <= k) {
-          const T rx = p[0] - anw[j][0], ry = p[1] - anw[j][1], rz = p[2] - anw[j][2];
-          jx = -(axw[j][1] * rz - axw[j][2] * ry);
-          jy = axw[j][2] * rx - axw[j][0] * rz;
-          jn = axw[j][0] * ry - axw[j][1] * rx;
+          const T rx = sub_(p[0], anw[j][0]), ry = sub_(p[1], anw[j][1]), rz = sub_(p[2], anw[j][2]);
+          jx = -det2_(axw[j][1], rz, axw[j][2], ry);
+          jy = det2_(axw[j][2], rx, axw[j][0], rz);
+          jn = det2_(axw[j][0], ry, axw[j][1], rx);
         }
         c.Jn[j] = jn; c.Jy[j] = jy; c.Jx[j] = jx;
-        c.vn += jn * qd[j]; c.vy += jy * qd[j]; c.vx += jx * qd[j];
+        vn = fma_(jn, qd[j], vn); vy = fma_(jy, qd[j], vy); vx = fma_(jx, qd[j], vx);
       }
+      c.vn = vn; c.vy = vy; c.vx = vx;
       const T imp = limit_impedance(m.con_imp, dist, m.con_margin);
       const T mu = m.con_mu;
-      const T R1 = max_(T(MJ_MINVAL), (T(1) - imp) * (m.con_tran[k] + mu * mu * m.con_tran[k]) / imp);
-      c.D = T(1) / (T(2) * mu * mu * R1);
-      c.c0 = -m.con_K * imp * (dist - m.con_margin);
+      const T tr = fma_(mul_(mu, mu), m.con_tran[k], m.con_tran[k]);
+      const T R1 = max_(T(MJ_MINVAL), mul_(sub_(T(1), imp), tr) / imp);
+      c.D = T(1) / mul_(mul_(T(2), mul_(mu, mu)), R1);
+      c.c0 = mul_(mul_(-m.con_K, imp), sub_(dist, m.con_margin));
     }
   }
   return ncon;

@@ -38,6 +38,9 @@ SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps,
   const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
   const bool trip = m.ntrip > 0;
   T q[NV], qd[NV];
+  int32_t vcache[SO101_MAXTRIP];   // lookout: support vertex of each hull when it was last tested (see contact_geometry)
+#pragma unroll
+  for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
   __syncthreads();   // (0) initial state published
 #pragma unroll
   for (int k = 0; k < NV; k++) { q[k] = x.q[k][lane]; qd[k] = x.qd[k][lane]; }
@@ -48,7 +51,7 @@ SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps,
     int ss = 0;
 #pragma unroll 1
     for (int64_t n = 0; n < nsteps; n++) {
-      split_lookout_step<T>(m, x, lane, q, qd, ss == frame_skip - 1, trip);
+      split_lookout_step<T>(m, x, lane, q, qd, ss == frame_skip - 1, trip, vcache);
       if (++ss == frame_skip) ss = 0;
     }
   }
@@ -61,9 +64,9 @@ template <typename T> SO101_DEV void publish_state(SplitXch<T>& x, const Env<T>&
 }
 template <typename T, bool SPLIT>
 SO101_DEV void step_env(const DevModel<T>& m, SplitXch<T>& x, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
-                        bool want_site, T (&site)[3], bool trip, Counters& cnt, int64_t nstep) {
+                        bool want_site, T (&site)[3], bool trip, Counters& cnt, int64_t nstep, int32_t* vcache) {
   if (SPLIT) split_dynamics_step<T>(m, x, threadIdx.x & 31, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, nstep);
-  else physics_step<T, true>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt);
+  else physics_step<T, true>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, vcache);
 }
 
 // thread -> env of a stepping kernel; `active` = this thread owns the env (loads, stores, writes rows); exit_block = the
@@ -306,9 +309,12 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   clamp_ctrl(m, u);
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
+  int32_t vcache[SO101_MAXTRIP];   // support vertex of each hull when it was last tested (see contact_geometry)
+#pragma unroll
+  for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
   const bool hold = sflags & SO101_ROLL_GRAVCOMP_HOLD;   // qfrc_applied = qfrc_bias of the state the env step starts from
 #pragma unroll 1
-  for (int ss = 0; ss < nsub; ss++) step_env<T, SPLIT>(m, xch, e, u, hold && ss == 0, ss == nsub - 1, site, trip, cnt, ss);
+  for (int ss = 0; ss < nsub; ss++) step_env<T, SPLIT>(m, xch, e, u, hold && ss == 0, ss == nsub - 1, site, trip, cnt, ss, vcache);
   if (nsub == 0) site_fk(m, e.q, site);
   if (active) {
     store_env(s, i, e);
@@ -353,6 +359,9 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   ctrl_init(spec, env, g);
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
+  int32_t vcache[SO101_MAXTRIP];   // support vertex of each hull when it was last tested (see contact_geometry)
+#pragma unroll
+  for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
   T site[3];
   site_fk(m, e.q, site);
@@ -365,7 +374,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
     if (t > t0) {
 #pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++, nstep++)
-        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
+        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep, vcache);
     }
     ctrl_gen<T>(spec, g, env, i, s.n, t, u);
 #pragma unroll
@@ -402,6 +411,9 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   for (int k = 0; k < NV; k++) { e.q[k] = (T)s0.v[k]; e.qd[k] = (T)s0.v[6 + k]; e.warm[k] = (T)s0.v[12 + k]; }
   Counters cnt = {0, 0, 0, 0};
   const bool trip = m.ntrip > 0;
+  int32_t vcache[SO101_MAXTRIP];   // support vertex of each hull when it was last tested (see contact_geometry)
+#pragma unroll
+  for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
   T site[3];
   site_fk(m, e.q, site);
@@ -416,7 +428,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
       clamp_ctrl(m, uc);
 #pragma unroll 1
       for (int ss = 0; ss < frame_skip; ss++, nstep++)
-        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep);
+        step_env<T, SPLIT>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, cnt, nstep, vcache);
     }
     if (active) {
       float* x = X + ((int64_t)i * (H + 1) + t) * SO101_NOBS;

@@ -627,14 +627,14 @@ struct Rows {
 // model creation: MuJoCo's default is 2)
 template <typename T> SO101_DEV T limit_impedance(const T* si, T pos, T margin) {
   if (si[0] == si[1] || si[2] <= T(MJ_MINVAL)) return T(0.5) * (si[0] + si[1]);
-  T x = abs_((pos - margin) / si[2]);
+  T x = abs_(sub_(pos, margin) / si[2]);
   if (x >= T(1)) return si[1];
   if (x <= T(0)) return si[0];
   T y;
   if (si[4] == T(1)) y = x;
-  else if (x <= si[3]) y = x * x / si[3];
-  else y = T(1) - (T(1) - x) * (T(1) - x) / (T(1) - si[3]);
-  return si[0] + y * (si[1] - si[0]);
+  else if (x <= si[3]) y = mul_(x, x) / si[3];
+  else y = sub_(T(1), mul_(sub_(T(1), x), sub_(T(1), x)) / sub_(T(1), si[3]));
+  return fma_(y, sub_(si[1], si[0]), si[0]);   // rounding-explicit: evaluated by the lookout warp and by the one-warp kernels
 }
 
 // mj_constraintUpdate + Gauss term: total cost at acceleration a, qfrc_constraint and the diagonal
@@ -944,10 +944,10 @@ namespace so101 {
 template <typename T>
 SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, const T* sn, const T* cs, int st,
                               Con3<T>* con, int ncon, const T (&M)[21], const T (&fsm)[NV], const Rows<T>& rw,
-                              T (&a)[NV], T (&qc)[NV], Counters& cnt) {
+                              T (&a)[NV], T (&qc)[NV], Counters& cnt, int32_t* vcache) {
   if (ncon < 0) {
     uint32_t fl = 0;
-    ncon = contact_geometry<T>(m, sn, cs, st, e.qd, hits, con, fl);
+    ncon = contact_geometry<T>(m, sn, cs, st, e.qd, hits, con, fl, vcache);
     e.flags |= fl;
   }
   if (ncon == 0) return false;
@@ -956,24 +956,22 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
   ContactIO<T> io;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
-    io.q[i] = e.q[i]; io.qd[i] = e.qd[i]; io.warm[i] = e.warm[i]; io.fsm[i] = fsm[i]; io.aref_f[i] = rw.aref_f[i];
+    io.warm[i] = e.warm[i]; io.fsm[i] = fsm[i]; io.aref_f[i] = rw.aref_f[i];
     io.lim_side[i] = rw.anylim ? rw.side[i] : T(0);
     io.lim_aref[i] = rw.anylim ? rw.aref_l[i] : T(0);
     io.lim_D[i] = rw.anylim ? rw.D_l[i] : T(0);
   }
 #pragma unroll
   for (int i = 0; i < 21; i++) io.M[i] = M[i];
-  io.hits = hits; io.anylim = rw.anylim ? 1u : 0u;
+  io.anylim = rw.anylim ? 1u : 0u;
   io.flags = 0; io.newton = 0; io.lsevals = 0;
-  const bool in_contact = contact_solve<T>(m, io);
+  contact_solve<T>(m, io, con, ncon);
   e.flags |= io.flags;
-  if (in_contact) {
 #pragma unroll
-    for (int i = 0; i < NV; i++) { a[i] = io.a[i]; qc[i] = io.qc[i]; }
-    cnt.newton += io.newton;
-    cnt.lsevals += io.lsevals;
-  }
-  return in_contact;
+  for (int i = 0; i < NV; i++) { a[i] = io.a[i]; qc[i] = io.qc[i]; }
+  cnt.newton += io.newton;
+  cnt.lsevals += io.lsevals;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -986,7 +984,7 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
 // ------------------------------------------------------------------------------------------
 template <typename T, bool SYNC>
 SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
-                            bool want_site, T (&site)[3], bool trip, Counters& cnt) {
+                            bool want_site, T (&site)[3], bool trip, Counters& cnt, int32_t* vcache) {
   if (SYNC) __syncthreads();
   // mj_checkPos / mj_checkVel
   {
@@ -1045,7 +1043,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     bool in_contact = false;
     if (m.con_enabled) {
       Con3<T> con[MAXCON];
-      in_contact = contact_branch<T>(m, e, hits, sn, cs, 1, con, -1, M, fsm, rw, a, qc, cnt);
+      in_contact = contact_branch<T>(m, e, hits, sn, cs, 1, con, -1, M, fsm, rw, a, qc, cnt, vcache);
     } else {
       e.flags |= SO101_FLAG_TRIP_TABLE;
     }
@@ -1369,7 +1367,7 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 // lookout warp: contact tripwire and (on the last substep of a control step) the observation site
 template <typename T>
 SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
-                                  bool want_site, bool trip) {
+                                  bool want_site, bool trip, int32_t* vcache) {
   team_check_state(m, q, qd);
   team_sincos(m, x, lane, 2, q);
   uint32_t fl = 0, hits = 0;
@@ -1383,7 +1381,7 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
     uint32_t nc = 0;
     if (hits && m.con_enabled) {
       Con3<T> con[MAXCON];
-      nc = (uint32_t)contact_geometry<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, qd, hits, con, fl);
+      nc = (uint32_t)contact_geometry<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, qd, hits, con, fl, vcache);
       if (nc > (uint32_t)XCON) {
         nc = XCON_MANY;
       } else {
@@ -1477,7 +1475,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
           }
         }
         solved = contact_branch<T>(m, e, x.hits[lane], &x.sn[0][lane], &x.cs[0][lane], 32, con,
-                                   nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, a, qc, cnt);
+                                   nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, a, qc, cnt, nullptr);
       }
     } else {
       e.flags |= SO101_FLAG_TRIP_TABLE;
