@@ -35,49 +35,52 @@ template <typename T> SO101_DEV uint64_t hull_word_(const DevModel<T>& m, int wh
   return ((uint64_t)(uint32_t)m.hull_ptr[2 * which + 1] << 32) | (uint64_t)(uint32_t)m.hull_ptr[2 * which];
 }
 
+// first vertex of a hull walk without a cached one: direction cube map (cold: once per hull and launch)
+template <typename T>
+__device__ __noinline__ int hull_cube_start(const DevModel<T>& m, int g, double d0, double d1, double d2) {
+  const int32_t* cube = reinterpret_cast<const int32_t*>(hull_word_(m, 3));
+  const int res = m.hull_res;
+  const double d[3] = {d0, d1, d2};
+  int ax = 0;
+  if (fabs(d[1]) > fabs(d[ax])) ax = 1;
+  if (fabs(d[2]) > fabs(d[ax])) ax = 2;
+  const double dm = fabs(d[ax]);
+  const double inv = dm > 0.0 ? 1.0 / dm : 0.0;
+  const double u = d[(ax + 1) % 3] * inv, w = d[(ax + 2) % 3] * inv;
+  int iu = (int)((u + 1.0) * 0.5 * res), iw = (int)((w + 1.0) * 0.5 * res);
+  iu = iu < 0 ? 0 : (iu >= res ? res - 1 : iu);
+  iw = iw < 0 ? 0 : (iw >= res ? res - 1 : iw);
+  const int face = 2 * ax + (d[ax] < 0.0 ? 1 : 0);
+  return cube[((g * 6 + face) * res + iu) * res + iw];
+}
+
 // support vertex of hull `g` for direction d (link frame): steepest ascent on the hull's edge graph from `start` (the
 // support vertex of the previous step, if the caller kept it) or from a direction cube map.  The hulls are convex and the
 // direction carries a generic tilt, so the ascent ends at the one global maximiser whatever the start.  Neighbours are
-// fetched four at a time so that their loads are in flight together (the walk is a chain of dependent global loads).
+// fetched two at a time so that their loads are in flight together (the walk is a chain of dependent global loads); the
+// code is kept small on purpose: in a team kernel every instruction line this rare path touches evicts one of the hot
+// step's from the SM's instruction cache (measured: tools/team_timing.py, profiles/README.md round 2).
+// The search runs in double whatever T is: the tie-breaking tilt (1e-7) is below float resolution, and without it a
+// face lying flat on the table is a plateau on which the answer would depend on where the walk started.
 template <typename T>
 SO101_DEV int hull_support(const DevModel<T>& m, int g, const double (&d)[3], T (&v)[3], int start = -1) {
-  // The search runs in double whatever T is: the tie-breaking tilt (1e-7) is below float resolution, and without it a
-  // face lying flat on the table is a plateau on which the answer would depend on where the walk started.
   const double* vert = reinterpret_cast<const double*>(hull_word_(m, 0));
   const int32_t* adj_start = reinterpret_cast<const int32_t*>(hull_word_(m, 1));
   const int32_t* adj = reinterpret_cast<const int32_t*>(hull_word_(m, 2));
   int cur = start;
-  if (cur < 0) {
-    const int32_t* cube = reinterpret_cast<const int32_t*>(hull_word_(m, 3));
-    const int res = m.hull_res;
-    int ax = 0;
-    if (fabs(d[1]) > fabs(d[ax])) ax = 1;
-    if (fabs(d[2]) > fabs(d[ax])) ax = 2;
-    const double dm = fabs(d[ax]);
-    const double inv = dm > 0.0 ? 1.0 / dm : 0.0;
-    const double u = d[(ax + 1) % 3] * inv, w = d[(ax + 2) % 3] * inv;
-    int iu = (int)((u + 1.0) * 0.5 * res), iw = (int)((w + 1.0) * 0.5 * res);
-    iu = iu < 0 ? 0 : (iu >= res ? res - 1 : iu);
-    iw = iw < 0 ? 0 : (iw >= res ? res - 1 : iw);
-    const int face = 2 * ax + (d[ax] < 0.0 ? 1 : 0);
-    cur = cube[((g * 6 + face) * res + iu) * res + iw];
-  }
+  if (cur < 0) cur = hull_cube_start(m, g, d[0], d[1], d[2]);
   double best = dot3_(d[0], vert[3 * cur], d[1], vert[3 * cur + 1], d[2], vert[3 * cur + 2]);
 #pragma unroll 1
   for (int it = 0; it < 4096; it++) {
     int nxt = -1;
     const int e0 = adj_start[cur], e1 = adj_start[cur + 1];
 #pragma unroll 1
-    for (int e = e0; e < e1; e += 4) {
-      int c[4];
-      double val[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) c[u] = adj[e + u < e1 ? e + u : e1 - 1];
-#pragma unroll
-      for (int u = 0; u < 4; u++) val[u] = dot3_(d[0], vert[3 * c[u]], d[1], vert[3 * c[u] + 1], d[2], vert[3 * c[u] + 2]);
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (val[u] > best) { best = val[u]; nxt = c[u]; }
+    for (int e = e0; e < e1; e += 2) {
+      const int c0 = adj[e], c1 = adj[e + 1 < e1 ? e + 1 : e];
+      const double v0 = dot3_(d[0], vert[3 * c0], d[1], vert[3 * c0 + 1], d[2], vert[3 * c0 + 2]);
+      const double v1 = dot3_(d[0], vert[3 * c1], d[1], vert[3 * c1 + 1], d[2], vert[3 * c1 + 2]);
+      if (v0 > best) { best = v0; nxt = c0; }
+      if (v1 > best) { best = v1; nxt = c1; }
     }
     if (nxt < 0) break;
     cur = nxt;
@@ -444,47 +447,54 @@ __device__ __noinline__ void contact_solve(const DevModel<T>& m, ContactIO<T>& i
 // Newton.  0 = no hull touches the table.
 // ----------------------------------------------------------------------------------------------------------------------
 
-// Geometry half, from the joint sines / cosines (element stride `st`: 1 = thread-local arrays, 32 = the team's shared
-// memory).  Pass 1 - every step in which a collision box is below the table top, mostly without a contact - needs no
-// world frames: the height of a hull vertex is zo + zw . v with the world z axis zw and the origin height zo carried down
-// the chain exactly as the tripwire does, so it is the exact hull test of every box in `hits` and nothing else.  Pass 2,
-// only for the hulls that do touch: world frames of the links, contact points, Jacobian rows and row constants.
-// vcache (nullable): the support vertex each hull had when it was last tested - where the next walk starts.
+// Geometry half.  Every step in which a collision box is below the table top - mostly without a contact - needs only
+// the exact hull test, and that needs no world frames: the height of a hull vertex is zo + zw . v with the world z axis
+// zw and the origin height zo of the link frame, carried down the chain exactly as the tripwire does.  The hulls that do
+// touch are noted in a HitList; only for them contact_rows forms world frames, contact points, Jacobian rows and row
+// constants.  vcache (nullable): the support vertex each hull had when it was last tested - where the next walk starts.
 template <typename T>
-SO101_DEV int contact_geometry(const DevModel<T>& m, const T* sn, const T* cs, int st, const T (&qd)[NV], uint32_t hits,
-                               Con3<T>* con, uint32_t& flags, int32_t* vcache = nullptr) {
-  int hk[SO101_MAXTRIP], hv[SO101_MAXTRIP];     // link and support vertex of the hulls that touch
-  T hdist[SO101_MAXTRIP], hz[SO101_MAXTRIP];
-  int nhit = 0;
-  {
-    T zw[3] = {T(0), T(0), T(1)}, zo = T(0);
+struct HitList {
+  int n;
+  int k[SO101_MAXTRIP], v[SO101_MAXTRIP];     // link and support vertex of the hulls that touch
+  T dist[SO101_MAXTRIP], z[SO101_MAXTRIP];
+};
+template <typename T>
+SO101_DEV void hull_test(const DevModel<T>& m, int k, int b, const T (&zw)[3], T zo, int32_t* vcache, HitList<T>& hl) {
+  // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
+  // ordered deterministically (same rule as the oracle's collision())
+  const double d[3] = {sub_((double)m.con_tilt[k][0], (double)zw[0]), sub_((double)m.con_tilt[k][1], (double)zw[1]),
+                       sub_((double)m.con_tilt[k][2], (double)zw[2])};
+  const int g = m.trip_geom[k][b];
+  T v[3];
+  const int vi = hull_support(m, g, d, v, vcache ? vcache[g] : -1);
+  if (vcache) vcache[g] = vi;
+  const T zmin = add_(zo, dot3_(zw[0], v[0], zw[1], v[1], zw[2], v[2]));
+  const T dist = sub_(zmin, m.trip_z);
+  if (!(dist < m.con_margin)) return;
+  hl.k[hl.n] = k; hl.v[hl.n] = vi; hl.dist[hl.n] = dist; hl.z[hl.n] = zmin;
+  hl.n++;
+}
+// exact test of every box in `hits` (the one-warp kernels: the chain of (zw, zo) is walked again here)
+template <typename T>
+SO101_DEV void hull_tests(const DevModel<T>& m, const T* sn, const T* cs, int st, uint32_t hits, int32_t* vcache,
+                          HitList<T>& hl) {
+  T zw[3] = {T(0), T(0), T(1)}, zo = T(0);
 #pragma unroll 1
-    for (int k = 0; k < NV; k++) {
-      if (!(hits >> (k * TRIP_PER_LINK))) break;            // no box further down the chain
-      T R[9];
-      make_R(m.E[k], cs[k * st], sn[k * st], R);
-      tripwire_frame(R, m.r[k], zw, zo);
-      if (!(hits >> (k * TRIP_PER_LINK) & 7u)) continue;
+  for (int k = 0; k < NV; k++) {
+    if (!(hits >> (k * TRIP_PER_LINK))) break;            // no box further down the chain
+    T R[9];
+    make_R(m.E[k], cs[k * st], sn[k * st], R);
+    tripwire_frame(R, m.r[k], zw, zo);
 #pragma unroll 1
-      for (int b = 0; b < m.trip_n[k]; b++) {
-        if (!(hits >> (k * TRIP_PER_LINK + b) & 1u)) continue;
-        // "down" in the link frame, tilted by 1e-7 so that the vertices of an edge that lies parallel to the table are
-        // ordered deterministically (same rule as the oracle's collision())
-        const double d[3] = {sub_((double)m.con_tilt[k][0], (double)zw[0]), sub_((double)m.con_tilt[k][1], (double)zw[1]),
-                             sub_((double)m.con_tilt[k][2], (double)zw[2])};
-        const int g = m.trip_geom[k][b];
-        T v[3];
-        const int vi = hull_support(m, g, d, v, vcache ? vcache[g] : -1);
-        if (vcache) vcache[g] = vi;
-        const T zmin = add_(zo, dot3_(zw[0], v[0], zw[1], v[1], zw[2], v[2]));
-        const T dist = sub_(zmin, m.trip_z);
-        if (!(dist < m.con_margin)) continue;
-        hk[nhit] = k; hv[nhit] = vi; hdist[nhit] = dist; hz[nhit] = zmin;
-        nhit++;
-      }
-    }
+    for (int b = 0; b < m.trip_n[k]; b++)
+      if (hits >> (k * TRIP_PER_LINK + b) & 1u) hull_test(m, k, b, zw, zo, vcache, hl);
   }
-  if (nhit == 0) return 0;
+}
+// the contacts of the hulls in the list -> con[], returns their number
+template <typename T>
+SO101_DEV int contact_rows(const DevModel<T>& m, const T* sn, const T* cs, int st, const T (&qd)[NV], const HitList<T>& hl,
+                           Con3<T>* con, uint32_t& flags) {
+  const int nhit = hl.n;
   const double* vert = reinterpret_cast<const double*>(hull_word_(m, 0));
   int ncon = 0, h = 0;
   T axw[NV][3], anw[NV][3];
@@ -504,12 +514,12 @@ SO101_DEV int contact_geometry(const DevModel<T>& m, const T* sn, const T* cs, i
     axw[k][0] = Rw[2]; axw[k][1] = Rw[5]; axw[k][2] = Rw[8];
     anw[k][0] = ow[0]; anw[k][1] = ow[1]; anw[k][2] = ow[2];
 #pragma unroll 1
-    for (; h < nhit && hk[h] == k; h++) {
-      const T dist = hdist[h];
-      const T v[3] = {(T)vert[3 * hv[h]], (T)vert[3 * hv[h] + 1], (T)vert[3 * hv[h] + 2]};
+    for (; h < nhit && hl.k[h] == k; h++) {
+      const T dist = hl.dist[h];
+      const T v[3] = {(T)vert[3 * hl.v[h]], (T)vert[3 * hl.v[h] + 1], (T)vert[3 * hl.v[h] + 2]};
       T p[3];
       rot(Rw, v, p);
-      p[0] = add_(p[0], ow[0]); p[1] = add_(p[1], ow[1]); p[2] = fma_(T(-0.5), dist, hz[h]);
+      p[0] = add_(p[0], ow[0]); p[1] = add_(p[1], ow[1]); p[2] = fma_(T(-0.5), dist, hl.z[h]);
       if (p[0] < m.con_box[0] || p[0] > m.con_box[1] || p[1] < m.con_box[2] || p[1] > m.con_box[3] || ncon == MAXCON) {
         flags |= SO101_FLAG_TRIP_TABLE;   // an edge of the table, or more contacts than rows: not simulated
         continue;
@@ -538,6 +548,15 @@ SO101_DEV int contact_geometry(const DevModel<T>& m, const T* sn, const T* cs, i
     }
   }
   return ncon;
+}
+template <typename T>
+SO101_DEV int contact_geometry(const DevModel<T>& m, const T* sn, const T* cs, int st, const T (&qd)[NV], uint32_t hits,
+                               Con3<T>* con, uint32_t& flags, int32_t* vcache = nullptr) {
+  HitList<T> hl;
+  hl.n = 0;
+  hull_tests(m, sn, cs, st, hits, vcache, hl);
+  if (hl.n == 0) return 0;
+  return contact_rows(m, sn, cs, st, qd, hl, con, flags);
 }
 
 // Solve half: direct active-set iteration over friction, limit and contact rows.  1 = solved (a, qc set), 2 = did not

@@ -2,5 +2,18 @@
 //   -DSO101_TU_T=double|float -DSO101_TU_SPLIT=false|true
 // so that the stepping kernels build in parallel.  Everything is in so101_kernels.cuh.
 #include "so101_kernels.cuh"
+#define SO101_CAT2(a, b) a##b
+#define SO101_CAT(a, b) SO101_CAT2(a, b)
+#define SO101_TIMING_NAME SO101_CAT(so101_debug_timing_, SO101_TU_T)
 
 SO101_LAUNCHERS(, SO101_TU_T, SO101_TU_SPLIT)
+
+#ifdef SO101_TIMING
+#if SO101_TU_SPLIT
+extern "C" int SO101_TIMING_NAME(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, so101::g_timing, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(so101::g_timing, z, sizeof z); }
+  return 0;
+}
+#endif
+#endif

@@ -1073,6 +1073,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
       }
     }
   }
+  __syncwarp();   // lanes that took the contact branch rejoin here
   while (phase != PH_DONE) {
     {
       T A[21];
@@ -1269,6 +1270,12 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 // bit-identical to the one-warp path (GPU test `test_split_team_is_bitwise_identical`): which kernel a batch size
 // selects never changes a trajectory.
 // ------------------------------------------------------------------------------------------
+#ifdef SO101_TIMING   // debug build: where the dynamics warp of a team spends its cycles, by kind of step (tools/team_timing.py)
+__device__ unsigned long long g_timing[16];
+#define SO101_TICK(var) const long long var = clock64()
+#else
+#define SO101_TICK(var)
+#endif
 constexpr int TEAM_WARPS = 3;
 constexpr int XCON = 2, XCON_MANY = 255;
 constexpr int CON3_N = 3 * NV + 5;     // Con3 as a flat array: Jn, Jy, Jx, D, c0, vn, vy, vx
@@ -1364,40 +1371,68 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   for (int i = 0; i < NV; i++) { q[i] = x.q[i][lane]; qd[i] = x.qd[i][lane]; }
 }
 
+// contact tripwire over all links with the exact hull test of every box that trips done on the spot, from the same
+// (zw, zo): one walk down the chain serves both (team lookout warp)
+template <typename T>
+SO101_DEV void tripwire_all_tests(const DevModel<T>& m, const T* sn, const T* cs, int st, const T* q, int qst,
+                                  uint32_t& flags, uint32_t& hits, int32_t* vcache, HitList<T>& hl) {
+  T zw[3] = {T(0), T(0), T(1)};  // world z axis in the current frame
+  T zo = T(0);                   // world height of the current frame origin
+#pragma unroll 1
+  for (int k = 0; k < NV; k++) {
+    T R[9];
+    make_R(m.E[k], cs[k * st], sn[k * st], R);
+    tripwire_frame(R, m.r[k], zw, zo);
+#pragma unroll 1
+    for (int b = 0; b < m.trip_n[k]; b++) {
+      const uint32_t before = hits;
+      tripwire_box(m, k, b, zw, zo, hits);
+      if (hits != before) hull_test(m, k, b, zw, zo, vcache, hl);
+    }
+    const T qk = q[k * qst];
+    if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
+  }
+}
+
 // lookout warp: contact tripwire and (on the last substep of a control step) the observation site
 template <typename T>
 SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
                                   bool want_site, bool trip, int32_t* vcache) {
   team_check_state(m, q, qd);
   team_sincos(m, x, lane, 2, q);
-  uint32_t fl = 0, hits = 0;
+  uint32_t fl = 0, hits = 0, nc = 0;
   if (trip) {
     T lq[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) lq[i] = q[i];
-    tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
-  }
-  {
-    uint32_t nc = 0;
-    if (hits && m.con_enabled) {
-      Con3<T> con[MAXCON];
-      nc = (uint32_t)contact_geometry<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, qd, hits, con, fl, vcache);
-      if (nc > (uint32_t)XCON) {
-        nc = XCON_MANY;
-      } else {
+    if (m.con_enabled) {
+      HitList<T> hl;
+      hl.n = 0;
+      tripwire_all_tests(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits, vcache, hl);
+#ifndef SO101_EXP_NOGEOM
+      if (hl.n) {      // the geometry half of the contact path runs here, beside the dynamics warp's RNEA
+        Con3<T> con[MAXCON];
+        nc = (uint32_t)contact_rows<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, qd, hl, con, fl);
+        if (nc > (uint32_t)XCON) {
+          nc = XCON_MANY;
+        } else {
 #pragma unroll 1
-        for (uint32_t c = 0; c < nc; c++) {
+          for (uint32_t c = 0; c < nc; c++) {
 #pragma unroll
-          for (int j = 0; j < NV; j++) {
-            x.con[c][j][lane] = con[c].Jn[j]; x.con[c][NV + j][lane] = con[c].Jy[j]; x.con[c][2 * NV + j][lane] = con[c].Jx[j];
+            for (int j = 0; j < NV; j++) {
+              x.con[c][j][lane] = con[c].Jn[j]; x.con[c][NV + j][lane] = con[c].Jy[j]; x.con[c][2 * NV + j][lane] = con[c].Jx[j];
+            }
+            x.con[c][3 * NV][lane] = con[c].D; x.con[c][3 * NV + 1][lane] = con[c].c0;
+            x.con[c][3 * NV + 2][lane] = con[c].vn; x.con[c][3 * NV + 3][lane] = con[c].vy; x.con[c][3 * NV + 4][lane] = con[c].vx;
           }
-          x.con[c][3 * NV][lane] = con[c].D; x.con[c][3 * NV + 1][lane] = con[c].c0;
-          x.con[c][3 * NV + 2][lane] = con[c].vn; x.con[c][3 * NV + 3][lane] = con[c].vy; x.con[c][3 * NV + 4][lane] = con[c].vx;
         }
       }
+#endif
+    } else {
+      tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
     }
-    x.ncon[lane] = nc;
   }
+  x.ncon[lane] = nc;
   x.trip[lane] = fl;
   x.hits[lane] = hits;
   if (want_site) {
@@ -1420,6 +1455,7 @@ template <typename T>
 SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lane, Env<T>& e, const T (&ctrl)[NV],
                                    bool gravcomp_capture, bool want_site, T (&site)[3], bool trip, Counters& cnt,
                                    int64_t nstep) {
+  SO101_TICK(tk0);
   if (team_check_state(m, e.q, e.qd)) {
 #pragma unroll
     for (int i = 0; i < NV; i++) { e.warm[i] = T(0); e.fa[i] = T(0); }
@@ -1446,7 +1482,9 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     for (int i = 0; i < NV; i++) asm_[i] = fsm[i];
     constrained = m.nfriction != 0 || rw.anylim;
   }
+  SO101_TICK(tk1);
   __syncthreads();   // (A) wait for the geometry and lookout warps
+  SO101_TICK(tk2);
   T Ls[15], Dinv[NV];
   T a[NV], Ma[NV], qc[NV], hd[NV];
   bool solved = false;
@@ -1458,7 +1496,11 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
+#ifdef SO101_EXP_HOTONLY
+  if (false) {
+#else
   if (trip && x.hits[lane]) {        // table contact (see physics_step)
+#endif
     if (m.con_enabled) {
       const uint32_t nc = x.ncon[lane];
       if (nc) {
@@ -1481,6 +1523,8 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
       e.flags |= SO101_FLAG_TRIP_TABLE;
     }
   }
+  __syncwarp();   // the lanes that took the contact branch rejoin here (measured: without it a lane whose box tripped ran the
+                  // direct solve below on its own, after the other 31: +2000 cycles per such step, tools/team_timing.py)
   if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     // zone guess from qacc_smooth approximated with the factor of the previous step's M (split_geometry_step)
     const int rb = LaggedGuess<T>::value ? (int)(nstep & 1) : 0;
@@ -1520,7 +1564,11 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #pragma unroll
     for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); hd[i] = T(0); }
   }
+#ifdef SO101_EXP_HOTONLY
+  if (false) {
+#else
   if (!solved && constrained) {
+#endif
     T cost;
     if (!rw.anylim) {   // prox start (see physics_step)
 #pragma unroll
@@ -1614,7 +1662,9 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     }
   }
   }
+  SO101_TICK(tk3);
   __syncthreads();   // (E) factors of M + h B
+  SO101_TICK(tk4);
   {
   // mj_checkAcc, mj_Euler
   bool bad = false;
@@ -1650,6 +1700,20 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #pragma unroll
   for (int i = 0; i < NV; i++) { x.q[i][lane] = e.q[i]; x.qd[i][lane] = e.qd[i]; }
   __syncthreads();   // (B) new state published
+#ifdef SO101_TIMING
+  {
+    SO101_TICK(tk5);
+    const uint32_t anyhit = __ballot_sync(0xffffffffu, trip && x.hits[lane] != 0), anycon = __ballot_sync(0xffffffffu, solved && (e.flags & SO101_FLAG_CONTACT));
+    if (lane == 0) {
+      const int kind = anycon ? 2 : (anyhit ? 1 : 0);     // 0: plain step, 1: a box tripped, 2: a contact was solved
+      atomicAdd(&g_timing[kind * 5 + 0], 1ull);
+      atomicAdd(&g_timing[kind * 5 + 1], (unsigned long long)(tk1 - tk0));   // own work before (A)
+      atomicAdd(&g_timing[kind * 5 + 2], (unsigned long long)(tk2 - tk1));   // waiting at (A)
+      atomicAdd(&g_timing[kind * 5 + 3], (unsigned long long)(tk3 - tk2));   // solve
+      atomicAdd(&g_timing[kind * 5 + 4], (unsigned long long)(tk5 - tk3));   // (E) .. end of step
+    }
+  }
+#endif
 }
 
 }  // namespace so101
