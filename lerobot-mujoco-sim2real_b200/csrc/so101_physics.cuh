@@ -944,7 +944,7 @@ namespace so101 {
 template <typename T>
 SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, const T* sn, const T* cs, int st,
                               Con3<T>* con, int ncon, const T (&M)[21], const T (&fsm)[NV], const Rows<T>& rw,
-                              T (&a)[NV], T (&qc)[NV], Counters& cnt, int32_t* vcache) {
+                              const T (&asm_)[NV], T (&a)[NV], T (&qc)[NV], Counters& cnt, int32_t* vcache) {
   if (ncon < 0) {
     uint32_t fl = 0;
     ncon = contact_geometry<T>(m, sn, cs, st, e.qd, hits, con, fl, vcache);
@@ -952,7 +952,10 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
   }
   if (ncon == 0) return false;
   e.flags |= SO101_FLAG_CONTACT;
-  if (contact_active_set<T>(m, con, ncon, e.warm, M, fsm, rw, a, qc, cnt) == 1) return true;
+  // start of the active-set iteration: qacc_smooth (`asm_`) with the per-dof friction guess; with an active joint-limit
+  // row (no per-dof rule for it) qacc_warmstart
+  if ((rw.anylim ? contact_active_set<T>(m, con, ncon, e.warm, false, M, fsm, rw, a, qc, cnt)
+                 : contact_active_set<T>(m, con, ncon, asm_, true, M, fsm, rw, a, qc, cnt)) == 1) return true;
   ContactIO<T> io;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
@@ -1037,43 +1040,6 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
   T asm_[NV], a[NV], Ma[NV], qc[NV], hd[NV], sr[NV], zone[NV];
   T cost = T(0);
   bool need_setup = false;
-  if (hits) {
-    // a collision box is below the table top: exact hull test and, if a hull does touch, the full constraint solve with
-    // contact rows - out of line (so101_contact.cuh); the phase machine then only runs its Euler solve
-    bool in_contact = false;
-    if (m.con_enabled) {
-      Con3<T> con[MAXCON];
-      in_contact = contact_branch<T>(m, e, hits, sn, cs, 1, con, -1, M, fsm, rw, a, qc, cnt, vcache);
-    } else {
-      e.flags |= SO101_FLAG_TRIP_TABLE;
-    }
-    if (in_contact) {
-      bool bad = false;
-#pragma unroll
-      for (int i = 0; i < NV; i++) bad |= bad_(a[i]);
-      if (bad) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) { e.q[i] = m.qpos0[i]; e.qd[i] = T(0); e.warm[i] = T(0); e.fa[i] = T(0); }
-        e.time = T(0);
-        e.flags |= SO101_FLAG_BADSTATE;
-        phase = PH_DONE;
-      } else if (m.any_damping) {
-#pragma unroll
-        for (int i = 0; i < NV; i++) { dd[i] = m.h * m.damping[i]; x[i] = fsm[i] + qc[i]; }
-        phase = PH_EULER;
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; i++) {
-          e.qd[i] += m.h * a[i];
-          e.q[i] += m.h * e.qd[i];
-          e.warm[i] = a[i];
-        }
-        e.time += m.h;
-        phase = PH_DONE;
-      }
-    }
-  }
-  __syncwarp();   // lanes that took the contact branch rejoin here
   while (phase != PH_DONE) {
     {
       T A[21];
@@ -1088,7 +1054,20 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
     if (ph == PH_SMOOTH) {
 #pragma unroll
       for (int i = 0; i < NV; i++) { asm_[i] = x[i]; a[i] = x[i]; qc[i] = T(0); hd[i] = T(0); }
-      if (!constrained) {
+      bool in_contact = false;
+      if (hits) {
+        // a collision box is below the table top: exact hull test and, if a hull does touch, the full constraint solve
+        // with contact rows (so101_contact.cuh); the phase machine then only runs its Euler solve
+        if (m.con_enabled) {
+          Con3<T> con[MAXCON];
+          in_contact = contact_branch<T>(m, e, hits, sn, cs, 1, con, -1, M, fsm, rw, asm_, a, qc, cnt, vcache);
+        } else {
+          e.flags |= SO101_FLAG_TRIP_TABLE;
+        }
+      }
+      if (in_contact) {
+        to_euler = true;
+      } else if (!constrained) {
         to_euler = true;  // nefc == 0: qacc = qacc_smooth
       } else if (!rw.anylim) {
         active_set_guess(m, rw, M, asm_, zone);
@@ -1496,11 +1475,17 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   }
 #pragma unroll
   for (int i = 0; i < 21; i++) M[i] = x.M[i][lane];
-#ifdef SO101_EXP_HOTONLY
-  if (false) {
-#else
+  if (constrained && !rw.anylim) {
+    // qacc_smooth approximated with the factor of the previous step's M (split_geometry_step): feeds the zone guess of
+    // the direct solve and the first piece of the contact solve
+    const int rb = LaggedGuess<T>::value ? (int)(nstep & 1) : 0;
+#pragma unroll
+    for (int i = 0; i < 15; i++) Ls[i] = x.L1[rb][i][lane];
+#pragma unroll
+    for (int i = 0; i < NV; i++) Dinv[i] = x.D1inv[rb][i][lane];
+    ldl6_solve(Ls, Dinv, asm_);
+  }
   if (trip && x.hits[lane]) {        // table contact (see physics_step)
-#endif
     if (m.con_enabled) {
       const uint32_t nc = x.ncon[lane];
       if (nc) {
@@ -1517,7 +1502,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
           }
         }
         solved = contact_branch<T>(m, e, x.hits[lane], &x.sn[0][lane], &x.cs[0][lane], 32, con,
-                                   nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, a, qc, cnt, nullptr);
+                                   nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, asm_, a, qc, cnt, nullptr);
       }
     } else {
       e.flags |= SO101_FLAG_TRIP_TABLE;
@@ -1526,13 +1511,6 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   __syncwarp();   // the lanes that took the contact branch rejoin here (measured: without it a lane whose box tripped ran the
                   // direct solve below on its own, after the other 31: +2000 cycles per such step, tools/team_timing.py)
   if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
-    // zone guess from qacc_smooth approximated with the factor of the previous step's M (split_geometry_step)
-    const int rb = LaggedGuess<T>::value ? (int)(nstep & 1) : 0;
-#pragma unroll
-    for (int i = 0; i < 15; i++) Ls[i] = x.L1[rb][i][lane];
-#pragma unroll
-    for (int i = 0; i < NV; i++) Dinv[i] = x.D1inv[rb][i][lane];
-    ldl6_solve(Ls, Dinv, asm_);
     T zone[NV], xs[NV], dh[NV];
     active_set_guess(m, rw, M, asm_, zone);
 #pragma unroll 1
@@ -1564,11 +1542,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #pragma unroll
     for (int i = 0; i < NV; i++) { a[i] = asm_[i]; qc[i] = T(0); hd[i] = T(0); }
   }
-#ifdef SO101_EXP_HOTONLY
-  if (false) {
-#else
   if (!solved && constrained) {
-#endif
     T cost;
     if (!rw.anylim) {   // prox start (see physics_step)
 #pragma unroll
