@@ -327,6 +327,37 @@ int so101_koopman_score(const double* A, const double* B, int nz, int nu, const 
                         double q_weight, double r_weight, const void* U, int H, int64_t n, int dtype, int device,
                         int nobs, void* Xhat, void* cost, void* stream);
 
+/* ---- the body of the reference's MPC loop for n environments at once -----------------------------------
+   Reference, per frame [REF Koopman_MPC.py:197-222, control/MPC_Controler.py:143-166]: z0 = Psi(state) = [x, encoder(x)]
+   (MLP with ReLU between layers [REF models/KoopmanBase.py:12-47]); the H reference rows of the window lifted the same
+   way (rows past the end of the trajectory stay zero in lifted space); the MPC problem ('mpc' over u, or the default
+   'delta_mpc' [REF args.py:75] over delta_u with u_t = u_prev + sum delta_u) solved; u0 = u_opt[0] + u_prev;
+   a = clip(u0, +-clip); u_prev <- u0 [REF Koopman_MPC.py:217].  The problem is an unconstrained quadratic, so
+   u_opt[0] = Kz z0 + sum_t Kr_t zref_t + Ku u_prev with gains that depend on the model only (computed by the host side,
+   koopman.py: mpc_gains).
+     so101_koopman_create       uploads the encoder: dims[0..n_layers] = layer widths (dims[0] = x_dim <= 16, the others even
+                                and <= 64), W[l] HOST row-major [dims[l+1]][dims[l]] (torch Linear.weight), b[l] [dims[l+1]]
+     so101_koopman_set_gains    HOST Kz [nu][nz], Kr [nu][H][nz], Ku [nu][nu] (zeros for 'mpc'); nz = dims[0] + dims[n_layers]
+     so101_koopman_lift         Z [n][nz] DEVICE double <- X: layout 0 = rows [n][ldx] (first x_dim columns), 1 = structure of
+                                arrays [x_dim][n] (the stepper's observation buffer); dtype of X: SO101_F64 / SO101_F32
+     so101_koopman_feedforward  uff [n][P][nu] DEVICE double <- Xref [n][P][x_dim] DEVICE double:
+                                uff[e][k] = sum_{t<H, k+1+t<P} Kr_t Psi(Xref[e][k+1+t]) - every reference row is lifted once
+     so101_koopman_mpc_step     one frame: obs as for lift; uff = pointer to frame k of the first env (uff_stride = doubles
+                                between envs, P * nu; NULL = no reference term); u_prev DEVICE double [nu][n] in/out; ctrl DEVICE
+                                [nu][n] in ctrl_dtype = the control rows so101_batch_step takes; a_out DEVICE double [n][nu] or
+                                NULL (the clipped controls as the dataset rows record them)
+   All launches are asynchronous on `stream`. */
+typedef struct So101Koopman So101Koopman;
+int so101_koopman_create(int n_layers, const int32_t* dims, const double* const* W, const double* const* b, int device,
+                         So101Koopman** out);
+void so101_koopman_destroy(So101Koopman* k);
+int so101_koopman_set_gains(So101Koopman* k, int H, int nu, const double* Kz, const double* Kr, const double* Ku);
+int so101_koopman_lift(So101Koopman* k, const void* X, int dtype, int layout, int64_t ldx, int64_t n, double* Z, void* stream);
+int so101_koopman_feedforward(So101Koopman* k, const double* Xref, int64_t n, int P, double* uff, void* stream);
+int so101_koopman_mpc_step(So101Koopman* k, const void* obs, int obs_dtype, int obs_layout, int64_t ldx, const double* uff,
+                           int64_t uff_stride, double* u_prev, void* ctrl, int ctrl_dtype, double* a_out, double clip,
+                           int64_t n, void* stream);
+
 /* ---- batched site-pose inverse kinematics along Cartesian way-point tracks ------------------------
    Replaces the loop of CartesianTrajectoryGenerator.generate [REF control/TrajectoryGenerator.py:180-210] around
    dm_control.utils.inverse_kinematics.qpos_from_site_pose [REF control/TrajectoryGenerator.py:96-107] for n

@@ -7,13 +7,21 @@ Reference loop [REF Koopman_MPC.py:83-90 (runBefore), 109-126 and 197-222 (runFu
   * runBefore: `qpos[:5] = joint_angle_traj[0]`, `mj_forward`, and the controller's state starts as `state_all_ref[0]`;
   * every frame: `qfrc_applied = qfrc_bias` (gravity compensation), the window `state_all_ref[k+1 : k+H+1]` is lifted
     row by row into a zero-initialised `[H, nz]` array (so the rows past the end of the trajectory stay ZERO in lifted
-    space), `z0 = Psi(state)`, the MPC returns `u`, `a = clip(u, -0.5, 0.5)`, `s_next = env.step(a)`, the state becomes
+    space), `z0 = Psi(state)`, the MPC (`args.MPC_type`: 'delta_mpc' by default [REF args.py:75], or 'mpc') returns
+    `u_opt`, `u0 = u_opt[0] + u_prev`, `a = clip(u0, -0.5, 0.5)` [REF control/MPC_Controler.py:143-152], the loop then
+    sets `u_prev = u0` (unclipped, in both modes [REF Koopman_MPC.py:217]), `s_next = env.step(a)`, the state becomes
     `s_next` and is appended to `actual_traj`; one way-point per env step, `total_frames` frames.
+    In 'mpc' mode `u_prev` still enters `u0` (the controller adds it whatever the formulation), so that mode integrates
+    its own output; the reference runs 'delta_mpc', where `u_prev` is also the problem's parameter.  Both are mirrored
+    as written.
 
-Here: the curves come from `TrajectoryGenerator.solve_tracks` (one IK launch), the MPC is the closed-form minimiser of
-the same problem (`KoopmanModel.mpc_gains`), the environment is `SOARM101VecEnv(gravity_compensation=True)`; the loop
-body is a handful of device launches per frame for all n curves.  Viewer, ZMQ bridge, the return-to-home phase and the
-50 Hz sleep of the reference loop are its control plane and are not mirrored.
+Here: the curves come from `TrajectoryGenerator.solve_tracks` (one IK launch); the MPC is the closed-form minimiser of
+the same problem (`KoopmanModel.mpc_gains3`); the reference part of the control law is folded once for the whole
+trajectory (`KoopmanModel.feedforward`: every reference row lifted once instead of H times); a frame is TWO launches
+for all n curves: `so101_koopman_mpc_step` (encoder MLP + gain product + clip, fused) and the stepper's
+`so101_batch_step_flags` with the gravity compensation as a launch flag.  No torch matmul on the path.
+Viewer, ZMQ bridge, the return-to-home phase and the 50 Hz sleep of the reference loop are its control plane and are
+not mirrored.
 """
 from __future__ import annotations
 
@@ -27,9 +35,10 @@ from .vec_env import SOARM101VecEnv
 
 class BatchedKoopmanMPC:
     def __init__(self, env: SOARM101VecEnv, model: KoopmanModel, cartesian_points: torch.Tensor,
-                 joint_angle_traj: torch.Tensor, H: int = 10, clip: float = 0.5):
+                 joint_angle_traj: torch.Tensor, H: int = 10, clip: float = 0.5, MPC_type: str = "delta_mpc"):
         """env: n environments (construct it with gravity_compensation=True to mirror [REF Koopman_MPC.py:119]);
-        cartesian_points [n, P, 3], joint_angle_traj [n, P, 5]: what `generate` / `generate_batch` return."""
+        cartesian_points [n, P, 3], joint_angle_traj [n, P, 5]: what `generate` / `generate_batch` return;
+        MPC_type: 'delta_mpc' (the reference's default, [REF args.py:75]) or 'mpc'."""
         n = env.num_envs
         cp = torch.as_tensor(cartesian_points, dtype=torch.float64, device=env.device)
         ja = torch.as_tensor(joint_angle_traj, dtype=torch.float64, device=env.device)
@@ -37,14 +46,18 @@ class BatchedKoopmanMPC:
             cp, ja = cp.unsqueeze(0), ja.unsqueeze(0)
         if cp.shape[0] != n or ja.shape[:2] != cp.shape[:2] or cp.shape[2] != 3 or ja.shape[2] != 5:
             raise ValueError(f"need cartesian_points [{n}, P, 3] and joint_angle_traj [{n}, P, 5]")
-        self.env, self.model, self.H, self.clip = env, model, int(H), float(clip)
-        self.state_all_ref = torch.cat([cp, ja], dim=2)                      # [n, P, 8]   (:50)
+        if MPC_type not in ("mpc", "delta_mpc"):
+            raise ValueError(f"MPC_type must be 'mpc' or 'delta_mpc', got {MPC_type!r}")
+        self.env, self.model, self.H, self.clip, self.MPC_type = env, model, int(H), float(clip), MPC_type
+        self.state_all_ref = torch.cat([cp, ja], dim=2).contiguous()         # [n, P, 8]   (:50)
         self.total_frames = int(cp.shape[1])
         self.traj_index = 0
         self.actual_traj = []
         self.state_tensor: Optional[torch.Tensor] = None
-        self.Kz, self.Kr = model.mpc_gains(self.H)
-        self._zwin: Optional[torch.Tensor] = None
+        # reference part of the control law for every frame of every curve: each reference row is lifted once
+        self.uff = model.feedforward(self.state_all_ref, self.H, MPC_type)   # [n, P, nu]
+        self.u_prev = torch.zeros((model.nu, n), dtype=torch.float64, device=env.device)
+        self._ctrl = torch.zeros((model.nu, n), dtype=env.torch_dtype, device=env.device)
 
     def runBefore(self) -> None:
         """[REF Koopman_MPC.py:83-90]"""
@@ -57,38 +70,21 @@ class BatchedKoopmanMPC:
         self.traj_index = 0
         self.actual_traj = []
         self.applied = []
-        self._zwin = None
-
-    def _lift_ref_row(self, j: int) -> torch.Tensor:
-        """Lifted reference row j of every curve, ZERO past the end of the trajectory (the reference fills a
-        zero-initialised array, [REF Koopman_MPC.py:199-203])."""
-        if j < self.total_frames:
-            return self.model.lift(self.state_all_ref[:, j])
-        return torch.zeros((self.env.num_envs, self.model.nz), dtype=torch.float64, device=self.env.device)
+        self.u_prev.zero_()                                                  # MPCController.__init__: u_prev = zeros
 
     def runMPC(self) -> torch.Tensor:
-        """One frame [REF Koopman_MPC.py:197-222] -> the applied control a [n, 5].
-
-        Consecutive windows [k+1, k+H] overlap in H-1 rows, so the lifted window lives in a circular buffer: each frame
-        lifts ONE new reference row per curve (the reference re-lifts all H) and the matching column blocks of the
-        reference gain are rotated instead of the data."""
-        n, H, nz, nu = self.env.num_envs, self.H, self.model.nz, self.model.nu
+        """One frame [REF Koopman_MPC.py:197-222] -> the applied control a [n, 5]."""
+        n = self.env.num_envs
         k = self.traj_index
-        if self._zwin is None:
-            self._zwin = torch.empty((n, H, nz), dtype=torch.float64, device=self.env.device)
-            for j in range(H):
-                self._zwin[:, (k + j) % H] = self._lift_ref_row(k + 1 + j)
-        else:
-            self._zwin[:, (k - 1) % H] = self._lift_ref_row(k + H)     # the slot of row k (just consumed) <- row k+H
-        # slot s holds row k+1+((s - k) mod H): window position j = (s - k) mod H  <=>  s = (k + j) mod H
-        order = [(k + j) % H for j in range(H)]
-        Kr_rot = torch.empty((nu, H, nz), dtype=torch.float64, device=self.env.device)
-        Kr_rot[:, order] = self.Kr[:nu].reshape(nu, H, nz)
-        z0 = self.model.lift(self.state_tensor)
-        u = z0 @ self.Kz[:nu].t() + self._zwin.reshape(n, H * nz) @ Kr_rot.reshape(nu, H * nz).t()
-        a = torch.clamp(u, -self.clip, self.clip)                            # get_control [REF MPC_Controler.py:149]
-        s_next = self.env.step(a)[0]
-        self.state_tensor = s_next.to(torch.float64).clone()
+        a = torch.empty((n, self.model.nu), dtype=torch.float64, device=self.env.device)
+        if k == 0:      # the controller's first state is the reference's first row (float64), then the env's observations
+            self.model.mpc_step(self.state_tensor.contiguous(), False, self.uff, k, self.u_prev, self._ctrl, a, self.H,
+                                self.MPC_type, self.clip)
+        else:           # the stepper's own observation buffer (float32, structure of arrays): no copy, no transpose
+            self.model.mpc_step(self.env._obs, True, self.uff, k, self.u_prev, self._ctrl, a, self.H, self.MPC_type,
+                                self.clip)
+        self.env.step_soa(self._ctrl)                                        # gravity compensation: a flag of the launch
+        self.state_tensor = self.env._obs.t().to(torch.float64)
         self.actual_traj.append(self.state_tensor)
         self.applied.append(a)
         self.traj_index += 1

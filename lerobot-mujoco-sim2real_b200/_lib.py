@@ -25,7 +25,8 @@ EXPORTS = [
     "so101_batch_get_state", "so101_batch_set_state", "so101_batch_set_qfrc_applied",
     "so101_batch_get_flags", "so101_batch_clear_flags", "so101_batch_stats", "so101_batch_set_option",
     "so101_shared_alloc", "so101_shared_open", "so101_shared_close", "so101_shared_free",
-    "so101_fma_peak", "so101_koopman_score", "so101_ik_track",
+    "so101_fma_peak", "so101_koopman_score", "so101_koopman_create", "so101_koopman_destroy", "so101_koopman_set_gains",
+    "so101_koopman_lift", "so101_koopman_feedforward", "so101_koopman_mpc_step", "so101_ik_track",
 ]
 
 
@@ -93,6 +94,13 @@ def lib() -> C.CDLL:
     L.so101_shared_free.argtypes = [i32, vp]
     L.so101_fma_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.so101_koopman_score.argtypes = [vp, vp, i32, i32, vp, vp, C.c_double, C.c_double, vp, i32, i64, i32, i32, i32, vp, vp, vp]
+    L.so101_koopman_create.argtypes = [i32, vp, vp, vp, i32, C.POINTER(vp)]
+    L.so101_koopman_destroy.argtypes = [vp]
+    L.so101_koopman_destroy.restype = None
+    L.so101_koopman_set_gains.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.so101_koopman_lift.argtypes = [vp, vp, i32, i32, i64, i64, vp, vp]
+    L.so101_koopman_feedforward.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.so101_koopman_mpc_step.argtypes = [vp, vp, i32, i32, i64, vp, i64, vp, vp, i32, vp, C.c_double, i64, vp]
     L.so101_ik_track.argtypes = [vp, C.POINTER(So101IkParams), vp, vp, vp, i32, i64, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

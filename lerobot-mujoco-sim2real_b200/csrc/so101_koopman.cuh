@@ -100,3 +100,374 @@ extern "C" int so101_koopman_score(const double* A, const double* B, int nz, int
   CUDA_TRY(cudaFreeAsync(pack, st));
   return SO101_OK;
 }
+
+// ======================================================================================================================
+// The reference's MPC loop body for a batch of environments: lift, gain product, clip.
+//
+// Reference, per frame [REF Koopman_MPC.py:197-222, control/MPC_Controler.py:143-152, 154-166]:
+//   z0 = Psi(state) = [x, encoder(x)]      encoder = MLP 8 -> 64 -> 64 -> 64 -> 64 -> 24, ReLU between layers
+//                                          [REF models/KoopmanBase.py:12-47, args.py:103]
+//   zref_t = Psi(state_all_ref[k+1+t]), t = 0..H-1 (rows past the end of the trajectory stay ZERO in lifted space)
+//   u_opt = argmin of the MPC problem  ('mpc': over u; 'delta_mpc', the default [REF args.py:75]: over delta_u with
+//           u_t = u_prev + sum_{s<=t} delta_u_s and the cost on delta_u)      [REF MPC_Controler.py:65-141]
+//   u0 = u_opt[0] + u_eso(=0) + u_prev ;  a = clip(u0, -0.5, 0.5) ;  u_prev <- u0 (runMPC overwrites get_control's
+//           `u_prev = a` with the unclipped u, in both modes [REF Koopman_MPC.py:217])
+// The problem is an unconstrained quadratic (linear model), so u_opt[0] = Kz z0 + sum_t Kr_t zref_t + Ku u_prev with
+// gain matrices that depend on the model only (host: koopman.py mpc_gains).  The reference part sum_t Kr_t zref_t does
+// not depend on the state: so101_koopman_feedforward lifts every reference row ONCE and folds the windows into
+// uff[n][P][nu]; the per-frame kernel then lifts the state, adds the three terms, clips and writes the control rows the
+// stepper takes.
+//
+// MLP kernel: a 256-thread block works on tiles of 64 rows (lane = 2 rows); warp w computes output neurons
+// [w*JT, (w+1)*JT) of the current layer for all 64 rows; activations ping-pong between two shared buffers [k][row]
+// (conflict-free loads), the transposed weights of all layers sit in shared memory (117 KB for the reference's encoder)
+// and are read as broadcasts.  FP64 throughout, as the reference's DoubleTensor network.  DFMA-bound in principle
+// (14.3 k FMA per lift); per k-step a warp issues 2 activation loads + JT/2 broadcast double2 loads for 2*JT DFMA.
+// ======================================================================================================================
+constexpr int KM_MAXL = 8, KM_ROWS = 64, KM_THREADS = 256, KM_MAXW = 64, KM_MAXX = 16;
+
+struct So101Koopman {
+  int device, n_layers, dims[KM_MAXL + 1];
+  int x_dim, nz;
+  size_t woff[KM_MAXL], boff[KM_MAXL], wcount;   // offsets (doubles) of Wt[l] ([din][dout], transposed) and b[l] in `weights`
+  double* weights;                               // device
+  // gains (so101_koopman_set_gains)
+  int H, nu;
+  double* gains;                                 // device: Kz [nu][nz] | Ku [nu][nu] | Kr [nu][H][nz]
+};
+
+struct KmLayers {
+  int n_layers, dims[KM_MAXL + 1];
+  int woff[KM_MAXL], boff[KM_MAXL], wcount;
+};
+
+// encoder of the 64 rows whose inputs sit in act0[k][row] (k < dims[0]); returns the buffer holding the last layer's output
+__device__ __forceinline__ double* km_encode(const KmLayers& L, const double* __restrict__ w, double* act0, double* act1) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* in = act0;
+  double* out = act1;
+  for (int l = 0; l < L.n_layers; l++) {
+    const int din = L.dims[l], dout = L.dims[l + 1];
+    const double* Wt = w + L.woff[l];
+    const double* bias = w + L.boff[l];
+    const bool relu = l != L.n_layers - 1;
+    const int JT = (dout + 7) / 8;
+    const int j0 = warp * JT;
+    if (dout == 64) {    // the wide layers: 8 neurons per warp, weights as four broadcast double2 loads per k
+      double acc0[8], acc1[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { acc0[j] = bias[j0 + j]; acc1[j] = acc0[j]; }
+#pragma unroll 4
+      for (int k = 0; k < din; k++) {
+        const double a0 = in[k * KM_ROWS + lane], a1 = in[k * KM_ROWS + 32 + lane];
+        const double2* wk = reinterpret_cast<const double2*>(Wt + k * dout + j0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double2 ww = wk[j];
+          acc0[2 * j] = fma(ww.x, a0, acc0[2 * j]); acc1[2 * j] = fma(ww.x, a1, acc1[2 * j]);
+          acc0[2 * j + 1] = fma(ww.y, a0, acc0[2 * j + 1]); acc1[2 * j + 1] = fma(ww.y, a1, acc1[2 * j + 1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        out[(j0 + j) * KM_ROWS + lane] = relu ? fmax(acc0[j], 0.0) : acc0[j];
+        out[(j0 + j) * KM_ROWS + 32 + lane] = relu ? fmax(acc1[j], 0.0) : acc1[j];
+      }
+    } else {
+      for (int j = j0; j < j0 + JT && j < dout; j++) {
+        double s0 = bias[j], s1 = s0;
+        for (int k = 0; k < din; k++) {
+          const double ww = Wt[k * dout + j];
+          s0 = fma(ww, in[k * KM_ROWS + lane], s0);
+          s1 = fma(ww, in[k * KM_ROWS + 32 + lane], s1);
+        }
+        out[j * KM_ROWS + lane] = relu ? fmax(s0, 0.0) : s0;
+        out[j * KM_ROWS + 32 + lane] = relu ? fmax(s1, 0.0) : s1;
+      }
+    }
+    __syncthreads();
+    double* t = in; in = out; out = t;
+  }
+  return in;
+}
+
+// X: layout 0 = rows [n][ldx] (first x_dim columns), 1 = structure of arrays [x_dim][n]
+template <typename TX>
+__device__ __forceinline__ void km_load_tile(const TX* X, int layout, int64_t ldx, int64_t n, int64_t row0, int x_dim,
+                                             double* xs /* [x_dim][KM_ROWS] */) {
+  for (int i = threadIdx.x; i < x_dim * KM_ROWS; i += KM_THREADS) {
+    int k, r;
+    if (layout == 0) { r = i / x_dim; k = i - r * x_dim; } else { k = i / KM_ROWS; r = i - k * KM_ROWS; }
+    const int64_t row = row0 + r;
+    double v = 0.0;
+    if (row < n) v = (double)(layout == 0 ? X[row * ldx + k] : X[(int64_t)k * n + row]);
+    xs[k * KM_ROWS + r] = v;
+  }
+}
+
+// z = [x | encoder(x)] for n rows -> Z [n][nz]
+template <typename TX>
+__global__ void __launch_bounds__(KM_THREADS, 1)
+k_koopman_lift(const __grid_constant__ KmLayers L, const double* __restrict__ wg, const TX* X, int layout, int64_t ldx,
+               int64_t n, double* Z) {
+  extern __shared__ double sh[];
+  double* w = sh;
+  double* xs = w + L.wcount;                       // [x_dim][64]: the inputs are kept (they are the first nz coordinates)
+  double* act0 = xs + KM_MAXX * KM_ROWS;
+  double* act1 = act0 + KM_MAXW * KM_ROWS;
+  for (int i = threadIdx.x; i < L.wcount; i += KM_THREADS) w[i] = wg[i];
+  const int x_dim = L.dims[0], enc = L.dims[L.n_layers], nz = x_dim + enc;
+  const int64_t ntile = (n + KM_ROWS - 1) / KM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t row0 = tile * KM_ROWS;
+    __syncthreads();
+    km_load_tile(X, layout, ldx, n, row0, x_dim, xs);
+    __syncthreads();
+    for (int i = threadIdx.x; i < x_dim * KM_ROWS; i += KM_THREADS) act0[i] = xs[i];
+    __syncthreads();
+    const double* h = km_encode(L, w, act0, act1);
+    for (int i = threadIdx.x; i < nz * KM_ROWS; i += KM_THREADS) {
+      const int r = i / nz, c = i - r * nz;
+      if (row0 + r < n) Z[(row0 + r) * nz + c] = c < x_dim ? xs[c * KM_ROWS + r] : h[(c - x_dim) * KM_ROWS + r];
+    }
+  }
+}
+
+// uff[e][k][i] = sum_{t < H, k+1+t < P} sum_c Kr[i][t][c] Z[e][k+1+t][c]  for the envs of one chunk; thread per (e, k)
+__global__ void k_koopman_window(const double* __restrict__ Z, const double* __restrict__ gains, int nz, int nu, int H,
+                                 int64_t ne, int P, double* uff) {
+  extern __shared__ double sh[];
+  const double* Kr_g = gains + (size_t)nu * nz + (size_t)nu * nu;
+  for (int i = threadIdx.x; i < nu * H * nz; i += blockDim.x) sh[i] = Kr_g[i];
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ne * P) return;
+  const int64_t e = idx / P;
+  const int k = (int)(idx - e * P);
+  double acc[KOOP_MAXU];
+  for (int i = 0; i < nu; i++) acc[i] = 0.0;
+  for (int t = 0; t < H && k + 1 + t < P; t++) {
+    const double* z = Z + ((size_t)e * P + k + 1 + t) * nz;
+    for (int c = 0; c < nz; c++) {
+      const double zc = z[c];
+      for (int i = 0; i < nu; i++) acc[i] = fma(sh[(i * H + t) * nz + c], zc, acc[i]);
+    }
+  }
+  for (int i = 0; i < nu; i++) uff[idx * nu + i] = acc[i];
+}
+
+// One MPC frame for n envs: lift the observation, u_opt0 = Kz z0 + uff + Ku u_prev, u0 = u_opt0 + u_prev, a = clip(u0),
+// u_prev <- u0; a goes to the control rows ctrl[nu][n] (the stepper's layout and dtype) and, if asked, to a_out[n][nu].
+template <typename TX, typename TC>
+__global__ void __launch_bounds__(KM_THREADS, 1)
+k_koopman_mpc(const __grid_constant__ KmLayers L, const double* __restrict__ wg, const double* __restrict__ gains, int nu,
+              const TX* X, int layout, int64_t ldx, int64_t n, const double* uff, int64_t uff_stride, double* u_prev,
+              TC* ctrl, double* a_out, double clip) {
+  extern __shared__ double sh[];
+  double* w = sh;
+  double* xs = w + L.wcount;
+  double* act0 = xs + KM_MAXX * KM_ROWS;
+  double* act1 = act0 + KM_MAXW * KM_ROWS;
+  double* g = act1 + KM_MAXW * KM_ROWS;            // Kz [nu][nz] | Ku [nu][nu]
+  const int x_dim = L.dims[0], enc = L.dims[L.n_layers], nz = x_dim + enc;
+  for (int i = threadIdx.x; i < L.wcount; i += KM_THREADS) w[i] = wg[i];
+  for (int i = threadIdx.x; i < nu * nz + nu * nu; i += KM_THREADS) g[i] = gains[i];
+  const int64_t ntile = (n + KM_ROWS - 1) / KM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int64_t row0 = tile * KM_ROWS;
+    __syncthreads();
+    km_load_tile(X, layout, ldx, n, row0, x_dim, xs);
+    __syncthreads();
+    for (int i = threadIdx.x; i < x_dim * KM_ROWS; i += KM_THREADS) act0[i] = xs[i];
+    __syncthreads();
+    const double* h = km_encode(L, w, act0, act1);
+    for (int i = threadIdx.x; i < nu * KM_ROWS; i += KM_THREADS) {
+      const int c = i / KM_ROWS, r = i - c * KM_ROWS;       // control component c of row r (consecutive threads: rows)
+      const int64_t row = row0 + r;
+      if (row >= n) continue;
+      double u = uff ? uff[row * uff_stride + c] : 0.0;
+      const double* kz = g + c * nz;
+      for (int k = 0; k < x_dim; k++) u = fma(kz[k], xs[k * KM_ROWS + r], u);
+      for (int k = 0; k < enc; k++) u = fma(kz[x_dim + k], h[k * KM_ROWS + r], u);
+      const double* ku = g + nu * nz + c * nu;
+      for (int j = 0; j < nu; j++) u = fma(ku[j], u_prev[(int64_t)j * n + row], u);
+      const double u0 = u + u_prev[(int64_t)c * n + row];
+      const double a = fmin(fmax(u0, -clip), clip);
+      // every component reads the whole u_prev of its row before any is overwritten: the write happens after the barrier
+      act1[(KM_MAXW - 1 - c) * KM_ROWS + r] = u0;           // parked in the far end of a buffer h does not occupy
+      ctrl[(int64_t)c * n + row] = (TC)a;
+      if (a_out) a_out[row * nu + c] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nu * KM_ROWS; i += KM_THREADS) {
+      const int c = i / KM_ROWS, r = i - c * KM_ROWS;
+      if (row0 + r < n) u_prev[(int64_t)c * n + row0 + r] = act1[(KM_MAXW - 1 - c) * KM_ROWS + r];
+    }
+  }
+}
+
+static size_t km_smem_bytes(const So101Koopman* k, bool mpc) {
+  size_t d = k->wcount + (size_t)KM_MAXX * KM_ROWS + 2 * (size_t)KM_MAXW * KM_ROWS;
+  if (mpc) d += (size_t)k->nu * k->nz + (size_t)k->nu * k->nu;
+  return d * sizeof(double);
+}
+static KmLayers km_layers(const So101Koopman* k) {
+  KmLayers L;
+  L.n_layers = k->n_layers;
+  for (int i = 0; i <= k->n_layers; i++) L.dims[i] = k->dims[i];
+  for (int i = 0; i < k->n_layers; i++) { L.woff[i] = (int)k->woff[i]; L.boff[i] = (int)k->boff[i]; }
+  L.wcount = (int)k->wcount;
+  return L;
+}
+static int km_grid(const So101Koopman* k, int64_t n) {
+  cudaDeviceProp prop;
+  int sms = 148;
+  if (cudaGetDeviceProperties(&prop, k->device) == cudaSuccess) sms = prop.multiProcessorCount;
+  const int64_t tiles = (n + KM_ROWS - 1) / KM_ROWS;
+  return (int)(tiles < sms ? tiles : sms);        // persistent: one block per SM (the weights fill its shared memory)
+}
+
+extern "C" int so101_koopman_create(int n_layers, const int32_t* dims, const double* const* W, const double* const* b,
+                                    int device, So101Koopman** out) {
+  if (!dims || !W || !b || !out) return fail(SO101_EINVAL, "null argument");
+  if (n_layers < 1 || n_layers > KM_MAXL) return fail(SO101_EINVAL, "koopman: 1..8 layers");
+  if (dims[0] < 1 || dims[0] > KM_MAXX) return fail(SO101_EINVAL, "koopman: input width 1..16");
+  for (int l = 1; l <= n_layers; l++)
+    if (dims[l] < 1 || dims[l] > KM_MAXW || (dims[l] % 2)) return fail(SO101_EINVAL, "koopman: layer widths must be even, 2..64");
+  if (dims[0] + dims[n_layers] > KOOP_MAXZ) return fail(SO101_EINVAL, "koopman: lifted dimension exceeds 64");
+  if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible: this library has no CPU fallback");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(SO101_ECUDA, "cudaSetDevice failed");
+  So101Koopman* k = new So101Koopman();
+  std::memset(k, 0, sizeof *k);
+  k->device = device; k->n_layers = n_layers;
+  for (int l = 0; l <= n_layers; l++) k->dims[l] = dims[l];
+  k->x_dim = dims[0]; k->nz = dims[0] + dims[n_layers];
+  size_t off = 0;
+  for (int l = 0; l < n_layers; l++) {
+    k->woff[l] = off; off += (size_t)dims[l] * dims[l + 1];
+    k->boff[l] = off; off += dims[l + 1];
+    off += off & 1;                                  // double2 loads of the transposed weights need 16-byte alignment
+  }
+  k->wcount = off;
+  if (km_smem_bytes(k, false) + 4096 > 227 * 1024) { delete k; return fail(SO101_EINVAL, "koopman: the encoder does not fit shared memory"); }
+  std::vector<double> host(off, 0.0);
+  for (int l = 0; l < n_layers; l++) {
+    if (!W[l] || !b[l]) { delete k; return fail(SO101_EINVAL, "null layer"); }
+    const int din = dims[l], dout = dims[l + 1];
+    for (int j = 0; j < dout; j++) {
+      for (int c = 0; c < din; c++) host[k->woff[l] + (size_t)c * dout + j] = W[l][(size_t)j * din + c];   // transposed
+      host[k->boff[l] + j] = b[l][j];
+    }
+  }
+  cudaError_t e = cudaMalloc(&k->weights, off * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(k->weights, host.data(), off * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(k->weights); delete k; return fail(SO101_ECUDA, std::string("koopman_create: ") + cudaGetErrorString(e)); }
+  *out = k;
+  return SO101_OK;
+}
+extern "C" void so101_koopman_destroy(So101Koopman* k) {
+  if (!k) return;
+  DeviceGuard g(k->device);
+  cudaFree(k->weights);
+  cudaFree(k->gains);
+  delete k;
+}
+extern "C" int so101_koopman_set_gains(So101Koopman* k, int H, int nu, const double* Kz, const double* Kr, const double* Ku) {
+  if (!k || !Kz || !Kr || !Ku) return fail(SO101_EINVAL, "null argument");
+  if (H < 1 || nu < 1 || nu > KOOP_MAXU) return fail(SO101_EINVAL, "koopman gains: H >= 1, 1 <= nu <= 8");
+  if ((size_t)nu * H * k->nz * sizeof(double) > 96 * 1024) return fail(SO101_EINVAL, "koopman gains: reference gain exceeds 96 KB");
+  if (k->dims[k->n_layers] + nu > KM_MAXW) return fail(SO101_EINVAL, "koopman gains: encoder width + nu exceeds 64");
+  DeviceGuard g(k->device);
+  const size_t nzv = (size_t)nu * k->nz, nuv = (size_t)nu * nu, nrv = (size_t)nu * H * k->nz;
+  std::vector<double> host(nzv + nuv + nrv);
+  std::memcpy(&host[0], Kz, nzv * sizeof(double));
+  std::memcpy(&host[nzv], Ku, nuv * sizeof(double));
+  std::memcpy(&host[nzv + nuv], Kr, nrv * sizeof(double));
+  cudaFree(k->gains);
+  k->gains = nullptr;
+  CUDA_TRY(cudaMalloc(&k->gains, host.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(k->gains, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice));
+  k->H = H; k->nu = nu;
+  return SO101_OK;
+}
+
+template <typename TX>
+static int km_launch_lift(So101Koopman* k, const TX* X, int layout, int64_t ldx, int64_t n, double* Z, cudaStream_t st) {
+  const size_t smem = km_smem_bytes(k, false);
+  CUDA_TRY(cudaFuncSetAttribute(k_koopman_lift<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_koopman_lift<TX><<<km_grid(k, n), KM_THREADS, smem, st>>>(km_layers(k), k->weights, X, layout, ldx, n, Z);
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+extern "C" int so101_koopman_lift(So101Koopman* k, const void* X, int dtype, int layout, int64_t ldx, int64_t n, double* Z,
+                                  void* stream) {
+  if (!k || !X || !Z || n <= 0) return fail(SO101_EINVAL, "null argument");
+  if (layout != 0 && layout != 1) return fail(SO101_EINVAL, "layout: 0 = rows [n][ldx], 1 = structure of arrays [x_dim][n]");
+  if (layout == 0 && ldx < k->x_dim) return fail(SO101_EINVAL, "ldx < x_dim");
+  DeviceGuard g(k->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SO101_F64) return km_launch_lift<double>(k, (const double*)X, layout, ldx, n, Z, st);
+  if (dtype == SO101_F32) return km_launch_lift<float>(k, (const float*)X, layout, ldx, n, Z, st);
+  return fail(SO101_EINVAL, "dtype must be SO101_F64 or SO101_F32");
+}
+
+extern "C" int so101_koopman_feedforward(So101Koopman* k, const double* Xref, int64_t n, int P, double* uff, void* stream) {
+  if (!k || !Xref || !uff || n <= 0 || P <= 0) return fail(SO101_EINVAL, "null argument");
+  if (!k->gains) return fail(SO101_EINVAL, "koopman_feedforward: set the gains first");
+  DeviceGuard g(k->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the lifted reference rows of a chunk of envs go through a scratch buffer of at most 256 MB
+  int64_t chunk = ((int64_t)256 << 20) / ((int64_t)P * k->nz * (int64_t)sizeof(double));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n) chunk = n;
+  double* Z = nullptr;
+  CUDA_TRY(cudaMallocAsync(&Z, (size_t)chunk * P * k->nz * sizeof(double), st));
+  const size_t wsmem = (size_t)k->nu * k->H * k->nz * sizeof(double);
+  cudaError_t err = cudaSuccess;
+  if (wsmem > 48 * 1024) err = cudaFuncSetAttribute(k_koopman_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+  int rc = SO101_OK;
+  for (int64_t e0 = 0; e0 < n && rc == SO101_OK && err == cudaSuccess; e0 += chunk) {
+    const int64_t ne = n - e0 < chunk ? n - e0 : chunk;
+    rc = km_launch_lift<double>(k, Xref + (size_t)e0 * P * k->x_dim, 0, k->x_dim, ne * P, Z, st);
+    if (rc != SO101_OK) break;
+    const int64_t items = ne * P;
+    k_koopman_window<<<(unsigned)((items + 127) / 128), 128, wsmem, st>>>(Z, k->gains, k->nz, k->nu, k->H, ne, P,
+                                                                         uff + (size_t)e0 * P * k->nu);
+    err = cudaGetLastError();
+  }
+  cudaFreeAsync(Z, st);
+  if (rc != SO101_OK) return rc;
+  if (err != cudaSuccess) return fail(SO101_ECUDA, std::string("koopman_feedforward: ") + cudaGetErrorString(err));
+  return SO101_OK;
+}
+
+template <typename TX, typename TC>
+static int km_launch_mpc(So101Koopman* k, const TX* X, int layout, int64_t ldx, int64_t n, const double* uff, int64_t uff_stride,
+                         double* u_prev, TC* ctrl, double* a_out, double clip, cudaStream_t st) {
+  const size_t smem = km_smem_bytes(k, true);
+  CUDA_TRY(cudaFuncSetAttribute(k_koopman_mpc<TX, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_koopman_mpc<TX, TC><<<km_grid(k, n), KM_THREADS, smem, st>>>(km_layers(k), k->weights, k->gains, k->nu, X, layout, ldx, n,
+                                                               uff, uff_stride, u_prev, ctrl, a_out, clip);
+  CUDA_TRY(cudaGetLastError());
+  return SO101_OK;
+}
+extern "C" int so101_koopman_mpc_step(So101Koopman* k, const void* obs, int obs_dtype, int obs_layout, int64_t ldx,
+                                      const double* uff, int64_t uff_stride, double* u_prev, void* ctrl, int ctrl_dtype,
+                                      double* a_out, double clip, int64_t n, void* stream) {
+  if (!k || !obs || !u_prev || !ctrl || n <= 0) return fail(SO101_EINVAL, "null argument");
+  if (!k->gains) return fail(SO101_EINVAL, "koopman_mpc_step: set the gains first");
+  if (obs_layout != 0 && obs_layout != 1) return fail(SO101_EINVAL, "layout: 0 = rows [n][ldx], 1 = structure of arrays [x_dim][n]");
+  if (obs_layout == 0 && ldx < k->x_dim) return fail(SO101_EINVAL, "ldx < x_dim");
+  if ((obs_dtype != SO101_F64 && obs_dtype != SO101_F32) || (ctrl_dtype != SO101_F64 && ctrl_dtype != SO101_F32))
+    return fail(SO101_EINVAL, "dtype must be SO101_F64 or SO101_F32");
+  DeviceGuard g(k->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (obs_dtype == SO101_F64 && ctrl_dtype == SO101_F64)
+    return km_launch_mpc<double, double>(k, (const double*)obs, obs_layout, ldx, n, uff, uff_stride, u_prev, (double*)ctrl, a_out, clip, st);
+  if (obs_dtype == SO101_F32 && ctrl_dtype == SO101_F64)
+    return km_launch_mpc<float, double>(k, (const float*)obs, obs_layout, ldx, n, uff, uff_stride, u_prev, (double*)ctrl, a_out, clip, st);
+  if (obs_dtype == SO101_F64 && ctrl_dtype == SO101_F32)
+    return km_launch_mpc<double, float>(k, (const double*)obs, obs_layout, ldx, n, uff, uff_stride, u_prev, (float*)ctrl, a_out, clip, st);
+  return km_launch_mpc<float, float>(k, (const float*)obs, obs_layout, ldx, n, uff, uff_stride, u_prev, (float*)ctrl, a_out, clip, st);
+}

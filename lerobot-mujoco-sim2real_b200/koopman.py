@@ -8,10 +8,15 @@ batched stepper:
   * `KoopmanModel`      weights (from a state_dict / .npz), the lift  z = [x, encoder(x)]  on the current torch device;
   * `score`             n control sequences rolled through  z+ = A z + B u  and costed as the reference's MPC does, in
                         one CUDA launch through the C ABI (`so101_koopman_score`) - the model-side twin of `shoot`;
-  * `mpc_gains/mpc_control`  the minimiser of the reference's MPC problem in closed form.  The NLP handed to IPOPT
-                        [REF MPC_Controler.py:65-107] has no constraints and a cost that is quadratic in u (linear model,
-                        `linearize_B` is the identity for the linear model), so its solution is one linear solve:
-                        u* = -(G'QG + R)^-1 G'Q (F z0 - zref); the gain matrices depend on the model only.
+  * `mpc_gains/mpc_control`  the minimiser of the reference's MPC problem in closed form, for both of its formulations:
+                        'mpc' (decision variable u) and 'delta_mpc' (decision variable delta_u, u_t = u_prev + sum delta_u,
+                        cost on delta_u; the reference's default [REF args.py:75]).  The NLP handed to IPOPT
+                        [REF MPC_Controler.py:65-141] has no constraints and a cost that is quadratic in the decision
+                        variable (linear model, `linearize_B` is the identity for it), so its solution is one linear solve;
+                        the gain matrices depend on the model only.
+  * `lift_device/feedforward/mpc_step`  the loop body on the device: fused encoder MLP + gain product + clip kernels
+                        behind the C ABI (`so101_koopman_lift`, `_feedforward`, `_mpc_step`); `lift` (torch matmuls) stays
+                        as the plain reference the kernels are tested against.
 Only torch plumbing and the C ABI are used; nothing here imports the oracle.
 """
 from __future__ import annotations
@@ -44,6 +49,86 @@ class KoopmanModel:
         self.x_dim = self.layers[0][0].shape[1]
         assert self.nz == self.x_dim + self.layers[-1][0].shape[0] and self.A.shape == (self.nz, self.nz)
         self._gains = {}
+        self._host_layers = [(np.ascontiguousarray(w[f"x_encode_net.linear_{j}.weight"]),
+                              np.ascontiguousarray(w[f"x_encode_net.linear_{j}.bias"])) for j in range(len(self.layers))]
+        self._h = None            # So101Koopman* (created on first use of a device kernel)
+        self._dev_gains = None    # key of the gains currently uploaded to it
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _lib is not None and _lib._LIB is not None:
+            _lib._LIB.so101_koopman_destroy(h)
+            self._h = None
+
+    # ---- the device-side encoder / MPC kernels -----------------------------------------------------------------------
+    def _handle(self):
+        if self._h is None:
+            L = _lib.lib()
+            n = len(self._host_layers)
+            dims = (C.c_int32 * (n + 1))(self.x_dim, *[Wb[0].shape[0] for Wb in self._host_layers])
+            Wp = (C.c_void_p * n)(*[Wb[0].ctypes.data for Wb in self._host_layers])
+            bp = (C.c_void_p * n)(*[Wb[1].ctypes.data for Wb in self._host_layers])
+            h = C.c_void_p()
+            _lib.check(L.so101_koopman_create(n, dims, Wp, bp, self.device.index or 0, C.byref(h)))
+            self._h = h
+        return self._h
+
+    @staticmethod
+    def _x_layout(x: torch.Tensor, x_dim: int) -> int:
+        """dtype code of an observation tensor (float64 or float32)"""
+        return {torch.float64: T.F64, torch.float32: T.F32}[x.dtype]
+
+    def lift_device(self, x: torch.Tensor, soa: bool = False) -> torch.Tensor:
+        """z = [x, encoder(x)] by the fused MLP kernel: x [n, >= x_dim] rows, or (soa) [x_dim, n]; float64 or float32."""
+        assert x.is_cuda and x.is_contiguous() and x.dim() == 2
+        n = x.shape[1] if soa else x.shape[0]
+        Z = torch.empty((n, self.nz), dtype=torch.float64, device=x.device)
+        _lib.check(_lib.lib().so101_koopman_lift(self._handle(), x.data_ptr(), self._x_layout(x, self.x_dim), 1 if soa else 0,
+                                                 0 if soa else x.shape[1], n, Z.data_ptr(),
+                                                 torch.cuda.current_stream(x.device).cuda_stream))
+        return Z
+
+    def _upload_gains(self, H: int, mpc_type: str, q_weight: float = 50.0, r_weight: float = 0.5):
+        key = (H, q_weight, r_weight, mpc_type)
+        if self._dev_gains != key:
+            Kz, Kr, Ku = self.mpc_gains3(H, q_weight, r_weight, mpc_type)
+            nu = self.nu
+            kz = np.ascontiguousarray(Kz[:nu].cpu().numpy()); kr = np.ascontiguousarray(Kr[:nu].cpu().numpy())
+            ku = np.ascontiguousarray(Ku[:nu].cpu().numpy())
+            _lib.check(_lib.lib().so101_koopman_set_gains(self._handle(), H, nu, kz.ctypes.data, kr.ctypes.data, ku.ctypes.data))
+            self._dev_gains = key
+
+    def feedforward(self, xref: torch.Tensor, H: int = 10, mpc_type: str = "delta_mpc") -> torch.Tensor:
+        """Reference part of the MPC law for whole trajectories: xref [n, P, x_dim] float64 ->
+        uff [n, P, nu], uff[e, k] = sum_t Kr_t Psi(xref[e, k+1+t]) over the window rows that exist (rows past the end of
+        the trajectory are zero in lifted space, as the reference leaves them [REF Koopman_MPC.py:199-203])."""
+        assert xref.is_cuda and xref.is_contiguous() and xref.dtype == torch.float64 and xref.shape[2] == self.x_dim
+        self._upload_gains(H, mpc_type)
+        n, P = xref.shape[:2]
+        uff = torch.empty((n, P, self.nu), dtype=torch.float64, device=xref.device)
+        _lib.check(_lib.lib().so101_koopman_feedforward(self._handle(), xref.data_ptr(), n, P, uff.data_ptr(),
+                                                        torch.cuda.current_stream(xref.device).cuda_stream))
+        return uff
+
+    def mpc_step(self, obs: torch.Tensor, soa: bool, uff: Optional[torch.Tensor], frame: int, u_prev: torch.Tensor,
+                 ctrl: torch.Tensor, a_out: Optional[torch.Tensor] = None, H: int = 10, mpc_type: str = "delta_mpc",
+                 clip: float = 0.5) -> None:
+        """One frame of the reference's loop body for all envs, one launch: lift(obs), u0 = Kz z0 + uff[:, frame] +
+        Ku u_prev + u_prev, a = clip(u0), u_prev <- u0 [REF MPC_Controler.py:143-152, Koopman_MPC.py:212-217].
+        obs: rows [n, >= x_dim] or (soa) [x_dim, n]; u_prev [nu, n] float64 (in/out); ctrl [nu, n] (out, the stepper's
+        control rows, its dtype); a_out [n, nu] float64 or None."""
+        self._upload_gains(H, mpc_type)
+        n = obs.shape[1] if soa else obs.shape[0]
+        assert u_prev.shape == (self.nu, n) and u_prev.dtype == torch.float64 and u_prev.is_contiguous()
+        assert ctrl.shape[0] >= self.nu and ctrl.shape[1] == n and ctrl.is_contiguous()
+        up, us = (None, 0)
+        if uff is not None:
+            assert uff.is_contiguous() and uff.shape[0] == n and uff.shape[2] == self.nu
+            up, us = uff.data_ptr() + frame * self.nu * 8, uff.shape[1] * self.nu
+        _lib.check(_lib.lib().so101_koopman_mpc_step(
+            self._handle(), obs.data_ptr(), self._x_layout(obs, self.x_dim), 1 if soa else 0, 0 if soa else obs.shape[1],
+            up, us, u_prev.data_ptr(), ctrl.data_ptr(), {torch.float64: T.F64, torch.float32: T.F32}[ctrl.dtype],
+            None if a_out is None else a_out.data_ptr(), float(clip), n, torch.cuda.current_stream(obs.device).cuda_stream))
 
     @classmethod
     def from_npz(cls, path: str, device: Optional[torch.device] = None) -> "KoopmanModel":
@@ -82,10 +167,21 @@ class KoopmanModel:
         return Xhat, cost
 
     # ---- the reference's MPC problem solved exactly ------------------------------------------------------------------
-    def mpc_gains(self, H: int = 10, q_weight: float = 50.0, r_weight: float = 0.5) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (Kz [H*nu, nz], Kr [H*nu, H*nz]) with u* = Kz z0 + Kr vec(zref): the minimiser of
-        sum_t q |z_{t+1} - zref_t|^2 + r |u_t|^2, z_{t+1} = A z_t + B u_t [REF MPC_Controler.py:65-98]."""
-        key = (H, q_weight, r_weight)
+    def mpc_gains(self, H: int = 10, q_weight: float = 50.0, r_weight: float = 0.5, mpc_type: str = "mpc"):
+        """'mpc'  -> (Kz [H*nu, nz], Kr [H*nu, H*nz]) with u* = Kz z0 + Kr vec(zref): the minimiser of
+                     sum_t q |z_{t+1} - zref_t|^2 + r |u_t|^2, z_{t+1} = A z_t + B u_t [REF MPC_Controler.py:65-98];
+        'delta_mpc' -> (Kz, Kr, Ku [H*nu, nu]) with delta_u* = Kz z0 + Kr vec(zref) + Ku u_prev: the minimiser of
+                     sum_t q |z_{t+1} - zref_t|^2 + r |delta_u_t|^2 with u_t = u_prev + sum_{s<=t} delta_u_s
+                     [REF MPC_Controler.py:100-141].  `mpc_gains3` returns three matrices for either formulation."""
+        if mpc_type == "mpc":
+            return self.mpc_gains3(H, q_weight, r_weight, "mpc")[:2]
+        return self.mpc_gains3(H, q_weight, r_weight, mpc_type)
+
+    def mpc_gains3(self, H: int = 10, q_weight: float = 50.0, r_weight: float = 0.5, mpc_type: str = "delta_mpc"):
+        """-> (Kz, Kr, Ku) for either formulation (Ku = 0 for 'mpc')."""
+        if mpc_type not in ("mpc", "delta_mpc"):
+            raise ValueError(f"MPC_type must be 'mpc' or 'delta_mpc', got {mpc_type!r}")
+        key = (H, q_weight, r_weight, mpc_type)
         if key not in self._gains:
             nz, nu = self.nz, self.nu
             F = np.zeros((H * nz, nz)); G = np.zeros((H * nz, H * nu))
@@ -97,10 +193,20 @@ class KoopmanModel:
                 F[t * nz:(t + 1) * nz] = Ap                                   # z_{t+1} = A^{t+1} z0 + sum_s A^{t-s} B u_s
                 for s in range(t + 1):
                     G[t * nz:(t + 1) * nz, s * nu:(s + 1) * nu] = pows[t - s] @ self.B
-            Hs = q_weight * G.T @ G + r_weight * np.eye(H * nu)
-            Kr = np.linalg.solve(Hs, q_weight * G.T)
-            Kz = -Kr @ F
-            self._gains[key] = (torch.as_tensor(Kz, device=self.device), torch.as_tensor(Kr, device=self.device))
+            if mpc_type == "mpc":
+                Hs = q_weight * G.T @ G + r_weight * np.eye(H * nu)
+                Kr = np.linalg.solve(Hs, q_weight * G.T)
+                Kz = -Kr @ F
+                Ku = np.zeros((H * nu, nu))
+            else:
+                S = np.kron(np.tril(np.ones((H, H))), np.eye(nu))             # u = S delta_u + E u_prev
+                E = np.kron(np.ones((H, 1)), np.eye(nu))
+                Gd = G @ S
+                Hs = q_weight * Gd.T @ Gd + r_weight * np.eye(H * nu)
+                Kr = np.linalg.solve(Hs, q_weight * Gd.T)
+                Kz = -Kr @ F
+                Ku = -Kr @ (G @ E)
+            self._gains[key] = tuple(torch.as_tensor(K, device=self.device) for K in (Kz, Kr, Ku))
         return self._gains[key]
 
     def mpc_control(self, x: torch.Tensor, xref: torch.Tensor, H: int = 10, clip: float = 0.5) -> torch.Tensor:

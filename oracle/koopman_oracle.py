@@ -35,17 +35,53 @@ def score(W, z0, U, zref=None, q=50.0, r=0.5, nobs=8):
     return np.stack(X, 1), cost
 
 
-def mpc_solve(W, z0, zref, H, q=50.0, r=0.5):
-    """The minimiser IPOPT converges to for the reference's unconstrained, quadratic problem: normal equations."""
+def mpc_solve(W, z0, zref, H, q=50.0, r=0.5, mpc_type="mpc", u_prev=None):
+    """The minimiser IPOPT converges to for the reference's unconstrained, quadratic problem.
+
+    'mpc'       [REF control/MPC_Controler.py:65-98]:  decision u,  cost sum_t q |z_{t+1} - zref_t|^2 + r |u_t|^2
+    'delta_mpc' [REF control/MPC_Controler.py:100-141]: decision delta_u, u_t = u_{t-1} + delta_u_t (u_{-1} = u_prev),
+                cost sum_t q |z_{t+1} - zref_t|^2 + r |delta_u_t|^2
+    Restated as the reference writes it - the model is rolled forward step by step for a given decision vector - and
+    solved as a linear least-squares problem: the residual vector is affine in the decision, its Jacobian is formed by
+    rolling unit perturbations.  Shares no structure with the closed-form gains of the product (koopman.py)."""
     A, B = W["lA.weight"], W["lB.weight"]
     nz, nu = B.shape
-    F = np.zeros((H * nz, nz)); G = np.zeros((H * nz, H * nu))
-    for t in range(H):
-        F[t * nz:(t + 1) * nz] = np.linalg.matrix_power(A, t + 1)
-        for s in range(t + 1):
-            G[t * nz:(t + 1) * nz, s * nu:(s + 1) * nu] = np.linalg.matrix_power(A, t - s) @ B
-    rhs = q * G.T @ (zref.reshape(-1) - F @ z0)
-    return np.linalg.solve(q * G.T @ G + r * np.eye(H * nu), rhs).reshape(H, nu)
+    u_prev = np.zeros(nu) if u_prev is None else np.asarray(u_prev, dtype=np.float64)
+
+    def residual(x):
+        x = x.reshape(H, nu)
+        z, u, res = z0.copy(), u_prev.copy(), []
+        for t in range(H):
+            u = u + x[t] if mpc_type == "delta_mpc" else x[t]
+            z = A @ z + B @ u
+            res.append(np.sqrt(q) * (z - zref[t]))
+            res.append(np.sqrt(r) * x[t])
+        return np.concatenate(res)
+
+    r0 = residual(np.zeros(H * nu))
+    J = np.stack([residual(e) - r0 for e in np.eye(H * nu)], axis=1)
+    return np.linalg.lstsq(J, -r0, rcond=None)[0].reshape(H, nu)
+
+
+class Controller:
+    """`MPCController.get_control` + the `u_prev` hand-off of `Koopman_MPC.runMPC`
+    [REF control/MPC_Controler.py:143-152, Koopman_MPC.py:206-217]: u0 = u_opt[0] + u_eso (= 0) + u_prev,
+    a = clip(u0, -0.5, 0.5); get_control stores a as u_prev in 'delta_mpc' mode, and runMPC then overwrites it with the
+    unclipped u0 in BOTH modes; in 'delta_mpc' mode u_prev is also a parameter of the problem."""
+
+    def __init__(self, W, H=10, mpc_type="delta_mpc", clip=0.5):
+        self.W, self.H, self.mpc_type, self.clip = W, H, mpc_type, clip
+        self.u_prev = np.zeros(W["lB.weight"].shape[1])
+
+    def step(self, state, zref):
+        u_opt = mpc_solve(self.W, lift(self.W, state), zref, self.H, mpc_type=self.mpc_type,
+                          u_prev=self.u_prev if self.mpc_type == "delta_mpc" else None)
+        u0 = u_opt[0] + self.u_prev
+        a = np.clip(u0, -self.clip, self.clip)
+        if self.mpc_type == "delta_mpc":
+            self.u_prev = a.copy()
+        self.u_prev = u0          # runMPC: `self.mpc_controller.u_prev = u`
+        return u0, a
 
 
 def k_linear_loss(W, x, u, start_idx, gamma=0.99, pre_length=5):

@@ -371,9 +371,10 @@ def test_cartesian_trajectory_generator_drop_in(tables_v, tables_p):
     assert dist.mean() < 0.03
 
 
-def _mpc_loop_oracle(tables, W, cp, ja, frames, H=10):
+def _mpc_loop_oracle(tables, W, cp, ja, frames, H=10, mpc_type="delta_mpc"):
     """CPU restatement of the reference loop [REF Koopman_MPC.py:83-90, 109-126, 197-222] for ONE curve: C-oracle
-    physics, numpy Koopman lift, the MPC's NLP solved by normal equations.  -> (actions [frames,5], actual [frames,8])."""
+    physics, numpy Koopman lift, the controller as the reference runs it (its NLP solved by least squares, u_prev
+    carried as get_control / runMPC do).  -> (actions [frames,5], actual [frames,8])."""
     from oracle import koopman_oracle as KO
     from oracle import oracle as O
     o = O.Oracle(tables)
@@ -383,6 +384,7 @@ def _mpc_loop_oracle(tables, W, cp, ja, frames, H=10):
     ref = np.hstack([cp, ja])
     state = ref[0].copy()
     nz = W["lA.weight"].shape[0]
+    ctl = KO.Controller(W, H, mpc_type)
     acts, actual = [], []
     for k in range(frames):
         o.set("qfrc_applied", np.array(o.arr("qfrc_bias")))          # gravity compensation (:119)
@@ -390,7 +392,7 @@ def _mpc_loop_oracle(tables, W, cp, ja, frames, H=10):
         zref = np.zeros((H, nz))
         if len(seg):
             zref[:len(seg)] = KO.lift(W, seg)
-        a = np.clip(KO.mpc_solve(W, KO.lift(W, state), zref, H)[0], -0.5, 0.5)
+        _, a = ctl.step(state, zref)
         ctrl = np.zeros(6); ctrl[:5] = a
         o.set("ctrl", ctrl)
         o.step(10)                                                   # env.step: frame_skip x mj_step
@@ -422,7 +424,15 @@ def test_koopman_mpc_loop_follows_ik_tracks(tables_v):
     assert (st & 1).all()
     cp, ja = torch.as_tensor(xyz).cuda(), q[:, :, :5].contiguous()
     env = SOARM101VecEnv(tables=tables_v, num_envs=n, gravity_compensation=True)
-    loop = BatchedKoopmanMPC(env, km, cp, ja, H=10)
+    # the non-default formulation first: a few frames against the CPU restatement
+    loop_m = BatchedKoopmanMPC(env, km, cp, ja, H=10, MPC_type="mpc")
+    actual_m = loop_m.run(6).cpu().numpy()
+    for b in (0, 3):
+        acts_o, actual_o = _mpc_loop_oracle(tables_v, W, xyz[b], ja[b].cpu().numpy(), 6, mpc_type="mpc")
+        assert np.abs(actual_m[b] - actual_o).max() < 5e-6
+        assert np.abs(torch.stack(loop_m.applied, 1)[b].cpu().numpy() - acts_o).max() < 1e-6
+    loop = BatchedKoopmanMPC(env, km, cp, ja, H=10)                  # MPC_type = 'delta_mpc', the reference's default
+    assert loop.MPC_type == "delta_mpc"
     actual = loop.run().cpu().numpy()                                # [n, 300, 8]
     assert actual.shape == (n, 300, 8) and loop.traj_index == 300
     # the run as a dataset in the reference's row layout [u | ee | q]: re-stepping row i's control from row i's state is
@@ -451,6 +461,7 @@ def test_koopman_mpc_loop_follows_ik_tracks(tables_v):
         acts_o, actual_o = _mpc_loop_oracle(tables_v, W, xyz[b], ja[b].cpu().numpy(), frames)
         d = np.abs(actual[b, :frames] - actual_o).max()
         assert d < 5e-6, (b, d)                                      # float32 observations, <= 80 physics steps
+        assert np.abs(rows[b, :frames, :5] - acts_o).max() < 1e-6    # the applied controls, u_prev carried as the reference does
     # (b) tracking: frame k has applied the control computed for reference k+1
     ee_err = np.linalg.norm(actual[:, 20:299, :3] - xyz[:, 21:300], axis=2)
     q_err = np.abs(actual[:, 20:299, 3:] - ja[:, 21:300].cpu().numpy())

@@ -43,6 +43,37 @@ def test_closed_form_mpc_matches_normal_equations_cpu():
     np.testing.assert_allclose(u1, np.clip(u_star[0], -0.5, 0.5), atol=1e-9)
 
 
+def test_delta_mpc_gains_match_the_restated_problem_cpu():
+    """The reference's default formulation, 'delta_mpc' [REF args.py:75, control/MPC_Controler.py:100-141]: decision
+    variable delta_u, u_t = u_prev + cumulative sum, cost on delta_u.  Closed-form gains == least-squares solve of the
+    problem as the reference rolls it, for random (z0, zref, u_prev); and with u_prev = 0 and r -> the same weights the
+    two formulations differ (so the test can tell them apart)."""
+    from oracle import koopman_oracle as KO
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    W = _weights()
+    km = KoopmanModel(W, device="cpu")
+    rng = np.random.default_rng(3)
+    H = 10
+    Kz, Kr, Ku = [K.numpy() for K in km.mpc_gains3(H, mpc_type="delta_mpc")]
+    assert Ku.shape == (H * 5, 5) and np.abs(Ku).max() > 1e-3
+    for _ in range(5):
+        x = rng.uniform(-0.3, 0.3, 8); xref = rng.uniform(-0.3, 0.3, (H, 8)); up = rng.uniform(-0.6, 0.6, 5)
+        z0, zref = KO.lift(W, x), KO.lift(W, xref)
+        d_star = KO.mpc_solve(W, z0, zref, H, mpc_type="delta_mpc", u_prev=up)
+        d_gain = (Kz @ z0 + Kr @ zref.reshape(-1) + Ku @ up).reshape(H, 5)
+        np.testing.assert_allclose(d_gain, d_star, rtol=0, atol=1e-9)
+        u_mpc = KO.mpc_solve(W, z0, zref, H, mpc_type="mpc")
+        assert np.abs(np.cumsum(d_star, 0) + up - u_mpc).max() > 1e-3
+    # 'mpc' through the same entry point: Ku = 0
+    Kz2, Kr2, Ku2 = [K.numpy() for K in km.mpc_gains3(H, mpc_type="mpc")]
+    assert not Ku2.any() and np.array_equal(Kz2, km.mpc_gains(H)[0].numpy())
+    # the controller's u_prev hand-off [REF MPC_Controler.py:143-152, Koopman_MPC.py:217]: u_prev <- u0 (unclipped)
+    ctl = KO.Controller(W, H, "delta_mpc")
+    x = rng.uniform(-0.3, 0.3, 8); zref = KO.lift(W, rng.uniform(-0.3, 0.3, (H, 8)) * 3)
+    u0, a = ctl.step(x, zref)
+    assert np.array_equal(ctl.u_prev, u0) and np.array_equal(a, np.clip(u0, -0.5, 0.5))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_koopman_score_matches_numpy(dtype):
@@ -180,3 +211,53 @@ def test_shooting_mpc_improves_on_the_model_solution(tables_v):
           f"{100 * np.mean(gains):.1f} %; closed-loop |q - qref| {np.mean(err_s[10:]):.2e} rad (sampled) vs "
           f"{np.mean(err_m[10:]):.2e} rad (model)")
     assert np.mean(err_s[10:]) < 1.25 * np.mean(err_m[10:]) + 1e-3
+
+
+@pytest.mark.gpu
+def test_lift_and_mpc_step_kernels_match_numpy():
+    """The fused encoder kernel (`so101_koopman_lift`), the reference fold (`so101_koopman_feedforward`) and one MPC frame
+    (`so101_koopman_mpc_step`) against the numpy restatement, for both formulations, both observation layouts / dtypes and
+    ragged batch sizes; float64 arithmetic on both sides: 1e-12."""
+    from oracle import koopman_oracle as KO
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    W = _weights()
+    km = KoopmanModel(W)
+    rng = np.random.default_rng(5)
+    H, P = 10, 37
+    for n in (1, 63, 64, 1000):
+        x = rng.uniform(-0.6, 0.6, (n, 8))
+        z_ref = KO.lift(W, x)
+        xt = torch.as_tensor(x).cuda()
+        np.testing.assert_allclose(km.lift_device(xt).cpu().numpy(), z_ref, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(km.lift_device(xt.t().contiguous(), soa=True).cpu().numpy(), z_ref, rtol=0, atol=1e-12)
+        x32 = xt.float()
+        np.testing.assert_allclose(km.lift_device(x32.t().contiguous(), soa=True).cpu().numpy(),
+                                   KO.lift(W, x32.double().cpu().numpy()), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(km.lift_device(xt).cpu().numpy(), km.lift(xt).cpu().numpy(), rtol=0, atol=1e-12)
+    n = 130
+    xref = rng.uniform(-0.4, 0.4, (n, P, 8))
+    x = rng.uniform(-0.4, 0.4, (n, 8)); up = rng.uniform(-0.7, 0.7, (n, 5))
+    for mpc_type in ("delta_mpc", "mpc"):
+        Kz, Kr, Ku = [K.cpu().numpy() for K in km.mpc_gains3(H, mpc_type=mpc_type)]
+        uff = km.feedforward(torch.as_tensor(xref).cuda(), H, mpc_type).cpu().numpy()
+        for k in (0, 5, P - 4, P - 1):
+            zr = np.zeros((n, H, km.nz))
+            m = min(H, P - 1 - k)
+            if m > 0:
+                zr[:, :m] = KO.lift(W, xref[:, k + 1:k + 1 + m])
+            np.testing.assert_allclose(uff[:, k], zr.reshape(n, -1) @ Kr[:5].T, rtol=0, atol=1e-11)
+        k = 5
+        u_prev = torch.as_tensor(up.T.copy()).cuda()
+        ctrl = torch.zeros((5, n), dtype=torch.float64, device="cuda")
+        a_out = torch.zeros((n, 5), dtype=torch.float64, device="cuda")
+        km.mpc_step(torch.as_tensor(x).cuda(), False, torch.as_tensor(uff).cuda(), k, u_prev, ctrl, a_out, H, mpc_type)
+        u0_ref = KO.lift(W, x) @ Kz[:5].T + uff[:, k] + up @ Ku[:5].T + up
+        np.testing.assert_allclose(u_prev.cpu().numpy().T, u0_ref, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(a_out.cpu().numpy(), np.clip(u0_ref, -0.5, 0.5), rtol=0, atol=1e-11)
+        assert np.array_equal(ctrl.cpu().numpy().T, a_out.cpu().numpy())
+        # one whole controller step against the restated NLP (least squares) for a few envs
+        for e in (0, 77):
+            zr = np.zeros((H, km.nz)); zr[:] = KO.lift(W, xref[e, k + 1:k + 1 + H])
+            ctl = KO.Controller(W, H, mpc_type); ctl.u_prev = up[e].copy()
+            u0_o, a_o = ctl.step(x[e], zr)
+            np.testing.assert_allclose(u_prev.cpu().numpy()[:, e], u0_o, rtol=0, atol=1e-9)
