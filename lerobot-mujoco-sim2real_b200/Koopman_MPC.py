@@ -54,13 +54,28 @@ class BatchedKoopmanMPC:
         self.traj_index = 0
         self.actual_traj = []
         self.state_tensor: Optional[torch.Tensor] = None
-        # reference part of the control law for every frame of every curve: each reference row is lifted once
-        self.uff = model.feedforward(self.state_all_ref, self.H, MPC_type)   # [n, P, nu]
+        # reference part of the control law, uff [n, rows, nu]: folded in runBefore for the frames that will run (each
+        # reference row is lifted once)
+        self.uff: Optional[torch.Tensor] = None
+        self._uff_frames = 0
         self.u_prev = torch.zeros((model.nu, n), dtype=torch.float64, device=env.device)
         self._ctrl = torch.zeros((model.nu, n), dtype=env.torch_dtype, device=env.device)
 
-    def runBefore(self) -> None:
-        """[REF Koopman_MPC.py:83-90]"""
+    def _fold_reference(self, frames: int) -> None:
+        """uff for frames [0, frames): needs reference rows [1, frames + H]."""
+        frames = min(int(frames), self.total_frames)
+        if self.uff is not None and self._uff_frames >= frames:
+            return
+        rows = min(self.total_frames, frames + self.H)
+        ref = self.state_all_ref if rows == self.total_frames else self.state_all_ref[:, :rows].contiguous()
+        self.uff = self.model.feedforward(ref, self.H, self.MPC_type)        # [n, rows, nu]
+        # a window that reaches past `rows` but not past the trajectory would miss rows: only frames < rows - H are
+        # complete unless the fold went to the end of the trajectory
+        self._uff_frames = self.total_frames if rows == self.total_frames else rows - self.H
+
+    def runBefore(self, frames: Optional[int] = None) -> None:
+        """[REF Koopman_MPC.py:83-90]; frames: how many frames will run (default: the whole trajectory)"""
+        self._fold_reference(self.total_frames if frames is None else frames)
         n = self.env.num_envs
         init = torch.cat([self.state_all_ref[:, 0, 3:8], torch.zeros((n, 5), dtype=torch.float64,
                                                                     device=self.env.device)], dim=1)
@@ -76,6 +91,8 @@ class BatchedKoopmanMPC:
         """One frame [REF Koopman_MPC.py:197-222] -> the applied control a [n, 5]."""
         n = self.env.num_envs
         k = self.traj_index
+        if k >= self._uff_frames:
+            self._fold_reference(self.total_frames)
         a = torch.empty((n, self.model.nu), dtype=torch.float64, device=self.env.device)
         if k == 0:      # the controller's first state is the reference's first row (float64), then the env's observations
             self.model.mpc_step(self.state_tensor.contiguous(), False, self.uff, k, self.u_prev, self._ctrl, a, self.H,
@@ -92,7 +109,7 @@ class BatchedKoopmanMPC:
 
     def run(self, frames: Optional[int] = None) -> torch.Tensor:
         """runBefore + `frames` (default: all) frames -> actual_traj [n, frames, 8]."""
-        self.runBefore()
+        self.runBefore(frames)
         for _ in range(self.total_frames if frames is None else int(frames)):
             self.runMPC()
         return torch.stack(self.actual_traj, dim=1)

@@ -127,7 +127,8 @@ extern "C" int so101_koopman_score(const double* A, const double* B, int nz, int
 constexpr int KM_MAXL = 8, KM_ROWS = 64, KM_THREADS = 256, KM_MAXW = 64, KM_MAXX = 16;
 
 struct So101Koopman {
-  int device, n_layers, dims[KM_MAXL + 1];
+  int device, sms, n_layers, dims[KM_MAXL + 1];
+  bool attr_lift[2], attr_mpc[4];                // dynamic shared memory limit raised (per kernel instantiation)
   int x_dim, nz;
   size_t woff[KM_MAXL], boff[KM_MAXL], wcount;   // offsets (doubles) of Wt[l] ([din][dout], transposed) and b[l] in `weights`
   double* weights;                               // device
@@ -320,11 +321,8 @@ static KmLayers km_layers(const So101Koopman* k) {
   return L;
 }
 static int km_grid(const So101Koopman* k, int64_t n) {
-  cudaDeviceProp prop;
-  int sms = 148;
-  if (cudaGetDeviceProperties(&prop, k->device) == cudaSuccess) sms = prop.multiProcessorCount;
   const int64_t tiles = (n + KM_ROWS - 1) / KM_ROWS;
-  return (int)(tiles < sms ? tiles : sms);        // persistent: one block per SM (the weights fill its shared memory)
+  return (int)(tiles < k->sms ? tiles : k->sms);  // persistent: one block per SM (the weights fill its shared memory)
 }
 
 extern "C" int so101_koopman_create(int n_layers, const int32_t* dims, const double* const* W, const double* const* b,
@@ -341,6 +339,8 @@ extern "C" int so101_koopman_create(int n_layers, const int32_t* dims, const dou
   So101Koopman* k = new So101Koopman();
   std::memset(k, 0, sizeof *k);
   k->device = device; k->n_layers = n_layers;
+  k->sms = 148;
+  cudaDeviceGetAttribute(&k->sms, cudaDevAttrMultiProcessorCount, device);
   for (int l = 0; l <= n_layers; l++) k->dims[l] = dims[l];
   k->x_dim = dims[0]; k->nz = dims[0] + dims[n_layers];
   size_t off = 0;
@@ -395,7 +395,8 @@ extern "C" int so101_koopman_set_gains(So101Koopman* k, int H, int nu, const dou
 template <typename TX>
 static int km_launch_lift(So101Koopman* k, const TX* X, int layout, int64_t ldx, int64_t n, double* Z, cudaStream_t st) {
   const size_t smem = km_smem_bytes(k, false);
-  CUDA_TRY(cudaFuncSetAttribute(k_koopman_lift<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bool& done = k->attr_lift[sizeof(TX) == 4];
+  if (!done) { CUDA_TRY(cudaFuncSetAttribute(k_koopman_lift<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
   k_koopman_lift<TX><<<km_grid(k, n), KM_THREADS, smem, st>>>(km_layers(k), k->weights, X, layout, ldx, n, Z);
   CUDA_TRY(cudaGetLastError());
   return SO101_OK;
@@ -446,7 +447,8 @@ template <typename TX, typename TC>
 static int km_launch_mpc(So101Koopman* k, const TX* X, int layout, int64_t ldx, int64_t n, const double* uff, int64_t uff_stride,
                          double* u_prev, TC* ctrl, double* a_out, double clip, cudaStream_t st) {
   const size_t smem = km_smem_bytes(k, true);
-  CUDA_TRY(cudaFuncSetAttribute(k_koopman_mpc<TX, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  bool& done = k->attr_mpc[(sizeof(TX) == 4) * 2 + (sizeof(TC) == 4)];
+  if (!done) { CUDA_TRY(cudaFuncSetAttribute(k_koopman_mpc<TX, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
   k_koopman_mpc<TX, TC><<<km_grid(k, n), KM_THREADS, smem, st>>>(km_layers(k), k->weights, k->gains, k->nu, X, layout, ldx, n,
                                                                uff, uff_stride, u_prev, ctrl, a_out, clip);
   CUDA_TRY(cudaGetLastError());
