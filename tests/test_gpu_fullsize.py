@@ -5,11 +5,14 @@ Where the CPU oracle finishes in seconds (config 1) the comparison is direct; at
 invariance to how the batch is sharded / which kernel family runs, agreement of independent kernels with each
 other (shoot vs rollout), plus oracle comparisons on sampled sub-ranges.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _vec(tables, n, dtype="float64", **kw):
@@ -149,3 +152,56 @@ def test_config5_full_size_shoot_equals_rollout(oracle_mod, tables_v, gravcomp):
     # and 32 of the sequences against the oracle over the first 5 env-steps (before chaos acts)
     ref = O.shoot(tables_v, s0, U[:5, :, :32].cpu().numpy(), 10, flags=flags)
     assert np.abs(X[:32, :6].cpu().numpy() - ref).max() <= 2e-7
+
+
+# ------------------------------------------------------------------------------------------------
+# config 4's wording, end to end: TrajectoryGenerator-driven closed-loop data at 2^20 curves
+# ------------------------------------------------------------------------------------------------
+def _curve_params(lo, hi):
+    """curve family / centre / scale as a pure function of the GLOBAL curve index (what makes the dataset shard-invariant)"""
+    i = np.arange(lo, hi, dtype=np.uint64)
+    h = (i * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(11)
+    u = [((h >> np.uint64(8 * k)) & np.uint64(0xFF)).astype(np.float64) / 255.0 for k in range(4)]
+    centers = np.stack([0.4 + 0 * u[1], 0.03 * (u[1] - 0.5), 0.2 + 0.03 * (u[2] - 0.5)], axis=1)    # y-z plane (idx = 1)
+    return u[0] < 0.5, centers, 0.4 + 0.2 * u[3]
+
+
+def _mpc_pipeline(tables, lo, hi, frames, P, MPC_type="delta_mpc"):
+    """curves [lo, hi) -> way-points on the device -> IK (one launch) -> Koopman_MPC loop -> rows [n, frames, 13]"""
+    from lerobot_mujoco_sim2real_b200.Koopman_MPC import BatchedKoopmanMPC
+    from lerobot_mujoco_sim2real_b200.TrajectoryGenerator import CartesianTrajectoryGenerator
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    n = hi - lo
+    km = KoopmanModel.from_npz(os.path.join(ROOT, "tests", "golden", "koopman_dkuc.npz"))
+    gen = CartesianTrajectoryGenerator(tables=tables)
+    names, centers, scale = _curve_params(lo, hi)
+    xyz, q, st = gen.generate_batch(names, idx=np.ones(n, dtype=np.int64), traj_scale=scale, centers=centers)
+    xyz, q = xyz[:, :P].contiguous(), q[:, :P].contiguous()                 # the first P way-points of every curve
+    env = SOARM101VecEnv(tables=tables, num_envs=n, gravity_compensation=True)
+    loop = BatchedKoopmanMPC(env, km, xyz, q, H=10, MPC_type=MPC_type)
+    actual = loop.run(frames)
+    return loop.dataset_rows(), actual, xyz, st[:, :P]
+
+
+def test_config4_size_trajectory_generator_pipeline(tables_v):
+    """2^20 Cartesian curves -> batched IK -> the reference's Koopman_MPC loop (delta_mpc, gravity compensation) ->
+    dataset rows, on one GPU in one piece; the same rows come out of what rank 3 of 8 would run alone (one-warp kernels)
+    and out of a 4096-curve slice (team kernels), bit for bit, and a re-run reproduces them."""
+    n, frames, P, G = 1 << 20, 20, 32, 8
+    rows, actual, xyz, st = _mpc_pipeline(tables_v, 0, n, frames, P)
+    assert rows.shape == (n, frames, 13) and rows.dtype == torch.float64
+    assert float((st & 1).double().mean()) > 0.99
+    assert torch.isfinite(rows).all() and float(rows[:, :, :5].abs().max()) <= 0.5
+    shard = n // G
+    part = _mpc_pipeline(tables_v, 3 * shard, 4 * shard, frames, P)[0]
+    assert torch.equal(rows[3 * shard:4 * shard], part)
+    del part
+    small = _mpc_pipeline(tables_v, 777_777, 777_777 + 4096, frames, P)[0]
+    assert torch.equal(rows[777_777:777_777 + 4096], small)
+    again = _mpc_pipeline(tables_v, 777_777, 777_777 + 4096, frames, P)[0]
+    assert torch.equal(small, again)
+    # the loop tracks: after the first frames the end effector is on the curve (y-z plane curves, the model's range)
+    ee_err = (actual[:, 10:, :3] - xyz[:, 11:frames + 1]).norm(dim=2)
+    print(f"2^20 curves x {frames} frames: ee error mean {float(ee_err.mean()) * 1e3:.2f} mm, p99 {float(ee_err.flatten()[::97].quantile(0.99)) * 1e3:.2f} mm")
+    assert float(ee_err.mean()) < 0.01

@@ -15,7 +15,16 @@ pytestmark = pytest.mark.gpu
 
 
 def _rel(a, b):
+    """relative error with the denominator floored at 1e-3 (absolute for smaller values)"""
     return np.abs(a - b) / (1e-3 + np.maximum(np.abs(a), np.abs(b)))
+
+
+def _rel_true(a, b, floor=1e-9):
+    """true relative error |a - b| / max(|a|, |b|) over the entries whose magnitude exceeds `floor` (an absolute error of
+    one ulp of 1.0 on a value of 1e-9 is a relative error of 1e-7: below the floor only the absolute error means anything)"""
+    m = np.maximum(np.abs(a), np.abs(b))
+    ok = m > floor
+    return (np.abs(a - b)[ok] / m[ok]) if ok.any() else np.zeros(1)
 
 
 def _oracle_traj(O, tables, n, steps, seed, ctrl_hold=10, qscale=0.3, uscale=0.5):
@@ -68,6 +77,10 @@ def test_p1_teacher_forced_fp64(oracle_mod, tables_v, tables_p, scene):
     print("   qacc rel err quantiles 50/99/99.9/max:",
           " ".join(f"{np.quantile(err[:, 12:], x):.2e}" for x in (0.5, 0.99, 0.999, 1.0)))
     assert err[:, :6].max() < 1e-12
+    # the same without the floor: qpos entries above 1e-6 rad in magnitude agree to 1e-9 relative, all to 1e-15 absolute
+    tr = _rel_true(out[:, :6], s_ref[:, :6], 1e-6)
+    print(f"   qpos true relative error (|q| > 1e-6): max {tr.max():.2e}; absolute: max {np.abs(out[:, :6] - s_ref[:, :6]).max():.2e}")
+    assert tr.max() < 1e-9 and np.abs(out[:, :6] - s_ref[:, :6]).max() < 1e-14
     # qacc is the Newton solver's output: both implementations stop at opt.tolerance = 1e-8, so it
     # agrees to rounding when the last step lands on the exact minimiser of the piecewise-quadratic
     # cost (the bulk) and to ~1e-10 otherwise; qvel inherits h * that.
@@ -144,7 +157,7 @@ def test_p2_free_running_scene_a_curve(oracle_mod, tables_v):
     env = SOARM101VecEnv(tables=tables_v, num_envs=n, dtype="float64")
     Ud = torch.as_tensor(U, dtype=torch.float64, device=env.device).contiguous()
     curve = []
-    for Tc in (1, 3, 10, 30, 100):
+    for Tc in (1, 3, 5, 7, 10, 30, 100):
         _, fin, _ = O.rollout(tables_v, spec, n, Tc, 10, qpos0=q0, want_rows=False)
         _, finp, _ = O.rollout(tables_v, spec, n, Tc, 10, qpos0=q0p, want_rows=False)
         env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
@@ -157,9 +170,12 @@ def test_p2_free_running_scene_a_curve(oracle_mod, tables_v):
         print(f"physics step {s:5d}: oracle 1-ulp self-divergence {a:.3e}   gpu-vs-oracle {b:.3e}")
     # before chaos amplifies rounding: tight agreement
     assert curve[0][2] < 1e-12
-    # afterwards the GPU error must stay within 100x of what a 1-ulp perturbation does to the oracle itself
+    # the same curve within 10x of what a 1-ulp perturbation does to the oracle itself, and <= 1e-9 up to the
+    # step where that self-divergence crosses 1e-10
     for s, a, b in curve:
-        assert b <= max(1e-12, 100 * a), (s, a, b)
+        assert b <= max(1e-12, 10 * a), (s, a, b)
+        if a < 1e-10:
+            assert b <= 1e-9, (s, a, b)
 
 
 def test_free_running_against_joint_limits_scene_b(contact_free, tables_p):
