@@ -170,15 +170,21 @@ class ClockSampler:
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
 
     def start(self):
+        """Starts nvidia-smi and waits for its first line (its start-up can take longer than a short timed region), then
+        marks where the samples taken under load begin."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(self.index),
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0:
+                time.sleep(0.01)
+            self.first = len(self.lines)
         except Exception:
             self.proc = None
 
@@ -186,9 +192,15 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self) -> dict:
+    def stop(self, busy=None) -> dict:
+        """busy: callable that keeps the GPU under the same load; used to extend the sampling when the timed region was
+        too short to catch two samples (the extension is not timed)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t0 = time.perf_counter()
+        while busy is not None and len(self.lines) - self.first < 3 and time.perf_counter() - t0 < 2.0:
+            busy()
+        self.lines = self.lines[self.first:] if len(self.lines) > self.first else self.lines
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -347,7 +359,7 @@ def wl_config1(ctx) -> None:
     if rank == 0:
         ctx.sampler.start()
     ms_per_step, wall_ms = ctx.timed(step_dev, K, W)
-    clocks = ctx.sampler.stop() if rank == 0 else None
+    clocks = ctx.sampler.stop(busy=lambda: (step_dev(0), torch.cuda.synchronize())) if rank == 0 else None
     st = env.stats()
     flags = env.flags()
     n_trip = int((flags & T.FLAG_TRIP).ne(0).sum().item())

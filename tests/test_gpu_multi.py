@@ -49,8 +49,12 @@ def _worker(rank, world, port, tmp):
             assert full is None
         del full
         sr.close()
-        # (2) the data generator: sharded generation, flagged trajectories regenerated on rank 0, files visible to all
-        gen = SOARM101DataGenerator(_args(tmp), tables=tables, device=rank)
+        # (2) the data generator: sharded generation, flagged trajectories regenerated on rank 0, files visible to all.
+        # Tables WITHOUT contact parameters: the kernels then only flag table contacts (with them they are simulated and a
+        # flag is the exception), which gives the regeneration path something to do
+        tables_nc = T.tables_from_dict(T.tables_to_dict(tables))
+        tables_nc.con_enabled = 0
+        gen = SOARM101DataGenerator(_args(tmp), tables=tables_nc, device=rank)
         data = gen.generate_physics_based_data(600, 200, "chirp", seed=5)
         if rank == 0:
             np.save(os.path.join(tmp, "gen.npy"), data)
@@ -75,7 +79,10 @@ def test_two_rank_dataset_equals_single_process(tmp_path, tables_v):
     ref = SOARM101VecEnv(tables=tables_v, num_envs=4097).rollout(7, "chirp", seed=3).cpu().numpy()
     np.testing.assert_array_equal(np.load(tmp_path / "shared.npy"), ref)          # peer-written == one GPU, bit for bit
     d1 = tmp_path / "single"
-    gen = SOARM101DataGenerator(_args(d1), tables=tables_v)
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    tables_nc = T_.tables_from_dict(T_.tables_to_dict(tables_v))
+    tables_nc.con_enabled = 0
+    gen = SOARM101DataGenerator(_args(d1), tables=tables_nc)
     want = gen.generate_physics_based_data(600, 200, "chirp", seed=5)
     np.testing.assert_array_equal(np.load(tmp_path / "gen.npy"), want)            # incl. the regenerated trajectories
     np.testing.assert_array_equal(np.load(tmp_path / "gen_flags.npy"), gen.last_flags)
