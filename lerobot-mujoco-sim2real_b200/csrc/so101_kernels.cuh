@@ -330,6 +330,36 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   add_stats(stats, cnt);
 }
 
+// Row t of the 32 envs of a warp -> rows[env][t][13].  A thread writing its own row issues 13 stores of 8 bytes at a
+// stride of (T+1) * 104 bytes between lanes: every store instruction touches 32 sectors and fills a quarter of each.
+// Harmless in local HBM (L2 merges them), but in the multi-GPU job the rows go straight into rank 0's memory over NVLink,
+// where the partial sectors capped the delivery at ~90 GB/s (8 GPUs: 21.8 ms exposed behind a 10.7 ms simulation).  Here
+// the warp transposes its rows through shared memory (two passes of 7 and 6 columns) and consecutive lanes store
+// consecutive words of the 104-byte rows: ~4x fewer sectors on the wire.  env0 = env of lane 0 (lanes hold consecutive
+// envs; lanes beyond the batch shadow a valid env and are skipped).
+template <typename ROW> struct RowBuf { ROW w[7 * 32]; };
+template <typename ROW>
+SO101_DEV void write_rows_warp(RowBuf<ROW>& buf, const ROW (&v)[SO101_ROW], ROW* rows, int64_t env0, int64_t n, int Tn, int t) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c0 = 0; c0 < SO101_ROW; c0 += 7) {
+    const int nc = SO101_ROW - c0 < 7 ? SO101_ROW - c0 : 7;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 7; c++)
+      if (c < nc) buf.w[lane * nc + c] = v[c0 + c];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const int el = j * 32 + lane;               // element of the [32 envs][nc] block
+      if (j < nc) {
+        const int envl = el / nc, c = el - envl * nc;
+        if (env0 + envl < n) rows[((env0 + envl) * (int64_t)(Tn + 1) + t) * SO101_ROW + c0 + c] = buf.w[el];
+      }
+    }
+  }
+}
+
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
 template <typename T, typename ROW, bool SPLIT>
@@ -339,6 +369,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   // control steps (t0, t1] of a rollout of Tn steps; t0 > 0 continues a previous launch (row t0 is already written,
   // u_t0 is regenerated: the control stream is a pure function of (seed, env, t)).
   __shared__ XchStorage<T, SPLIT> xst;
+  __shared__ RowBuf<ROW> rowbuf[SPLIT ? 1 : SO101_LB_THREADS / 32];
   SplitXch<T>& xch = xch_of(xst);
   bool active, exit_block;
   const int64_t i = env_slot<T, SPLIT>(s, active, exit_block);
@@ -380,14 +411,16 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
 #pragma unroll
     for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
     clamp_ctrl(m, uc);   // rows keep the unclamped u, as the reference's dataset does
-    if (rows && active && (t > t0 || t0 == 0)) {
-      ROW* row = rows + ((int64_t)i * (Tn + 1) + t) * SO101_ROW;
+    if (rows && (t > t0 || t0 == 0)) {     // warp-uniform: the whole warp writes its 32 rows together
+      ROW v[SO101_ROW];
 #pragma unroll
-      for (int k = 0; k < 5; k++) row[k] = (ROW)u[k];
+      for (int k = 0; k < 5; k++) v[k] = (ROW)u[k];
 #pragma unroll
-      for (int k = 0; k < 3; k++) row[5 + k] = (ROW)(float)site[k];
+      for (int k = 0; k < 3; k++) v[5 + k] = (ROW)(float)site[k];
 #pragma unroll
-      for (int k = 0; k < 5; k++) row[8 + k] = (ROW)(float)e.q[k];
+      for (int k = 0; k < 5; k++) v[8 + k] = (ROW)(float)e.q[k];
+      write_rows_warp<ROW>(rowbuf[SPLIT ? 0 : threadIdx.x >> 5], v, rows,
+                           SPLIT ? (int64_t)blockIdx.x * 32 : (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u), s.n, Tn, t);
     }
   }
   if (active) store_env(s, i, e);
