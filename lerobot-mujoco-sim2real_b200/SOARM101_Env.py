@@ -182,9 +182,13 @@ class SOARM101Env(_EnvBase):
 
     def __init__(self, xml_path: str, dt: float = 0.02, render_mode=False, dtype: str = "float64",
                  device: int = 0, gravity_compensation: bool = False):
-        """gravity_compensation=True re-enables the line the reference keeps commented out in step()
-        (`self.data.qfrc_applied[:] = self.data.qfrc_bias[:]`, [REF SOARM101_Env.py:120]); the reference's
-        shipped Koopman model was trained on data generated that way."""
+        """gravity_compensation=True: qfrc_applied = qfrc_bias before every env step, with qfrc_bias evaluated AT THE STATE
+        THE STEP STARTS FROM - the semantics of the reference's control loop [REF Koopman_MPC.py:119-126: the assignment
+        follows an explicit mj_forward], which is what `data.qfrc_bias` returns here.  The line the reference keeps
+        commented out inside step() (`self.data.qfrc_applied[:] = self.data.qfrc_bias[:]`, [REF SOARM101_Env.py:120]) would
+        read the qfrc_bias left by the LAST SUB-STEP's forward pass, i.e. one sub-step (2 ms) behind, like ee_pos (F6); the
+        difference is O(h) in a gravity torque and no test distinguishes the two on the oracle either (it recomputes, too).
+        The reference's shipped Koopman model was trained on data generated with gravity compensation."""
         super().__init__()
         self.gravity_compensation = bool(gravity_compensation)
         if render_mode:

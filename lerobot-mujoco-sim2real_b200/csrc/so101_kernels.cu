@@ -12,7 +12,12 @@ SO101_LAUNCHERS(, SO101_TU_T, SO101_TU_SPLIT)
 #if SO101_TU_SPLIT
 extern "C" int SO101_TIMING_NAME(unsigned long long* out, int reset) {
   cudaMemcpyFromSymbol(out, so101::g_timing, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(so101::g_timing, z, sizeof z); }
+  cudaMemcpyFromSymbol(out + 16, so101::g_timing_helpers, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(so101::g_timing, z, sizeof z);
+    cudaMemcpyToSymbol(so101::g_timing_helpers, z, sizeof(unsigned long long) * 8);
+  }
   return 0;
 }
 #endif

@@ -1250,7 +1250,8 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 // selects never changes a trajectory.
 // ------------------------------------------------------------------------------------------
 #ifdef SO101_TIMING   // debug build: where the dynamics warp of a team spends its cycles, by kind of step (tools/team_timing.py)
-__device__ unsigned long long g_timing[16];
+__device__ unsigned long long g_timing[16];   // [0..14]: dynamics warp by kind of step; [15]: unused
+__device__ unsigned long long g_timing_helpers[8];   // geometry: steps, cycles to (A), (A)..(E); lookout: steps, cycles to (A)
 #define SO101_TICK(var) const long long var = clock64()
 #else
 #define SO101_TICK(var)
@@ -1312,6 +1313,7 @@ template <> struct LaggedGuess<float> { static constexpr bool value = false; };
 template <typename T>
 SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
                                     int64_t n) {
+  SO101_TICK(tg0);
   team_check_state(m, q, qd);
   team_sincos(m, x, lane, 1, q);
   crba_mass(m, &x.sn[0][lane], &x.cs[0][lane], 32, &x.M[0][lane], 32);
@@ -1330,7 +1332,13 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #pragma unroll
     for (int i = 0; i < NV; i++) x.D1inv[0][i][lane] = Dinv[i];
   }
+#ifdef SO101_TIMING
+  const long long tg1 = clock64();
+#endif
   __syncthreads();   // (A) M published
+#ifdef SO101_TIMING
+  const long long tg2 = clock64();
+#endif
   if (LaggedGuess<T>::value) {
     const int nb = (int)((n + 1) & 1);
     ldl6_factor(M, zero, Ls, Dinv);
@@ -1344,6 +1352,14 @@ SO101_DEV void split_geometry_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   for (int i = 0; i < 15; i++) x.L2[i][lane] = Ls[i];
 #pragma unroll
   for (int i = 0; i < NV; i++) x.D2inv[i][lane] = Dinv[i];
+#ifdef SO101_TIMING
+  if (lane == 0) {
+    atomicAdd(&g_timing_helpers[0], 1ull);
+    atomicAdd(&g_timing_helpers[1], (unsigned long long)(tg1 - tg0));
+    atomicAdd(&g_timing_helpers[2], (unsigned long long)(clock64() - tg2));
+    atomicAdd(&g_timing_helpers[3], (unsigned long long)(tg2 - tg1));
+  }
+#endif
   __syncthreads();   // (E) factors of M + h B published
   __syncthreads();   // (B) new state published by the dynamics warp
 #pragma unroll
@@ -1377,6 +1393,7 @@ SO101_DEV void tripwire_all_tests(const DevModel<T>& m, const T* sn, const T* cs
 template <typename T>
 SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane, T (&q)[NV], T (&qd)[NV],
                                   bool want_site, bool trip, int32_t* vcache) {
+  SO101_TICK(tl0);
   team_check_state(m, q, qd);
   team_sincos(m, x, lane, 2, q);
   uint32_t fl = 0, hits = 0, nc = 0;
@@ -1420,7 +1437,14 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
 #pragma unroll
     for (int c = 0; c < 3; c++) x.site[c][lane] = p[c];
   }
+#ifdef SO101_TIMING
+  const long long tl1 = clock64();
+#endif
   __syncthreads();   // (A)
+#ifdef SO101_TIMING
+  if (lane == 0) { atomicAdd(&g_timing_helpers[4], 1ull); atomicAdd(&g_timing_helpers[5], (unsigned long long)(tl1 - tl0));
+                   atomicAdd(&g_timing_helpers[6], (unsigned long long)(clock64() - tl1)); }
+#endif
   __syncthreads();   // (E)
   __syncthreads();   // (B)
 #pragma unroll

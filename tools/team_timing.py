@@ -12,7 +12,7 @@ env = SOARM101VecEnv(tables=builtin_tables(), num_envs=32, dtype="float64", hull
 env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_TEAM)
 spec = env.make_spec("random", seed, g * 32)
 L = _lib.lib()
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 24)()
 for rep in range(2):
     L.so101_debug_timing_double(out, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -25,3 +25,6 @@ print(f"group {g}: {e0.elapsed_time(e1):.3f} ms")
 for k, name in enumerate(("plain", "box tripped", "contact solved")):
     n = max(t[k, 0], 1)
     print(f"  {name:15s} steps {int(t[k,0]):5d}  cycles/step: before (A) {t[k,1]/n:7.0f}  wait (A) {t[k,2]/n:7.0f}  solve {t[k,3]/n:7.0f}  (E)..end {t[k,4]/n:7.0f}  total {t[k,1:].sum()/n:7.0f}")
+h = np.array(list(out)[16:24], dtype=np.float64)
+print(f"  geometry warp: {h[1] / max(h[0], 1):.0f} cycles from step start to (A), {h[2] / max(h[0], 1):.0f} cycles of work after (A); "
+      f"waits {h[3] / max(h[0], 1):.0f} at (A); lookout warp: {h[5] / max(h[4], 1):.0f} cycles to (A), waits {h[6] / max(h[4], 1):.0f}")
