@@ -478,11 +478,19 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   const size_t rb = (size_t)b->n * (T + 1) * SO101_ROW * rs;
   if ((rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
   // chunking: worth it only when there is something to overlap
+  // A chunk boundary is not free: every launch lasts as long as its slowest block, and with table contact the slow block
+  // is a different one in every chunk, so the sum of the chunks exceeds the undivided launch (measured, 4096 envs x 100
+  // steps, 43 MB of rows: 1 / 2 / 3 / 4 / 8 / 12 chunks 8.67 / 8.33 / 8.53 / 8.61 / 8.65 / 8.75 ms, tools/e2e_probe.py).
+  // Two chunks while the copies are small beside the compute; more only where the download dominates (>= 128 MB of
+  // rows) and has to start early.
   int nchunk = 1;
-  if (T >= 8 && rb >= ((size_t)4 << 20)) {   // >= 2 MB of rows per chunk
-    nchunk = (int)(rb >> 21);
-    if (nchunk > So101Batch::MAXCHUNK) nchunk = So101Batch::MAXCHUNK;
-    if (nchunk < 2) nchunk = 2;
+  if (T >= 8 && rb >= ((size_t)4 << 20)) {
+    nchunk = 2;
+    if (rb >= ((size_t)128 << 20)) {
+      nchunk = (int)(rb >> 25);                 // >= 32 MB of rows per chunk
+      if (nchunk > So101Batch::MAXCHUNK) nchunk = So101Batch::MAXCHUNK;
+      if (nchunk < 3) nchunk = 3;
+    }
   }
   if (b->opt_host_chunks) nchunk = b->opt_host_chunks;
   if (nchunk > T) nchunk = T > 0 ? T : 1;

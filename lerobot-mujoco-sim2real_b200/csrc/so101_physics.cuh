@@ -1532,8 +1532,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
       e.flags |= SO101_FLAG_TRIP_TABLE;
     }
   }
-  __syncwarp();   // the lanes that took the contact branch rejoin here (measured: without it a lane whose box tripped ran the
-                  // direct solve below on its own, after the other 31: +2000 cycles per such step, tools/team_timing.py)
+  __syncwarp();   // the lanes that took the contact branch rejoin here
   if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     T zone[NV], xs[NV], dh[NV];
     active_set_guess(m, rw, M, asm_, zone);

@@ -22,7 +22,7 @@ def timed(fn, reps=10):
 print("device rollout(tensor U resident, rows to device):", timed(lambda: env.rollout(TC, "tensor", u=Ud, out=rows_d, flags=T.ROLL_NO_RESET)))
 print("H2D U only:", timed(lambda: Ud.copy_(U, non_blocking=True)))
 print("D2H rows only (contiguous):", timed(lambda: rows.copy_(rows_d, non_blocking=True)))
-for ch in ("1", "2", "4", "8"):
+for ch in ("1", "2", "3", "4", "6", "8", "12"):
     env.set_option(T.OPT_HOST_CHUNKS, int(ch))
     for even in (False, True):
         env.set_option(T.OPT_HOST_EVEN, int(even))
