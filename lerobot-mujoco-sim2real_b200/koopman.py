@@ -220,6 +220,59 @@ class KoopmanModel:
         u = z0 @ Kz[:self.nu].t() + zref @ Kr[:self.nu].t()
         return torch.clamp(u, -clip, clip)
 
+    # ---- bilinear model variants (DBKN / IBKN) --------------------------------------------------------------------------
+    def set_bilinear(self, H_weight: np.ndarray, u_z: bool = False) -> None:
+        """Attach the bilinear term of `KoopmanBlinear` [REF models/KoopmanBase.py:62-110]: z+ = A z + B u + H (z (x) u),
+        `H_weight` = net.H.weight [nz, nz*nu] (u_z: the Kronecker product is taken as u (x) z and permuted, as
+        `get_Hi_numpy` does).  The reference's MPC then freezes B over the horizon at B_total(z0) = B + sum_j z0_j H_hat_j
+        (`linearize_B`, [REF control/MPC_Controler.py:46-63]), so the problem stays an unconstrained quadratic - with gains
+        that depend on z0: one 50 x 50 solve per env (`mpc_control_bilinear`, batched tensor algebra: this variant is not
+        on the measured hot path; the reference ships no bilinear checkpoint)."""
+        Hd = np.asarray(H_weight, dtype=np.float64)
+        nz, nu = self.nz, self.nu
+        assert Hd.shape == (nz, nz * nu)
+        if u_z:   # columns ordered (u_i, z_j) -> (z_j, u_i)
+            Hd = Hd.reshape(nz, nu, nz).transpose(0, 2, 1).reshape(nz, nz * nu)
+        self.H_hat = torch.as_tensor(Hd.reshape(nz, nz, nu).transpose(1, 0, 2).copy(), device=self.device)   # [j][nz][nu]
+
+    def mpc_control_bilinear(self, x: torch.Tensor, xref: torch.Tensor, u_prev: Optional[torch.Tensor] = None, H: int = 10,
+                             mpc_type: str = "delta_mpc", q_weight: float = 50.0, r_weight: float = 0.5,
+                             clip: float = 0.5) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One controller step of the bilinear variants for a batch: x [N, x_dim], xref [N, H, x_dim] (rows past the end of a
+        trajectory: pass zeros and `valid` rows only are lifted - here all rows are lifted), u_prev [N, nu] (zeros if None)
+        -> (u0 [N, nu] unclipped = u_opt[0] + u_prev, a = clip(u0)) [REF control/MPC_Controler.py:143-152]."""
+        N, nz, nu = x.shape[0], self.nz, self.nu
+        dev = self.device
+        u_prev = torch.zeros((N, nu), dtype=torch.float64, device=dev) if u_prev is None else u_prev.to(dev, torch.float64)
+        z0 = self.lift(x)                                                        # [N, nz]
+        zref = self.lift(xref.reshape(N * H, -1)).reshape(N, H * nz)
+        A = torch.as_tensor(self.A, device=dev)
+        Bt = torch.as_tensor(self.B, device=dev)[None] + torch.einsum("nj,jab->nab", z0, self.H_hat)   # linearize_B
+        pows = [torch.eye(nz, dtype=torch.float64, device=dev)]
+        for _ in range(H):
+            pows.append(A @ pows[-1])
+        P = torch.stack(pows)                                                    # [H+1, nz, nz]
+        AB = torch.einsum("kab,nbc->nkac", P[:H], Bt)                            # A^k B_total, k = 0..H-1
+        G = torch.zeros((N, H, nz, H, nu), dtype=torch.float64, device=dev)
+        for t in range(H):
+            for s_ in range(t + 1):
+                G[:, t, :, s_, :] = AB[:, t - s_]
+        G = G.reshape(N, H * nz, H * nu)
+        Fz = torch.einsum("kab,nb->nka", P[1:], z0).reshape(N, H * nz)           # F z0
+        if mpc_type == "delta_mpc":
+            S = torch.kron(torch.tril(torch.ones((H, H), dtype=torch.float64, device=dev)), torch.eye(nu, dtype=torch.float64, device=dev))
+            Gd = G @ S
+            off = Fz + (G.reshape(N, H * nz, H, nu).sum(dim=2) @ u_prev[:, :, None])[:, :, 0] - zref
+        elif mpc_type == "mpc":
+            Gd, off = G, Fz - zref
+        else:
+            raise ValueError(f"MPC_type must be 'mpc' or 'delta_mpc', got {mpc_type!r}")
+        Hs = q_weight * Gd.transpose(1, 2) @ Gd + r_weight * torch.eye(H * nu, dtype=torch.float64, device=dev)
+        rhs = -q_weight * (Gd.transpose(1, 2) @ off[:, :, None])
+        sol = torch.linalg.solve(Hs, rhs)[:, :nu, 0]
+        u0 = sol + u_prev
+        return u0, torch.clamp(u0, -clip, clip)
+
     # ---- sampling MPC through the physics (SURVEY 8f N4: "replaces IPOPT with sampling MPC") -----------------------
     def shooting_mpc(self, shooter, state0, x: torch.Tensor, xref: torch.Tensor, sigma: float = 0.05,
                      clip: float = 0.5, q_weight: float = 50.0, r_weight: float = 0.5, flags: int = 0,

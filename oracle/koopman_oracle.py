@@ -35,7 +35,27 @@ def score(W, z0, U, zref=None, q=50.0, r=0.5, nobs=8):
     return np.stack(X, 1), cost
 
 
-def mpc_solve(W, z0, zref, H, q=50.0, r=0.5, mpc_type="mpc", u_prev=None):
+def linearize_B(W, z0, u_z=False):
+    """B_total = Bd + sum_j z0[j] H_hat_j with H_hat_j as `KoopmanBlinear.get_Hi_numpy` builds them
+    [REF control/MPC_Controler.py:46-63, models/KoopmanBase.py:85-110]; the model's own B when it has no H layer."""
+    B = W["lB.weight"]
+    if "H.weight" not in W:
+        return B
+    nz, nu = B.shape
+    Hd = W["H.weight"]
+    if u_z:       # P of build_permutation_matrix: vec(u (x) z) -> vec(z (x) u)
+        P = np.zeros((nu * nz, nu * nz))
+        for i in range(nu):
+            for j in range(nz):
+                P[j * nu + i, i * nz + j] = 1
+        Hd = Hd @ P.T
+    Bt = B.copy()
+    for j in range(nz):
+        Bt = Bt + z0[j] * Hd[:, j * nu:(j + 1) * nu]
+    return Bt
+
+
+def mpc_solve(W, z0, zref, H, q=50.0, r=0.5, mpc_type="mpc", u_prev=None, u_z=False):
     """The minimiser IPOPT converges to for the reference's unconstrained, quadratic problem.
 
     'mpc'       [REF control/MPC_Controler.py:65-98]:  decision u,  cost sum_t q |z_{t+1} - zref_t|^2 + r |u_t|^2
@@ -44,7 +64,7 @@ def mpc_solve(W, z0, zref, H, q=50.0, r=0.5, mpc_type="mpc", u_prev=None):
     Restated as the reference writes it - the model is rolled forward step by step for a given decision vector - and
     solved as a linear least-squares problem: the residual vector is affine in the decision, its Jacobian is formed by
     rolling unit perturbations.  Shares no structure with the closed-form gains of the product (koopman.py)."""
-    A, B = W["lA.weight"], W["lB.weight"]
+    A, B = W["lA.weight"], linearize_B(W, z0, u_z)      # the bilinear variants freeze B at B_total(z0) over the horizon
     nz, nu = B.shape
     u_prev = np.zeros(nu) if u_prev is None else np.asarray(u_prev, dtype=np.float64)
 

@@ -213,6 +213,35 @@ def test_shooting_mpc_improves_on_the_model_solution(tables_v):
     assert np.mean(err_s[10:]) < 1.25 * np.mean(err_m[10:]) + 1e-3
 
 
+@pytest.mark.parametrize("u_z", [False, True])
+def test_bilinear_variant_mpc_matches_the_restated_problem_cpu(u_z):
+    """The bilinear model variants (DBKN / IBKN: z+ = A z + B u + H (z (x) u)) under the reference's MPC: `linearize_B`
+    freezes B_total(z0) over the horizon [REF control/MPC_Controler.py:46-63, models/KoopmanBase.py:62-110], gains then
+    depend on z0 (one solve per env).  The reference ships no bilinear checkpoint: the shipped linear model plus a random H
+    layer.  Batched solve == the problem restated and solved by least squares, both formulations, both Kronecker orders."""
+    from oracle import koopman_oracle as KO
+    from lerobot_mujoco_sim2real_b200.koopman import KoopmanModel
+    W = _weights()
+    rng = np.random.default_rng(12)
+    nz, nu = W["lB.weight"].shape
+    W["H.weight"] = rng.standard_normal((nz, nz * nu)) * 0.05
+    km = KoopmanModel({k: v for k, v in W.items() if k != "H.weight"}, device="cpu")
+    km.set_bilinear(W["H.weight"], u_z=u_z)
+    H, N = 10, 6
+    x = rng.uniform(-0.3, 0.3, (N, 8)); xref = rng.uniform(-0.3, 0.3, (N, H, 8)); up = rng.uniform(-0.4, 0.4, (N, 5))
+    for mpc_type in ("delta_mpc", "mpc"):
+        u0, a = km.mpc_control_bilinear(torch.as_tensor(x), torch.as_tensor(xref), torch.as_tensor(up), H, mpc_type)
+        for e in range(N):
+            z0, zref = KO.lift(W, x[e]), KO.lift(W, xref[e])
+            sol = KO.mpc_solve(W, z0, zref, H, mpc_type=mpc_type, u_prev=up[e] if mpc_type == "delta_mpc" else None, u_z=u_z)
+            np.testing.assert_allclose(u0[e].numpy(), sol[0] + up[e], rtol=0, atol=1e-8)
+        assert np.array_equal(a.numpy(), np.clip(u0.numpy(), -0.5, 0.5))
+    # and it differs from the linear model's answer (the H layer matters)
+    lin = KO.mpc_solve({k: v for k, v in W.items() if k != "H.weight"}, KO.lift(W, x[0]), KO.lift(W, xref[0]), H, mpc_type="mpc")
+    assert np.abs(lin[0] + up[0] - km.mpc_control_bilinear(torch.as_tensor(x[:1]), torch.as_tensor(xref[:1]),
+                                                            torch.as_tensor(up[:1]), H, "mpc")[0][0].numpy()).max() > 1e-4
+
+
 @pytest.mark.gpu
 def test_lift_and_mpc_step_kernels_match_numpy():
     """The fused encoder kernel (`so101_koopman_lift`), the reference fold (`so101_koopman_feedforward`) and one MPC frame
