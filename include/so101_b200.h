@@ -243,7 +243,9 @@ enum {
   SO101_OPT_KERNEL_FAMILY = 0,  /* SO101_FAMILY_*: force the one-warp or the three-warp team kernels           */
   SO101_OPT_BLOCK         = 1,  /* threads per block of the one-warp kernels (multiple of 32, <= launch bound)  */
   SO101_OPT_HOST_CHUNKS   = 2,  /* pipeline depth of so101_batch_rollout_host, 1..12                            */
-  SO101_OPT_HOST_EVEN     = 3   /* 1: equal time chunks in so101_batch_rollout_host                             */
+  SO101_OPT_HOST_EVEN     = 3,  /* 1: equal time chunks in so101_batch_rollout_host                             */
+  SO101_OPT_SLICED        = 4   /* time-sliced persistent rollout of the one-warp kernels (large batches whose env groups
+                                   do not fill whole waves): 0 = automatic, 1 = always, 2 = never                    */
 };
 enum { SO101_FAMILY_AUTO = 0, SO101_FAMILY_ONEWARP = 1, SO101_FAMILY_TEAM = 2 };
 int so101_batch_set_option(So101Batch* b, int option, int value);

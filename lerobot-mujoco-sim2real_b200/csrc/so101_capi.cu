@@ -15,6 +15,8 @@ SO101_LAUNCHERS(extern, double, false)
 SO101_LAUNCHERS(extern, double, true)
 SO101_LAUNCHERS(extern, float, false)
 SO101_LAUNCHERS(extern, float, true)
+SO101_SLICED_LAUNCHERS(extern, double)
+SO101_SLICED_LAUNCHERS(extern, float)
 
 // ==========================================================================================
 // host side
@@ -48,6 +50,8 @@ struct So101Batch {
   DevModel<float> dm_f;
   void* hull_dev[4];          // vert, adj_start, adj, cube on b->device (null: no hulls -> tripwire flags only)
   unsigned long long* stats;  // device, 4 counters
+  // time-sliced rollout (k_rollout_sliced): chunks done per env group, fault flag, resident blocks of the kernel
+  int32_t* sched_progress; size_t sched_groups; int32_t* sched_fault; int sched_resident;
   void* ctrl_stage;   // [6][n] batch dtype (host variants)
   float* obs_stage;   // [8][n]
   void* init_stage;   // [12][n] (reset_host)
@@ -61,7 +65,7 @@ struct So101Batch {
   cudaStream_t s_up, s_down;
   cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
   // explicit experiment options (so101_batch_set_option); 0 = automatic.  Nothing on this path reads the environment.
-  int opt_family, opt_block, opt_host_chunks, opt_host_even;
+  int opt_family, opt_block, opt_host_chunks, opt_host_even, opt_sliced;
 };
 
 struct DeviceGuard {
@@ -239,6 +243,7 @@ void so101_batch_destroy(So101Batch* b) {
   if (b->owns_state) cudaFree(b->state);
   cudaFree(b->stats);
   for (int k = 0; k < 4; k++) cudaFree(b->hull_dev[k]);
+  cudaFree(b->sched_progress); cudaFree(b->sched_fault);
   cudaFree(b->ctrl_stage);
   cudaFree(b->obs_stage);
   cudaFree(b->init_stage);
@@ -272,6 +277,10 @@ int so101_batch_set_option(So101Batch* b, int option, int value) {
       return SO101_OK;
     case SO101_OPT_HOST_EVEN:
       b->opt_host_even = value != 0;
+      return SO101_OK;
+    case SO101_OPT_SLICED:
+      if (value < 0 || value > 2) return fail(SO101_EINVAL, "sliced rollout must be 0 (auto), 1 (always, one-warp kernels) or 2 (never)");
+      b->opt_sliced = value;
       return SO101_OK;
     default:
       return fail(SO101_EINVAL, "unknown option");
@@ -414,6 +423,43 @@ static int rollout_range(So101Batch* b, const So101CtrlSpec* spec, int t0, int t
   ds.reset_lo = spec->reset_lo; ds.reset_hi = spec->reset_hi; ds.u = spec->u;
   int blk; unsigned grid; bool split;
   const bool r32 = flags & SO101_ROLL_ROWS_F32;
+  {
+    // Large batches whose groups do not fill whole waves of resident blocks: time-sliced persistent launch (k_rollout_sliced)
+    if (b->dtype == SO101_F64) step_view<double>(b, blk, grid, split); else step_view<float>(b, blk, grid, split);
+    if (!split && !b->opt_block && b->opt_sliced != 2 && t1 - t0 >= 2) {
+      if (!b->sched_resident) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, b->device));
+        const int bps = b->dtype == SO101_F64 ? rollout_sliced_blocks_per_sm<double>(blk) : rollout_sliced_blocks_per_sm<float>(blk);
+        b->sched_resident = bps > 0 ? bps * prop.multiProcessorCount : -1;
+      }
+      const int64_t ngroups = (b->n + blk - 1) / blk;
+      const int64_t res = b->sched_resident;
+      const int64_t waves_up = res > 0 ? (ngroups + res - 1) / res : 0;
+      // gain of even waves over whole ones; below 3 % (or a single wave) the plain launch is as good
+      const bool worth = res > 0 && ngroups > res && (double)ngroups / (double)(waves_up * res) < 0.97;
+      if (worth || (b->opt_sliced == 1 && res > 0 && ngroups > 1)) {
+        int nchunks = (int)((24 * res + ngroups - 1) / ngroups);
+        if (nchunks > t1 - t0) nchunks = t1 - t0;
+        if (nchunks < 2) nchunks = 2;
+        const int tchunk = (t1 - t0 + nchunks - 1) / nchunks;
+        if ((size_t)ngroups > b->sched_groups) {
+          cudaFree(b->sched_progress);
+          b->sched_progress = nullptr; b->sched_groups = 0;
+          CUDA_TRY(cudaMalloc(&b->sched_progress, (size_t)ngroups * sizeof(int32_t)));
+          b->sched_groups = (size_t)ngroups;
+        }
+        if (!b->sched_fault) { CUDA_TRY(cudaMalloc(&b->sched_fault, sizeof(int32_t))); CUDA_TRY(cudaMemset(b->sched_fault, 0, sizeof(int32_t))); }
+        CUDA_TRY(cudaMemsetAsync(b->sched_progress, 0, (size_t)ngroups * sizeof(int32_t), st));
+        const unsigned pgrid = (unsigned)(res < ngroups * nchunks ? res : ngroups * nchunks);
+        if (b->dtype == SO101_F64)
+          CUDA_TRY(launch_rollout_sliced<double>(b->dm_d, view<double>(b), pgrid, blk, st, ds, t0, t1, T, frame_skip, rows, r32, flags, b->stats, tchunk, b->sched_progress, b->sched_fault));
+        else
+          CUDA_TRY(launch_rollout_sliced<float>(b->dm_f, view<float>(b), pgrid, blk, st, ds, t0, t1, T, frame_skip, rows, r32, flags, b->stats, tchunk, b->sched_progress, b->sched_fault));
+        return SO101_OK;
+      }
+    }
+  }
   if (b->dtype == SO101_F64) {
     StateView<double> v = step_view<double>(b, blk, grid, split);
     CUDA_TRY((split ? launch_rollout<double, true>(b->dm_d, v, grid, blk, st, ds, t0, t1, T, frame_skip, rows, r32, flags, b->stats)
@@ -638,7 +684,10 @@ int so101_batch_stats(So101Batch* b, uint64_t* stats_host, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUDA_TRY(cudaMemcpyAsync(stats_host, b->stats, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemsetAsync(b->stats, 0, 4 * sizeof(uint64_t), st));
+  int32_t fault = 0;
+  if (b->sched_fault) CUDA_TRY(cudaMemcpyAsync(&fault, b->sched_fault, sizeof fault, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (fault) return fail(SO101_ECUDA, "time-sliced rollout: a unit waited for its predecessor beyond the bound (scheduling fault)");
   return SO101_OK;
 }
 

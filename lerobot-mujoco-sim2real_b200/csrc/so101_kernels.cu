@@ -7,6 +7,9 @@
 #define SO101_TIMING_NAME SO101_CAT(so101_debug_timing_, SO101_TU_T)
 
 SO101_LAUNCHERS(, SO101_TU_T, SO101_TU_SPLIT)
+#if !SO101_TU_SPLIT
+SO101_SLICED_LAUNCHERS(, SO101_TU_T)
+#endif
 
 #ifdef SO101_TIMING
 #if SO101_TU_SPLIT

@@ -428,6 +428,132 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   add_stats(stats, cnt);
 }
 
+// ---- the same rollout, time-sliced over a persistent grid (one-warp kernels, large batches) ---------------------------
+// A resident block is latency bound, so a launch of `k_rollout` lasts ceil(groups / resident blocks) block times: 131072
+// envs = 512 groups of 256 on 148 SMs are 3.46 waves and take 4 (a 13 % tail).  Here the unit of work is
+// (group, time chunk): `gridDim` = the resident blocks, each walks units u = blockIdx, blockIdx + gridDim, ... in
+// chunk-major order (u = chunk * groups + group), so every SM stays busy until the last chunk and the launch takes
+// groups * T / resident block-steps.  Chunk c of a group continues from the state chunk c-1 stored (the continuation of
+// `k_rollout`: row t0 already written, u_t0 regenerated), possibly on another SM: `progress[group]` counts the chunks
+// done (release store after a fence, acquire load before the state is read through L2).  A unit's predecessor lies a
+// whole pass over the groups back, i.e. it finished long ago; the wait exists for correctness, and is bounded.
+__device__ __forceinline__ int ld_acquire_(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <typename T> SO101_DEV void load_env_cg(const StateView<T>& s, int64_t i, Env<T>& e) {   // through L2: another SM wrote it
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    e.q[k] = __ldcg(&s.base[(ROW_Q + k) * s.n + i]);
+    e.qd[k] = __ldcg(&s.base[(ROW_QD + k) * s.n + i]);
+    e.warm[k] = __ldcg(&s.base[(ROW_WARM + k) * s.n + i]);
+    e.fa[k] = __ldcg(&s.base[(ROW_FA + k) * s.n + i]);
+  }
+  e.time = __ldcg(&s.base[ROW_TIME * s.n + i]);
+  e.flags = __ldcg(&s.flags[i]);
+}
+template <typename T, typename ROW>
+__global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
+k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
+                 ROW* rows, uint32_t rflags, unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault) {
+  __shared__ RowBuf<ROW> rowbuf[SO101_LB_THREADS / 32];
+  SplitXch<T>& xch = *reinterpret_cast<SplitXch<T>*>(rowbuf);      // never touched by the one-warp path
+  const int64_t ngroups = (s.n + blockDim.x - 1) / blockDim.x;
+  const int nchunks = (t1 - t0 + tchunk - 1) / tchunk;
+  const bool trip = m.ntrip > 0;
+  const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
+  Counters cnt = {0, 0, 0, 0};
+#pragma unroll 1
+  for (int64_t unit = blockIdx.x; unit < ngroups * nchunks; unit += gridDim.x) {
+    const int c = (int)(unit / ngroups);
+    const int64_t grp = unit - (int64_t)c * ngroups;
+    const int ut0 = t0 + c * tchunk, ut1 = ut0 + tchunk < t1 ? ut0 + tchunk : t1;
+    const int64_t j = grp * blockDim.x + threadIdx.x;
+    const bool active = j < s.n;
+    const int64_t i = active ? j : s.n - 1;                         // tail threads shadow a valid env and never store
+    const int64_t env = spec.env_offset + i;
+    if (c > 0) {
+      if (threadIdx.x == 0) {
+        long long spins = 0;
+        while (ld_acquire_(progress + grp) < c) {
+          __nanosleep(200);
+          if (++spins > (1ll << 24)) { atomicExch(fault, 1); break; }   // ~seconds: never in a correct schedule
+        }
+      }
+      __syncthreads();
+    }
+    Env<T> e;
+    if (c > 0 || (rflags & SO101_ROLL_NO_RESET)) {
+      load_env_cg(s, i, e);
+    } else {
+      reset_env(m, e);
+      double r[5];
+      uniform5(spec.seed, env, 0, STREAM_RESET, r);
+#pragma unroll
+      for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(spec.reset_lo, spec.reset_hi - spec.reset_lo, r[k]);
+    }
+    CtrlGen g;
+    ctrl_init(spec, env, g);
+    Counters ucnt = {0, 0, 0, 0};
+    int32_t vcache[SO101_MAXTRIP];
+#pragma unroll
+    for (int k = 0; k < SO101_MAXTRIP; k++) vcache[k] = -1;
+    T site[3];
+    site_fk(m, e.q, site);
+    double u[5];
+    T uc[NV] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+#pragma unroll 1
+    for (int t = ut0; t <= ut1; t++) {
+      if (t > ut0) {
+#pragma unroll 1
+        for (int ss = 0; ss < frame_skip; ss++)
+          step_env<T, false>(m, xch, e, uc, hold && ss == 0, ss == frame_skip - 1, site, trip, ucnt, 0, vcache);
+      }
+      ctrl_gen<T>(spec, g, env, i, s.n, t, u);
+#pragma unroll
+      for (int k = 0; k < 5; k++) uc[k] = (T)u[k];
+      clamp_ctrl(m, uc);
+      if (rows && (t > ut0 || ut0 == 0)) {
+        ROW v[SO101_ROW];
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[k] = (ROW)u[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) v[5 + k] = (ROW)(float)site[k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[8 + k] = (ROW)(float)e.q[k];
+        write_rows_warp<ROW>(rowbuf[threadIdx.x >> 5], v, rows, grp * blockDim.x + (threadIdx.x & ~31u), s.n, Tn, t);
+      }
+    }
+    if (active) {
+      store_env(s, i, e);
+      cnt.steps += ucnt.steps; cnt.newton += ucnt.newton; cnt.lsevals += ucnt.lsevals; cnt.limsteps += ucnt.limsteps;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_(progress + grp, c + 1);
+  }
+  add_stats(stats, cnt);
+}
+template <typename T>
+cudaError_t launch_rollout_sliced(const DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st, const DevSpec& ds,
+                                  int t0, int t1, int Tn, int frame_skip, void* rows, bool rows_f32, uint32_t rflags,
+                                  unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault) {
+  if (rows_f32) k_rollout_sliced<T, float><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (float*)rows, rflags, stats, tchunk, progress, fault);
+  else k_rollout_sliced<T, double><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (double*)rows, rflags, stats, tchunk, progress, fault);
+  return cudaGetLastError();
+}
+template <typename T> int rollout_sliced_blocks_per_sm(int blk) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rollout_sliced<T, double>, blk, 0) != cudaSuccess) return 0;
+  int nf = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, k_rollout_sliced<T, float>, blk, 0) != cudaSuccess) return 0;
+  return nb < nf ? nb : nf;
+}
+
 // B control sequences U[H][5][B] from one shared state; X[B][H+1][8] float32 observations
 SO101_STEP_KERNEL2(T)
 k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_constant__ State0 s0, const T* U, int H,

@@ -38,6 +38,17 @@ template <typename T, bool SPLIT>
 cudaError_t launch_shoot(const so101::DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st,
                          const State0& s0, const T* U, int H, int frame_skip, float* X, uint32_t rflags,
                          unsigned long long* stats);
+// the time-sliced rollout of the one-warp kernels (see k_rollout_sliced) and the number of its blocks an SM holds
+template <typename T>
+cudaError_t launch_rollout_sliced(const so101::DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st,
+                                  const DevSpec& ds, int t0, int t1, int Tn, int frame_skip, void* rows, bool rows_f32,
+                                  uint32_t rflags, unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault);
+template <typename T> int rollout_sliced_blocks_per_sm(int blk);
+#define SO101_SLICED_LAUNCHERS(KW, T)                                                                                      \
+  KW template cudaError_t launch_rollout_sliced<T>(const so101::DevModel<T>&, StateView<T>, unsigned, int, cudaStream_t,    \
+                                                   const DevSpec&, int, int, int, int, void*, bool, uint32_t,              \
+                                                   unsigned long long*, int, int32_t*, int32_t*);                           \
+  KW template int rollout_sliced_blocks_per_sm<T>(int);
 #define SO101_LAUNCHERS(KW, T, SPLIT)                                                                                      \
   KW template cudaError_t launch_step<T, SPLIT>(const so101::DevModel<T>&, StateView<T>, unsigned, int, cudaStream_t,       \
                                                 const T*, int, int, float*, unsigned long long*, uint32_t);                 \

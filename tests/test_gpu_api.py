@@ -536,3 +536,31 @@ def test_zero_length_calls(tables_v, n):
     X = env.shoot(s0, torch.empty((0, 5, n), dtype=env.torch_dtype, device=env.device))
     assert X.shape == (n, 1, 8) and bool((X == X[0]).all())
     assert env.stats()["physics_steps"] == 0
+
+
+@pytest.mark.parametrize("dtype,kind", [("float64", "random"), ("float64", "chirp"), ("float32", "random")])
+def test_time_sliced_rollout_is_invisible(tables_v, dtype, kind):
+    """Large batches whose env groups do not fill whole waves of resident blocks run the rollout time-sliced over a
+    persistent grid (k_rollout_sliced: units = (group, time chunk), chunk c of a group possibly on another SM than chunk
+    c-1).  Rows, final state, flags and solver statistics equal the plain launch bit for bit - also for a continuation
+    (t0 > 0 through rollout_host's chunks), ragged sizes and with table contact."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    n, Tn = 40_003, 12
+    res = []
+    for mode in (2, 1):                                     # never / always
+        env = _vec(tables_v, n, dtype=dtype)
+        env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_ONEWARP)
+        env.set_option(T_.OPT_SLICED, mode)
+        rows = env.rollout(Tn, kind, seed=11)
+        q, v, w = env.get_state()
+        st = env.stats()
+        res.append((rows.clone(), q.clone(), v.clone(), w.clone(), env.flags().clone(), st))
+    a, b = res
+    for x, y in zip(a[:5], b[:5]):
+        assert torch.equal(x, y)
+    assert a[5] == b[5] and a[5]["physics_steps"] == n * Tn * 10
+    assert int((a[4] & T_.FLAG_CONTACT).ne(0).sum()) >= 0
+    # automatic choice: this size (157 groups of 256 on 148 SMs in f64) is worth slicing; the result is the same again
+    env = _vec(tables_v, n, dtype=dtype)
+    rows = env.rollout(Tn, kind, seed=11)
+    assert torch.equal(rows, a[0])
