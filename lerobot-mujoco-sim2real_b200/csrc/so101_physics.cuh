@@ -1490,7 +1490,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
   SO101_TICK(tk2);
   T Ls[15], Dinv[NV];
   T a[NV], Ma[NV], qc[NV], hd[NV];
-  bool solved = false;
+  bool solved = false, had_contact = false;
   {
   if (trip) e.flags |= x.trip[lane];
   if (want_site) {
@@ -1527,6 +1527,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
         }
         solved = contact_branch<T>(m, e, x.hits[lane], &x.sn[0][lane], &x.cs[0][lane], 32, con,
                                    nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, asm_, a, qc, cnt, nullptr);
+        had_contact = solved;
       }
     } else {
       e.flags |= SO101_FLAG_TRIP_TABLE;
@@ -1700,7 +1701,7 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
 #ifdef SO101_TIMING
   {
     SO101_TICK(tk5);
-    const uint32_t anyhit = __ballot_sync(0xffffffffu, trip && x.hits[lane] != 0), anycon = __ballot_sync(0xffffffffu, solved && (e.flags & SO101_FLAG_CONTACT));
+    const uint32_t anyhit = __ballot_sync(0xffffffffu, trip && x.hits[lane] != 0), anycon = __ballot_sync(0xffffffffu, had_contact);
     if (lane == 0) {
       const int kind = anycon ? 2 : (anyhit ? 1 : 0);     // 0: plain step, 1: a box tripped, 2: a contact was solved
       atomicAdd(&g_timing[kind * 5 + 0], 1ull);
