@@ -16,10 +16,12 @@ SO101_SLICED_LAUNCHERS(, SO101_TU_T)
 extern "C" int SO101_TIMING_NAME(unsigned long long* out, int reset) {
   cudaMemcpyFromSymbol(out, so101::g_timing, sizeof(unsigned long long) * 16);
   cudaMemcpyFromSymbol(out + 16, so101::g_timing_helpers, sizeof(unsigned long long) * 8);
+  cudaMemcpyFromSymbol(out + 24, so101::g_timing_con, sizeof(unsigned long long) * 4);
   if (reset) {
     unsigned long long z[16] = {0};
     cudaMemcpyToSymbol(so101::g_timing, z, sizeof z);
     cudaMemcpyToSymbol(so101::g_timing_helpers, z, sizeof(unsigned long long) * 8);
+    cudaMemcpyToSymbol(so101::g_timing_con, z, sizeof(unsigned long long) * 4);
   }
   return 0;
 }

@@ -1251,14 +1251,13 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 // ------------------------------------------------------------------------------------------
 #ifdef SO101_TIMING   // debug build: where the dynamics warp of a team spends its cycles, by kind of step (tools/team_timing.py)
 __device__ unsigned long long g_timing[16];   // [0..14]: dynamics warp by kind of step; [15]: unused
-__device__ unsigned long long g_timing_helpers[8];   // geometry: steps, cycles to (A), (A)..(E); lookout: steps, cycles to (A)
+__device__ unsigned long long g_timing_helpers[8];
+__device__ unsigned long long g_timing_con[4];   // geometry: steps, cycles to (A), (A)..(E); lookout: steps, cycles to (A)
 #define SO101_TICK(var) const long long var = clock64()
 #else
 #define SO101_TICK(var)
 #endif
 constexpr int TEAM_WARPS = 3;
-constexpr int XCON = 2, XCON_MANY = 255;
-constexpr int CON3_N = 3 * NV + 5;     // Con3 as a flat array: Jn, Jy, Jx, D, c0, vn, vy, vx
 template <typename T>
 struct SplitXch {      // shared memory of one team, structure-of-arrays over the 32 lanes
   T sn[NV][32], cs[NV][32];
@@ -1267,11 +1266,14 @@ struct SplitXch {      // shared memory of one team, structure-of-arrays over th
   T L2[15][32], D2inv[NV][32];   // M + h B = L2 D2 L2^T
   T site[3][32];
   uint32_t trip[32], hits[32];   // TRIP_SELF flag / tripwire boxes below the table top (lookout warp)
-  // contact kernels: the lookout warp runs the geometry half of the contact path (exact hull test, Jacobian rows) beside
-  // the dynamics warp's RNEA and hands over up to XCON contacts per env; ncon = XCON_MANY: more than that, the dynamics
-  // warp computes them itself
-  uint32_t ncon[32];
-  T con[XCON][CON3_N][32];
+  // table contact: the lookout warp does the exact hull test of every tripped box beside the dynamics warp's RNEA and hands
+  // over the hulls that touch (link, support vertex, distance, height of the lowest point); the dynamics warp forms the
+  // contact rows itself, inside its contact branch.  (Round 2, late: when the lookout warp formed the rows too, its rare
+  // code ran just before barrier (A) and the dynamics warp paid ~5.5 k cycles of instruction-cache misses right after it,
+  // profiles/r2_team_timing.txt.)
+  uint32_t ncon[32];             // number of hulls that touch
+  int32_t hit_k[SO101_MAXTRIP][32], hit_v[SO101_MAXTRIP][32];
+  T hit_dist[SO101_MAXTRIP][32], hit_z[SO101_MAXTRIP][32];
   T q[NV][32], qd[NV][32];       // state handed back by the dynamics warp
 };
 
@@ -1405,25 +1407,11 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
       HitList<T> hl;
       hl.n = 0;
       tripwire_all_tests(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits, vcache, hl);
-#ifndef SO101_EXP_NOGEOM
-      if (hl.n) {      // the geometry half of the contact path runs here, beside the dynamics warp's RNEA
-        Con3<T> con[MAXCON];
-        nc = (uint32_t)contact_rows<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, qd, hl, con, fl);
-        if (nc > (uint32_t)XCON) {
-          nc = XCON_MANY;
-        } else {
+      nc = (uint32_t)hl.n;
 #pragma unroll 1
-          for (uint32_t c = 0; c < nc; c++) {
-#pragma unroll
-            for (int j = 0; j < NV; j++) {
-              x.con[c][j][lane] = con[c].Jn[j]; x.con[c][NV + j][lane] = con[c].Jy[j]; x.con[c][2 * NV + j][lane] = con[c].Jx[j];
-            }
-            x.con[c][3 * NV][lane] = con[c].D; x.con[c][3 * NV + 1][lane] = con[c].c0;
-            x.con[c][3 * NV + 2][lane] = con[c].vn; x.con[c][3 * NV + 3][lane] = con[c].vy; x.con[c][3 * NV + 4][lane] = con[c].vx;
-          }
-        }
+      for (int h = 0; h < hl.n; h++) {
+        x.hit_k[h][lane] = hl.k[h]; x.hit_v[h][lane] = hl.v[h]; x.hit_dist[h][lane] = hl.dist[h]; x.hit_z[h][lane] = hl.z[h];
       }
-#endif
     } else {
       tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
     }
@@ -1509,32 +1497,12 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
     for (int i = 0; i < NV; i++) Dinv[i] = x.D1inv[rb][i][lane];
     ldl6_solve(Ls, Dinv, asm_);
   }
-  if (trip && x.hits[lane]) {        // table contact (see physics_step)
-    if (m.con_enabled) {
-      const uint32_t nc = x.ncon[lane];
-      if (nc) {
-        Con3<T> con[MAXCON];
-        if (nc != (uint32_t)XCON_MANY) {
-#pragma unroll 1
-          for (uint32_t c = 0; c < nc; c++) {
-#pragma unroll
-            for (int j = 0; j < NV; j++) {
-              con[c].Jn[j] = x.con[c][j][lane]; con[c].Jy[j] = x.con[c][NV + j][lane]; con[c].Jx[j] = x.con[c][2 * NV + j][lane];
-            }
-            con[c].D = x.con[c][3 * NV][lane]; con[c].c0 = x.con[c][3 * NV + 1][lane];
-            con[c].vn = x.con[c][3 * NV + 2][lane]; con[c].vy = x.con[c][3 * NV + 3][lane]; con[c].vx = x.con[c][3 * NV + 4][lane];
-          }
-        }
-        solved = contact_branch<T>(m, e, x.hits[lane], &x.sn[0][lane], &x.cs[0][lane], 32, con,
-                                   nc == (uint32_t)XCON_MANY ? -1 : (int)nc, M, fsm, rw, asm_, a, qc, cnt, nullptr);
-        had_contact = solved;
-      }
-    } else {
-      e.flags |= SO101_FLAG_TRIP_TABLE;
-    }
-  }
-  __syncwarp();   // the lanes that took the contact branch rejoin here
-  if (!solved && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
+  // The lanes without a contact solve FIRST: their code is the hot code of every step and still sits in the instruction
+  // cache; the contact lane's solver (rare, ~1400 instructions of its own) runs after them instead of displacing it before
+  // they get to it (profiles/r2_team_timing.txt).
+  SO101_TICK(tp0);
+  const bool clane = trip && x.hits[lane] && m.con_enabled && x.ncon[lane] != 0;
+  if (!clane && constrained && !rw.anylim) {   // direct active-set solve (see active_set_guess)
     T zone[NV], xs[NV], dh[NV];
     active_set_guess(m, rw, M, asm_, zone);
 #pragma unroll 1
@@ -1558,6 +1526,43 @@ SO101_DEV void split_dynamics_step(const DevModel<T>& m, SplitXch<T>& x, int lan
       active_set_zones_at(m, rw, xs, zone);
     }
   }
+  __syncwarp();
+  SO101_TICK(tp1);
+  if (trip && x.hits[lane]) {        // table contact (see physics_step)
+    if (m.con_enabled) {
+      const uint32_t nc = x.ncon[lane];
+      if (nc) {
+        Con3<T> con[MAXCON];
+        HitList<T> hl;
+        hl.n = (int)nc;
+#pragma unroll 1
+        for (int h = 0; h < hl.n; h++) {
+          hl.k[h] = x.hit_k[h][lane]; hl.v[h] = x.hit_v[h][lane]; hl.dist[h] = x.hit_dist[h][lane]; hl.z[h] = x.hit_z[h][lane];
+        }
+        uint32_t fl = 0;
+        const int ncon = contact_rows<T>(m, &x.sn[0][lane], &x.cs[0][lane], 32, e.qd, hl, con, fl);
+        e.flags |= fl;
+        if (ncon)
+          solved = contact_branch<T>(m, e, x.hits[lane], &x.sn[0][lane], &x.cs[0][lane], 32, con, ncon, M, fsm, rw, asm_, a, qc,
+                                     cnt, nullptr);
+        had_contact = solved;
+      }
+    } else {
+      e.flags |= SO101_FLAG_TRIP_TABLE;
+    }
+  }
+  __syncwarp();   // the lanes that took the contact branch rejoin here
+#ifdef SO101_TIMING
+  {
+    const long long tp2 = clock64();
+    if (__ballot_sync(0xffffffffu, had_contact) && lane == 0) {
+      atomicAdd(&g_timing_helpers[7], 1ull);
+      atomicAdd(&g_timing[15], (unsigned long long)(tp0 - tk2));          // M load + lagged qacc_smooth
+      atomicAdd(&g_timing_con[0], (unsigned long long)(tp1 - tp0));       // direct solve of the lanes without contact
+      atomicAdd(&g_timing_con[1], (unsigned long long)(tp2 - tp1));       // contact block
+    }
+  }
+#endif
   if (!solved) {
     // general path (no friction rows, an active limit row, or the direct solve was rejected): exact qacc_smooth
 #pragma unroll

@@ -8,11 +8,12 @@ from lerobot_mujoco_sim2real_b200 import builtin_tables, tables as T_, _lib
 from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
 g = int(sys.argv[1]); seed = int(sys.argv[2]) if len(sys.argv) > 2 else 42
 hulls = "auto" if (len(sys.argv) <= 3 or sys.argv[3] == "1") else None
-env = SOARM101VecEnv(tables=builtin_tables(), num_envs=32, dtype="float64", hulls=hulls)
+nenv = int(sys.argv[4]) if len(sys.argv) > 4 else 32        # 4096 with group 0: the whole bench batch (128 teams at once)
+env = SOARM101VecEnv(tables=builtin_tables(), num_envs=nenv, dtype="float64", hulls=hulls)
 env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_TEAM)
 spec = env.make_spec("random", seed, g * 32)
 L = _lib.lib()
-out = (C.c_ulonglong * 24)()
+out = (C.c_ulonglong * 28)()
 for rep in range(2):
     L.so101_debug_timing_double(out, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -28,3 +29,5 @@ for k, name in enumerate(("plain", "box tripped", "contact solved")):
 h = np.array(list(out)[16:24], dtype=np.float64)
 print(f"  geometry warp: {h[1] / max(h[0], 1):.0f} cycles from step start to (A), {h[2] / max(h[0], 1):.0f} cycles of work after (A); "
       f"waits {h[3] / max(h[0], 1):.0f} at (A); lookout warp: {h[5] / max(h[4], 1):.0f} cycles to (A), waits {h[6] / max(h[4], 1):.0f}")
+n7 = max(float(out[23]), 1.0)
+print(f"  contact steps ({int(out[23])}): M load + lagged qacc_smooth {out[15] / n7:.0f} cycles, direct solve of the other lanes {out[24] / n7:.0f}, contact block {out[25] / n7:.0f}")
