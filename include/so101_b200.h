@@ -337,8 +337,8 @@ int so101_koopman_score(const double* A, const double* B, int nz, int nu, const 
    a = clip(u0, +-clip); u_prev <- u0 [REF Koopman_MPC.py:217].  The problem is an unconstrained quadratic, so
    u_opt[0] = Kz z0 + sum_t Kr_t zref_t + Ku u_prev with gains that depend on the model only (computed by the host side,
    koopman.py: mpc_gains).
-     so101_koopman_create       uploads the encoder: dims[0..n_layers] = layer widths (dims[0] = x_dim <= 16, the others even
-                                and <= 64), W[l] HOST row-major [dims[l+1]][dims[l]] (torch Linear.weight), b[l] [dims[l+1]]
+     so101_koopman_create       uploads the encoder: dims[0..n_layers] = layer widths (dims[0] = x_dim <= 16, the others
+                                multiples of 8, <= 64), W[l] HOST row-major [dims[l+1]][dims[l]] (torch Linear.weight), b[l] [dims[l+1]]
      so101_koopman_set_gains    HOST Kz [nu][nz], Kr [nu][H][nz], Ku [nu][nu] (zeros for 'mpc'); nz = dims[0] + dims[n_layers]
      so101_koopman_lift         Z [n][nz] DEVICE double <- X: layout 0 = rows [n][ldx] (first x_dim columns), 1 = structure of
                                 arrays [x_dim][n] (the stepper's observation buffer); dtype of X: SO101_F64 / SO101_F32

@@ -125,6 +125,8 @@ extern "C" int so101_koopman_score(const double* A, const double* B, int nz, int
 // (14.3 k FMA per lift); per k-step a warp issues 2 activation loads + JT/2 broadcast double2 loads for 2*JT DFMA.
 // ======================================================================================================================
 constexpr int KM_MAXL = 8, KM_ROWS = 64, KM_THREADS = 256, KM_MAXW = 64, KM_MAXX = 16;
+constexpr int KM_PAD = 4, KM_AS = KM_MAXW + KM_PAD;   // activations [row][KM_AS], weights [k][dout + KM_PAD]: the strides (= 4 mod 16
+                                                      // doubles) make the 8-byte fragment loads of mma.m8n8k4 conflict-free
 
 struct So101Koopman {
   int device, sms, n_layers, dims[KM_MAXL + 1];
@@ -142,52 +144,62 @@ struct KmLayers {
   int woff[KM_MAXL], boff[KM_MAXL], wcount;
 };
 
-// encoder of the 64 rows whose inputs sit in act0[k][row] (k < dims[0]); returns the buffer holding the last layer's output
+// encoder of the 64 rows whose inputs sit in act0[row][k] (row stride KM_AS, k < dims[0] rounded up to 4 with zeros);
+// returns the buffer holding the last layer's output in the same layout.  The layers are GEMMs [64 rows x din] x
+// [din x dout] in FP64: they run on the tensor cores as mma.sync.m8n8k4.f64 (DMMA; tcgen05 has no FP64 kind).  A warp
+// owns 32 rows x 16 neurons = 4 x 2 accumulator tiles of 8 x 8 (16 doubles per lane); per k-step of 4 it loads 4 A
+// fragments (activations) and 2 B fragments (weights), one double per lane each, for 8 DMMA = 2048 FMA.  (The first
+// version of this kernel did the same tile with DFMA: 64 DFMA + 16 shared loads for the same 2048 FMA; 35 % of the FP64
+// pipe with the shared-memory path 67 % busy, profiles/r2_koopman_mpc_ncu_summary.json.)
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ double* km_encode(const KmLayers& L, const double* __restrict__ w, double* act0, double* act1) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;                   // fragment coordinates: groupID, threadID_in_group
+  const int row0 = (warp >> 2) * 32;                       // this warp's 32 rows
+  const int col0 = (warp & 3) * 16;                        // this warp's 16 neurons
   double* in = act0;
   double* out = act1;
   for (int l = 0; l < L.n_layers; l++) {
-    const int din = L.dims[l], dout = L.dims[l + 1];
+    const int din = (L.dims[l] + 3) & ~3, dout = L.dims[l + 1], ws = dout + KM_PAD;
     const double* Wt = w + L.woff[l];
     const double* bias = w + L.boff[l];
     const bool relu = l != L.n_layers - 1;
-    const int JT = (dout + 7) / 8;
-    const int j0 = warp * JT;
-    if (dout == 64) {    // the wide layers: 8 neurons per warp, weights as four broadcast double2 loads per k
-      double acc0[8], acc1[8];
+    const bool jb_on[2] = {col0 < dout, col0 + 8 < dout};  // widths are multiples of 8 here (checked at creation)
+    if (jb_on[0]) {
+      double acc[4][2][2];
 #pragma unroll
-      for (int j = 0; j < 8; j++) { acc0[j] = bias[j0 + j]; acc1[j] = acc0[j]; }
-#pragma unroll 4
-      for (int k = 0; k < din; k++) {
-        const double a0 = in[k * KM_ROWS + lane], a1 = in[k * KM_ROWS + 32 + lane];
-        const double2* wk = reinterpret_cast<const double2*>(Wt + k * dout + j0);
+      for (int jb = 0; jb < 2; jb++) {
+        const double b0 = jb_on[jb] ? bias[col0 + jb * 8 + 2 * t] : 0.0, b1 = jb_on[jb] ? bias[col0 + jb * 8 + 2 * t + 1] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const double2 ww = wk[j];
-          acc0[2 * j] = fma(ww.x, a0, acc0[2 * j]); acc1[2 * j] = fma(ww.x, a1, acc1[2 * j]);
-          acc0[2 * j + 1] = fma(ww.y, a0, acc0[2 * j + 1]); acc1[2 * j + 1] = fma(ww.y, a1, acc1[2 * j + 1]);
+        for (int rb = 0; rb < 4; rb++) { acc[rb][jb][0] = b0; acc[rb][jb][1] = b1; }
+      }
+#pragma unroll 2
+      for (int k0 = 0; k0 < din; k0 += 4) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int rb = 0; rb < 4; rb++) af[rb] = in[(row0 + rb * 8 + g) * KM_AS + k0 + t];       // A[row = g][k = t]
+#pragma unroll
+        for (int jb = 0; jb < 2; jb++) bf[jb] = jb_on[jb] ? Wt[(k0 + t) * ws + col0 + jb * 8 + g] : 0.0;   // B[k = t][col = g]
+#pragma unroll
+        for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+          for (int jb = 0; jb < 2; jb++) dmma884(acc[rb][jb][0], acc[rb][jb][1], af[rb], bf[jb]);
+      }
+#pragma unroll
+      for (int rb = 0; rb < 4; rb++)
+#pragma unroll
+        for (int jb = 0; jb < 2; jb++) {
+          if (!jb_on[jb]) continue;
+          double2 y;                                                                            // C[row = g][col = 2t, 2t+1]
+          y.x = relu ? fmax(acc[rb][jb][0], 0.0) : acc[rb][jb][0];
+          y.y = relu ? fmax(acc[rb][jb][1], 0.0) : acc[rb][jb][1];
+          *reinterpret_cast<double2*>(out + (row0 + rb * 8 + g) * KM_AS + col0 + jb * 8 + 2 * t) = y;
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        out[(j0 + j) * KM_ROWS + lane] = relu ? fmax(acc0[j], 0.0) : acc0[j];
-        out[(j0 + j) * KM_ROWS + 32 + lane] = relu ? fmax(acc1[j], 0.0) : acc1[j];
-      }
-    } else {
-      for (int j = j0; j < j0 + JT && j < dout; j++) {
-        double s0 = bias[j], s1 = s0;
-        for (int k = 0; k < din; k++) {
-          const double ww = Wt[k * dout + j];
-          s0 = fma(ww, in[k * KM_ROWS + lane], s0);
-          s1 = fma(ww, in[k * KM_ROWS + 32 + lane], s1);
-        }
-        out[j * KM_ROWS + lane] = relu ? fmax(s0, 0.0) : s0;
-        out[j * KM_ROWS + 32 + lane] = relu ? fmax(s1, 0.0) : s1;
-      }
     }
     __syncthreads();
-    double* t = in; in = out; out = t;
+    double* tmp = in; in = out; out = tmp;
   }
   return in;
 }
@@ -195,14 +207,16 @@ __device__ __forceinline__ double* km_encode(const KmLayers& L, const double* __
 // X: layout 0 = rows [n][ldx] (first x_dim columns), 1 = structure of arrays [x_dim][n]
 template <typename TX>
 __device__ __forceinline__ void km_load_tile(const TX* X, int layout, int64_t ldx, int64_t n, int64_t row0, int x_dim,
-                                             double* xs /* [x_dim][KM_ROWS] */) {
-  for (int i = threadIdx.x; i < x_dim * KM_ROWS; i += KM_THREADS) {
+                                             double* xs /* [x_dim][KM_ROWS] */, double* act /* [KM_ROWS][KM_AS] */) {
+  const int xpad = (x_dim + 3) & ~3;
+  for (int i = threadIdx.x; i < xpad * KM_ROWS; i += KM_THREADS) {
     int k, r;
-    if (layout == 0) { r = i / x_dim; k = i - r * x_dim; } else { k = i / KM_ROWS; r = i - k * KM_ROWS; }
+    if (layout == 0) { r = i / xpad; k = i - r * xpad; } else { k = i / KM_ROWS; r = i - k * KM_ROWS; }
     const int64_t row = row0 + r;
     double v = 0.0;
-    if (row < n) v = (double)(layout == 0 ? X[row * ldx + k] : X[(int64_t)k * n + row]);
-    xs[k * KM_ROWS + r] = v;
+    if (row < n && k < x_dim) v = (double)(layout == 0 ? X[row * ldx + k] : X[(int64_t)k * n + row]);
+    if (k < x_dim) xs[k * KM_ROWS + r] = v;
+    act[r * KM_AS + k] = v;
   }
 }
 
@@ -215,21 +229,19 @@ k_koopman_lift(const __grid_constant__ KmLayers L, const double* __restrict__ wg
   double* w = sh;
   double* xs = w + L.wcount;                       // [x_dim][64]: the inputs are kept (they are the first nz coordinates)
   double* act0 = xs + KM_MAXX * KM_ROWS;
-  double* act1 = act0 + KM_MAXW * KM_ROWS;
+  double* act1 = act0 + KM_ROWS * KM_AS;
   for (int i = threadIdx.x; i < L.wcount; i += KM_THREADS) w[i] = wg[i];
   const int x_dim = L.dims[0], enc = L.dims[L.n_layers], nz = x_dim + enc;
   const int64_t ntile = (n + KM_ROWS - 1) / KM_ROWS;
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t row0 = tile * KM_ROWS;
     __syncthreads();
-    km_load_tile(X, layout, ldx, n, row0, x_dim, xs);
-    __syncthreads();
-    for (int i = threadIdx.x; i < x_dim * KM_ROWS; i += KM_THREADS) act0[i] = xs[i];
+    km_load_tile(X, layout, ldx, n, row0, x_dim, xs, act0);
     __syncthreads();
     const double* h = km_encode(L, w, act0, act1);
     for (int i = threadIdx.x; i < nz * KM_ROWS; i += KM_THREADS) {
       const int r = i / nz, c = i - r * nz;
-      if (row0 + r < n) Z[(row0 + r) * nz + c] = c < x_dim ? xs[c * KM_ROWS + r] : h[(c - x_dim) * KM_ROWS + r];
+      if (row0 + r < n) Z[(row0 + r) * nz + c] = c < x_dim ? xs[c * KM_ROWS + r] : h[r * KM_AS + c - x_dim];
     }
   }
 }
@@ -268,18 +280,17 @@ k_koopman_mpc(const __grid_constant__ KmLayers L, const double* __restrict__ wg,
   double* w = sh;
   double* xs = w + L.wcount;
   double* act0 = xs + KM_MAXX * KM_ROWS;
-  double* act1 = act0 + KM_MAXW * KM_ROWS;
-  double* g = act1 + KM_MAXW * KM_ROWS;            // Kz [nu][nz] | Ku [nu][nu]
+  double* act1 = act0 + KM_ROWS * KM_AS;
+  double* g = act1 + KM_ROWS * KM_AS;              // Kz [nu][nz] | Ku [nu][nu]
   const int x_dim = L.dims[0], enc = L.dims[L.n_layers], nz = x_dim + enc;
+  double* park = g + nu * nz + nu * nu;            // u0 of the tile [nu][KM_ROWS], until every component has read u_prev
   for (int i = threadIdx.x; i < L.wcount; i += KM_THREADS) w[i] = wg[i];
   for (int i = threadIdx.x; i < nu * nz + nu * nu; i += KM_THREADS) g[i] = gains[i];
   const int64_t ntile = (n + KM_ROWS - 1) / KM_ROWS;
   for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int64_t row0 = tile * KM_ROWS;
     __syncthreads();
-    km_load_tile(X, layout, ldx, n, row0, x_dim, xs);
-    __syncthreads();
-    for (int i = threadIdx.x; i < x_dim * KM_ROWS; i += KM_THREADS) act0[i] = xs[i];
+    km_load_tile(X, layout, ldx, n, row0, x_dim, xs, act0);
     __syncthreads();
     const double* h = km_encode(L, w, act0, act1);
     for (int i = threadIdx.x; i < nu * KM_ROWS; i += KM_THREADS) {
@@ -289,27 +300,27 @@ k_koopman_mpc(const __grid_constant__ KmLayers L, const double* __restrict__ wg,
       double u = uff ? uff[row * uff_stride + c] : 0.0;
       const double* kz = g + c * nz;
       for (int k = 0; k < x_dim; k++) u = fma(kz[k], xs[k * KM_ROWS + r], u);
-      for (int k = 0; k < enc; k++) u = fma(kz[x_dim + k], h[k * KM_ROWS + r], u);
+      for (int k = 0; k < enc; k++) u = fma(kz[x_dim + k], h[r * KM_AS + k], u);
       const double* ku = g + nu * nz + c * nu;
       for (int j = 0; j < nu; j++) u = fma(ku[j], u_prev[(int64_t)j * n + row], u);
       const double u0 = u + u_prev[(int64_t)c * n + row];
       const double a = fmin(fmax(u0, -clip), clip);
       // every component reads the whole u_prev of its row before any is overwritten: the write happens after the barrier
-      act1[(KM_MAXW - 1 - c) * KM_ROWS + r] = u0;           // parked in the far end of a buffer h does not occupy
+      park[c * KM_ROWS + r] = u0;
       ctrl[(int64_t)c * n + row] = (TC)a;
       if (a_out) a_out[row * nu + c] = a;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < nu * KM_ROWS; i += KM_THREADS) {
       const int c = i / KM_ROWS, r = i - c * KM_ROWS;
-      if (row0 + r < n) u_prev[(int64_t)c * n + row0 + r] = act1[(KM_MAXW - 1 - c) * KM_ROWS + r];
+      if (row0 + r < n) u_prev[(int64_t)c * n + row0 + r] = park[c * KM_ROWS + r];
     }
   }
 }
 
 static size_t km_smem_bytes(const So101Koopman* k, bool mpc) {
-  size_t d = k->wcount + (size_t)KM_MAXX * KM_ROWS + 2 * (size_t)KM_MAXW * KM_ROWS;
-  if (mpc) d += (size_t)k->nu * k->nz + (size_t)k->nu * k->nu;
+  size_t d = k->wcount + (size_t)KM_MAXX * KM_ROWS + 2 * (size_t)KM_ROWS * KM_AS;
+  if (mpc) d += (size_t)k->nu * k->nz + (size_t)k->nu * k->nu + (size_t)k->nu * KM_ROWS;
   return d * sizeof(double);
 }
 static KmLayers km_layers(const So101Koopman* k) {
@@ -331,7 +342,7 @@ extern "C" int so101_koopman_create(int n_layers, const int32_t* dims, const dou
   if (n_layers < 1 || n_layers > KM_MAXL) return fail(SO101_EINVAL, "koopman: 1..8 layers");
   if (dims[0] < 1 || dims[0] > KM_MAXX) return fail(SO101_EINVAL, "koopman: input width 1..16");
   for (int l = 1; l <= n_layers; l++)
-    if (dims[l] < 1 || dims[l] > KM_MAXW || (dims[l] % 2)) return fail(SO101_EINVAL, "koopman: layer widths must be even, 2..64");
+    if (dims[l] < 8 || dims[l] > KM_MAXW || (dims[l] % 8)) return fail(SO101_EINVAL, "koopman: layer widths must be multiples of 8, 8..64");
   if (dims[0] + dims[n_layers] > KOOP_MAXZ) return fail(SO101_EINVAL, "koopman: lifted dimension exceeds 64");
   if (so101_device_count() <= 0) return fail(SO101_ENODEVICE, "no CUDA device visible: this library has no CPU fallback");
   DeviceGuard g(device);
@@ -344,10 +355,10 @@ extern "C" int so101_koopman_create(int n_layers, const int32_t* dims, const dou
   for (int l = 0; l <= n_layers; l++) k->dims[l] = dims[l];
   k->x_dim = dims[0]; k->nz = dims[0] + dims[n_layers];
   size_t off = 0;
-  for (int l = 0; l < n_layers; l++) {
-    k->woff[l] = off; off += (size_t)dims[l] * dims[l + 1];
+  for (int l = 0; l < n_layers; l++) {               // Wt[l]: [din rounded up to 4][dout + KM_PAD], zero padded
+    k->woff[l] = off; off += (size_t)((dims[l] + 3) & ~3) * (dims[l + 1] + KM_PAD);
     k->boff[l] = off; off += dims[l + 1];
-    off += off & 1;                                  // double2 loads of the transposed weights need 16-byte alignment
+    off += off & 1;
   }
   k->wcount = off;
   if (km_smem_bytes(k, false) + 4096 > 227 * 1024) { delete k; return fail(SO101_EINVAL, "koopman: the encoder does not fit shared memory"); }
@@ -356,7 +367,7 @@ extern "C" int so101_koopman_create(int n_layers, const int32_t* dims, const dou
     if (!W[l] || !b[l]) { delete k; return fail(SO101_EINVAL, "null layer"); }
     const int din = dims[l], dout = dims[l + 1];
     for (int j = 0; j < dout; j++) {
-      for (int c = 0; c < din; c++) host[k->woff[l] + (size_t)c * dout + j] = W[l][(size_t)j * din + c];   // transposed
+      for (int c = 0; c < din; c++) host[k->woff[l] + (size_t)c * (dout + KM_PAD) + j] = W[l][(size_t)j * din + c];   // transposed
       host[k->boff[l] + j] = b[l][j];
     }
   }
@@ -377,7 +388,6 @@ extern "C" int so101_koopman_set_gains(So101Koopman* k, int H, int nu, const dou
   if (!k || !Kz || !Kr || !Ku) return fail(SO101_EINVAL, "null argument");
   if (H < 1 || nu < 1 || nu > KOOP_MAXU) return fail(SO101_EINVAL, "koopman gains: H >= 1, 1 <= nu <= 8");
   if ((size_t)nu * H * k->nz * sizeof(double) > 96 * 1024) return fail(SO101_EINVAL, "koopman gains: reference gain exceeds 96 KB");
-  if (k->dims[k->n_layers] + nu > KM_MAXW) return fail(SO101_EINVAL, "koopman gains: encoder width + nu exceeds 64");
   DeviceGuard g(k->device);
   const size_t nzv = (size_t)nu * k->nz, nuv = (size_t)nu * nu, nrv = (size_t)nu * H * k->nz;
   std::vector<double> host(nzv + nuv + nrv);
