@@ -246,27 +246,47 @@ k_koopman_lift(const __grid_constant__ KmLayers L, const double* __restrict__ wg
   }
 }
 
-// uff[e][k][i] = sum_{t < H, k+1+t < P} sum_c Kr[i][t][c] Z[e][k+1+t][c]  for the envs of one chunk; thread per (e, k)
-__global__ void k_koopman_window(const double* __restrict__ Z, const double* __restrict__ gains, int nz, int nu, int H,
-                                 int64_t ne, int P, double* uff) {
-  extern __shared__ double sh[];
-  const double* Kr_g = gains + (size_t)nu * nz + (size_t)nu * nu;
-  for (int i = threadIdx.x; i < nu * H * nz; i += blockDim.x) sh[i] = Kr_g[i];
+// uff[e][k][i] = sum_{t < H, k+1+t < P} sum_c Kr[i][t][c] Z[e][k+1+t][c] for the envs of one chunk: per env a banded
+// product [P frames x (H nz)] x [(H nz) x nu], on the FP64 tensor cores as well.  A warp takes 8 consecutive frames of one
+// env: A fragment (frame g, column t of the k-step) = Z[e][k0 + g + 1 + tw][c0 + t] straight from global memory (rows past
+// the end of the trajectory are zero in lifted space), B fragment = the reference gain in shared memory as [tw][c][8]
+// (the nu outputs padded to 8: the 32 lanes of a load hit 32 consecutive doubles), 8 x 8 accumulator tile, nu columns kept.
+__global__ void __launch_bounds__(128)
+k_koopman_window(const double* __restrict__ Z, const double* __restrict__ gains, int nz, int nu, int H, int64_t ne, int P,
+                 double* uff) {
+  extern __shared__ double sh[];                     // KrS[H][nz][8]
+  const double* Kr_g = gains + (size_t)nu * nz + (size_t)nu * nu;      // [nu][H][nz]
+  for (int i = threadIdx.x; i < H * nz * 8; i += blockDim.x) {
+    const int o = i & 7, c = (i >> 3) % nz, tw = (i >> 3) / nz;
+    sh[i] = o < nu ? Kr_g[((size_t)o * H + tw) * nz + c] : 0.0;
+  }
   __syncthreads();
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= ne * P) return;
-  const int64_t e = idx / P;
-  const int k = (int)(idx - e * P);
-  double acc[KOOP_MAXU];
-  for (int i = 0; i < nu; i++) acc[i] = 0.0;
-  for (int t = 0; t < H && k + 1 + t < P; t++) {
-    const double* z = Z + ((size_t)e * P + k + 1 + t) * nz;
-    for (int c = 0; c < nz; c++) {
-      const double zc = z[c];
-      for (int i = 0; i < nu; i++) acc[i] = fma(sh[(i * H + t) * nz + c], zc, acc[i]);
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t nblk = (P + 7) / 8;
+  const int64_t ntask = ne * nblk, nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); task < ntask; task += nwarp) {
+    const int64_t e = task / nblk;
+    const int k0 = (int)(task - e * nblk) * 8;
+    const double* Ze = Z + (size_t)e * P * nz;
+    double c0 = 0.0, c1 = 0.0;
+    for (int tw = 0; tw < H; tw++) {
+      const int row = k0 + g + 1 + tw;
+      const bool live = row < P;
+      const double* zr = Ze + (size_t)(live ? row : 0) * nz;
+      const double* kb = sh + (size_t)tw * nz * 8;
+      for (int cc = 0; cc < nz; cc += 4) {           // nz is a multiple of 4 (checked by the caller)
+        const double af = live ? zr[cc + t] : 0.0;
+        const double bf = kb[(cc + t) * 8 + g];
+        dmma884(c0, c1, af, bf);
+      }
+    }
+    const int k = k0 + g;
+    if (k < P) {
+      double* o = uff + ((size_t)e * P + k) * nu;
+      if (2 * t < nu) o[2 * t] = c0;
+      if (2 * t + 1 < nu) o[2 * t + 1] = c1;
     }
   }
-  for (int i = 0; i < nu; i++) uff[idx * nu + i] = acc[i];
 }
 
 // One MPC frame for n envs: lift the observation, u_opt0 = Kz z0 + uff + Ku u_prev, u0 = u_opt0 + u_prev, a = clip(u0),
@@ -434,7 +454,8 @@ extern "C" int so101_koopman_feedforward(So101Koopman* k, const double* Xref, in
   if (chunk > n) chunk = n;
   double* Z = nullptr;
   CUDA_TRY(cudaMallocAsync(&Z, (size_t)chunk * P * k->nz * sizeof(double), st));
-  const size_t wsmem = (size_t)k->nu * k->H * k->nz * sizeof(double);
+  if (k->nz % 4) return fail(SO101_EINVAL, "koopman_feedforward: the lifted dimension must be a multiple of 4");
+  const size_t wsmem = (size_t)8 * k->H * k->nz * sizeof(double);
   cudaError_t err = cudaSuccess;
   if (wsmem > 48 * 1024) err = cudaFuncSetAttribute(k_koopman_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
   int rc = SO101_OK;
@@ -442,9 +463,10 @@ extern "C" int so101_koopman_feedforward(So101Koopman* k, const double* Xref, in
     const int64_t ne = n - e0 < chunk ? n - e0 : chunk;
     rc = km_launch_lift<double>(k, Xref + (size_t)e0 * P * k->x_dim, 0, k->x_dim, ne * P, Z, st);
     if (rc != SO101_OK) break;
-    const int64_t items = ne * P;
-    k_koopman_window<<<(unsigned)((items + 127) / 128), 128, wsmem, st>>>(Z, k->gains, k->nz, k->nu, k->H, ne, P,
-                                                                         uff + (size_t)e0 * P * k->nu);
+    const int64_t tasks = ne * ((P + 7) / 8);       // one warp per 8 frames of an env, grid-stride
+    const int64_t wblocks = (tasks + 3) / 4;
+    k_koopman_window<<<(unsigned)(wblocks < (int64_t)k->sms * 8 ? wblocks : (int64_t)k->sms * 8), 128, wsmem, st>>>(
+        Z, k->gains, k->nz, k->nu, k->H, ne, P, uff + (size_t)e0 * P * k->nu);
     err = cudaGetLastError();
   }
   cudaFreeAsync(Z, st);
