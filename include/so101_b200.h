@@ -244,8 +244,10 @@ enum {
   SO101_OPT_BLOCK         = 1,  /* threads per block of the one-warp kernels (multiple of 32, <= launch bound)  */
   SO101_OPT_HOST_CHUNKS   = 2,  /* pipeline depth of so101_batch_rollout_host, 1..12                            */
   SO101_OPT_HOST_EVEN     = 3,  /* 1: equal time chunks in so101_batch_rollout_host                             */
-  SO101_OPT_SLICED        = 4   /* time-sliced persistent rollout of the one-warp kernels (large batches whose env groups
+  SO101_OPT_SLICED        = 4,  /* time-sliced persistent rollout of the one-warp kernels (large batches whose env groups
                                    do not fill whole waves): 0 = automatic, 1 = always, 2 = never                    */
+  SO101_OPT_REGROUP       = 5   /* long rollouts of large batches: regroup the envs that touch the table into the same
+                                   blocks every few control steps: 0 = automatic, 1 = always (one-warp kernels), 2 = never */
 };
 enum { SO101_FAMILY_AUTO = 0, SO101_FAMILY_ONEWARP = 1, SO101_FAMILY_TEAM = 2 };
 int so101_batch_set_option(So101Batch* b, int option, int value);

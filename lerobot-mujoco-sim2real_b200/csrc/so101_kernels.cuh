@@ -360,6 +360,33 @@ SO101_DEV void write_rows_warp(RowBuf<ROW>& buf, const ROW (&v)[SO101_ROW], ROW*
   }
 }
 
+// the same for lanes that hold arbitrary envs (regrouped batches, see k_rollout_sliced): env ids through shared memory
+template <typename ROW> struct RowBufP { ROW w[7 * 32]; int64_t env[32]; };
+template <typename ROW>
+SO101_DEV void write_rows_warp_perm(RowBufP<ROW>& buf, const ROW (&v)[SO101_ROW], ROW* rows, int64_t env, bool active, int Tn, int t) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  buf.env[lane] = active ? env : -1;
+#pragma unroll
+  for (int c0 = 0; c0 < SO101_ROW; c0 += 7) {
+    const int nc = SO101_ROW - c0 < 7 ? SO101_ROW - c0 : 7;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 7; c++)
+      if (c < nc) buf.w[lane * nc + c] = v[c0 + c];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const int el = j * 32 + lane;
+      if (j < nc) {
+        const int envl = el / nc, c = el - envl * nc;
+        const int64_t ei = buf.env[envl];
+        if (ei >= 0) rows[(ei * (int64_t)(Tn + 1) + t) * SO101_ROW + c0 + c] = buf.w[el];
+      }
+    }
+  }
+}
+
 // SOARM101DataGenerator.generate_physics_based_data, one env per thread:
 // rows[N][T+1][13] = [u_t(5) | float32(ee_pos)(3) | float32(qpos[0:5])(5)]
 template <typename T, typename ROW, bool SPLIT>
@@ -459,8 +486,12 @@ template <typename T> SO101_DEV void load_env_cg(const StateView<T>& s, int64_t 
 template <typename T, typename ROW>
 __global__ void __launch_bounds__(SO101_LB_THREADS, SO101_LB_BLOCKS)
 k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, int t0, int t1, int Tn, int frame_skip,
-                 ROW* rows, uint32_t rflags, unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault) {
-  __shared__ RowBuf<ROW> rowbuf[SO101_LB_THREADS / 32];
+                 ROW* rows, uint32_t rflags, unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault,
+                 const int32_t* perm, uint8_t* recent) {
+  // perm (nullable): slot -> env.  A block pays for a table contact of any of its lanes (its warps meet at two barriers per
+  // step), so between the time chunks of a long rollout the host regroups the envs that touched the table into the same
+  // blocks (so101_capi.cu: regroup); recent[env] reports which envs did during this launch.
+  __shared__ RowBufP<ROW> rowbuf[SO101_LB_THREADS / 32];
   SplitXch<T>& xch = *reinterpret_cast<SplitXch<T>*>(rowbuf);      // never touched by the one-warp path
   const int64_t ngroups = (s.n + blockDim.x - 1) / blockDim.x;
   const int nchunks = (t1 - t0 + tchunk - 1) / tchunk;
@@ -474,7 +505,8 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
     const int ut0 = t0 + c * tchunk, ut1 = ut0 + tchunk < t1 ? ut0 + tchunk : t1;
     const int64_t j = grp * blockDim.x + threadIdx.x;
     const bool active = j < s.n;
-    const int64_t i = active ? j : s.n - 1;                         // tail threads shadow a valid env and never store
+    const int64_t slot = active ? j : s.n - 1;                      // tail threads shadow a valid env and never store
+    const int64_t i = perm ? (int64_t)perm[slot] : slot;
     const int64_t env = spec.env_offset + i;
     if (c > 0) {
       if (threadIdx.x == 0) {
@@ -496,6 +528,8 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
 #pragma unroll
       for (int k = 0; k < 5; k++) e.q[k] = (T)muladd_rn(spec.reset_lo, spec.reset_hi - spec.reset_lo, r[k]);
     }
+    const uint32_t flags_in = e.flags;
+    e.flags &= ~(uint32_t)SO101_FLAG_CONTACT;                       // so that the flag tells what happened in THIS unit
     CtrlGen g;
     ctrl_init(spec, env, g);
     Counters ucnt = {0, 0, 0, 0};
@@ -525,9 +559,16 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
         for (int k = 0; k < 3; k++) v[5 + k] = (ROW)(float)site[k];
 #pragma unroll
         for (int k = 0; k < 5; k++) v[8 + k] = (ROW)(float)e.q[k];
-        write_rows_warp<ROW>(rowbuf[threadIdx.x >> 5], v, rows, grp * blockDim.x + (threadIdx.x & ~31u), s.n, Tn, t);
+        write_rows_warp_perm<ROW>(rowbuf[threadIdx.x >> 5], v, rows, i, active, Tn, t);
       }
     }
+    if (active && recent) {   // a hull of this env was tested during the unit: one of its boxes was below the table top
+      bool tested = (e.flags & SO101_FLAG_CONTACT) != 0;
+#pragma unroll
+      for (int k = 0; k < SO101_MAXTRIP; k++) tested |= vcache[k] >= 0;
+      if (tested) recent[i] = 1;
+    }
+    e.flags |= flags_in;
     if (active) {
       store_env(s, i, e);
       cnt.steps += ucnt.steps; cnt.newton += ucnt.newton; cnt.lsevals += ucnt.lsevals; cnt.limsteps += ucnt.limsteps;
@@ -541,9 +582,10 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
 template <typename T>
 cudaError_t launch_rollout_sliced(const DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st, const DevSpec& ds,
                                   int t0, int t1, int Tn, int frame_skip, void* rows, bool rows_f32, uint32_t rflags,
-                                  unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault) {
-  if (rows_f32) k_rollout_sliced<T, float><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (float*)rows, rflags, stats, tchunk, progress, fault);
-  else k_rollout_sliced<T, double><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (double*)rows, rflags, stats, tchunk, progress, fault);
+                                  unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault,
+                                  const int32_t* perm, uint8_t* recent) {
+  if (rows_f32) k_rollout_sliced<T, float><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (float*)rows, rflags, stats, tchunk, progress, fault, perm, recent);
+  else k_rollout_sliced<T, double><<<grid, blk, 0, st>>>(m, v, ds, t0, t1, Tn, frame_skip, (double*)rows, rflags, stats, tchunk, progress, fault, perm, recent);
   return cudaGetLastError();
 }
 template <typename T> int rollout_sliced_blocks_per_sm(int blk) {

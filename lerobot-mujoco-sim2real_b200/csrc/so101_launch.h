@@ -42,12 +42,13 @@ cudaError_t launch_shoot(const so101::DevModel<T>& m, StateView<T> v, unsigned g
 template <typename T>
 cudaError_t launch_rollout_sliced(const so101::DevModel<T>& m, StateView<T> v, unsigned grid, int blk, cudaStream_t st,
                                   const DevSpec& ds, int t0, int t1, int Tn, int frame_skip, void* rows, bool rows_f32,
-                                  uint32_t rflags, unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault);
+                                  uint32_t rflags, unsigned long long* stats, int tchunk, int32_t* progress, int32_t* fault,
+                                  const int32_t* perm, uint8_t* recent);
 template <typename T> int rollout_sliced_blocks_per_sm(int blk);
 #define SO101_SLICED_LAUNCHERS(KW, T)                                                                                      \
   KW template cudaError_t launch_rollout_sliced<T>(const so101::DevModel<T>&, StateView<T>, unsigned, int, cudaStream_t,    \
                                                    const DevSpec&, int, int, int, int, void*, bool, uint32_t,              \
-                                                   unsigned long long*, int, int32_t*, int32_t*);                           \
+                                                   unsigned long long*, int, int32_t*, int32_t*, const int32_t*, uint8_t*); \
   KW template int rollout_sliced_blocks_per_sm<T>(int);
 #define SO101_LAUNCHERS(KW, T, SPLIT)                                                                                      \
   KW template cudaError_t launch_step<T, SPLIT>(const so101::DevModel<T>&, StateView<T>, unsigned, int, cudaStream_t,       \

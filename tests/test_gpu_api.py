@@ -564,3 +564,27 @@ def test_time_sliced_rollout_is_invisible(tables_v, dtype, kind):
     env = _vec(tables_v, n, dtype=dtype)
     rows = env.rollout(Tn, kind, seed=11)
     assert torch.equal(rows, a[0])
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_regrouped_rollout_is_invisible(tables_v, dtype):
+    """Long rollouts of large batches are launched per chunk of control steps with the envs regrouped in between (the ones that
+    touched the table share blocks afterwards: a block pays for a contact of any of its lanes).  Which lane or block an env sits
+    in changes nothing: rows, final state, flags and statistics equal the plain launch bit for bit."""
+    from lerobot_mujoco_sim2real_b200 import tables as T_
+    n, Tn = 20_011, 60
+    res = []
+    for regroup in (2, 1):
+        env = _vec(tables_v, n, dtype=dtype)
+        env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_ONEWARP)
+        env.set_option(T_.OPT_REGROUP, regroup)
+        if regroup == 2:
+            env.set_option(T_.OPT_SLICED, 2)
+        rows = env.rollout(Tn, "chirp", seed=7)
+        q, v, w = env.get_state()
+        res.append((rows.clone(), q.clone(), v.clone(), w.clone(), env.flags().clone(), env.stats()))
+    a, b = res
+    assert int((a[4] & T_.FLAG_CONTACT).ne(0).sum()) > 10          # the case has contacts to regroup
+    for x, y in zip(a[:5], b[:5]):
+        assert torch.equal(x, y)
+    assert a[5] == b[5]

@@ -10,11 +10,13 @@ from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
 t = builtin_tables()
 cases = sys.argv[1:] or ["4096:100:random:float64", "131072:20:random:float64", "131072:200:chirp:float64", "65536:200:random:float32"]
 for case in cases:
-    n, Tn, kind, dtype = case.split(":")
+    n, Tn, kind, dtype, *opt = case.split(":")          # optional 5th field: SO101_OPT_REGROUP value for the "on" run
     n, Tn = int(n), int(Tn)
     res = {}
     for name, hulls in (("off", None), ("on", "auto")):
         env = SOARM101VecEnv(tables=t, num_envs=n, dtype=dtype, hulls=hulls)
+        if opt and name == "on":
+            env.set_option(T.OPT_REGROUP, int(opt[0]))
         env.rollout_discard(2, kind)
         torch.cuda.synchronize()
         best = 1e30
