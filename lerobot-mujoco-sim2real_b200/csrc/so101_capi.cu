@@ -283,6 +283,7 @@ int so101_batch_set_option(So101Batch* b, int option, int value) {
       const int lim = b->dtype == SO101_F64 ? SO101_F64_THREADS : SO101_F32_THREADS;   // the kernels' __launch_bounds__
       if (value != 0 && (value < 32 || value > lim || value % 32)) return fail(SO101_EINVAL, "block size must be 0 (auto) or a multiple of 32 up to the launch bound (256 f64 / 512 f32)");
       b->opt_block = value;
+      b->sched_resident = 0;                              // resident blocks of the time-sliced kernel depend on the block size
       return SO101_OK;
     }
     case SO101_OPT_HOST_CHUNKS:

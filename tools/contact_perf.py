@@ -17,6 +17,9 @@ for case in cases:
         env = SOARM101VecEnv(tables=t, num_envs=n, dtype=dtype, hulls=hulls)
         if opt and name == "on":
             env.set_option(T.OPT_REGROUP, int(opt[0]))
+        if len(opt) > 1:                                    # optional 6th field: block size of the one-warp kernels (both runs)
+            env.set_option(T.OPT_KERNEL_FAMILY, T.FAMILY_ONEWARP)
+            env.set_option(T.OPT_BLOCK, int(opt[1]))
         env.rollout_discard(2, kind)
         torch.cuda.synchronize()
         best = 1e30
