@@ -408,6 +408,28 @@ def wl_config1(ctx) -> None:
         "physics step is one dependent instruction chain on the team's dynamics warp; the large-batch fraction is in "
         "extra / --config 4", st, traffic)
 
+    # like for like with round 1 (contact-free physics: envs that reach the table are only flagged): the same batch and seeds
+    # with the hull data left out.  Not the product's physics; it separates what the contact path costs from the rest.
+    env_cf = SOARM101VecEnv(tables=tables, num_envs=N_ENVS, dtype="float64", device=dev.index, seed=SEED, hulls=None)
+    cf = []
+    for i in range(3 + min(K, 10)):                        # rank 0 only: no barrier in here
+        ctx.flush_buf.fill_(i & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        env_cf.rollout(T_CTRL, "random", seed=SEED + i, env_offset=env_offset, out=rows)
+        b.record()
+        torch.cuda.synchronize()
+        cf.append(a.elapsed_time(b))
+    cf_ms = sum(cf[3:]) / len(cf[3:])
+    cf_flagged = int((env_cf.flags() & T.FLAG_TRIP).ne(0).sum().item())
+    del env_cf
+    roofline["contact_free_same_batch"] = {
+        "kernel_ms": cf_ms, "frac": FLOP_PER_PHYSICS_STEP * phys_per_launch / (cf_ms * 1e-3) / 1e12 / peak64,
+        "envs_flagged_not_simulated": cf_flagged,
+        "note": "round-1 physics (table contact only flagged) on the same batch and seeds: the launch lasts as long as its "
+                "slowest team, and with contact simulated that team carries an env that keeps touching the table "
+                "(a contact step costs its team 2.5x a plain one, DESIGN 4a)"}
+
     extra = {}
     if not ctx.args.no_extra:
         extra = config1_extras(ctx, peak64, peak32)

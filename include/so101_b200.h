@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SO101_ABI_VERSION 7
+#define SO101_ABI_VERSION 8
 #define SO101_NV       6   /* hinge dofs: 5 arm joints + gripper */
 #define SO101_MAXBODY  8   /* world, fixed base, 6 links */
 #define SO101_MAXTRIP 16   /* contact-tripwire boxes (<= 3 per link) */
@@ -70,7 +70,7 @@ enum {
   SO101_FLAG_BADSTATE   = 1u << 0,  /* qpos/qvel/qacc NaN or |x|>1e10 (mj_checkPos/Vel/Acc) */
   SO101_FLAG_TRIP_TABLE = 1u << 1,  /* a table contact that is NOT simulated occurred: no hull data loaded, more than
                                        SO101_MAXCON simultaneous contacts, or a contact beyond the table's footprint */
-  SO101_FLAG_TRIP_SELF  = 1u << 2,  /* joint vector left the self-collision-free box       */
+  SO101_FLAG_TRIP_SELF  = 1u << 2,  /* outside the self-collision-free joint box AND the oriented boxes of two non-adjacent links overlap */
   SO101_FLAG_LIMIT      = 1u << 3,  /* a joint-limit row was active at least once (info)   */
   SO101_FLAG_MAXITER    = 1u << 4,  /* Newton hit opt.iterations (info)                    */
   SO101_FLAG_CONTACT    = 1u << 5   /* table-plane contact rows were active at least once (info; simulated) */
@@ -159,7 +159,9 @@ typedef struct So101Tables {
   int32_t act_dof[SO101_NV];
   int32_t act_ctrllimited[SO101_NV];
   int32_t act_forcelimited[SO101_NV];
-  int32_t pad0_[2];
+  int32_t nself;                 /* boxes [ntrip, ntrip + nself) of the trip_* arrays: colliding geoms that cannot reach the
+                                    table (no tripwire box, no hull) and take part in the self-collision test only          */
+  int32_t pad0_;
   double  act_gear[SO101_NV];
   double  act_gain[SO101_NV];                 /* gainprm[0]                                */
   double  act_bias[SO101_NV][3];              /* biasprm[0..2]                             */
@@ -246,8 +248,11 @@ enum {
   SO101_OPT_HOST_EVEN     = 3,  /* 1: equal time chunks in so101_batch_rollout_host                             */
   SO101_OPT_SLICED        = 4,  /* time-sliced persistent rollout of the one-warp kernels (large batches whose env groups
                                    do not fill whole waves): 0 = automatic, 1 = always, 2 = never                    */
-  SO101_OPT_REGROUP       = 5   /* long rollouts of large batches: regroup the envs that touch the table into the same
+  SO101_OPT_REGROUP       = 5,  /* long rollouts of large batches: regroup the envs that touch the table into the same
                                    blocks every few control steps: 0 = automatic, 1 = always (one-warp kernels), 2 = never */
+  SO101_OPT_SELF_TEST     = 6   /* SO101_FLAG_TRIP_SELF: 0 = box-box test of the non-adjacent links for poses outside the
+                                   fast-accept joint box (default), 1 = flag every pose outside the joint box (no test:
+                                   cheaper on workloads that leave the box often, flags 10-100x more trajectories)     */
 };
 enum { SO101_FAMILY_AUTO = 0, SO101_FAMILY_ONEWARP = 1, SO101_FAMILY_TEAM = 2 };
 int so101_batch_set_option(So101Batch* b, int option, int value);

@@ -293,6 +293,10 @@ int so101_batch_set_option(So101Batch* b, int option, int value) {
     case SO101_OPT_HOST_EVEN:
       b->opt_host_even = value != 0;
       return SO101_OK;
+    case SO101_OPT_SELF_TEST:
+      if (value < 0 || value > 1) return fail(SO101_EINVAL, "self-collision test must be 0 (box-box test) or 1 (joint box only)");
+      b->dm_d.self_boxes = b->dm_f.self_boxes = value == 0;
+      return SO101_OK;
     case SO101_OPT_REGROUP:
       if (value < 0 || value > 2) return fail(SO101_EINVAL, "regrouping must be 0 (auto), 1 (always, one-warp kernels) or 2 (never)");
       b->opt_regroup = value;

@@ -25,6 +25,8 @@ namespace so101 {
 
 constexpr int NV = SO101_NV;
 constexpr int TRIP_PER_LINK = 3;
+constexpr int SELF_BUDGET_SLOT = SO101_MAXTRIP - 1;   // word of the per-env hull cache that holds the self-collision budget
+constexpr int SELF_EXTRA = 4;      // colliding geoms without a tripwire box (self-collision test only)
 
 template <typename T>
 struct DevModel {
@@ -56,6 +58,11 @@ struct DevModel {
   // parameters, includemargin, translational body_invweight0 of every link, footprint of the table top
   T con_mu, con_K, con_B, con_margin, con_imp[5], con_tran[NV], con_box[4];
   T con_tilt[NV][3];   // tie-breaking tilt of the support direction (1e-7 * (2,3,4)/sqrt(29) in the BODY frame) in link axes
+  // self-collision test (self_boxes_overlap): the boxes of the colliding geoms that have no tripwire box (link frame); the
+  // others are the tripwire boxes above.  Kept small: with these tables the float32 kernels' parameters stay below 4 KB
+  // (beyond it the float32 one-warp kernel lost 35 %).
+  T sx_c[SELF_EXTRA][3], sx_ax[SELF_EXTRA][9], sx_half[SELF_EXTRA][3], sx_rad[SELF_EXTRA];
+  T self_rlen[NV];   // |r_k|: with the distance of a box's far corner from its link origin, the lever arm of the joints between two boxes
   int32_t trip_n[NV];   // <- first non-T field (see hostbuild::convert)
   int32_t trip_geom[NV][TRIP_PER_LINK];   // hull (= tripwire box) index of slot b of link k
   // device pointers of the hull data as (lo, hi) words - int32 so that DevModel<double> and DevModel<float> share the
@@ -66,6 +73,9 @@ struct DevModel {
   int32_t site_link;
   int32_t iterations, ls_iterations;
   int32_t limited_mask, ctrllim_mask, frclim_mask, nfriction, ctrl_of_dof[NV];
+  // flat list of all boxes for the self-collision test: link, and slot b of trip_*[link][b] (>= 0) or -(1 + index into sx_*)
+  int32_t sb_n, sb_link[SO101_MAXTRIP], sb_slot[SO101_MAXTRIP];
+  int32_t self_boxes;   // 1: poses outside the joint box get the box-box test; 0: they are flagged (SO101_OPT_SELF_TEST)
   int32_t any_damping, any_stiffness, pad_;
 };
 
@@ -129,6 +139,8 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
   if (t.nv != NV || t.nu != NV) return "model must have exactly 6 hinge dofs and 6 actuators";
   if (t.nbody < NV + 1 || t.nbody > SO101_MAXBODY) return "unsupported body count";
   if (t.ntrip < 0 || t.ntrip > SO101_MAXTRIP) return "ntrip exceeds SO101_MAXTRIP: a truncated tripwire could miss a contact";
+  if (t.nself < 0 || t.ntrip + t.nself > SO101_MAXTRIP) return "ntrip + nself exceeds SO101_MAXTRIP";
+  if (t.ntrip > SELF_BUDGET_SLOT) return "ntrip leaves no room for the self-collision budget word";
   // ---- chain check: link k = jnt_body[k]; parent(link k) == link k-1; link 0 hangs off fixed bodies
   int link[NV];
   for (int k = 0; k < NV; k++) {
@@ -221,6 +233,21 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
       m.trip_rad[k][slot] = std::sqrt(t.trip_half[i][0] * t.trip_half[i][0] + t.trip_half[i][1] * t.trip_half[i][1] +
                                       t.trip_half[i][2] * t.trip_half[i][2]) * (1 + 1e-5);  // margin covers f32 rounding of |zw|
       m.trip_n[k] = slot + 1;
+      m.sb_link[m.sb_n] = k; m.sb_slot[m.sb_n] = slot; m.sb_n++;
+    }
+    for (int i = t.ntrip; i < t.ntrip + t.nself; i++) {   // geoms without a tripwire box: self-collision test only
+      if (t.trip_body[i] != b) continue;
+      int g = 0;
+      while (g < SELF_EXTRA && m.sx_rad[g] != 0) g++;
+      if (g == SELF_EXTRA) return "more than 4 colliding geoms without a tripwire box";
+      double c3[3];
+      for (int c = 0; c < 3; c++) c3[c] = t.trip_center[i][c] - t.jnt_pos[k][c];
+      mv(At, c3, m.sx_c[g]);
+      for (int a = 0; a < 3; a++) mv(At, &t.trip_axes[i][3 * a], &m.sx_ax[g][3 * a]);
+      for (int c = 0; c < 3; c++) m.sx_half[g][c] = t.trip_half[i][c];
+      m.sx_rad[g] = std::sqrt(t.trip_half[i][0] * t.trip_half[i][0] + t.trip_half[i][1] * t.trip_half[i][1] +
+                              t.trip_half[i][2] * t.trip_half[i][2]) * (1 + 1e-5);
+      m.sb_link[m.sb_n] = k; m.sb_slot[m.sb_n] = -(1 + g); m.sb_n++;
     }
     std::memcpy(Aprev, A, sizeof A);
     std::memcpy(jprev, t.jnt_pos[k], sizeof jprev);
@@ -231,11 +258,13 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
     if (!site_ok) return "observation site must sit on a chain link";
   }
   m.ntrip = t.ntrip < SO101_MAXTRIP ? t.ntrip : SO101_MAXTRIP;
-  for (int i = 0; i < m.ntrip; i++) {
+  for (int i = 0; i < t.ntrip + t.nself; i++) {
     bool ok = false;
     for (int k = 0; k < NV; k++) ok |= (link[k] == t.trip_body[i]);
     if (!ok) return "tripwire box on a non-chain body";
   }
+  for (int k = 0; k < NV; k++) m.self_rlen[k] = std::sqrt(m.r[k][0] * m.r[k][0] + m.r[k][1] * m.r[k][1] + m.r[k][2] * m.r[k][2]);
+  m.self_boxes = m.sb_n > 0;
   m.trip_z = t.trip_plane_z;
   for (int k = 0; k < NV; k++) { m.trip_qlo[k] = t.trip_qbox[k][0]; m.trip_qhi[k] = t.trip_qbox[k][1]; }
 

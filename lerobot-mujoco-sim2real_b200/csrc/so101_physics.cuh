@@ -253,6 +253,148 @@ template <typename T> SO101_DEV void tripwire_frame(const T (&R)[9], const T (&r
   zw[0] = zc[0]; zw[1] = zc[1]; zw[2] = zc[2];
 }
 
+// Self-collision flag.  The joint box trip_qlo..trip_qhi is the fast accept (inside it no pair of non-adjacent link hulls
+// intersected in the host's sampling, tripwire.py); a pose outside it (outside_self_box, at the start of a step) gets the test below:
+// do the oriented boxes of two colliding geoms on non-adjacent links overlap?  Separating-axis test, exact for the boxes
+// and conservative for the hulls inside them (box contains hull contains mesh), restated in tripwire.self_overlap_numpy.  Rare, out
+// of line and called where little is live (a call in the middle of the step cost the float32 kernels 40 %: 128 registers),
+// in double for both dtypes; world frames of the links from the joint sines / cosines.
+template <typename T> SO101_DEV bool outside_self_box(const DevModel<T>& m, const T (&q)[NV]) {
+  bool out = false;
+#pragma unroll
+  for (int k = 0; k < NV; k++) out |= (q[k] < m.trip_qlo[k]) | (q[k] > m.trip_qhi[k]);
+  return out;
+}
+// constants of box g of the flat list: a tripwire box of its link (slot sl >= 0) or one of the extra boxes.  Indexed reads of
+// the kernel parameter (constant bank); pointers into it would turn every read into a generic load.
+template <typename T> struct SelfBox {
+  const DevModel<T>& m; int k, sl;
+  SO101_DEV double c(int i) const { return sl >= 0 ? (double)m.trip_c[k][sl][i] : (double)m.sx_c[-1 - sl][i]; }
+  SO101_DEV double ax(int i) const { return sl >= 0 ? (double)m.trip_ax[k][sl][i] : (double)m.sx_ax[-1 - sl][i]; }
+  SO101_DEV double half(int i) const { return sl >= 0 ? (double)m.trip_half[k][sl][i] : (double)m.sx_half[-1 - sl][i]; }
+  SO101_DEV double rad() const { return sl >= 0 ? (double)m.trip_rad[k][sl] : (double)m.sx_rad[-1 - sl]; }
+};
+template <typename T> SO101_DEV SelfBox<T> self_box(const DevModel<T>& m, int g) { return SelfBox<T>{m, m.sb_link[g], m.sb_slot[g]}; }
+// The double instantiation keeps everything in registers (fully unrolled: ~4 k instructions when a handful of pairs pass the
+// sphere pre-check); the float one rolls its loops over local arrays: what a callee needs in registers is taken from its
+// caller, and the float32 one-warp kernels sit at 128 registers (unrolled they spilled 80 % more and lost 35 % on every
+// workload; rolled the test itself is ~10x slower, on the few steps that run it).
+// Returns a lower bound, in radians of joint travel, of how far the arm is from two such boxes touching (< 0: two of them
+// overlap): min over the pairs of gap / lever arm, gap = their distance along a separating unit axis, lever arm = the largest
+// distance of a point of the outer box from the axes of the joints between the two links (only those joints move one box
+// against the other).  The caller keeps it as a budget and spends h * sum |qvel| of it per step: the test runs again only
+// when the budget is gone, i.e. every few dozen steps for an arm that is not about to fold onto itself.
+template <typename T>
+__device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T s1, T s2, T s3, T s4, T s5, T c0, T c1, T c2, T c3,
+                                                T c4, T c5) {
+  constexpr int UR3 = sizeof(T) == 8 ? 3 : 1, UR9 = sizeof(T) == 8 ? 9 : 1, URNV = sizeof(T) == 8 ? NV : 1;
+  double Rw[NV][9], cw[SO101_MAXTRIP][3];
+  {
+    const double sn[NV] = {(double)s0, (double)s1, (double)s2, (double)s3, (double)s4, (double)s5};
+    const double cs[NV] = {(double)c0, (double)c1, (double)c2, (double)c3, (double)c4, (double)c5};
+    double Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0};
+#pragma unroll(URNV)
+    for (int k = 0; k < NV; k++) {
+      const double c = cs[k], s_ = sn[k];
+      double R[9], Rn[9];     // v_{k-1} = E_k Rz(theta_k) v_k
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) {
+        const double e0 = (double)m.E[k][3 * i], e1 = (double)m.E[k][3 * i + 1];
+        R[3 * i] = c * e0 + s_ * e1; R[3 * i + 1] = c * e1 - s_ * e0; R[3 * i + 2] = (double)m.E[k][3 * i + 2];
+      }
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) pp[i] += Rp[3 * i] * (double)m.r[k][0] + Rp[3 * i + 1] * (double)m.r[k][1] + Rp[3 * i + 2] * (double)m.r[k][2];
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++)
+#pragma unroll(UR3)
+        for (int j = 0; j < 3; j++) Rn[3 * i + j] = Rp[3 * i] * R[j] + Rp[3 * i + 1] * R[3 + j] + Rp[3 * i + 2] * R[6 + j];
+#pragma unroll(UR9)
+      for (int i = 0; i < 9; i++) { Rp[i] = Rn[i]; Rw[k][i] = Rn[i]; }
+#pragma unroll 1
+      for (int g = 0; g < m.sb_n; g++) {
+        if (m.sb_link[g] != k) continue;
+        const SelfBox<T> bx = self_box(m, g);
+#pragma unroll(UR3)
+        for (int i = 0; i < 3; i++)
+          cw[g][i] = pp[i] + Rn[3 * i] * bx.c(0) + Rn[3 * i + 1] * bx.c(1) + Rn[3 * i + 2] * bx.c(2);
+      }
+    }
+  }
+  double sep = 1.0;   // radians
+#pragma unroll 1
+  for (int a = 0; a + 1 < m.sb_n; a++) {
+    const int ka = m.sb_link[a];
+    const SelfBox<T> ba = self_box(m, a);
+#pragma unroll 1
+    for (int b = a + 1; b < m.sb_n; b++) {
+      const int kb = m.sb_link[b];
+      if (kb - ka < 2 && ka - kb < 2) continue;               // same or adjacent links never collide (filterparent)
+      const SelfBox<T> bb = self_box(m, b);
+      // lever arm of the joints between the two links on the box of the outer link
+      double rho;
+      {
+        const SelfBox<T>& bo = kb > ka ? bb : ba;
+        const int klo = kb > ka ? ka : kb, khi = kb > ka ? kb : ka;
+        rho = sqrt(bo.c(0) * bo.c(0) + bo.c(1) * bo.c(1) + bo.c(2) * bo.c(2)) + bo.rad();
+#pragma unroll 1
+        for (int k = klo + 2; k <= khi; k++) rho += (double)m.self_rlen[k];
+      }
+      double d[3], Aa[9], Ab[9], R[9], AR[9], tv[3], ha[3], hb[3];
+      double dd = 0.0;
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) { d[i] = cw[b][i] - cw[a][i]; dd += d[i] * d[i]; }
+      const double rr = ba.rad() + bb.rad();
+      if (dd > rr * rr) {                                     // bounding spheres apart
+        sep = fmin(sep, (sqrt(dd) - rr) / rho);
+        continue;
+      }
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) {                           // box axes (rows) in the world frame
+        ha[i] = ba.half(i); hb[i] = bb.half(i);
+#pragma unroll(UR3)
+        for (int c = 0; c < 3; c++) {
+          Aa[3 * i + c] = Rw[ka][3 * c] * ba.ax(3 * i) + Rw[ka][3 * c + 1] * ba.ax(3 * i + 1) + Rw[ka][3 * c + 2] * ba.ax(3 * i + 2);
+          Ab[3 * i + c] = Rw[kb][3 * c] * bb.ax(3 * i) + Rw[kb][3 * c + 1] * bb.ax(3 * i + 1) + Rw[kb][3 * c + 2] * bb.ax(3 * i + 2);
+        }
+      }
+      bool apart = false;
+      double gap = 0.0;                                       // along a face normal (unit axis): a true distance bound
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) {                           // rotation b -> a, translation in a's axes
+        tv[i] = Aa[3 * i] * d[0] + Aa[3 * i + 1] * d[1] + Aa[3 * i + 2] * d[2];
+#pragma unroll(UR3)
+        for (int j = 0; j < 3; j++) {
+          R[3 * i + j] = Aa[3 * i] * Ab[3 * j] + Aa[3 * i + 1] * Ab[3 * j + 1] + Aa[3 * i + 2] * Ab[3 * j + 2];
+          AR[3 * i + j] = fabs(R[3 * i + j]) + 1e-12;
+        }
+      }
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) gap = fmax(gap, fabs(tv[i]) - (ha[i] + AR[3 * i] * hb[0] + AR[3 * i + 1] * hb[1] + AR[3 * i + 2] * hb[2]));
+#pragma unroll(UR3)
+      for (int j = 0; j < 3; j++)
+        gap = fmax(gap, fabs(tv[0] * R[j] + tv[1] * R[3 + j] + tv[2] * R[6 + j]) - (ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j]));
+      if (gap > 0.0) {                                        // a face normal separates (the common case)
+        sep = fmin(sep, gap / rho);
+        continue;
+      }
+#pragma unroll(UR3)
+      for (int i = 0; i < 3; i++) {
+        const int i1 = i == 2 ? 0 : i + 1, i2 = i == 0 ? 2 : i - 1;
+#pragma unroll(UR3)
+        for (int j = 0; j < 3; j++) {
+          const int j1 = j == 2 ? 0 : j + 1, j2 = j == 0 ? 2 : j - 1;
+          const double ra = ha[i1] * AR[3 * i2 + j] + ha[i2] * AR[3 * i1 + j];
+          const double rb = hb[j1] * AR[3 * i + j2] + hb[j2] * AR[3 * i + j1];
+          apart |= fabs(tv[i2] * R[3 * i1 + j] - tv[i1] * R[3 * i2 + j]) > ra + rb;
+        }
+      }
+      if (!apart) return -1.0;
+      sep = 0.0;                                              // only an edge-edge axis separates: no distance bound, test again next step
+    }
+  }
+  return sep;
+}
+
 // ------------------------------------------------------------------------------------------
 // dense 6x6 LDL^T on a packed lower triangle (A = L D L^T, unit L), and solve
 // ------------------------------------------------------------------------------------------
@@ -375,7 +517,6 @@ SO101_DEV void tripwire_link(const DevModel<T>& m, int k, const T (&R)[9], T qk,
   for (int b = 0; b < TRIP_PER_LINK; b++) {
     if (m.trip_n[k] > b) tripwire_box(m, k, b, zw, zo, hits);
   }
-  if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
 }
 
 template <typename T, bool WANT_M, bool WANT_BIAS = true>
@@ -575,8 +716,6 @@ SO101_DEV void tripwire_all(const DevModel<T>& m, const T* sn, const T* cs, int 
     tripwire_frame(R, m.r[k], zw, zo);
 #pragma unroll 1
     for (int b = 0; b < m.trip_n[k]; b++) tripwire_box(m, k, b, zw, zo, hits);
-    const T qk = q[k * qst];
-    if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
   }
 }
 
@@ -985,10 +1124,39 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
 // on a barrier at the phase boundaries so that its warps stream the same instructions through
 // the instruction cache together (the step is ~50 KB of SASS; ncu: stall_no_instruction).
 // ------------------------------------------------------------------------------------------
+// rare: box-box test of the non-adjacent links, right after the joint sines / cosines (little else is live yet).  The budget
+// (float bits in the env's hull cache word SELF_BUDGET_SLOT) is spent by every step, whether the pose is inside the fast-accept
+// box or not, so it is always a valid bound for the pose it is compared at.
+template <typename T> SO101_DEV float self_budget_spend(const DevModel<T>& m, const T (&qd)[NV], int32_t* vcache) {
+  float mv = 0.f;
+#pragma unroll
+  for (int k = 1; k < NV; k++) mv += fabsf((float)qd[k]);
+  const float b = __int_as_float(vcache[SELF_BUDGET_SLOT]) - 1.001f * (float)m.h * mv;
+  vcache[SELF_BUDGET_SLOT] = __float_as_int(b);
+  return b;
+}
+// When one env of a block (its warps meet at a barrier here anyway; of a warp elsewhere) has used up its budget, every env of it
+// that is outside the fast-accept box takes the test with it and refreshes its own budget: the lanes of a warp pay for the code
+// together, so testing them together makes the test as rare as the neediest env needs it instead of 32 times that.
+#define SO101_SELF_TEST_ONEWARP                                                                                            \
+  if (self_any && self_cand) {                                                                                             \
+    const double sep_ = !m.self_boxes ? -1.0 :                                                                             \
+                        self_boxes_overlap<T>(m, sn[0], sn[1], sn[2], sn[3], sn[4], sn[5], cs[0], cs[1], cs[2], cs[3],     \
+                                              cs[4], cs[5]);                                                               \
+    if (sep_ < 0.0) e.flags |= SO101_FLAG_TRIP_SELF;                                                                       \
+    vcache[SELF_BUDGET_SLOT] = __float_as_int(sep_ > 0.0 ? 0.999f * (float)sep_ : 0.f);                                     \
+  }
 template <typename T, bool SYNC>
 SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
                             bool want_site, T (&site)[3], bool trip, Counters& cnt, int32_t* vcache) {
-  if (SYNC) __syncthreads();
+  bool self_cand = false, self_any = false;
+  if (trip && vcache) {
+    const float bud = self_budget_spend(m, e.qd, vcache);
+    self_cand = !(e.flags & SO101_FLAG_TRIP_SELF) && outside_self_box(m, e.q);
+    self_any = self_cand && bud <= 0.f;
+  }
+  if (SYNC) self_any = __syncthreads_or(self_any);
+  else self_any = __any_sync(__activemask(), self_any);
   // mj_checkPos / mj_checkVel
   {
     bool bad = false;
@@ -1011,6 +1179,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 #pragma unroll
     for (int i = 0; i < NV; i++) { lq[i] = e.q[i]; lqd[i] = e.qd[i]; }
     joint_sincos_range(m, lq, 1, sn, cs, 1, 0, NV);
+    SO101_SELF_TEST_ONEWARP
     rnea_bias(m, sn, cs, 1, lqd, 1, bias);
     crba_mass(m, sn, cs, 1, M, 1);
     if (trip) tripwire_all(m, sn, cs, 1, lq, 1, e.flags, hits);
@@ -1019,6 +1188,7 @@ SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV]
 #else
   {
     joint_sincos(m, e.q, sn, cs);
+    SO101_SELF_TEST_ONEWARP
     smooth_dynamics<T, true>(m, e.q, e.qd, sn, cs, M, bias, want_site, site, trip, e.flags, hits);
   }
 #endif
@@ -1386,8 +1556,6 @@ SO101_DEV void tripwire_all_tests(const DevModel<T>& m, const T* sn, const T* cs
       tripwire_box(m, k, b, zw, zo, hits);
       if (hits != before) hull_test(m, k, b, zw, zo, vcache, hl);
     }
-    const T qk = q[k * qst];
-    if (qk < m.trip_qlo[k] || qk > m.trip_qhi[k]) flags |= SO101_FLAG_TRIP_SELF;
   }
 }
 
@@ -1414,6 +1582,18 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
       }
     } else {
       tripwire_all(m, &x.sn[0][lane], &x.cs[0][lane], 32, lq, 1, fl, hits);
+    }
+  }
+  if (trip) {   // see physics_step; x.trip still holds this lane's flags of the previous step (sticky within the launch)
+    const float bud = self_budget_spend(m, qd, vcache);
+    const bool cand = !(x.trip[lane] & SO101_FLAG_TRIP_SELF) && outside_self_box(m, q);
+    const bool any = __any_sync(__activemask(), cand && bud <= 0.f);       // the warp's candidates take the test together
+    if (x.trip[lane] & SO101_FLAG_TRIP_SELF) fl |= SO101_FLAG_TRIP_SELF;
+    else if (any && cand) {
+      const double sep = !m.self_boxes ? -1.0 : self_boxes_overlap<T>(m, x.sn[0][lane], x.sn[1][lane], x.sn[2][lane], x.sn[3][lane], x.sn[4][lane], x.sn[5][lane],
+                                               x.cs[0][lane], x.cs[1][lane], x.cs[2][lane], x.cs[3][lane], x.cs[4][lane], x.cs[5][lane]);
+      if (sep < 0.0) fl |= SO101_FLAG_TRIP_SELF;
+      vcache[SELF_BUDGET_SLOT] = __float_as_int(sep > 0.0 ? 0.999f * (float)sep : 0.f);
     }
   }
   x.ncon[lane] = nc;

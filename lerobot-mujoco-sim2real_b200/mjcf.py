@@ -350,7 +350,7 @@ def _principal(full6: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     return w, mat_q(V)
 
 
-_TRIP_FIELDS = ("ntrip", "trip_body", "trip_center", "trip_axes", "trip_half", "trip_plane_z", "trip_qbox",
+_TRIP_FIELDS = ("ntrip", "nself", "trip_body", "trip_center", "trip_axes", "trip_half", "trip_plane_z", "trip_qbox",
                 "con_friction", "con_solref", "con_solimp", "con_margin", "con_box", "con_enabled", "con_condim")
 
 
@@ -704,6 +704,7 @@ def compile_mjcf(xml_path: str, site_name: str = "gripperframe") -> CompiledMode
 
     # tripwire defaults: disabled until tools/gen_tables.py fills it from the collision meshes
     t.ntrip = 0
+    t.nself = 0
     t.trip_plane_z = -1e30
     for k in range(nv):
         t.trip_qbox[k][0], t.trip_qbox[k][1] = -1e30, 1e30

@@ -8,8 +8,11 @@ but the CUDA kernels do not simulate contact.  Instead every env carries two fla
               static support plane (the table top).  Box ⊇ convex hull ⊇ mesh, so a table contact
               can never be missed (no false negatives); it may fire slightly early.
   TRIP_SELF   the joint vector left a box |q_i| <= qbox_i inside which no pair of non-adjacent
-              link hulls intersects.  The box is found by sampling (hull-hull LP feasibility) and
-              shrunk by a safety factor: a heuristic, documented as such.
+              link hulls intersects (found by sampling hull-hull LP feasibility and shrunk by a
+              safety factor: a heuristic fast accept, documented as such) AND the oriented boxes of
+              two geoms on non-adjacent links overlap (separating-axis test, exact for the boxes;
+              box ⊇ hull, so outside the joint box no self-collision is missed and the flag fires only
+              slightly early: `self_overlap_numpy` is the restatement the kernels are tested against).
 
 Parity and throughput claims are made over flag-free envs.  This module needs the STL meshes of the
 reference tree, so it only runs in the build container (tools/gen_tables.py); the resulting numbers
@@ -110,32 +113,28 @@ def _hulls_intersect(A: np.ndarray, B: np.ndarray) -> bool:
     return res.status == 0
 
 
-def self_collision_box(cm: mjcf.CompiledModel, hulls: Dict[int, np.ndarray], samples: int = 120,
-                       seed: int = 0, safety: float = 0.8) -> np.ndarray:
-    """Largest (of a fixed ladder) symmetric joint box without sampled self-intersection, x safety."""
+def self_collision_box(cm: mjcf.CompiledModel, samples: int = 3000, seed: int = 0, safety: float = 0.9) -> np.ndarray:
+    """Fast-accept joint box of the self-collision flag: the largest (of a fixed ladder) symmetric box in which no sampled
+    pose has overlapping boxes of non-adjacent links (`self_overlap_numpy`, itself conservative for the hulls), x safety.
+    Joints up to and including the first link that carries a colliding geom do not change the relative pose of any two
+    such geoms: they are left free.  A heuristic (sampling), which is why poses outside it get the box-box test instead of
+    a flag.  Needs the trip_* boxes of the tables (fill_tripwire calls it last)."""
     t = cm.tables
     rng = np.random.default_rng(seed)
-    bodies = sorted(hulls)
-    pairs = [(a, b) for i, a in enumerate(bodies) for b in bodies[i + 1:]
-             if t.body_parent[b] != a and t.body_parent[a] != b]
-    small = {b: hulls[b][np.linspace(0, len(hulls[b]) - 1, min(len(hulls[b]), 60)).astype(int)] for b in bodies}
     lo = np.array([t.jnt_range[k][0] for k in range(t.nv)])
     hi = np.array([t.jnt_range[k][1] for k in range(t.nv)])
+    nb = t.ntrip + t.nself
+    first_link = min(t.body_jnt[t.trip_body[i]] for i in range(nb)) if nb else t.nv
+    free = np.arange(t.nv) <= first_link
     best = 0.0
-    for scale in (0.3, 0.45, 0.6, 0.8, 1.0, 1.2, 1.5):
-        ok = True
-        for _ in range(samples):
-            q = rng.uniform(np.maximum(lo, -scale), np.minimum(hi, scale))
-            xpos, xmat, _, _ = mjcf.fk_numpy(t, q)
-            world = {b: xpos[b] + small[b] @ xmat[b].T for b in bodies}
-            if any(_hulls_intersect(world[a], world[b]) for a, b in pairs):
-                ok = False
-                break
-        if not ok:
+    for scale in (0.3, 0.45, 0.6, 0.7, 0.8, 0.85, 0.9, 0.95, 1.0, 1.1, 1.2, 1.35, 1.5):
+        blo, bhi = np.where(free, lo, np.maximum(lo, -scale)), np.where(free, hi, np.minimum(hi, scale))
+        if any(self_overlap_numpy(t, rng.uniform(blo, bhi)) for _ in range(samples)):
             break
         best = scale
     box = np.zeros((t.nv, 2))
-    box[:, 0], box[:, 1] = np.maximum(lo, -best * safety), np.minimum(hi, best * safety)
+    box[:, 0] = np.where(free, -1e30, np.maximum(lo, -best * safety))
+    box[:, 1] = np.where(free, 1e30, np.minimum(hi, best * safety))
     return box
 
 
@@ -147,6 +146,7 @@ def fill_tripwire(cm: mjcf.CompiledModel, with_self_box: bool = True) -> None:
     t = cm.tables
     plane = support_plane_z(cm)
     t.ntrip = 0
+    t.nself = 0
     if not np.isfinite(plane):
         return
     xpos0, xmat0, _, axis0 = mjcf.fk_numpy(t, np.array(t.qpos0[:]))
@@ -161,10 +161,15 @@ def fill_tripwire(cm: mjcf.CompiledModel, with_self_box: bool = True) -> None:
     for b, name, pts in _contact_geoms(cm):
         c, ax, half = obb(pts)
         boxes.append((b, c, ax, half))
-    if len(boxes) > T.MAXTRIP:
+    # colliding geoms without a tripwire box (they cannot reach the plane) still take part in the self-collision test:
+    # their boxes follow the tripwire boxes in the same arrays, [ntrip, ntrip + nself)
+    have = {(b, name) for b, name, _ in _contact_geoms(cm)}
+    extra = [(b,) + obb(pts) for b, name, pts in geom_hulls(cm) if (b, name) not in have and t.body_jnt[b] >= 0]
+    if len(boxes) + len(extra) > T.MAXTRIP:
         raise mjcf.MjcfError("too many tripwire boxes")
     t.ntrip = len(boxes)
-    for i, (b, c, ax, half) in enumerate(boxes):
+    t.nself = len(extra)
+    for i, (b, c, ax, half) in enumerate(boxes + extra):
         t.trip_body[i] = b
         t.trip_center[i][:] = list(c)
         t.trip_axes[i][:] = list(ax.reshape(-1))
@@ -172,7 +177,7 @@ def fill_tripwire(cm: mjcf.CompiledModel, with_self_box: bool = True) -> None:
     t.trip_plane_z = plane
     fill_contact_params(cm)
     if with_self_box:
-        box = self_collision_box(cm, body_hulls(cm))
+        box = self_collision_box(cm)
         for k in range(t.nv):
             t.trip_qbox[k][0], t.trip_qbox[k][1] = float(box[k, 0]), float(box[k, 1])
 
@@ -300,3 +305,48 @@ def table_clearance_numpy(t: T.So101Tables, q: np.ndarray) -> float:
         ext = np.sum(np.abs(ax[:, 2]) * np.array(t.trip_half[i][:]))
         best = min(best, c[2] - ext - t.trip_plane_z)
     return float(best)
+
+
+def obb_overlap(c1: np.ndarray, A1: np.ndarray, h1: np.ndarray, c2: np.ndarray, A2: np.ndarray, h2: np.ndarray) -> bool:
+    """Separating-axis test of two oriented boxes (centre, rows = axes, half sizes; all in one frame): the 15 candidate
+    axes (3 + 3 face normals, 9 edge cross products), with the customary 1e-12 guard on the absolute rotation for
+    near-parallel edges (it can only make the answer 'overlap', i.e. keeps the test conservative)."""
+    R = A1 @ A2.T
+    tv = A1 @ (c2 - c1)
+    AR = np.abs(R) + 1e-12
+    for i in range(3):
+        if abs(tv[i]) > h1[i] + AR[i] @ h2:
+            return False
+    for j in range(3):
+        if abs(tv @ R[:, j]) > h1 @ AR[:, j] + h2[j]:
+            return False
+    for i in range(3):
+        i1, i2 = (i + 1) % 3, (i + 2) % 3
+        for j in range(3):
+            j1, j2 = (j + 1) % 3, (j + 2) % 3
+            ra = h1[i1] * AR[i2, j] + h1[i2] * AR[i1, j]
+            rb = h2[j1] * AR[i, j2] + h2[j2] * AR[i, j1]
+            if abs(tv[i2] * R[i1, j] - tv[i1] * R[i2, j]) > ra + rb:
+                return False
+    return True
+
+
+def self_overlap_numpy(t: T.So101Tables, q: np.ndarray, margin: bool = False):
+    """Do the oriented boxes of two colliding geoms on non-adjacent links overlap at pose q?  All `ntrip + nself` boxes of
+    the tables; links a, b are non-adjacent when neither is the other's parent.  With `margin` returns the smallest
+    slack over all axes of all pairs as well (how close the decision is), for tests."""
+    xpos, xmat, _, _ = mjcf.fk_numpy(t, q)
+    nb = t.ntrip + t.nself
+    W = []
+    for i in range(nb):
+        b = t.trip_body[i]
+        ax = np.array(t.trip_axes[i][:]).reshape(3, 3)
+        W.append((b, xpos[b] + xmat[b] @ np.array(t.trip_center[i][:]), ax @ xmat[b].T, np.array(t.trip_half[i][:])))
+    hit = False
+    for i in range(nb):
+        for j in range(i + 1, nb):
+            a, b = W[i][0], W[j][0]
+            if a == b or t.body_parent[a] == b or t.body_parent[b] == a:
+                continue
+            hit |= obb_overlap(*W[i][1:], *W[j][1:])
+    return hit
