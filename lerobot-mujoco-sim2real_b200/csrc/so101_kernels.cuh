@@ -41,7 +41,7 @@ SO101_DEV void helper_role(const DevModel<T>& m, SplitXch<T>& x, int64_t nsteps,
   int32_t vcache[SO101_MAXTRIP];   // lookout: support vertex of each hull when it was last tested (see contact_geometry)
 #pragma unroll
   for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
-  vcache[SELF_BUDGET_SLOT] = 0;      // float bits: separation budget of the self-collision test (so101_physics.cuh)
+  vcache[SELF_BUDGET_SLOT] = vcache[SELF_REST_SLOT] = 0;   // float bits: separation budgets of the self-collision test (so101_physics.cuh)
   __syncthreads();   // (0) initial state published
 #pragma unroll
   for (int k = 0; k < NV; k++) { q[k] = x.q[k][lane]; qd[k] = x.qd[k][lane]; }
@@ -314,7 +314,7 @@ k_step(const __grid_constant__ DevModel<T> m, StateView<T> s, const T* ctrl, int
   int32_t vcache[SO101_MAXTRIP];   // support vertex of each hull when it was last tested (see contact_geometry)
 #pragma unroll
   for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
-  vcache[SELF_BUDGET_SLOT] = 0;      // float bits: separation budget of the self-collision test (so101_physics.cuh)
+  vcache[SELF_BUDGET_SLOT] = vcache[SELF_REST_SLOT] = 0;   // float bits: separation budgets of the self-collision test (so101_physics.cuh)
   const bool hold = sflags & SO101_ROLL_GRAVCOMP_HOLD;   // qfrc_applied = qfrc_bias of the state the env step starts from
 #pragma unroll 1
   for (int ss = 0; ss < nsub; ss++) step_env<T, SPLIT>(m, xch, e, u, hold && ss == 0, ss == nsub - 1, site, trip, cnt, ss, vcache);
@@ -423,7 +423,7 @@ k_rollout(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec spec, i
   int32_t vcache[SO101_MAXTRIP];   // support vertex of each hull when it was last tested (see contact_geometry)
 #pragma unroll
   for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
-  vcache[SELF_BUDGET_SLOT] = 0;      // float bits: separation budget of the self-collision test (so101_physics.cuh)
+  vcache[SELF_BUDGET_SLOT] = vcache[SELF_REST_SLOT] = 0;   // float bits: separation budgets of the self-collision test (so101_physics.cuh)
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
   T site[3];
   site_fk(m, e.q, site);
@@ -540,7 +540,7 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
     int32_t vcache[SO101_MAXTRIP];
 #pragma unroll
     for (int k = 0; k < SO101_MAXTRIP; k++) vcache[k] = -1;
-    vcache[SELF_BUDGET_SLOT] = 0;
+    vcache[SELF_BUDGET_SLOT] = vcache[SELF_REST_SLOT] = 0;
     T site[3];
     site_fk(m, e.q, site);
     double u[5];
@@ -570,7 +570,7 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
     if (active && recent) {   // a hull of this env was tested during the unit: one of its boxes was below the table top
       bool tested = (e.flags & SO101_FLAG_CONTACT) != 0;
 #pragma unroll
-      for (int k = 0; k < SELF_BUDGET_SLOT; k++) tested |= vcache[k] >= 0;
+      for (int k = 0; k < SELF_PAIR_SLOT; k++) tested |= vcache[k] >= 0;
       if (tested) recent[i] = 1;
     }
     e.flags |= flags_in;
@@ -620,7 +620,7 @@ k_shoot(const __grid_constant__ DevModel<T> m, StateView<T> s, const __grid_cons
   int32_t vcache[SO101_MAXTRIP];   // support vertex of each hull when it was last tested (see contact_geometry)
 #pragma unroll
   for (int g = 0; g < SO101_MAXTRIP; g++) vcache[g] = -1;
-  vcache[SELF_BUDGET_SLOT] = 0;      // float bits: separation budget of the self-collision test (so101_physics.cuh)
+  vcache[SELF_BUDGET_SLOT] = vcache[SELF_REST_SLOT] = 0;   // float bits: separation budgets of the self-collision test (so101_physics.cuh)
   const bool hold = rflags & SO101_ROLL_GRAVCOMP_HOLD;
   T site[3];
   site_fk(m, e.q, site);

@@ -25,7 +25,9 @@ namespace so101 {
 
 constexpr int NV = SO101_NV;
 constexpr int TRIP_PER_LINK = 3;
-constexpr int SELF_BUDGET_SLOT = SO101_MAXTRIP - 1;   // word of the per-env hull cache that holds the self-collision budget
+// words of the per-env hull cache that belong to the self-collision test: budget of the critical pair (float bits), budget of
+// all other pairs (float bits), the critical pair (16 a + b, -1: none yet)
+constexpr int SELF_BUDGET_SLOT = SO101_MAXTRIP - 1, SELF_REST_SLOT = SO101_MAXTRIP - 2, SELF_PAIR_SLOT = SO101_MAXTRIP - 3;
 constexpr int SELF_EXTRA = 4;      // colliding geoms without a tripwire box (self-collision test only)
 
 template <typename T>
@@ -140,7 +142,7 @@ inline std::string build(const So101Tables& t, DevModel<double>& m) {
   if (t.nbody < NV + 1 || t.nbody > SO101_MAXBODY) return "unsupported body count";
   if (t.ntrip < 0 || t.ntrip > SO101_MAXTRIP) return "ntrip exceeds SO101_MAXTRIP: a truncated tripwire could miss a contact";
   if (t.nself < 0 || t.ntrip + t.nself > SO101_MAXTRIP) return "ntrip + nself exceeds SO101_MAXTRIP";
-  if (t.ntrip > SELF_BUDGET_SLOT) return "ntrip leaves no room for the self-collision budget word";
+  if (t.ntrip > SELF_PAIR_SLOT) return "ntrip leaves no room for the self-collision budget words";
   // ---- chain check: link k = jnt_body[k]; parent(link k) == link k-1; link 0 hangs off fixed bodies
   int link[NV];
   for (int k = 0; k < NV; k++) {

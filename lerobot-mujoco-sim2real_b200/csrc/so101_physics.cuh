@@ -279,14 +279,17 @@ template <typename T> SO101_DEV SelfBox<T> self_box(const DevModel<T>& m, int g)
 // sphere pre-check); the float one rolls its loops over local arrays: what a callee needs in registers is taken from its
 // caller, and the float32 one-warp kernels sit at 128 registers (unrolled they spilled 80 % more and lost 35 % on every
 // workload; rolled the test itself is ~10x slower, on the few steps that run it).
-// Returns a lower bound, in radians of joint travel, of how far the arm is from two such boxes touching (< 0: two of them
-// overlap): min over the pairs of gap / lever arm, gap = their distance along a separating unit axis, lever arm = the largest
-// distance of a point of the outer box from the axes of the joints between the two links (only those joints move one box
-// against the other).  The caller keeps it as a budget and spends h * sum |qvel| of it per step: the test runs again only
-// when the budget is gone, i.e. every few dozen steps for an arm that is not about to fold onto itself.
+// Returns < 0 when two such boxes overlap.  Otherwise it leaves, in the env's hull-cache words, lower bounds in radians of joint
+// travel of how far the arm is from two boxes touching: per pair, gap / lever arm with gap = their distance along a separating
+// unit axis and lever arm = the largest distance of a point of the outer box from the axes of the joints between the two
+// links (only those joints move one box against the other) - the smallest of them with its pair (the critical pair), and the
+// smallest over all other pairs.  The caller spends h * sum |qvel| of both per step: while the second one lasts only the
+// critical pair can have closed, and `only` = that pair tests it alone (a sixth of the work); the full test runs again when
+// the second budget is gone, i.e. every few dozen steps for an arm that is not about to fold onto itself.
 template <typename T>
 __device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T s1, T s2, T s3, T s4, T s5, T c0, T c1, T c2, T c3,
-                                                T c4, T c5) {
+                                                T c4, T c5, int32_t* vcache, int only) {
+  const int oa = only >> 4, ob = only & 15;      // only < 0: every pair
   constexpr int UR3 = sizeof(T) == 8 ? 3 : 1, UR9 = sizeof(T) == 8 ? 9 : 1, URNV = sizeof(T) == 8 ? NV : 1;
   double Rw[NV][9], cw[SO101_MAXTRIP][3];
   {
@@ -312,7 +315,7 @@ __device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T 
       for (int i = 0; i < 9; i++) { Rp[i] = Rn[i]; Rw[k][i] = Rn[i]; }
 #pragma unroll 1
       for (int g = 0; g < m.sb_n; g++) {
-        if (m.sb_link[g] != k) continue;
+        if (m.sb_link[g] != k || (only >= 0 && g != oa && g != ob)) continue;
         const SelfBox<T> bx = self_box(m, g);
 #pragma unroll(UR3)
         for (int i = 0; i < 3; i++)
@@ -320,15 +323,17 @@ __device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T 
       }
     }
   }
-  double sep = 1.0;   // radians
+  double sep = 1.0, sep2 = 1.0;   // radians: smallest (its pair: cp) and second smallest
+  int cp = -1;
 #pragma unroll 1
-  for (int a = 0; a + 1 < m.sb_n; a++) {
+  for (int a = only >= 0 ? oa : 0; a + 1 < m.sb_n && (only < 0 || a == oa); a++) {
     const int ka = m.sb_link[a];
     const SelfBox<T> ba = self_box(m, a);
 #pragma unroll 1
-    for (int b = a + 1; b < m.sb_n; b++) {
+    for (int b = only >= 0 ? ob : a + 1; b < m.sb_n && (only < 0 || b == ob); b++) {
       const int kb = m.sb_link[b];
       if (kb - ka < 2 && ka - kb < 2) continue;               // same or adjacent links never collide (filterparent)
+      double ps;                                              // this pair's bound
       const SelfBox<T> bb = self_box(m, b);
       // lever arm of the joints between the two links on the box of the outer link
       double rho;
@@ -345,7 +350,8 @@ __device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T 
       for (int i = 0; i < 3; i++) { d[i] = cw[b][i] - cw[a][i]; dd += d[i] * d[i]; }
       const double rr = ba.rad() + bb.rad();
       if (dd > rr * rr) {                                     // bounding spheres apart
-        sep = fmin(sep, (sqrt(dd) - rr) / rho);
+        ps = (sqrt(dd) - rr) / rho;
+        if (ps < sep) { sep2 = sep; sep = ps; cp = 16 * a + b; } else sep2 = fmin(sep2, ps);
         continue;
       }
 #pragma unroll(UR3)
@@ -374,7 +380,8 @@ __device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T 
       for (int j = 0; j < 3; j++)
         gap = fmax(gap, fabs(tv[0] * R[j] + tv[1] * R[3 + j] + tv[2] * R[6 + j]) - (ha[0] * AR[j] + ha[1] * AR[3 + j] + ha[2] * AR[6 + j] + hb[j]));
       if (gap > 0.0) {                                        // a face normal separates (the common case)
-        sep = fmin(sep, gap / rho);
+        ps = gap / rho;
+        if (ps < sep) { sep2 = sep; sep = ps; cp = 16 * a + b; } else sep2 = fmin(sep2, ps);
         continue;
       }
 #pragma unroll(UR3)
@@ -389,8 +396,13 @@ __device__ __noinline__ double self_boxes_overlap(const DevModel<T>& m, T s0, T 
         }
       }
       if (!apart) return -1.0;
-      sep = 0.0;                                              // only an edge-edge axis separates: no distance bound, test again next step
+      sep2 = sep; sep = 0.0; cp = 16 * a + b;                 // only an edge-edge axis separates: no distance bound, test again next step
     }
+  }
+  vcache[SELF_BUDGET_SLOT] = __float_as_int(sep > 0.0 ? 0.999f * (float)sep : 0.f);
+  if (only < 0) {
+    vcache[SELF_REST_SLOT] = __float_as_int(0.999f * (float)sep2);
+    vcache[SELF_PAIR_SLOT] = cp;
   }
   return sep;
 }
@@ -1127,36 +1139,37 @@ SO101_DEV bool contact_branch(const DevModel<T>& m, Env<T>& e, uint32_t hits, co
 // rare: box-box test of the non-adjacent links, right after the joint sines / cosines (little else is live yet).  The budget
 // (float bits in the env's hull cache word SELF_BUDGET_SLOT) is spent by every step, whether the pose is inside the fast-accept
 // box or not, so it is always a valid bound for the pose it is compared at.
-template <typename T> SO101_DEV float self_budget_spend(const DevModel<T>& m, const T (&qd)[NV], int32_t* vcache) {
+// -> bit 0: the critical pair's budget is gone, bit 1: the budget of the other pairs is gone
+template <typename T> SO101_DEV int self_budget_spend(const DevModel<T>& m, const T (&qd)[NV], int32_t* vcache) {
   float mv = 0.f;
 #pragma unroll
   for (int k = 1; k < NV; k++) mv += fabsf((float)qd[k]);
-  const float b = __int_as_float(vcache[SELF_BUDGET_SLOT]) - 1.001f * (float)m.h * mv;
+  mv *= 1.001f * (float)m.h;
+  const float b = __int_as_float(vcache[SELF_BUDGET_SLOT]) - mv, r = __int_as_float(vcache[SELF_REST_SLOT]) - mv;
   vcache[SELF_BUDGET_SLOT] = __float_as_int(b);
-  return b;
+  vcache[SELF_REST_SLOT] = __float_as_int(r);
+  return (b <= 0.f ? 1 : 0) | (r <= 0.f ? 2 : 0);
 }
-// When one env of a block (its warps meet at a barrier here anyway; of a warp elsewhere) has used up its budget, every env of it
-// that is outside the fast-accept box takes the test with it and refreshes its own budget: the lanes of a warp pay for the code
-// together, so testing them together makes the test as rare as the neediest env needs it instead of 32 times that.
+// When one env of a warp needs the full test, every env of the warp that is outside the fast-accept box takes it with it and
+// refreshes its own budgets: the lanes pay for the code together.
 #define SO101_SELF_TEST_ONEWARP                                                                                            \
-  if (self_any && self_cand) {                                                                                             \
+  if (self_cand && (self_full || self_pair)) {                                                                             \
     const double sep_ = !m.self_boxes ? -1.0 :                                                                             \
                         self_boxes_overlap<T>(m, sn[0], sn[1], sn[2], sn[3], sn[4], sn[5], cs[0], cs[1], cs[2], cs[3],     \
-                                              cs[4], cs[5]);                                                               \
+                                              cs[4], cs[5], vcache, self_full ? -1 : vcache[SELF_PAIR_SLOT]);              \
     if (sep_ < 0.0) e.flags |= SO101_FLAG_TRIP_SELF;                                                                       \
-    vcache[SELF_BUDGET_SLOT] = __float_as_int(sep_ > 0.0 ? 0.999f * (float)sep_ : 0.f);                                     \
   }
 template <typename T, bool SYNC>
 SO101_DEV void physics_step(const DevModel<T>& m, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
                             bool want_site, T (&site)[3], bool trip, Counters& cnt, int32_t* vcache) {
-  bool self_cand = false, self_any = false;
+  bool self_cand = false, self_full = false, self_pair = false;
   if (trip && vcache) {
-    const float bud = self_budget_spend(m, e.qd, vcache);
+    const int gone = self_budget_spend(m, e.qd, vcache);
     self_cand = !(e.flags & SO101_FLAG_TRIP_SELF) && outside_self_box(m, e.q);
-    self_any = self_cand && bud <= 0.f;
+    self_full = __any_sync(__activemask(), self_cand && (gone & 2));
+    self_pair = self_cand && (gone & 1);
   }
-  if (SYNC) self_any = __syncthreads_or(self_any);
-  else self_any = __any_sync(__activemask(), self_any);
+  if (SYNC) __syncthreads();
   // mj_checkPos / mj_checkVel
   {
     bool bad = false;
@@ -1585,15 +1598,15 @@ SO101_DEV void split_lookout_step(const DevModel<T>& m, SplitXch<T>& x, int lane
     }
   }
   if (trip) {   // see physics_step; x.trip still holds this lane's flags of the previous step (sticky within the launch)
-    const float bud = self_budget_spend(m, qd, vcache);
+    const int gone = self_budget_spend(m, qd, vcache);
     const bool cand = !(x.trip[lane] & SO101_FLAG_TRIP_SELF) && outside_self_box(m, q);
-    const bool any = __any_sync(__activemask(), cand && bud <= 0.f);       // the warp's candidates take the test together
+    const bool full = __any_sync(__activemask(), cand && (gone & 2));        // the warp's candidates take the full test together
     if (x.trip[lane] & SO101_FLAG_TRIP_SELF) fl |= SO101_FLAG_TRIP_SELF;
-    else if (any && cand) {
+    else if (cand && (full || (gone & 1))) {
       const double sep = !m.self_boxes ? -1.0 : self_boxes_overlap<T>(m, x.sn[0][lane], x.sn[1][lane], x.sn[2][lane], x.sn[3][lane], x.sn[4][lane], x.sn[5][lane],
-                                               x.cs[0][lane], x.cs[1][lane], x.cs[2][lane], x.cs[3][lane], x.cs[4][lane], x.cs[5][lane]);
+                                               x.cs[0][lane], x.cs[1][lane], x.cs[2][lane], x.cs[3][lane], x.cs[4][lane], x.cs[5][lane],
+                                               vcache, full ? -1 : vcache[SELF_PAIR_SLOT]);
       if (sep < 0.0) fl |= SO101_FLAG_TRIP_SELF;
-      vcache[SELF_BUDGET_SLOT] = __float_as_int(sep > 0.0 ? 0.999f * (float)sep : 0.f);
     }
   }
   x.ncon[lane] = nc;
