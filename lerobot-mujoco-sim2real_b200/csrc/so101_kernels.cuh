@@ -570,7 +570,7 @@ k_rollout_sliced(const __grid_constant__ DevModel<T> m, StateView<T> s, DevSpec 
     if (active && recent) {   // a hull of this env was tested during the unit: one of its boxes was below the table top
       bool tested = (e.flags & SO101_FLAG_CONTACT) != 0;
 #pragma unroll
-      for (int k = 0; k < SELF_PAIR_SLOT; k++) tested |= vcache[k] >= 0;
+      for (int k = 0; k <= SELF_PAIR_SLOT; k++) tested |= vcache[k] >= 0;   // ... or it took the self-collision test (outside the joint box)
       if (tested) recent[i] = 1;
     }
     e.flags |= flags_in;
