@@ -441,13 +441,14 @@ def wl_config1(ctx) -> None:
         "physics_steps_per_s": value * FRAME_SKIP,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms,
-                "path": "so101_batch_rollout_host: pinned host control tensor [T+1,5,N] + initial angles [6,N] -> "
-                        "k_reset + 2 time-chunked k_rollout launches (SO101_CTRL_TENSOR; up to 12 for datasets >= 128 MB) overlapped with the upload "
-                        "of the next chunk's controls and the download of the previous chunk's rows -> dataset rows "
-                        "[N,T+1,13] in pinned host memory, stream sync"},
+                "path": "so101_batch_rollout_host: pinned host control tensor [T+1,5,N] + initial angles [6,N] uploaded -> "
+                        "k_reset + ONE k_rollout launch (SO101_CTRL_TENSOR) whose row writer stores the dataset rows "
+                        "[N,T+1,13] straight into the caller's pinned host buffer over PCIe while it computes (no staging "
+                        "copy, no download phase; datasets >= 128 MB take the time-chunked copy-engine pipeline instead) "
+                        "-> stream sync.  d2h_bytes_per_step = the bytes those stores carry"},
         "gpu_launches": K,
         "gpu_launches_note": "one k_rollout<double,double,true> launch per step in the device-resident region; "
-                             "the e2e region launches k_reset + 2 k_rollout chunks per step",
+                             "the e2e region launches k_reset + one k_rollout per step",
         "roofline": roofline, "cpu_baseline": cpu_baseline_for("1"), "clocks": clocks,
         "wall_ms_timed_region": wall_ms,
         "flags": {"envs_tripwire": n_trip, "envs_badstate": n_bad, "envs_in_contact": n_contact, "of": N_ENVS},

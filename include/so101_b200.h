@@ -250,6 +250,9 @@ enum {
                                    do not fill whole waves): 0 = automatic, 1 = always, 2 = never                    */
   SO101_OPT_REGROUP       = 5,  /* long rollouts of large batches: regroup the envs that touch the table into the same
                                    blocks every few control steps: 0 = automatic, 1 = always (one-warp kernels), 2 = never */
+  SO101_OPT_HOST_DIRECT   = 7,  /* so101_batch_rollout_host: the kernels store the rows straight into the caller's pinned host
+                                   buffer (no staging copy, no download phase): 0 = automatic (pinned buffer, < 128 MB of
+                                   rows, >= 200 physics steps), 1 = whenever the buffer is device-accessible, 2 = never  */
   SO101_OPT_SELF_TEST     = 6   /* SO101_FLAG_TRIP_SELF: 0 = box-box test of the non-adjacent links for poses outside the
                                    fast-accept joint box (default), 1 = flag every pose outside the joint box (no test:
                                    cheaper on workloads that leave the box often, flags 10-100x more trajectories)     */

@@ -68,7 +68,7 @@ struct So101Batch {
   cudaStream_t s_up, s_down;
   cudaEvent_t ev_up[MAXCHUNK], ev_k[MAXCHUNK], ev_start;
   // explicit experiment options (so101_batch_set_option); 0 = automatic.  Nothing on this path reads the environment.
-  int opt_family, opt_block, opt_host_chunks, opt_host_even, opt_sliced, opt_regroup;
+  int opt_family, opt_block, opt_host_chunks, opt_host_even, opt_sliced, opt_regroup, opt_host_direct;
 };
 
 struct DeviceGuard {
@@ -292,6 +292,10 @@ int so101_batch_set_option(So101Batch* b, int option, int value) {
       return SO101_OK;
     case SO101_OPT_HOST_EVEN:
       b->opt_host_even = value != 0;
+      return SO101_OK;
+    case SO101_OPT_HOST_DIRECT:
+      if (value < 0 || value > 2) return fail(SO101_EINVAL, "direct host rows must be 0 (auto), 1 (whenever possible) or 2 (never)");
+      b->opt_host_direct = value;
       return SO101_OK;
     case SO101_OPT_SELF_TEST:
       if (value < 0 || value > 1) return fail(SO101_EINVAL, "self-collision test must be 0 (box-box test) or 1 (joint box only)");
@@ -571,7 +575,22 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
     dspec.u = b->u_stage;
   }
   const size_t rb = (size_t)b->n * (T + 1) * SO101_ROW * rs;
-  if ((rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
+  // Rows straight into the caller's buffer: pinned host memory is device-accessible under unified addressing, and the row
+  // writer's stores (a warp's 32 rows, consecutive words) go over PCIe while the launch computes - 43 MB in 7 ms is a
+  // fraction of the link.  No staging copy, no download phase, and no chunk boundaries (a boundary costs what the slowest
+  // block of each chunk costs).  Large datasets keep the copy-engine pipeline below: there the link is the bottleneck and
+  // stores that wait for it would stall the SMs (measured, tools/e2e_probe.py: the stores sustain ~16 GB/s; 43 / 71 / 89 MB
+  // of rows over 1000 / 200 / 500 physics steps: 8.34 -> 7.92, 4.55 -> 4.36, 9.67 -> 8.98 ms; 143 / 286 MB over 200 steps:
+  // 6.6 -> 9.2, 12.5 -> 19.2 ms).
+  void* rows_direct = nullptr;
+  if (b->opt_host_direct != 2 && (b->opt_host_direct == 1 || (rb < ((size_t)128 << 20) && (int64_t)T * frame_skip >= 200))) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, rows_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer)
+      rows_direct = pa.devicePointer;
+    else
+      cudaGetLastError();   // pageable memory: not an error, the staged path takes it
+  }
+  if (!rows_direct && (rc = grow(&b->rows_stage, &b->rows_stage_bytes, rb))) return rc;
   // chunking: worth it only when there is something to overlap
   // A chunk boundary is not free: every launch lasts as long as its slowest block, and with table contact the slow block
   // is a different one in every chunk, so the sum of the chunks exceeds the undivided launch (measured, 4096 envs x 100
@@ -587,6 +606,7 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
       if (nchunk < 3) nchunk = 3;
     }
   }
+  if (rows_direct) nchunk = 1;
   if (b->opt_host_chunks) nchunk = b->opt_host_chunks;
   if (nchunk > T) nchunk = T > 0 ? T : 1;
   // An error return inside the pipeline must not leave copies in flight that touch the caller's host buffers.
@@ -632,6 +652,12 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   } else {
     for (int c = 0; c <= nchunk; c++) tb[c] = (int)((int64_t)T * c / nchunk);
   }
+  if (rows_direct && tensor && !b->opt_host_chunks && T >= 20) {
+    // direct rows leave one copy exposed, the upload of the control tensor: start on the first tenth of it and let the rest
+    // arrive while that computes.  The one boundary comes early, before the blocks have drifted apart.
+    nchunk = 2;
+    tb[0] = 0; tb[1] = T / 10 < 2 ? 2 : T / 10; tb[2] = T;
+  }
   if (tensor) {
     for (int c = 0; c < nchunk; c++) {   // u_t for t in [first, tb[c+1]]: chunk c reads u at tb[c] .. tb[c+1]
       const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];
@@ -645,7 +671,8 @@ int so101_batch_rollout_host(So101Batch* b, const So101CtrlSpec* spec, const voi
   for (int c = 0; c < nchunk; c++) {
     if (tensor) PIPE_TRY(cudaStreamWaitEvent(st, b->ev_up[c], 0));
     const uint32_t f = c == 0 ? flags : (flags | SO101_ROLL_NO_RESET);
-    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, b->rows_stage, f, stream))) { drain(); return rc; }
+    if ((rc = rollout_range(b, &dspec, tb[c], tb[c + 1], T, frame_skip, rows_direct ? rows_direct : b->rows_stage, f, stream))) { drain(); return rc; }
+    if (rows_direct) continue;
     PIPE_TRY(cudaEventRecord(b->ev_k[c], st));
     PIPE_TRY(cudaStreamWaitEvent(b->s_down, b->ev_k[c], 0));
     const int first = c == 0 ? 0 : tb[c] + 1, last = tb[c + 1];

@@ -447,10 +447,13 @@ def test_rollout_host_single_abi_call(tables_v):
     assert torch.equal(out, env2.rollout(T, "random", seed=5).cpu())
 
 
+@pytest.mark.parametrize("direct", [2, 1])
 @pytest.mark.parametrize("kind", ["tensor", "random", "chirp"])
-def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind):
+def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind, direct):
     """rollout_host cuts long rollouts into time chunks that overlap upload / compute / download; the rows and the
-    final state must not depend on the number of chunks (continuation launches regenerate u_t0 and skip row t0)."""
+    final state must not depend on the number of chunks (continuation launches regenerate u_t0 and skip row t0), nor on
+    whether the rows are staged on the device and downloaded (direct = 2) or stored by the kernels straight into the pinned
+    host buffer (direct = 1, the default for datasets below 128 MB)."""
     from lerobot_mujoco_sim2real_b200 import tables as T_
     n, T = 300, 23                             # 23 control steps: uneven chunks
     g = torch.Generator().manual_seed(9)
@@ -459,6 +462,7 @@ def test_rollout_host_pipeline_chunks_are_invisible(tables_v, monkeypatch, kind)
     for chunks in ("1", "2", "4", "8", "12"):
         env = _vec(tables_v, n)
         env.set_option(T_.OPT_HOST_CHUNKS, int(chunks))
+        env.set_option(T_.OPT_HOST_DIRECT, direct)
         out = torch.full((n, T + 1, 13), float("nan"), dtype=torch.float64).pin_memory()
         env.rollout_host(T, kind, seed=21, u_host=U if kind == "tensor" else None, out_host=out,
                          flags=T_.ROLL_GRAVCOMP_HOLD)

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lerobot_mujoco_sim2real_b200 import builtin_tables, tables as T
 from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
-N, TC = 4096, 100
+N, TC = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (4096, 100)
 env = SOARM101VecEnv(tables=builtin_tables(), num_envs=N)
 g = torch.Generator().manual_seed(0)
 U = (torch.rand((TC + 1, 5, N), generator=g, dtype=torch.float64) - 0.5).pin_memory()
@@ -22,7 +22,14 @@ def timed(fn, reps=10):
 print("device rollout(tensor U resident, rows to device):", timed(lambda: env.rollout(TC, "tensor", u=Ud, out=rows_d, flags=T.ROLL_NO_RESET)))
 print("H2D U only:", timed(lambda: Ud.copy_(U, non_blocking=True)))
 print("D2H rows only (contiguous):", timed(lambda: rows.copy_(rows_d, non_blocking=True)))
-for ch in ("1", "2", "3", "4", "6", "8", "12"):
+for direct in (2, 1):
+    env.set_option(T.OPT_HOST_DIRECT, direct)
+    for ch in ("0", "1", "2", "3"):
+        env.set_option(T.OPT_HOST_CHUNKS, int(ch))
+        print(f"rollout_host direct={direct} (1: rows stored into the pinned host buffer by the kernel, 2: staged) chunks={ch}:",
+              timed(lambda: env.rollout_host(TC, "tensor", u_host=U, qpos0_host=q0, out_host=rows)))
+env.set_option(T.OPT_HOST_DIRECT, 2)
+for ch in (("1", "2", "3", "4", "6", "8", "12") if len(sys.argv) <= 2 else ()):
     env.set_option(T.OPT_HOST_CHUNKS, int(ch))
     for even in (False, True):
         env.set_option(T.OPT_HOST_EVEN, int(even))
