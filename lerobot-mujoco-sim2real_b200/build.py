@@ -32,8 +32,19 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
+STAMP = os.path.join(OBJ, "extra_flags.txt")   # the -D flags of the build that produced LIB (experiments); absent = none
+
+
 def up_to_date() -> bool:
-    return os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in DEPS)
+    """The library is newer than its sources AND was built without experiment flags (a library built with
+    `-DSO101_EXP_...` for a measurement must never pass for the product build)."""
+    if not (os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in DEPS)):
+        return False
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() == ""
+    except OSError:
+        return True
 
 
 def build(force: bool = False, verbose: bool = False, extra=()) -> str:
@@ -68,6 +79,8 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
         sys.stderr.write(log if verbose else "\n".join(l for l in log.split("\n") if "error" in l or "rror:" in l)[:8000] + "\n")
     if bad:
         raise RuntimeError(f"nvcc failed ({', '.join(bad)}), see csrc/build.log")
+    with open(STAMP, "w") as f:
+        f.write(" ".join(extra) + "\n")
     return LIB
 
 

@@ -68,7 +68,11 @@ template <typename T, bool SPLIT>
 SO101_DEV void step_env(const DevModel<T>& m, SplitXch<T>& x, Env<T>& e, const T (&ctrl)[NV], bool gravcomp_capture,
                         bool want_site, T (&site)[3], bool trip, Counters& cnt, int64_t nstep, int32_t* vcache) {
   if (SPLIT) split_dynamics_step<T>(m, x, threadIdx.x & 31, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, nstep);
+#ifdef SO101_EXP_NOSYNC   // experiment: no block barriers in the one-warp kernels (see profiles/README.md)
+  else physics_step<T, false>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, vcache);
+#else
   else physics_step<T, true>(m, e, ctrl, gravcomp_capture, want_site, site, trip, cnt, vcache);
+#endif
 }
 
 // thread -> env of a stepping kernel; `active` = this thread owns the env (loads, stores, writes rows); exit_block = the
