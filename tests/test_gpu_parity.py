@@ -242,3 +242,46 @@ def test_model_variants_teacher_forced(oracle_mod, tables_v, monkeypatch, varian
     err = _rel(out, ref)
     print(f"{variant} split={split}: qpos {err[:, :6].max():.2e} qvel {err[:, 6:12].max():.2e} qacc {err[:, 12:].max():.2e}")
     assert err[:, :6].max() < 1e-12 and err[:, 6:12].max() < 1e-9 and np.quantile(err[:, 12:], 0.99) < 1e-9
+
+
+@pytest.mark.gpu
+def test_mechanical_energy_is_dissipated(tables_p):
+    """A property that needs no oracle.  Position-servo scene, constant targets: every force on the arm is conservative (gravity,
+    the servos' kp (q* - q) = a spring) or dissipative (kv, joint damping, friction loss), so E = 1/2 qd' M(q) qd + V_gravity(q)
+    + 1/2 kp |q - q*|^2 can only fall.  M and V come from the textbook formulas in mjcf.py (world-frame Jacobians), not from the
+    kernels' link-local recursion, so this checks mass matrix, bias forces, actuation and integrator of the CUDA path against
+    mechanics itself."""
+    from lerobot_mujoco_sim2real_b200 import mjcf
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    t = tables_p
+    n, steps = 24, 80
+    rng = np.random.default_rng(3)
+    q0 = rng.uniform(-0.3, 0.3, (n, 6)); q0[:, 5] = 0.2
+    v0 = rng.uniform(-1.0, 1.0, (n, 6))
+    target = q0 + rng.uniform(-0.1, 0.1, (n, 6))
+    kp = np.array([t.act_gain[i] for i in range(6)])
+    grav = np.array(t.gravity[:])
+
+    def energy(q, v, qs):
+        xpos, xmat, _, _ = mjcf.fk_numpy(t, q)
+        V = -sum(t.body_mass[b] * grav @ (xpos[b] + xmat[b] @ np.array(t.body_ipos[b][:])) for b in range(1, t.nbody))
+        return 0.5 * v @ mjcf.mass_matrix_numpy(t, q) @ v + V + 0.5 * np.sum(kp * (q - qs) ** 2)
+
+    env = SOARM101VecEnv(tables=t, num_envs=n, hulls=None)
+    env.set_state(q0, v0, np.zeros((n, 6)))
+    u = torch.as_tensor(target[:, :5].T.copy(), dtype=torch.float64, device="cuda")
+    # the gripper's servo target is 0 in step() (ctrl[5] stays 0): its spring is anchored there
+    target[:, 5] = 0.0
+    E = np.zeros((steps + 1, n))
+    E[0] = [energy(q0[i], v0[i], target[i]) for i in range(n)]
+    for s in range(steps):
+        env.step_soa(u, 1)
+        q, v, _ = env.get_state()
+        q, v = q.cpu().numpy(), v.cpu().numpy()
+        E[s + 1] = [energy(q[i], v[i], target[i]) for i in range(n)]
+    drop = E[0] - E[-1]
+    rise = np.diff(E, axis=0).max(axis=0)
+    print(f"energy: start {E[0].mean():.4f} J, after {steps} steps {E[-1].mean():.4f} J; largest single-step rise / total drop: "
+          f"{(rise / drop).max():.2e}")
+    assert (drop > 0.01).all()                       # most of the kinetic energy is gone
+    assert (rise <= 1e-3 * drop).all()               # and it never comes back (semi-implicit Euler: O(h^2) wiggles at most)
