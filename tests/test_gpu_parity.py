@@ -285,3 +285,27 @@ def test_mechanical_energy_is_dissipated(tables_p):
           f"{(rise / drop).max():.2e}")
     assert (drop > 0.01).all()                       # most of the kinetic energy is gone
     assert (rise <= 1e-3 * drop).all()               # and it never comes back (semi-implicit Euler: O(h^2) wiggles at most)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-5)])
+def test_gravity_compensation_is_a_static_equilibrium(tables_v, dtype, tol):
+    """A property that needs no oracle: qfrc_applied = qfrc_bias [REF Koopman_MPC.py:119] at rest cancels gravity exactly, the
+    velocity servos command zero velocity, so the arm does not move - for any pose, over 500 physics steps.  Without the
+    compensation the same arms sag (the servos are dampers, not position holds)."""
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    n = 512
+    rng = np.random.default_rng(12)
+    q0 = rng.uniform(-0.6, 0.6, (n, 6)); q0[:, 5] = rng.uniform(0.0, 0.5, n)
+    u = torch.zeros((5, n), dtype=getattr(torch, dtype), device="cuda")
+    moved = {}
+    for comp in (True, False):
+        env = SOARM101VecEnv(tables=tables_v, num_envs=n, dtype=dtype, hulls=None, gravity_compensation=comp)
+        env.set_state(q0, np.zeros((n, 6)), np.zeros((n, 6)))
+        for _ in range(50):
+            env.step_soa(u, 10)
+        q, v, _ = env.get_state()
+        moved[comp] = (np.abs(q.cpu().numpy().astype(np.float64) - q0).max(), float(v.abs().max()))
+    print(f"{dtype}: with compensation moved {moved[True][0]:.2e} rad (max |qvel| {moved[True][1]:.2e}); without {moved[False][0]:.2e} rad")
+    assert moved[True][0] < tol and moved[True][1] < 100 * tol
+    assert moved[False][0] > 1e-3
