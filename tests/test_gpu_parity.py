@@ -309,3 +309,71 @@ def test_gravity_compensation_is_a_static_equilibrium(tables_v, dtype, tol):
     print(f"{dtype}: with compensation moved {moved[True][0]:.2e} rad (max |qvel| {moved[True][1]:.2e}); without {moved[False][0]:.2e} rad")
     assert moved[True][0] < tol and moved[True][1] < 100 * tol
     assert moved[False][0] > 1e-3
+
+
+@pytest.mark.gpu
+def test_bias_forces_against_the_lagrangian(tables_v):
+    """A property that needs no oracle: mj_forward's qfrc_bias on the CUDA path (link-local RNEA) equals the bias force of the
+    Lagrangian built from the textbook M(q) and V(q) of mjcf.py (world-frame Jacobians), by central differences:
+    c_i = dV/dq_i + sum_jk (dM_ij/dq_k - 1/2 dM_jk/dq_i) qd_j qd_k."""
+    from lerobot_mujoco_sim2real_b200 import mjcf
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    t = tables_v
+    n, h = 48, 1e-5
+    rng = np.random.default_rng(21)
+    q = rng.uniform(-1.0, 1.0, (n, 6)); q[:, 5] = rng.uniform(0.0, 1.0, n)
+    v = rng.uniform(-2.0, 2.0, (n, 6))
+    grav = np.array(t.gravity[:])
+
+    def V(x):
+        xpos, xmat, _, _ = mjcf.fk_numpy(t, x)
+        return -sum(t.body_mass[b] * grav @ (xpos[b] + xmat[b] @ np.array(t.body_ipos[b][:])) for b in range(1, t.nbody))
+
+    env = SOARM101VecEnv(tables=t, num_envs=n, hulls=None)
+    env.set_state(q, v, np.zeros((n, 6)))
+    _, bias = env.forward()
+    bias = bias.cpu().numpy()
+    worst = 0.0
+    for e in range(n):
+        dM = np.zeros((6, 6, 6)); dV = np.zeros(6)
+        for k in range(6):
+            d = np.zeros(6); d[k] = h
+            dM[k] = (mjcf.mass_matrix_numpy(t, q[e] + d) - mjcf.mass_matrix_numpy(t, q[e] - d)) / (2 * h)
+            dV[k] = (V(q[e] + d) - V(q[e] - d)) / (2 * h)
+        c = dV + np.einsum("kij,j,k->i", dM, v[e], v[e]) - 0.5 * np.einsum("ijk,j,k->i", dM, v[e], v[e])
+        worst = max(worst, np.abs(bias[e] - c).max() / (1e-3 + np.abs(c).max()))
+    print(f"qfrc_bias vs Lagrangian by central differences: worst relative difference {worst:.2e}")
+    assert worst < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["onewarp", "team"])
+def test_one_step_obeys_newtons_law(tables_v, family):
+    """A property that needs no oracle: without friction loss and joint damping (a model variant; no constraint row is active
+    away from the limits) one physics step from rest gives qvel' = h a with  M(q) a = gear * (gain * clip(u) + bias terms) - c(q, 0):
+    the textbook mass matrix and gravity vector of mjcf.py against the CUDA path's CRBA, factorisation, actuation and Euler step."""
+    from lerobot_mujoco_sim2real_b200 import mjcf, tables as T_
+    from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
+    t = T_.tables_from_dict(T_.tables_to_dict(tables_v))
+    for k in range(6):
+        t.dof_frictionloss[k] = 0.0
+        t.dof_damping[k] = 0.0
+    n = 64
+    rng = np.random.default_rng(31)
+    q = rng.uniform(-1.0, 1.0, (n, 6)); q[:, 5] = rng.uniform(0.0, 1.0, n)
+    u = np.zeros((n, 6)); u[:, :5] = rng.uniform(-0.05, 0.05, (n, 5))      # small: the force clamp (+-3.5) stays inactive
+    env = SOARM101VecEnv(tables=t, num_envs=n, hulls=None)
+    env.set_option(T_.OPT_KERNEL_FAMILY, T_.FAMILY_ONEWARP if family == "onewarp" else T_.FAMILY_TEAM)
+    env.set_state(q, np.zeros((n, 6)), np.zeros((n, 6)))
+    env.step_soa(torch.as_tensor(u[:, :5].T.copy(), dtype=torch.float64, device="cuda"), 1)
+    q1, v1, _ = [x.cpu().numpy() for x in env.get_state()]
+    h = t.timestep
+    worst = 0.0
+    for e in range(n):
+        M = mjcf.mass_matrix_numpy(t, q[e])
+        tau = np.array([t.act_gain[i] * u[e, i] for i in range(6)]) - mjcf.gravity_bias_numpy(t, q[e])   # qvel = 0: no velocity feedback, no Coriolis
+        a = np.linalg.solve(M, tau)
+        worst = max(worst, np.abs(v1[e] / h - a).max() / (1e-3 + np.abs(a).max()))
+        assert np.abs(q1[e] - (q[e] + h * v1[e])).max() < 1e-15        # semi-implicit Euler: the new velocity moves the position
+    print(f"{family}: one step from rest, qvel'/h against M^-1 (tau - g): worst relative difference {worst:.2e}")
+    assert worst < 1e-10
