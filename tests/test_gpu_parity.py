@@ -347,17 +347,21 @@ def test_bias_forces_against_the_lagrangian(tables_v):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("damped", [False, True])
 @pytest.mark.parametrize("family", ["onewarp", "team"])
-def test_one_step_obeys_newtons_law(tables_v, family):
-    """A property that needs no oracle: without friction loss and joint damping (a model variant; no constraint row is active
-    away from the limits) one physics step from rest gives qvel' = h a with  M(q) a = gear * (gain * clip(u) + bias terms) - c(q, 0):
-    the textbook mass matrix and gravity vector of mjcf.py against the CUDA path's CRBA, factorisation, actuation and Euler step."""
+def test_one_step_obeys_newtons_law(tables_v, family, damped):
+    """A property that needs no oracle: without friction loss (a model variant; no constraint row is active away from the
+    limits) one physics step from rest gives qvel' = h a with (M(q) + h B) a = gain * u - g(q), B = the joint damping that
+    mj_Euler treats implicitly (or none): the textbook mass matrix and gravity vector of mjcf.py against the CUDA path's CRBA,
+    factorisation, actuation and Euler step."""
     from lerobot_mujoco_sim2real_b200 import mjcf, tables as T_
     from lerobot_mujoco_sim2real_b200.vec_env import SOARM101VecEnv
     t = T_.tables_from_dict(T_.tables_to_dict(tables_v))
     for k in range(6):
         t.dof_frictionloss[k] = 0.0
-        t.dof_damping[k] = 0.0
+        if not damped:
+            t.dof_damping[k] = 0.0
+    B = np.diag([t.dof_damping[k] for k in range(6)])      # damped: mj_Euler's implicit step solves (M + h B) a = force
     n = 64
     rng = np.random.default_rng(31)
     q = rng.uniform(-1.0, 1.0, (n, 6)); q[:, 5] = rng.uniform(0.0, 1.0, n)
@@ -372,7 +376,7 @@ def test_one_step_obeys_newtons_law(tables_v, family):
     for e in range(n):
         M = mjcf.mass_matrix_numpy(t, q[e])
         tau = np.array([t.act_gain[i] * u[e, i] for i in range(6)]) - mjcf.gravity_bias_numpy(t, q[e])   # qvel = 0: no velocity feedback, no Coriolis
-        a = np.linalg.solve(M, tau)
+        a = np.linalg.solve(M + t.timestep * B, tau)
         worst = max(worst, np.abs(v1[e] / h - a).max() / (1e-3 + np.abs(a).max()))
         assert np.abs(q1[e] - (q[e] + h * v1[e])).max() < 1e-15        # semi-implicit Euler: the new velocity moves the position
     print(f"{family}: one step from rest, qvel'/h against M^-1 (tau - g): worst relative difference {worst:.2e}")
